@@ -1,0 +1,176 @@
+/*
+ * b200unet.h  --  C-ABI of the B200-native 3D U-Net forward/backward engine (libb200unet.so)
+ *
+ * Drop-in boundary for the ONE hot path of wolny/pytorch-3dunet (reference @ a33e2c7): everything that
+ * `pytorch3dunet.unet3d.model.get_model(cfg)(x)` and its autograd execute.  The reference has no FFI of its
+ * own (it is pure Python over torch.nn); each entry point below names the reference call site
+ * (file:line relative to the reference checkout) whose ATen library call it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch types.  All pointers are DEVICE pointers unless noted.
+ *   - activations are bf16 "NDHWC": [N][D][H][W][C] contiguous, C % 8 == 0 (16-byte channel vectors).
+ *   - every function only ENQUEUES work on `stream` (a cudaStream_t passed as void*); it never
+ *     allocates, frees or synchronises.  Buffers are owned by the caller (PyTorch caching allocator).
+ *   - return 0 on success, non-zero on error; b200_last_error() returns the message (thread local).
+ *   - "partials": float [N][P][C][2] per-block partial sums (sum v, sum v*w); P is returned by the
+ *     matching *_partials_count() query; reduce them with b200_partials_finalize (deterministic, fp64).
+ */
+#ifndef B200UNET_H_
+#define B200UNET_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* b200_stream_t; /* cudaStream_t */
+
+/* activation kinds (create_conv buildingblocks.py:45-51; ResNetBlock non_linearity :270-275) */
+enum { B200_ACT_NONE = 0, B200_ACT_RELU = 1, B200_ACT_LEAKY = 2, B200_ACT_ELU = 3 };
+/* conv implementation selector */
+enum { B200_IMPL_AUTO = 0, B200_IMPL_DIRECT = 1, B200_IMPL_TCGEN05 = 2 };
+/* final activation (model.py:93-98) */
+enum { B200_FINAL_NONE = 0, B200_FINAL_SIGMOID = 1, B200_FINAL_SOFTMAX = 2 };
+
+int b200_version(void);
+/* copies the calling thread's last error message into buf (NUL terminated), returns its length */
+int b200_last_error(char* buf, size_t len);
+/* 1 if the current device is sm_100 (tcgen05 kernels usable), else 0 */
+int b200_device_is_sm100(void);
+
+/* ---- layout / input (datasets' ToTensor yields NCDHW fp32, augment/transforms.py:816-826) ---------- */
+int b200_ncdhw_f32_to_ndhwc_f32(const float* src, float* dst, int N, int C, int D, int H, int W, b200_stream_t s);
+int b200_ncdhw_f32_to_ndhwc_bf16(const float* src, void* dst, int N, int C, int D, int H, int W, b200_stream_t s);
+int b200_ndhwc_bf16_to_ncdhw_f32(const void* src, float* dst, int N, int C, int D, int H, int W, b200_stream_t s);
+
+/* ---- GroupNorm statistics (nn.GroupNorm, buildingblocks.py:75 -> native_group_norm) -------------- */
+/* per-(n,c) sum / sum-of-squares of an NDHWC tensor -> partials [N][P][C][2]; P = b200_stats_partials_count */
+int b200_stats_partials_count(int N, int C, long long voxels);          /* for b200_stats_ndhwc_bf16 */
+int b200_stats_ndhwc_bf16(const void* x, int N, int C, long long voxels, float* partials, b200_stream_t s);
+int b200_stats_ncdhw_f32_partials_count(long long voxels);              /* for b200_stats_ncdhw_f32 */
+/* the raw network input, NCDHW fp32, any C (the first GroupNorm of order 'gcr' normalises the input itself) */
+int b200_stats_ncdhw_f32(const float* x, int N, int C, long long voxels, float* partials, b200_stream_t s);
+/* partials of (sum a, sum a*b) over two bf16 NDHWC tensors; P = b200_stats_partials_count */
+int b200_stats2_ndhwc_bf16(const void* a, const void* b, int N, int C, long long voxels, float* partials, b200_stream_t s);
+/* sums[N][C][2] (double) = sum over P of partials */
+int b200_partials_finalize(const float* partials, int N, int P, int C, double* sums, b200_stream_t s);
+
+/* Fold GroupNorm into the following conv (order 'g' before 'c'):
+ *   x_hat = a[n,c]*x + b[n,c]   with a = gamma*rstd, b = beta - gamma*mean*rstd  (group stats from `sums`)
+ *   wf[n][tap][co][ci] = bf16( W[co][ci][tap] * a[n][ci] )
+ *   biascls[n][cls][co] = sum over the taps that are in-bounds for border class `cls` of sum_ci W[co][ci][tap]*b[n][ci]
+ * (the reference zero-pads AFTER normalising, so the shift term only exists for in-bounds taps).
+ * With sums == NULL (no GroupNorm before the conv): a=1, b=0, n_w = 1 weight copy, biascls = conv bias (or 0).
+ * mean_rstd[N][G][2], ab[N][C][2] are saved for backward. */
+int b200_gn_fold(const double* sums, const float* gamma, const float* beta, int G, double count,
+                 const float* W, const float* conv_bias, int N, int Cin, int Cout,
+                 void* wf, float* biascls, float* mean_rstd, float* ab, b200_stream_t s);
+/* GroupNorm applied as a standalone op AFTER a conv (orders like 'cgr'): y = act(a*x+b), emits partials of y */
+int b200_gn_apply_act(const void* x, const float* ab, int N, int C, long long voxels, int act, float slope,
+                      void* y, float* partials, b200_stream_t s);
+/* a,b only (no weight folding): ab[N][C][2], mean_rstd[N][G][2] */
+int b200_gn_coeffs(const double* sums, const float* gamma, const float* beta, int G, double count,
+                   int N, int C, float* mean_rstd, float* ab, b200_stream_t s);
+
+/* ---- 3x3x3 convolution, padding 1 (nn.Conv3d, buildingblocks.py:56 -> cudnn_convolution) --------
+ * y[n,v,co] = act( sum_{tap,ci} wf[n or 0][tap][co][ci] * x[n,v+tap-1,ci] + biascls[n or 0][cls(v)][co] (+ residual) )
+ * x: bf16 NDHWC, or (x_is_f32) fp32 NDHWC (the network input; reference keeps fp32, transforms.py:816-826)
+ * n_w: number of per-sample weight copies (N when GroupNorm is folded in, else 1)
+ * n_b: same for biascls (N, 1 or 0 = no bias)
+ * pmode: 0 no partials; 1 partials of (y, y*y) for the next GroupNorm; 2 partials of (y, y*aux) (GroupNorm backward)
+ * P must equal b200_conv3_partials_count(...) for the chosen impl. */
+int b200_conv3_partials_count(int impl, int N, int D, int H, int W, int Cin, int Cout);
+int b200_conv3_resolve_impl(int impl, int N, int D, int H, int W, int Cin, int Cout, int x_is_f32);
+int b200_conv3_fwd(int impl, const void* x, int x_is_f32, const void* wf, int n_w, const float* biascls, int n_b,
+                   const void* residual, int act, float slope,
+                   int N, int D, int H, int W, int Cin, int Cout,
+                   void* y, int pmode, const void* aux, float* partials, b200_stream_t s);
+/* dgrad weights: wd[tap'][ci][co] = bf16(W[co][ci][26-tap'])  (convolution_backward's input gradient) */
+int b200_prep_dgrad_weights(const float* W, int Cin, int Cout, void* wd, b200_stream_t s);
+
+/* wgrad: G[n][split][tap][ci][co] (fp32) = sum_v dz[n,v,co] * x[n,v+tap-1,ci]  (raw, zero padded x)
+ * S = b200_conv3_wgrad_splits(...) */
+int b200_conv3_wgrad_resolve_impl(int impl, int N, int D, int H, int W, int Cin, int Cout, int x_is_f32);
+int b200_conv3_wgrad_splits(int impl, int N, int D, int H, int W, int Cin, int Cout, int x_is_f32);
+int b200_conv3_wgrad(int impl, const void* x, int x_is_f32, const void* dz,
+                     int N, int D, int H, int W, int Cin, int Cout, float* G, b200_stream_t s);
+/* T[n][tap][co] = sum over v with v+tap-1 in bounds of dz[n,v,co]  (the GroupNorm shift term of wgrad);
+ * scratch: b200_border_tap_sums_workspace(...) floats */
+int b200_border_tap_sums_workspace(int N, int D, int H, int W, int C);
+int b200_border_tap_sums(const void* dz, int N, int D, int H, int W, int C, float* T, float* scratch, b200_stream_t s);
+/* dW[co][ci][tap] = sum_n ( a[n][ci] * sum_split G + b[n][ci] * T[n][tap][co] ); ab == NULL -> a=1,b=0 */
+int b200_wgrad_finalize(const float* G, int N, int S, int Cin, int Cout, const float* ab, const float* T,
+                        float* dW, b200_stream_t s);
+/* bias gradient for convs that have one: db[co] = sum_{n,tap=center...}: simply sum_n,v dz = T[n][13][co] summed */
+int b200_bias_grad_from_T(const float* T, int N, int C, float* db, b200_stream_t s);
+
+/* GroupNorm-backward sums of a conv's INPUT from the wgrad by-products (G, T) and the weights:
+ * sums2[n][ci] = ( sum_v dxhat , sum_v dxhat*x ) -- no extra pass over activations */
+int b200_gn_bwd_sums_from_wgrad(const float* G, int S, const float* T, const float* W, int N, int Cin, int Cout,
+                                double* sums2, b200_stream_t s);
+
+/* ---- GroupNorm backward (native_group_norm_backward) ------------------------------------------------
+ * sums2[N][C][2] = (sum dxhat, sum dxhat*x) ; coef[N][C][3] = (A,B,Cc) with dx = A*dxhat + B*x + Cc */
+int b200_gn_bwd_coeffs(const double* sums2, const float* gamma, const float* mean_rstd, int G, double count,
+                       int N, int C, float* coef, float* dgamma, float* dbeta, b200_stream_t s);
+/* out = (A*dxhat + B*x + Cc) * act'(x) [+ gadd]
+ * (x is the post-activation output of its producer when act != NONE; gadd: an already accumulated gradient of the
+ *  same shape in "dz form", may alias out) */
+int b200_gn_bwd_apply(const void* dxhat, const void* x, const float* coef, int N, int C, long long voxels,
+                      int act, float slope, const void* gadd, void* out, b200_stream_t s);
+/* out = g[..., g_co:g_co+C] * act'(y) [+ gadd] : plain masking / accumulation; g is read with channel stride g_cs */
+int b200_act_bwd(const void* g, int g_cs, int g_co, const void* y, int N, int C, long long voxels, int act, float slope,
+                 const void* gadd, void* out, b200_stream_t s);
+
+/* ---- MaxPool3d(2) (buildingblocks.py:356 -> max_pool3d_with_indices), floor mode ---------------- */
+int b200_maxpool_fwd(const void* x, int N, int D, int H, int W, int C, void* y, float* partials, b200_stream_t s);
+int b200_maxpool_partials_count(int N, int D, int H, int W, int C);
+/* dz_full = scatter(dpooled to first argmax of x_full) * act'(x_full) [+ gadd] */
+int b200_maxpool_bwd(const void* dpooled, const void* x_full, int N, int D, int H, int W, int C,
+                     int act, float slope, const void* gadd, void* dz_full, b200_stream_t s);
+
+/* ---- nearest upsample to the encoder's size + channel concat (buildingblocks.py:614, :491) ------ */
+int b200_upcat_fwd(const void* enc, int C0, const void* x, int C1, int N, int D, int H, int W, int d, int h, int w,
+                   void* cat, float* partials, b200_stream_t s);
+int b200_upcat_partials_count(int N, int D, int H, int W, int C);
+/* dx_small = (sum over destination voxels that map to each source voxel of dcat[..., C0:]) * act'(x_small) */
+int b200_upcat_bwd(const void* dcat, int C0, int C1, const void* x_small, int N, int D, int H, int W, int d, int h, int w,
+                   int act, float slope, void* dx_small, b200_stream_t s);
+
+/* ---- final 1x1x1 conv + Sigmoid/Softmax (model.py:89,141-147) ------------------------------------ */
+int b200_final_conv_fwd(const void* x, int N, long long voxels, int C, const float* W, const float* bias, int Cout,
+                        int final_act, float* logits, float* probs, b200_stream_t s);
+int b200_final_conv_bwd_partials_count(int N, long long voxels, int C, int Cout);
+/* dz = (sum_o dlogits[o] W[o][c]) * act'(x); partials[P][Cout*C + Cout] for dW and dbias */
+int b200_final_conv_bwd(const float* dlogits, const void* x, int N, long long voxels, int C, const float* W, int Cout,
+                        int act, float slope, void* dz, float* partials, b200_stream_t s);
+/* generic deterministic reduction out[K] = sum_p partials[p][K] */
+int b200_reduce_rows(const float* partials, int P, int K, float* out, b200_stream_t s);
+
+/* ---- implementation-specific entry points (what the dispatchers above call; exported for tests/profiling) --- */
+int b200_conv3_igemm_supported(int N, int D, int H, int W, int Cin, int Cout);
+int b200_conv3_igemm_partials_count(int N, int D, int H, int W, int Cin, int Cout);
+int b200_conv3_igemm_fwd(const void* x, const void* wf, int n_w, const float* biascls, int n_b, const void* residual, int act,
+                         float slope, int N, int D, int H, int W, int Cin, int Cout, void* y, int pmode, const void* aux,
+                         float* partials, b200_stream_t s);
+int b200_conv3_direct_partials_count(int N, int D, int H, int W, int Cout);
+int b200_conv3_direct_fwd(const void* x, int x_is_f32, const void* wf, int n_w, const float* biascls, int n_b, const void* residual,
+                          int act, float slope, int N, int D, int H, int W, int Cin, int Cout, void* y, int pmode, const void* aux,
+                          float* partials, b200_stream_t s);
+int b200_conv3_direct_wgrad(const void* x, int x_is_f32, const void* dz, int N, int D, int H, int W, int Cin, int Cout, float* G,
+                            b200_stream_t s);
+int b200_conv3_wgrad_igemm_supported(int N, int D, int H, int W, int Cin, int Cout);
+int b200_conv3_wgrad_igemm_splits(int N, int D, int H, int W, int Cin, int Cout);
+int b200_conv3_wgrad_igemm(const void* x, const void* dz, int N, int D, int H, int W, int Cin, int Cout, float* G, b200_stream_t s);
+
+
+/* hardware probe (test tooling): tcgen05.mma on a row-shifted / odd-strided view of a SWIZZLE_128B tile.
+ * A: [rows][64] bf16, B: [16][64] bf16, D: [128][16] f32 with D[r][n] = sum_k A[shift + (r/8)*group_rows + r%8][k] * B[n][k] */
+int b200_probe_umma_rowshift(const void* A, int rows, const void* B, int shift, int group_rows, float* D, b200_stream_t s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200UNET_H_ */

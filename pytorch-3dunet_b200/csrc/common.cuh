@@ -1,0 +1,85 @@
+// Shared helpers for libb200unet.so (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/b200unet.h"
+
+namespace b200 {
+
+void set_error(const char* fmt, ...);
+
+#define B200_CHECK_ARG(cond, ...)            \
+  do {                                       \
+    if (!(cond)) {                           \
+      b200::set_error(__VA_ARGS__);          \
+      return 1;                              \
+    }                                        \
+  } while (0)
+
+#define B200_CHECK_LAUNCH(name)                                                     \
+  do {                                                                              \
+    cudaError_t e__ = cudaGetLastError();                                           \
+    if (e__ != cudaSuccess) {                                                       \
+      b200::set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));      \
+      return 2;                                                                     \
+    }                                                                               \
+  } while (0)
+
+typedef __nv_bfloat16 bf16;
+
+struct alignas(16) bf16x8 {
+  __nv_bfloat162 v[4];
+};
+
+__device__ __forceinline__ void unpack8(const bf16x8& p, float f[8]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(p.v[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ bf16x8 pack8(const float f[8]) {
+  bf16x8 p;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return p;
+}
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+// activation and its derivative expressed through the OUTPUT y (valid for relu / leaky / elu(alpha=1))
+__device__ __forceinline__ float act_fwd(float z, int act, float slope) {
+  switch (act) {
+    case B200_ACT_RELU: return z > 0.f ? z : 0.f;
+    case B200_ACT_LEAKY: return z > 0.f ? z : z * slope;
+    case B200_ACT_ELU: return z > 0.f ? z : expm1f(z);
+    default: return z;
+  }
+}
+__device__ __forceinline__ float act_grad_from_out(float y, int act, float slope) {
+  switch (act) {
+    case B200_ACT_RELU: return y > 0.f ? 1.f : 0.f;
+    case B200_ACT_LEAKY: return y > 0.f ? 1.f : slope;
+    case B200_ACT_ELU: return y > 0.f ? 1.f : y + 1.f;
+    default: return 1.f;
+  }
+}
+
+// Border class of a voxel coordinate along one axis: 0 = low face, 1 = interior, 2 = high face, 3 = both (dim == 1)
+__host__ __device__ __forceinline__ int axis_cls(int p, int dim) {
+  int lo = (p == 0), hi = (p == dim - 1);
+  return lo ? (hi ? 3 : 0) : (hi ? 2 : 1);
+}
+// is tap t (0,1,2 -> offset -1,0,+1) in bounds for axis class c
+__host__ __device__ __forceinline__ bool tap_valid(int c, int t) {
+  if (t == 1) return true;
+  if (t == 0) return c == 1 || c == 2;  // needs p-1 >= 0
+  return c == 1 || c == 0;              // needs p+1 < dim
+}
+
+inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+}  // namespace b200

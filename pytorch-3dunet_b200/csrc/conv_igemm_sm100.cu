@@ -1,0 +1,406 @@
+// 3x3x3 convolution (padding 1) as an implicit GEMM on the sm_100a tensor cores.
+//
+//   D[128 voxels, NT out-channels] = sum over (tap, 64-channel chunk) of  A_tap[128, KC] * B_tap[NT, KC]^T
+//
+//   A_tap : a BDxBHxBW box of the NDHWC activation, shifted by the filter tap, fetched by ONE 5-D TMA tile load
+//           whose out-of-bounds elements are zero-filled by the hardware (= the conv's zero padding); the im2col
+//           matrix never exists in memory.  Rows land K-major in shared memory with the TMA 128/64/32-byte swizzle.
+//   B_tap : [NT, KC] slice of the (GroupNorm-folded, per-sample) weights wf[n][tap][co][ci], one 3-D TMA tile load.
+//   MMA   : tcgen05.mma.cta_group::1.kind::f16, M=128, N=NT, K=16, issued by one thread; fp32 accumulators in TMEM.
+//   Epilogue (4 warps): tcgen05.ld -> + border-class bias (the GroupNorm shift through zero padding) -> + residual
+//           -> activation -> bf16 -> global; per-channel (sum, sum*w) partials for the next GroupNorm / GN backward.
+//
+// The same kernel is the dgrad (input gradient): x := dz, weights := tap-flipped transposed weights.
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
+#include <string.h>
+
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace b200 {
+
+constexpr int CONV_THREADS = 192;
+constexpr int CONV_MAX_STAGES = 8;
+
+struct ConvParams {
+  int N, D, H, W, Cin, Cout;
+  int BD, BH, BW;
+  int tilesD, tilesH, tilesW;
+  int n_w, n_b;
+  int NT;       // output channels per CTA
+  int KC;       // channels per k-block (16/32/64)
+  int kchunks;  // Cin / KC
+  int stages;
+  int a_bytes, b_bytes;  // per-stage tile sizes (1024-aligned)
+  int tmem_cols;
+  int act;
+  float slope;
+  int pmode;
+  const float* biascls;
+  const bf16* residual;
+  const bf16* aux;
+  bf16* y;
+  float* partials;
+};
+
+// one 32-/16-column slab of the accumulator tile for one thread (= one output voxel row)
+template <int CW>
+__device__ __forceinline__ void conv_epilogue_slab(const ConvParams& p, uint32_t taddr, int c0 /*col in tile*/, int n0, bool valid,
+                                                   size_t vox_off /* (n*vox+v) */, const float* bias_row /* or null */, int lane,
+                                                   float* scratch /* [NT][2] for this warp */) {
+  uint32_t raw[CW];
+  if constexpr (CW == 32) tmem_ld_32x32b_x32(taddr + c0, raw);
+  else tmem_ld_32x32b_x16(taddr + c0, raw);
+  tmem_ld_wait();
+  float v[CW];
+#pragma unroll
+  for (int i = 0; i < CW; ++i) v[i] = __uint_as_float(raw[i]);
+  const size_t goff = vox_off * p.Cout + n0 + c0;
+  if (valid) {
+    if (bias_row) {
+      const float4* bp = reinterpret_cast<const float4*>(bias_row + n0 + c0);
+#pragma unroll
+      for (int i = 0; i < CW / 4; ++i) {
+        float4 b = __ldg(bp + i);
+        v[4 * i] += b.x;
+        v[4 * i + 1] += b.y;
+        v[4 * i + 2] += b.z;
+        v[4 * i + 3] += b.w;
+      }
+    }
+    if (p.residual) {
+      const bf16x8* rp = reinterpret_cast<const bf16x8*>(p.residual + goff);
+#pragma unroll
+      for (int i = 0; i < CW / 8; ++i) {
+        float f[8];
+        unpack8(rp[i], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[8 * i + j] += f[j];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < CW; ++i) v[i] = bf16_round(act_fwd(v[i], p.act, p.slope));
+    bf16x8* op = reinterpret_cast<bf16x8*>(p.y + goff);
+#pragma unroll
+    for (int i = 0; i < CW / 8; ++i) op[i] = pack8(&v[8 * i]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < CW; ++i) v[i] = 0.f;
+  }
+  if (p.pmode) {
+    float w[CW];
+    if (p.pmode == 1) {
+#pragma unroll
+      for (int i = 0; i < CW; ++i) w[i] = v[i] * v[i];
+    } else {
+      if (valid) {
+        const bf16x8* ap = reinterpret_cast<const bf16x8*>(p.aux + goff);
+#pragma unroll
+        for (int i = 0; i < CW / 8; ++i) {
+          float f[8];
+          unpack8(ap[i], f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) w[8 * i + j] = v[8 * i + j] * f[j];
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < CW; ++i) w[i] = 0.f;
+      }
+    }
+    float s = warp_reduce_scatter<CW>(v, lane);
+    float q = warp_reduce_scatter<CW>(w, lane);
+    if (lane < CW) {
+      scratch[(c0 + lane) * 2] = s;
+      scratch[(c0 + lane) * 2 + 1] = q;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(CONV_THREADS)
+conv3_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, const ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[CONV_MAX_STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[CONV_MAX_STAGES];
+  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_slot;
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int stage_bytes = p.a_bytes + p.b_bytes;
+
+  // tile coordinates
+  int t = blockIdx.x;
+  const int tw_i = t % p.tilesW;
+  t /= p.tilesW;
+  const int th_i = t % p.tilesH;
+  t /= p.tilesH;
+  const int td_i = t % p.tilesD;
+  const int n = t / p.tilesD;
+  const int tile_in_sample = blockIdx.x - n * (p.tilesD * p.tilesH * p.tilesW);
+  const int d0 = td_i * p.BD, h0 = th_i * p.BH, w0 = tw_i * p.BW;
+  const int n0 = blockIdx.y * p.NT;
+  const int numK = 27 * p.kchunks;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(&tmem_full_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmapA);
+    tma_prefetch_desc(&tmapB);
+  }
+  if (warp == 1) tmem_alloc(&tmem_slot, (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      const int wsample = p.n_w > 1 ? n : 0;
+      for (int kb = 0; kb < numK; ++kb) {
+        const int stage = kb % p.stages;
+        const uint32_t phase = (uint32_t)(kb / p.stages) & 1u;
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        const int tap = kb / p.kchunks, kc = kb - tap * p.kchunks;
+        const int td = tap / 9, th = (tap / 3) % 3, tw = tap % 3;
+        uint8_t* sa = smem + (size_t)stage * stage_bytes;
+        uint8_t* sb = sa + p.a_bytes;
+        mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(128 * p.KC * 2 + p.NT * p.KC * 2));
+        tma_load_5d(sa, &tmapA, &full_bar[stage], kc * p.KC, w0 + tw - 1, h0 + th - 1, d0 + td - 1, n);
+        tma_load_3d(sb, &tmapB, &full_bar[stage], kc * p.KC, n0, wsample * 27 + tap);
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, p.NT, 0, 0);
+      const int rb = p.KC * 2;
+      const uint32_t layout = umma_layout_for_row_bytes(rb);
+      const uint32_t sbo = 8u * (uint32_t)rb;
+      for (int kb = 0; kb < numK; ++kb) {
+        const int stage = kb % p.stages;
+        const uint32_t phase = (uint32_t)(kb / p.stages) & 1u;
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+        const uint32_t sb = sa + (uint32_t)p.a_bytes;
+        for (int k = 0; k < p.KC / 16; ++k) {
+          const uint64_t adesc = umma_smem_desc(sa + (uint32_t)k * 32u, 16u, sbo, layout);
+          const uint64_t bdesc = umma_smem_desc(sb + (uint32_t)k * 32u, 16u, sbo, layout);
+          umma_bf16(tmem_base, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+      }
+      umma_commit(&tmem_full_bar);  // accumulator complete
+    }
+  } else {
+    // ================= epilogue (warps 2..5) =================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const int bx = row % p.BW, by = (row / p.BW) % p.BH, bz = row / (p.BW * p.BH);
+    const int xd = d0 + bz, xh = h0 + by, xw = w0 + bx;
+    const bool valid = xd < p.D && xh < p.H && xw < p.W;
+    const size_t vox_off = (size_t)n * p.D * p.H * p.W + ((size_t)xd * p.H + xh) * p.W + xw;
+    const float* bias_row = nullptr;
+    if (p.n_b && valid) {
+      const int cls = (axis_cls(xd, p.D) << 4) | (axis_cls(xh, p.H) << 2) | axis_cls(xw, p.W);
+      bias_row = p.biascls + ((size_t)(p.n_b > 1 ? n : 0) * 64 + cls) * p.Cout;
+    }
+    mbar_wait(&tmem_full_bar, 0);
+    __syncwarp();
+    tc_fence_after();
+    // all MMAs have completed -> every smem stage is free; reuse stage 0 as the stats scratch [4][NT][2]
+    float* scratch = reinterpret_cast<float*>(smem) + (size_t)q * p.NT * 2;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    int c0 = 0;
+    for (; c0 + 32 <= p.NT; c0 += 32) conv_epilogue_slab<32>(p, taddr, c0, n0, valid, vox_off, bias_row, lane, scratch);
+    if (c0 < p.NT) conv_epilogue_slab<16>(p, taddr, c0, n0, valid, vox_off, bias_row, lane, scratch);
+    if (p.pmode) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // the 4 epilogue warps only
+      const int et = threadIdx.x - 64;
+      const float* sc = reinterpret_cast<const float*>(smem);
+      float* out = p.partials + (((size_t)n * (p.tilesD * p.tilesH * p.tilesW) + tile_in_sample) * p.Cout + n0) * 2;
+      for (int i = et; i < p.NT * 2; i += 128) out[i] = sc[i] + sc[p.NT * 2 + i] + sc[p.NT * 4 + i] + sc[p.NT * 6 + i];
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+static CUtensorMapSwizzle swizzle_for_row_bytes(int rb) {
+  return rb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (rb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+// NDHWC bf16 activation viewed as a rank-5 tensor {C, W, H, D, N}; box {kc, bw, bh, bd, 1}
+int make_act_tmap(CUtensorMap* tm, const void* ptr, int N, int D, int H, int W, int C, int kc, int bd, int bh, int bw) {
+  EncodeTiledFn enc = get_encode_tiled();
+  B200_CHECK_ARG(enc, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+  cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2, (cuuint64_t)D * H * W * C * 2};
+  cuuint32_t box[5] = {(cuuint32_t)kc, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bd, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_row_bytes(kc * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B200_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activation %dx%dx%dx%dx%d, box %d,%d,%d,%d) failed: %d", N, D, H, W, C, kc,
+                 bw, bh, bd, (int)r);
+  return 0;
+}
+// weights [rows2][rows1][C] bf16 viewed as rank-3 {C, rows1, rows2}; box {kc, nt, 1}
+int make_w_tmap(CUtensorMap* tm, const void* ptr, int rows2, int rows1, int C, int kc, int nt) {
+  EncodeTiledFn enc = get_encode_tiled();
+  B200_CHECK_ARG(enc, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)rows1, (cuuint64_t)rows2};
+  cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)rows1 * C * 2};
+  cuuint32_t box[3] = {(cuuint32_t)kc, (cuuint32_t)nt, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_row_bytes(kc * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B200_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weights %dx%dx%d, box %d,%d) failed: %d", rows2, rows1, C, kc, nt, (int)r);
+  return 0;
+}
+
+// pick the 128-voxel box that wastes the fewest padded voxels; 0 on success
+int choose_box(int D, int H, int W, int* bd, int* bh, int* bw) {
+  static const int cand[][3] = {{2, 8, 8},  {1, 8, 16}, {4, 4, 8},  {1, 16, 8}, {2, 4, 16}, {4, 8, 4}, {8, 4, 4},  {1, 4, 32},
+                                {2, 2, 32}, {1, 2, 64}, {1, 1, 128}, {8, 8, 2}, {16, 8, 1}, {4, 2, 16}, {2, 16, 4}, {8, 2, 8},
+                                {16, 4, 2}, {32, 4, 1}, {128, 1, 1}, {1, 128, 1}, {64, 2, 1}, {1, 32, 4}, {1, 64, 2}, {16, 2, 4},
+                                {32, 2, 2}, {2, 32, 2}, {2, 64, 1}, {4, 16, 2}, {4, 32, 1}, {8, 16, 1}, {16, 1, 8}, {8, 1, 16},
+                                {4, 1, 32}, {2, 1, 64}, {32, 1, 4}, {64, 1, 2}};
+  long long best = -1;
+  for (auto& c : cand) {
+    if (c[0] > D || c[1] > H || c[2] > W) continue;
+    long long padded = (long long)((D + c[0] - 1) / c[0]) * c[0] * ((H + c[1] - 1) / c[1]) * c[1] * ((W + c[2] - 1) / c[2]) * c[2];
+    if (best < 0 || padded < best) {
+      best = padded;
+      *bd = c[0];
+      *bh = c[1];
+      *bw = c[2];
+    }
+  }
+  return best < 0 ? 1 : 0;
+}
+
+bool conv_igemm_supported(int N, int D, int H, int W, int Cin, int Cout) {
+  (void)N;
+  int bd, bh, bw;
+  if (Cin % 16 != 0 || Cout % 16 != 0) return false;
+  if (choose_box(D, H, W, &bd, &bh, &bw)) return false;
+  return true;
+}
+
+static int pick_nt(int Cout) {
+  if (Cout <= 256) return Cout;
+  if (Cout % 256 == 0) return 256;
+  if (Cout % 128 == 0) return 128;
+  if (Cout % 64 == 0) return 64;
+  if (Cout % 32 == 0) return 32;
+  return 16;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+int b200_conv3_igemm_supported(int N, int D, int H, int W, int Cin, int Cout) {
+  return conv_igemm_supported(N, D, H, W, Cin, Cout) ? 1 : 0;
+}
+
+int b200_conv3_igemm_partials_count(int N, int D, int H, int W, int Cin, int Cout) {
+  (void)N;
+  (void)Cin;
+  (void)Cout;
+  int bd, bh, bw;
+  if (choose_box(D, H, W, &bd, &bh, &bw)) return 0;
+  return ((D + bd - 1) / bd) * ((H + bh - 1) / bh) * ((W + bw - 1) / bw);
+}
+
+int b200_conv3_igemm_fwd(const void* x, const void* wf, int n_w, const float* biascls, int n_b, const void* residual, int act,
+                         float slope, int N, int D, int H, int W, int Cin, int Cout, void* y, int pmode, const void* aux,
+                         float* partials, b200_stream_t s) {
+  B200_CHECK_ARG(conv_igemm_supported(N, D, H, W, Cin, Cout), "conv3_igemm: unsupported shape N=%d D=%d H=%d W=%d Cin=%d Cout=%d", N, D,
+                 H, W, Cin, Cout);
+  ConvParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
+  choose_box(D, H, W, &p.BD, &p.BH, &p.BW);
+  p.tilesD = (D + p.BD - 1) / p.BD;
+  p.tilesH = (H + p.BH - 1) / p.BH;
+  p.tilesW = (W + p.BW - 1) / p.BW;
+  p.n_w = n_w;
+  p.n_b = biascls ? n_b : 0;
+  p.NT = pick_nt(Cout);
+  p.KC = (Cin % 64 == 0) ? 64 : (Cin % 32 == 0 ? 32 : 16);
+  p.kchunks = Cin / p.KC;
+  p.a_bytes = (128 * p.KC * 2 + 1023) & ~1023;
+  p.b_bytes = (p.NT * p.KC * 2 + 1023) & ~1023;
+  const int stage_bytes = p.a_bytes + p.b_bytes;
+  int stages = (96 * 1024) / stage_bytes;
+  if (stages < 3) stages = 3;
+  if (stages > CONV_MAX_STAGES) stages = CONV_MAX_STAGES;
+  p.stages = stages;
+  int cols = 32;
+  while (cols < p.NT) cols <<= 1;
+  p.tmem_cols = cols;
+  p.act = act;
+  p.slope = slope;
+  p.pmode = pmode;
+  p.biascls = biascls;
+  p.residual = (const bf16*)residual;
+  p.aux = (const bf16*)aux;
+  p.y = (bf16*)y;
+  p.partials = partials;
+  B200_CHECK_ARG(pmode == 0 || partials, "conv3_igemm: pmode=%d needs a partials buffer", pmode);
+  B200_CHECK_ARG(pmode != 2 || aux, "conv3_igemm: pmode=2 needs aux");
+
+  CUtensorMap tmA, tmB;
+  int rc = make_act_tmap(&tmA, x, N, D, H, W, Cin, p.KC, p.BD, p.BH, p.BW);
+  if (rc) return rc;
+  rc = make_w_tmap(&tmB, wf, 27 * n_w, Cout, Cin, p.KC, p.NT);
+  if (rc) return rc;
+
+  size_t smem = (size_t)stages * stage_bytes + 1024;
+  size_t scratch = (size_t)4 * p.NT * 2 * sizeof(float);
+  if (smem < scratch + 1024) smem = scratch + 1024;
+  cudaError_t e = cudaFuncSetAttribute(conv3_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  B200_CHECK_ARG(e == cudaSuccess, "conv3_igemm: cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e));
+  dim3 grid((unsigned)(N * p.tilesD * p.tilesH * p.tilesW), (unsigned)(Cout / p.NT));
+  conv3_igemm_kernel<<<grid, CONV_THREADS, smem, (cudaStream_t)s>>>(tmA, tmB, p);
+  B200_CHECK_LAUNCH("conv3_igemm");
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,1165 @@
+// HBM-bound kernels of the 3D U-Net path: layout, GroupNorm statistics / folding / backward, MaxPool3d(2),
+// nearest-upsample + concat, final 1x1x1 conv + sigmoid/softmax, and the small deterministic reductions.
+// Every tensor pass here is a straight 16-byte-vector stream over NDHWC bf16; the roofline for all of them
+// is HBM bandwidth (bytes listed per kernel in DESIGN.md).
+#include <stdarg.h>
+
+#include <string.h>
+
+#include "common.cuh"
+#include "ew.cuh"
+
+namespace b200 {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// ------------------------------------------------------------------------------------------------
+// layout
+// ------------------------------------------------------------------------------------------------
+template <typename OutT>
+__global__ void ncdhw_to_ndhwc_kernel(const float* __restrict__ src, OutT* __restrict__ dst, int C, long long voxels) {
+  // grid: (blocks over voxels, N); each thread handles one voxel, loops channels (C is small for network inputs;
+  // for block-level entry points C is a feature-map count and this is test plumbing, not the hot path)
+  int n = blockIdx.y;
+  long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= voxels) return;
+  const float* s = src + (size_t)n * C * voxels + v;
+  OutT* d = dst + ((size_t)n * voxels + v) * C;
+  for (int c = 0; c < C; ++c) {
+    float f = s[(size_t)c * voxels];
+    if constexpr (sizeof(OutT) == 2) d[c] = __float2bfloat16_rn(f);
+    else d[c] = f;
+  }
+}
+__global__ void ndhwc_to_ncdhw_kernel(const bf16* __restrict__ src, float* __restrict__ dst, int C, long long voxels) {
+  int n = blockIdx.y;
+  long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= voxels) return;
+  const bf16* s = src + ((size_t)n * voxels + v) * C;
+  float* d = dst + (size_t)n * C * voxels + v;
+  for (int c = 0; c < C; ++c) d[(size_t)c * voxels] = __bfloat162float(s[c]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// statistics
+// ------------------------------------------------------------------------------------------------
+// NCDHW fp32 input planes: grid (P, N*C); partials [N][P][C][2]
+__global__ void stats_ncdhw_f32_kernel(const float* __restrict__ x, int C, long long voxels, int P, float* __restrict__ partials) {
+  int p = blockIdx.x, nc = blockIdx.y;
+  int n = nc / C, c = nc % C;
+  long long v0, v1;
+  ew_range(voxels, p, P, v0, v1);
+  const float* s = x + (size_t)nc * voxels;
+  float a = 0.f, q = 0.f;
+  for (long long v = v0 + threadIdx.x; v < v1; v += blockDim.x) {
+    float f = s[v];
+    a += f;
+    q += f * f;
+  }
+  __shared__ float ra[32], rq[32];
+  for (int o = 16; o; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) {
+    ra[w] = a;
+    rq[w] = q;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float ta = 0.f, tq = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) {
+      ta += ra[i];
+      tq += rq[i];
+    }
+    float* o = partials + (((size_t)n * P + p) * C + c) * 2;
+    o[0] = ta;
+    o[1] = tq;
+  }
+}
+
+__global__ void stats_ndhwc_bf16_kernel(const bf16* __restrict__ x, int C, long long voxels, int P, float* __restrict__ partials) {
+  extern __shared__ float red[];
+  int p = blockIdx.x, n = blockIdx.y;
+  EwMap m = ew_map(C);
+  long long v0, v1;
+  ew_range(voxels, p, P, v0, v1);
+  float s[8] = {0}, q[8] = {0};
+  if (m.active) {
+    const bf16x8* xp = reinterpret_cast<const bf16x8*>(x + (size_t)n * voxels * C);
+    for (long long v = v0 + m.vl; v < v1; v += m.VL) {
+      float f[8];
+      unpack8(xp[v * m.CG + m.cg], f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s[i] += f[i];
+        q[i] += f[i] * f[i];
+      }
+    }
+  }
+  ew_write_partials(s, q, m, partials + ((size_t)n * P + p) * C * 2, red);
+}
+
+
+// partials of (sum v, sum v*w) over two bf16 NDHWC tensors (GroupNorm-after-conv backward); grid (P, N)
+__global__ void stats2_ndhwc_bf16_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, int C, long long voxels, int P,
+                                         float* __restrict__ partials) {
+  extern __shared__ float red[];
+  int p = blockIdx.x, n = blockIdx.y;
+  EwMap m = ew_map(C);
+  long long v0, v1;
+  ew_range(voxels, p, P, v0, v1);
+  float s[8] = {0}, q[8] = {0};
+  if (m.active) {
+    const bf16x8* ap = reinterpret_cast<const bf16x8*>(a + (size_t)n * voxels * C);
+    const bf16x8* bp = reinterpret_cast<const bf16x8*>(b + (size_t)n * voxels * C);
+    for (long long v = v0 + m.vl; v < v1; v += m.VL) {
+      float f[8], g[8];
+      unpack8(ap[v * m.CG + m.cg], f);
+      unpack8(bp[v * m.CG + m.cg], g);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s[i] += f[i];
+        q[i] += f[i] * g[i];
+      }
+    }
+  }
+  ew_write_partials(s, q, m, partials + ((size_t)n * P + p) * C * 2, red);
+}
+
+// GroupNorm-backward sums of the conv INPUT from the wgrad by-products (no pass over dxhat needed):
+//   sum_v dxhat[n,v,ci]          = sum_{tap,co} W[co][ci][tap] * T[n][tap][co]
+//   sum_v dxhat[n,v,ci]*x[n,v,ci] = sum_{tap,co} W[co][ci][tap] * sum_s G[n][s][tap][ci][co]
+// grid (Cin, N), block 128
+__global__ void gn_bwd_sums_from_wgrad_kernel(const float* __restrict__ G, int S, const float* __restrict__ T, const float* __restrict__ W,
+                                              int Cin, int Cout, double* __restrict__ sums2) {
+  __shared__ double r1[128], r2[128];
+  int ci = blockIdx.x, n = blockIdx.y;
+  double a1 = 0.0, a2 = 0.0;
+  for (int idx = threadIdx.x; idx < 27 * Cout; idx += blockDim.x) {
+    int tap = idx / Cout, co = idx % Cout;
+    double w = (double)W[((size_t)co * Cin + ci) * 27 + tap];
+    a1 += w * (double)T[((size_t)n * 27 + tap) * Cout + co];
+    double g = 0.0;
+    for (int s = 0; s < S; ++s) g += (double)G[((((size_t)n * S + s) * 27 + tap) * Cin + ci) * Cout + co];
+    a2 += w * g;
+  }
+  r1[threadIdx.x] = a1;
+  r2[threadIdx.x] = a2;
+  __syncthreads();
+  for (int o = 64; o; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      r1[threadIdx.x] += r1[threadIdx.x + o];
+      r2[threadIdx.x] += r2[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    sums2[((size_t)n * Cin + ci) * 2] = r1[0];
+    sums2[((size_t)n * Cin + ci) * 2 + 1] = r2[0];
+  }
+}
+
+// sums[N][C][2] (double) = sum_p partials[n][p][c][k]; grid (ceil(C*2/32), N), block (32, 32)
+__global__ void partials_finalize_kernel(const float* __restrict__ partials, int P, int C, double* __restrict__ sums) {
+  __shared__ double red[32][33];
+  int n = blockIdx.y;
+  int col = blockIdx.x * 32 + threadIdx.x;  // index into C*2
+  double acc = 0.0;
+  if (col < C * 2) {
+    const float* base = partials + (size_t)n * P * C * 2 + col;
+    for (int p = threadIdx.y; p < P; p += 32) acc += (double)base[(size_t)p * C * 2];
+  }
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && col < C * 2) {
+    double t = 0.0;
+    for (int i = 0; i < 32; ++i) t += red[i][threadIdx.x];
+    sums[(size_t)n * C * 2 + col] = t;
+  }
+}
+
+// out[K] = sum_p partials[p][K]; grid ceil(K/32), block (32,32)
+__global__ void reduce_rows_kernel(const float* __restrict__ partials, int P, int K, float* __restrict__ out) {
+  __shared__ double red[32][33];
+  int col = blockIdx.x * 32 + threadIdx.x;
+  double acc = 0.0;
+  if (col < K)
+    for (int p = threadIdx.y; p < P; p += 32) acc += (double)partials[(size_t)p * K + col];
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && col < K) {
+    double t = 0.0;
+    for (int i = 0; i < 32; ++i) t += red[i][threadIdx.x];
+    out[col] = (float)t;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm coefficients and folding
+// ------------------------------------------------------------------------------------------------
+// grid N, block 128.  ab[N][C][2] = (a,b), mean_rstd[N][G][2]
+__global__ void gn_coeffs_kernel(const double* __restrict__ sums, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                 int G, double count, int C, float* __restrict__ mean_rstd, float* __restrict__ ab) {
+  extern __shared__ float sm[];  // [G][2]
+  int n = blockIdx.x;
+  int cpg = C / G;
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    double s = 0.0, q = 0.0;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+      s += sums[((size_t)n * C + c) * 2];
+      q += sums[((size_t)n * C + c) * 2 + 1];
+    }
+    double m = count * cpg;
+    double mean = s / m;
+    double var = q / m - mean * mean;  // biased variance, as native_group_norm
+    if (var < 0.0) var = 0.0;
+    float rstd = (float)(1.0 / sqrt(var + 1e-5));
+    sm[g * 2] = (float)mean;
+    sm[g * 2 + 1] = rstd;
+    if (mean_rstd) {
+      mean_rstd[((size_t)n * G + g) * 2] = (float)mean;
+      mean_rstd[((size_t)n * G + g) * 2 + 1] = rstd;
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    int g = c / cpg;
+    float a = gamma[c] * sm[g * 2 + 1];
+    float b = beta[c] - sm[g * 2] * a;
+    ab[((size_t)n * C + c) * 2] = a;
+    ab[((size_t)n * C + c) * 2 + 1] = b;
+  }
+}
+
+// wf[n][tap][co][ci] = bf16(W[co][ci][tap] * a[n][ci]); one thread per output element
+__global__ void fold_weights_kernel(const float* __restrict__ W, const float* __restrict__ ab, int n_w, int Cin, int Cout,
+                                    bf16* __restrict__ wf) {
+  size_t total = (size_t)n_w * 27 * Cout * Cin;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int ci = (int)(i % Cin);
+    size_t r = i / Cin;
+    int co = (int)(r % Cout);
+    r /= Cout;
+    int tap = (int)(r % 27);
+    int n = (int)(r / 27);
+    float a = ab ? ab[((size_t)n * Cin + ci) * 2] : 1.f;
+    wf[i] = __float2bfloat16_rn(W[((size_t)co * Cin + ci) * 27 + tap] * a);
+  }
+}
+
+// biascls[n][cls][co] : grid (Cout, n_b), block 128
+__global__ void fold_bias_kernel(const float* __restrict__ W, const float* __restrict__ ab, const float* __restrict__ conv_bias,
+                                 int Cin, int Cout, float* __restrict__ biascls) {
+  __shared__ float bt[27];
+  __shared__ float red[128];
+  int co = blockIdx.x, n = blockIdx.y;
+  for (int tap = 0; tap < 27; ++tap) {
+    float acc = 0.f;
+    if (ab)
+      for (int ci = threadIdx.x; ci < Cin; ci += blockDim.x)
+        acc += W[((size_t)co * Cin + ci) * 27 + tap] * ab[((size_t)n * Cin + ci) * 2 + 1];
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 64; o; o >>= 1) {
+      if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) bt[tap] = red[0];
+    __syncthreads();
+  }
+  float cb = conv_bias ? conv_bias[co] : 0.f;
+  for (int cls = threadIdx.x; cls < 64; cls += blockDim.x) {
+    int cd = cls >> 4, ch = (cls >> 2) & 3, cw = cls & 3;
+    float acc = cb;
+    for (int td = 0; td < 3; ++td)
+      if (tap_valid(cd, td))
+        for (int th = 0; th < 3; ++th)
+          if (tap_valid(ch, th))
+            for (int tw = 0; tw < 3; ++tw)
+              if (tap_valid(cw, tw)) acc += bt[(td * 3 + th) * 3 + tw];
+    biascls[((size_t)n * 64 + cls) * Cout + co] = acc;
+  }
+}
+
+// wd[tap'][ci][co] = bf16(W[co][ci][26 - tap'])
+__global__ void prep_dgrad_weights_kernel(const float* __restrict__ W, int Cin, int Cout, bf16* __restrict__ wd) {
+  size_t total = (size_t)27 * Cin * Cout;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int co = (int)(i % Cout);
+    size_t r = i / Cout;
+    int ci = (int)(r % Cin);
+    int tap = (int)(r / Cin);
+    wd[i] = __float2bfloat16_rn(W[((size_t)co * Cin + ci) * 27 + (26 - tap)]);
+  }
+}
+
+// y = act(a*x + b) with partials of y; grid (P, N)
+__global__ void gn_apply_act_kernel(const bf16* __restrict__ x, const float* __restrict__ ab, int C, long long voxels, int P,
+                                    int act, float slope, bf16* __restrict__ y, float* __restrict__ partials) {
+  extern __shared__ float red[];
+  int p = blockIdx.x, n = blockIdx.y;
+  EwMap m = ew_map(C);
+  long long v0, v1;
+  ew_range(voxels, p, P, v0, v1);
+  float s[8] = {0}, q[8] = {0};
+  if (m.active) {
+    float a[8], b[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      a[i] = ab[((size_t)n * C + m.cg * 8 + i) * 2];
+      b[i] = ab[((size_t)n * C + m.cg * 8 + i) * 2 + 1];
+    }
+    const bf16x8* xp = reinterpret_cast<const bf16x8*>(x + (size_t)n * voxels * C);
+    bf16x8* yp = reinterpret_cast<bf16x8*>(y + (size_t)n * voxels * C);
+    for (long long v = v0 + m.vl; v < v1; v += m.VL) {
+      float f[8];
+      unpack8(xp[v * m.CG + m.cg], f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        f[i] = bf16_round(act_fwd(a[i] * f[i] + b[i], act, slope));
+        s[i] += f[i];
+        q[i] += f[i] * f[i];
+      }
+      yp[v * m.CG + m.cg] = pack8(f);
+    }
+  }
+  if (partials) ew_write_partials(s, q, m, partials + ((size_t)n * P + p) * C * 2, red);
+}
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm backward
+// ------------------------------------------------------------------------------------------------
+// grid 1, block 256.  coef[N][C][3], dgamma[C], dbeta[C]
+__global__ void gn_bwd_coeffs_kernel(const double* __restrict__ sums2, const float* __restrict__ gamma,
+                                     const float* __restrict__ mean_rstd, int G, double count, int N, int C,
+                                     float* __restrict__ coef, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  int cpg = C / G;
+  // per-channel parameter grads (deterministic serial sum over n)
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    int g = c / cpg;
+    double dg = 0.0, db = 0.0;
+    for (int n = 0; n < N; ++n) {
+      double mean = mean_rstd[((size_t)n * G + g) * 2], rstd = mean_rstd[((size_t)n * G + g) * 2 + 1];
+      double s1 = sums2[((size_t)n * C + c) * 2], s2 = sums2[((size_t)n * C + c) * 2 + 1];
+      dg += (s2 - mean * s1) * rstd;
+      db += s1;
+    }
+    dgamma[c] = (float)dg;
+    dbeta[c] = (float)db;
+  }
+  // per-(n,group) coefficients expanded per channel
+  for (int idx = threadIdx.x; idx < N * G; idx += blockDim.x) {
+    int n = idx / G, g = idx % G;
+    double mean = mean_rstd[((size_t)n * G + g) * 2], rstd = mean_rstd[((size_t)n * G + g) * 2 + 1];
+    double S1 = 0.0, S2x = 0.0;  // sum gamma*dxhat, sum gamma*dxhat*x over the group
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+      S1 += (double)gamma[c] * sums2[((size_t)n * C + c) * 2];
+      S2x += (double)gamma[c] * sums2[((size_t)n * C + c) * 2 + 1];
+    }
+    double m = count * cpg;
+    double S2 = rstd * (S2x - mean * S1);  // sum gamma*dxhat*xtilde
+    double B = -rstd * rstd * S2 / m;
+    double Cc = -rstd * S1 / m + rstd * rstd * mean * S2 / m;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+      float* o = coef + ((size_t)n * C + c) * 3;
+      o[0] = (float)(rstd * gamma[c]);
+      o[1] = (float)B;
+      o[2] = (float)Cc;
+    }
+  }
+}
+
+// out = (A*dxhat + B*x + Cc) * act'(x) [+ gadd]; grid (P, N).  gadd: gradient already in dz form (same shape), may alias out
+__global__ void gn_bwd_apply_kernel(const bf16* __restrict__ dxhat, const bf16* __restrict__ x, const float* __restrict__ coef,
+                                    int C, long long voxels, int P, int act, float slope, const bf16* gadd, bf16* out) {
+  int p = blockIdx.x, n = blockIdx.y;
+  EwMap m = ew_map(C);
+  long long v0, v1;
+  ew_range(voxels, p, P, v0, v1);
+  if (!m.active) return;
+  float A[8], B[8], Cc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float* cf = coef + ((size_t)n * C + m.cg * 8 + i) * 3;
+    A[i] = cf[0];
+    B[i] = cf[1];
+    Cc[i] = cf[2];
+  }
+  const bf16x8* dp = reinterpret_cast<const bf16x8*>(dxhat + (size_t)n * voxels * C);
+  const bf16x8* xp = reinterpret_cast<const bf16x8*>(x + (size_t)n * voxels * C);
+  bf16x8* op = reinterpret_cast<bf16x8*>(out + (size_t)n * voxels * C);
+  for (long long v = v0 + m.vl; v < v1; v += m.VL) {
+    float d[8], f[8], ga[8];
+    unpack8(dp[v * m.CG + m.cg], d);
+    unpack8(xp[v * m.CG + m.cg], f);
+    if (gadd) unpack8(*reinterpret_cast<const bf16x8*>(gadd + ((size_t)n * voxels + v) * C + m.cg * 8), ga);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float g = (A[i] * d[i] + B[i] * f[i] + Cc[i]) * act_grad_from_out(f[i], act, slope);
+      if (gadd) g += ga[i];
+      d[i] = g;
+    }
+    op[v * m.CG + m.cg] = pack8(d);
+  }
+}
+
+// out = g[..., g_co : g_co + C] * act'(y) [+ gadd]; g has channel stride g_cs; gadd (dz form, contiguous) may alias out
+__global__ void act_bwd_kernel(const bf16* g, int g_cs, int g_co, const bf16* __restrict__ y, int C, long long voxels, int P, int act,
+                               float slope, const bf16* gadd, bf16* out) {
+  int p = blockIdx.x, n = blockIdx.y;
+  EwMap m = ew_map(C);
+  long long v0, v1;
+  ew_range(voxels, p, P, v0, v1);
+  if (!m.active) return;
+  const bf16x8* yp = reinterpret_cast<const bf16x8*>(y + (size_t)n * voxels * C);
+  bf16x8* op = reinterpret_cast<bf16x8*>(out + (size_t)n * voxels * C);
+  for (long long v = v0 + m.vl; v < v1; v += m.VL) {
+    float d[8], f[8], ga[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(g + ((size_t)n * voxels + v) * g_cs + g_co + m.cg * 8), d);
+    unpack8(yp[v * m.CG + m.cg], f);
+    if (gadd) unpack8(*reinterpret_cast<const bf16x8*>(gadd + ((size_t)n * voxels + v) * C + m.cg * 8), ga);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float t = d[i] * act_grad_from_out(f[i], act, slope);
+      if (gadd) t += ga[i];
+      d[i] = t;
+    }
+    op[v * m.CG + m.cg] = pack8(d);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// MaxPool3d(2), floor mode
+// ------------------------------------------------------------------------------------------------
+__global__ void maxpool_fwd_kernel(const bf16* __restrict__ x, int D, int H, int W, int C, int P, bf16* __restrict__ y,
+                                   float* __restrict__ partials) {
+  extern __shared__ float red[];
+  int p = blockIdx.x, n = blockIdx.y;
+  int oD = D / 2, oH = H / 2, oW = W / 2;
+  long long ovox = (long long)oD * oH * oW;
+  EwMap m = ew_map(C);
+  long long v0, v1;
+  ew_range(ovox, p, P, v0, v1);
+  float s[8] = {0}, q[8] = {0};
+  if (m.active) {
+    const bf16x8* xp = reinterpret_cast<const bf16x8*>(x + (size_t)n * D * H * W * C);
+    bf16x8* yp = reinterpret_cast<bf16x8*>(y + (size_t)n * ovox * C);
+    for (long long v = v0 + m.vl; v < v1; v += m.VL) {
+      int ow = (int)(v % oW);
+      long long r = v / oW;
+      int oh = (int)(r % oH), od = (int)(r / oH);
+      float mx[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) mx[i] = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        int dz = k >> 2, dy = (k >> 1) & 1, dx = k & 1;
+        size_t iv = ((size_t)(2 * od + dz) * H + (2 * oh + dy)) * W + (2 * ow + dx);
+        float f[8];
+        unpack8(xp[iv * m.CG + m.cg], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) mx[i] = fmaxf(mx[i], f[i]);
+      }
+      yp[v * m.CG + m.cg] = pack8(mx);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s[i] += mx[i];
+        q[i] += mx[i] * mx[i];
+      }
+    }
+  }
+  if (partials) ew_write_partials(s, q, m, partials + ((size_t)n * P + p) * C * 2, red);
+}
+
+// iterates over 2x2x2 cells of the FULL-resolution grid (ceil), so ragged borders still get gadd*mask (or 0)
+__global__ void maxpool_bwd_kernel(const bf16* __restrict__ dpooled, const bf16* __restrict__ xf, int D, int H, int W, int C, int P,
+                                   int act, float slope, const bf16* gadd, bf16* out) {
+  int p = blockIdx.x, n = blockIdx.y;
+  int oD = D / 2, oH = H / 2, oW = W / 2;
+  int cD = (D + 1) / 2, cH = (H + 1) / 2, cW = (W + 1) / 2;
+  long long cells = (long long)cD * cH * cW;
+  EwMap m = ew_map(C);
+  long long v0, v1;
+  ew_range(cells, p, P, v0, v1);
+  if (!m.active) return;
+  size_t fvox = (size_t)D * H * W;
+  const bf16x8* xp = reinterpret_cast<const bf16x8*>(xf + (size_t)n * fvox * C);
+  const bf16x8* dp = reinterpret_cast<const bf16x8*>(dpooled + (size_t)n * oD * oH * oW * C);
+  bf16x8* op = reinterpret_cast<bf16x8*>(out + (size_t)n * fvox * C);
+  for (long long v = v0 + m.vl; v < v1; v += m.VL) {
+    int cw = (int)(v % cW);
+    long long r = v / cW;
+    int ch = (int)(r % cH), cd = (int)(r / cH);
+    bool pooled = cd < oD && ch < oH && cw < oW;
+    float xv[8][8];
+    bool inb[8];
+    int arg[8];
+    float mx[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      mx[i] = -INFINITY;
+      arg[i] = 0;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      int z = 2 * cd + (k >> 2), yy = 2 * ch + ((k >> 1) & 1), xx = 2 * cw + (k & 1);
+      inb[k] = z < D && yy < H && xx < W;
+      if (inb[k]) {
+        unpack8(xp[(((size_t)z * H + yy) * W + xx) * m.CG + m.cg], xv[k]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (xv[k][i] > mx[i]) {  // strict '>' : first maximum in (d,h,w) scan order wins, as max_pool3d_with_indices
+            mx[i] = xv[k][i];
+            arg[i] = k;
+          }
+      }
+    }
+    float g[8] = {0};
+    if (pooled) unpack8(dp[(((size_t)cd * oH + ch) * oW + cw) * m.CG + m.cg], g);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (!inb[k]) continue;
+      int z = 2 * cd + (k >> 2), yy = 2 * ch + ((k >> 1) & 1), xx = 2 * cw + (k & 1);
+      size_t iv = ((size_t)z * H + yy) * W + xx;
+      float ga[8], o[8];
+      if (gadd) unpack8(*reinterpret_cast<const bf16x8*>(gadd + ((size_t)n * fvox + iv) * C + m.cg * 8), ga);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float t = (pooled && arg[i] == k) ? g[i] * act_grad_from_out(xv[k][i], act, slope) : 0.f;
+        if (gadd) t += ga[i];
+        o[i] = t;
+      }
+      op[iv * m.CG + m.cg] = pack8(o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// nearest upsample (to the encoder feature size) + concat (encoder channels first)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int nearest_src(int dst, int in, int out) {
+  // upsample_nearest3d: src = min(floor(dst * (float)in / out), in - 1)
+  float scale = (float)in / (float)out;
+  int s = (int)floorf((float)dst * scale);
+  return s < in - 1 ? s : in - 1;
+}
+
+__global__ void upcat_fwd_kernel(const bf16* __restrict__ enc, int C0, const bf16* __restrict__ x, int C1, int D, int H, int W, int d,
+                                 int h, int w, int P, bf16* __restrict__ cat, float* __restrict__ partials) {
+  extern __shared__ float red[];
+  int p = blockIdx.x, n = blockIdx.y;
+  int C = C0 + C1;
+  long long vox = (long long)D * H * W;
+  EwMap m = ew_map(C);
+  long long v0, v1;
+  ew_range(vox, p, P, v0, v1);
+  float s[8] = {0}, q[8] = {0};
+  if (m.active) {
+    int c = m.cg * 8;
+    bf16x8* op = reinterpret_cast<bf16x8*>(cat + (size_t)n * vox * C);
+    for (long long v = v0 + m.vl; v < v1; v += m.VL) {
+      bf16x8 val;
+      if (c < C0) {
+        val = *reinterpret_cast<const bf16x8*>(enc + ((size_t)n * vox + v) * C0 + c);
+      } else {
+        int xw = (int)(v % W);
+        long long r = v / W;
+        int xh = (int)(r % H), xd = (int)(r / H);
+        size_t sv = ((size_t)nearest_src(xd, d, D) * h + nearest_src(xh, h, H)) * w + nearest_src(xw, w, W);
+        val = *reinterpret_cast<const bf16x8*>(x + ((size_t)n * d * h * w + sv) * C1 + (c - C0));
+      }
+      op[v * m.CG + m.cg] = val;
+      float f[8];
+      unpack8(val, f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s[i] += f[i];
+        q[i] += f[i] * f[i];
+      }
+    }
+  }
+  if (partials) ew_write_partials(s, q, m, partials + ((size_t)n * P + p) * C * 2, red);
+}
+
+// destination index range [lo,hi] along one axis that maps to source index s (empty if lo>hi)
+__device__ __forceinline__ void nearest_dst_range(int s, int in, int out, int& lo, int& hi) {
+  float inv = (float)out / (float)in;
+  int a = (int)floorf((float)s * inv) - 2, b = (int)ceilf((float)(s + 1) * inv) + 2;
+  if (a < 0) a = 0;
+  if (b > out - 1) b = out - 1;
+  lo = out;
+  hi = -1;
+  for (int t = a; t <= b; ++t)
+    if (nearest_src(t, in, out) == s) {
+      if (t < lo) lo = t;
+      if (t > hi) hi = t;
+    }
+}
+
+__global__ void upcat_bwd_kernel(const bf16* __restrict__ dcat, int C0, int C1, const bf16* __restrict__ xs, int D, int H, int W, int d,
+                                 int h, int w, int P, int act, float slope, bf16* __restrict__ out) {
+  int p = blockIdx.x, n = blockIdx.y;
+  int C = C0 + C1;
+  long long svox = (long long)d * h * w, vox = (long long)D * H * W;
+  EwMap m = ew_map(C1);
+  long long v0, v1;
+  ew_range(svox, p, P, v0, v1);
+  if (!m.active) return;
+  for (long long v = v0 + m.vl; v < v1; v += m.VL) {
+    int sw = (int)(v % w);
+    long long r = v / w;
+    int sh = (int)(r % h), sd = (int)(r / h);
+    int d0, d1, h0, h1, w0, w1;
+    nearest_dst_range(sd, d, D, d0, d1);
+    nearest_dst_range(sh, h, H, h0, h1);
+    nearest_dst_range(sw, w, W, w0, w1);
+    float acc[8] = {0};
+    for (int z = d0; z <= d1; ++z)
+      for (int y = h0; y <= h1; ++y)
+        for (int x = w0; x <= w1; ++x) {
+          size_t dv = ((size_t)z * H + y) * W + x;
+          float f[8];
+          unpack8(*reinterpret_cast<const bf16x8*>(dcat + ((size_t)n * vox + dv) * C + C0 + m.cg * 8), f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] += f[i];
+        }
+    float xv[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(xs + ((size_t)n * svox + v) * C1 + m.cg * 8), xv);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] *= act_grad_from_out(xv[i], act, slope);
+    *reinterpret_cast<bf16x8*>(out + ((size_t)n * svox + v) * C1 + m.cg * 8) = pack8(acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// border tap sums: T[n][tap][c] = sum_{v : v+tap-1 in bounds} dz[n,v,c]
+// ------------------------------------------------------------------------------------------------
+// stage 1: class sums R partials [N][P][64][C]; grid (P, N, C/CC) ; interior class accumulated in registers
+constexpr int BT_CC = 64;
+__global__ void border_class_sums_kernel(const bf16* __restrict__ dz, int D, int H, int W, int C, int P, float* __restrict__ Rp) {
+  __shared__ float bins[64][BT_CC];
+  int p = blockIdx.x, n = blockIdx.y, c0 = blockIdx.z * BT_CC;
+  int CC = min(BT_CC, C - c0);
+  int CG = CC >> 3;
+  int VL = EW_THREADS / CG;
+  int cg = threadIdx.x % CG, vl = threadIdx.x / CG;
+  for (int i = threadIdx.x; i < 64 * BT_CC; i += EW_THREADS) (&bins[0][0])[i] = 0.f;
+  __syncthreads();
+  long long vox = (long long)D * H * W, v0, v1;
+  ew_range(vox, p, P, v0, v1);
+  const int interior = (1 << 4) | (1 << 2) | 1;
+  float acc[8] = {0};
+  if (vl < VL) {
+    for (long long v = v0 + vl; v < v1; v += VL) {
+      int xw = (int)(v % W);
+      long long r = v / W;
+      int xh = (int)(r % H), xd = (int)(r / H);
+      int cls = (axis_cls(xd, D) << 4) | (axis_cls(xh, H) << 2) | axis_cls(xw, W);
+      float f[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(dz + ((size_t)n * vox + v) * C + c0 + cg * 8), f);
+      if (cls == interior) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += f[i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) atomicAdd(&bins[cls][cg * 8 + i], f[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) atomicAdd(&bins[interior][cg * 8 + i], acc[i]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 64 * CC; i += EW_THREADS) {
+    int cls = i / CC, c = i % CC;
+    Rp[(((size_t)n * P + p) * 64 + cls) * C + c0 + c] = bins[cls][c];
+  }
+}
+// stage 2: T[n][tap][c] = sum_p sum_{cls: tap valid} Rp ; grid (N), block 256
+__global__ void border_tap_from_class_kernel(const float* __restrict__ Rp, int P, int C, float* __restrict__ T) {
+  int n = blockIdx.x;
+  for (int idx = threadIdx.x; idx < 27 * C; idx += blockDim.x) {
+    int tap = idx / C, c = idx % C;
+    int td = tap / 9, th = (tap / 3) % 3, tw = tap % 3;
+    double acc = 0.0;
+    for (int cls = 0; cls < 64; ++cls) {
+      if (!(tap_valid(cls >> 4, td) && tap_valid((cls >> 2) & 3, th) && tap_valid(cls & 3, tw))) continue;
+      for (int p = 0; p < P; ++p) acc += (double)Rp[(((size_t)n * P + p) * 64 + cls) * C + c];
+    }
+    T[((size_t)n * 27 + tap) * C + c] = (float)acc;
+  }
+}
+
+// dW[co][ci][tap] = sum_n ( a[n][ci] * sum_s G[n][s][tap][ci][co] + b[n][ci] * T[n][tap][co] )
+__global__ void wgrad_finalize_kernel(const float* __restrict__ G, int N, int S, int Cin, int Cout, const float* __restrict__ ab,
+                                      const float* __restrict__ T, float* __restrict__ dW) {
+  size_t total = (size_t)27 * Cin * Cout;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int co = (int)(i % Cout);
+    size_t r = i / Cout;
+    int ci = (int)(r % Cin);
+    int tap = (int)(r / Cin);
+    double acc = 0.0;
+    for (int n = 0; n < N; ++n) {
+      double g = 0.0;
+      for (int s = 0; s < S; ++s) g += (double)G[((((size_t)n * S + s) * 27 + tap) * Cin + ci) * Cout + co];
+      if (ab) {
+        acc += (double)ab[((size_t)n * Cin + ci) * 2] * g;
+        if (T) acc += (double)ab[((size_t)n * Cin + ci) * 2 + 1] * (double)T[((size_t)n * 27 + tap) * Cout + co];
+      } else {
+        acc += g;
+      }
+    }
+    dW[((size_t)co * Cin + ci) * 27 + tap] = (float)acc;
+  }
+}
+
+__global__ void bias_grad_from_T_kernel(const float* __restrict__ T, int N, int C, float* __restrict__ db) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double acc = 0.0;
+  for (int n = 0; n < N; ++n) acc += (double)T[((size_t)n * 27 + 13) * C + c];  // centre tap is valid everywhere
+  db[c] = (float)acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// final 1x1x1 conv (+bias) + sigmoid / softmax; logits & probs are NCDHW fp32 (predictor.py:169 needs fp32)
+// ------------------------------------------------------------------------------------------------
+constexpr int FC_MAXO = 16;
+__global__ void final_conv_fwd_kernel(const bf16* __restrict__ x, long long voxels, int C, const float* __restrict__ Wt,
+                                      const float* __restrict__ bias, int Cout, int final_act, float* __restrict__ logits,
+                                      float* __restrict__ probs) {
+  extern __shared__ float wsm[];  // [Cout][C] + [Cout]
+  int n = blockIdx.y;
+  for (int i = threadIdx.x; i < Cout * C; i += blockDim.x) wsm[i] = Wt[i];
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) wsm[Cout * C + i] = bias ? bias[i] : 0.f;
+  __syncthreads();
+  long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= voxels) return;
+  float acc[FC_MAXO];
+#pragma unroll
+  for (int o = 0; o < FC_MAXO; ++o) acc[o] = o < Cout ? wsm[Cout * C + o] : 0.f;
+  const bf16x8* xp = reinterpret_cast<const bf16x8*>(x + ((size_t)n * voxels + v) * C);
+  for (int cg = 0; cg < C / 8; ++cg) {
+    float f[8];
+    unpack8(xp[cg], f);
+#pragma unroll
+    for (int o = 0; o < FC_MAXO; ++o)
+      if (o < Cout) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[o] += f[i] * wsm[o * C + cg * 8 + i];
+      }
+  }
+  float mx = -INFINITY, den = 0.f;
+  if (final_act == B200_FINAL_SOFTMAX) {
+#pragma unroll
+    for (int o = 0; o < FC_MAXO; ++o)
+      if (o < Cout) mx = fmaxf(mx, acc[o]);
+#pragma unroll
+    for (int o = 0; o < FC_MAXO; ++o)
+      if (o < Cout) den += expf(acc[o] - mx);
+  }
+#pragma unroll
+  for (int o = 0; o < FC_MAXO; ++o)
+    if (o < Cout) {
+      size_t idx = ((size_t)n * Cout + o) * voxels + v;
+      logits[idx] = acc[o];
+      if (probs) {
+        float pr = acc[o];
+        if (final_act == B200_FINAL_SIGMOID) pr = 1.f / (1.f + expf(-acc[o]));
+        else if (final_act == B200_FINAL_SOFTMAX) pr = expf(acc[o] - mx) / den;
+        probs[idx] = pr;
+      }
+    }
+}
+
+// dz = (sum_o dl[o] W[o][c]) * act'(x); partial sums of dW[o][c] and db[o]; grid (P, N)
+// partials row layout: [Cout*C] dW then [Cout] db
+__global__ void final_conv_bwd_kernel(const float* __restrict__ dl, const bf16* __restrict__ x, long long voxels, int C,
+                                      const float* __restrict__ Wt, int Cout, int P, int act, float slope, bf16* __restrict__ dz,
+                                      float* __restrict__ partials) {
+  extern __shared__ float sm[];  // red[EW_THREADS*16] then W[Cout*C]
+  float* red = sm;
+  float* wsm = sm + EW_THREADS * 16;
+  int p = blockIdx.x, n = blockIdx.y;
+  for (int i = threadIdx.x; i < Cout * C; i += blockDim.x) wsm[i] = Wt[i];
+  __syncthreads();
+  EwMap m = ew_map(C);
+  long long v0, v1;
+  ew_range(voxels, p, P, v0, v1);
+  float* prow = partials + ((size_t)n * P + p) * ((size_t)Cout * C + Cout);
+  const bf16x8* xp = reinterpret_cast<const bf16x8*>(x + (size_t)n * voxels * C);
+  bf16x8* zp = reinterpret_cast<bf16x8*>(dz + (size_t)n * voxels * C);
+  // pass over output channels in pairs; dz is produced in the first pass (needs all o, cheap recompute)
+  for (int o0 = 0; o0 < Cout; o0 += 2) {
+    float s[8] = {0}, q[8] = {0};  // dW[o0][8ch], dW[o0+1][8ch]
+    float db0 = 0.f, db1 = 0.f;
+    if (m.active) {
+      for (long long v = v0 + m.vl; v < v1; v += m.VL) {
+        float f[8];
+        unpack8(xp[v * m.CG + m.cg], f);
+        float d0 = dl[((size_t)n * Cout + o0) * voxels + v];
+        float d1 = (o0 + 1 < Cout) ? dl[((size_t)n * Cout + o0 + 1) * voxels + v] : 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          s[i] += d0 * f[i];
+          q[i] += d1 * f[i];
+        }
+        if (m.cg == 0) {
+          db0 += d0;
+          db1 += d1;
+        }
+        if (o0 == 0) {
+          float g[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) g[i] = 0.f;
+          for (int o = 0; o < Cout; ++o) {
+            float d = dl[((size_t)n * Cout + o) * voxels + v];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) g[i] += d * wsm[o * C + m.cg * 8 + i];
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) g[i] *= act_grad_from_out(f[i], act, slope);
+          zp[v * m.CG + m.cg] = pack8(g);
+        }
+      }
+    }
+    // reduce over voxel lanes: reuse the (s,q) -> [C][2] machinery into a temp in smem-free fashion
+    if (m.active) {
+      float* r = red + (size_t)(m.vl * m.CG + m.cg) * 16;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        r[i] = s[i];
+        r[8 + i] = q[i];
+      }
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < m.CG * 16; idx += EW_THREADS) {
+      int cg = idx >> 4, i = idx & 15;
+      float acc = 0.f;
+      for (int vl = 0; vl < m.VL; ++vl) acc += red[(size_t)(vl * m.CG + cg) * 16 + i];
+      int c = cg * 8 + (i & 7), k = i >> 3;
+      if (o0 + k < Cout) prow[(size_t)(o0 + k) * C + c] = acc;
+    }
+    __syncthreads();
+    // bias partials: lanes with cg==0 hold db; reduce through smem
+    if (m.active && m.cg == 0) {
+      red[m.vl * 2] = db0;
+      red[m.vl * 2 + 1] = db1;
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 && o0 + (int)threadIdx.x < Cout) {
+      float acc = 0.f;
+      for (int vl = 0; vl < m.VL; ++vl) acc += red[vl * 2 + threadIdx.x];
+      prow[(size_t)Cout * C + o0 + threadIdx.x] = acc;
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace b200
+
+// ================================================================================================
+// C-ABI
+// ================================================================================================
+using namespace b200;
+#define ST(s) ((cudaStream_t)(s))
+
+extern "C" {
+
+int b200_version(void) { return 1; }
+
+int b200_last_error(char* buf, size_t len) {
+  size_t n = strlen(g_err);
+  if (buf && len) {
+    size_t k = n < len - 1 ? n : len - 1;
+    memcpy(buf, g_err, k);
+    buf[k] = 0;
+  }
+  return (int)n;
+}
+
+int b200_device_is_sm100(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  return major == 10;
+}
+
+int b200_ncdhw_f32_to_ndhwc_f32(const float* src, float* dst, int N, int C, int D, int H, int W, b200_stream_t s) {
+  long long vox = (long long)D * H * W;
+  dim3 grid(ceil_div(vox, 256), N);
+  ncdhw_to_ndhwc_kernel<float><<<grid, 256, 0, ST(s)>>>(src, dst, C, vox);
+  B200_CHECK_LAUNCH("ncdhw_f32_to_ndhwc_f32");
+  return 0;
+}
+int b200_ncdhw_f32_to_ndhwc_bf16(const float* src, void* dst, int N, int C, int D, int H, int W, b200_stream_t s) {
+  long long vox = (long long)D * H * W;
+  dim3 grid(ceil_div(vox, 256), N);
+  ncdhw_to_ndhwc_kernel<bf16><<<grid, 256, 0, ST(s)>>>(src, (bf16*)dst, C, vox);
+  B200_CHECK_LAUNCH("ncdhw_f32_to_ndhwc_bf16");
+  return 0;
+}
+int b200_ndhwc_bf16_to_ncdhw_f32(const void* src, float* dst, int N, int C, int D, int H, int W, b200_stream_t s) {
+  long long vox = (long long)D * H * W;
+  dim3 grid(ceil_div(vox, 256), N);
+  ndhwc_to_ncdhw_kernel<<<grid, 256, 0, ST(s)>>>((const bf16*)src, dst, C, vox);
+  B200_CHECK_LAUNCH("ndhwc_bf16_to_ncdhw_f32");
+  return 0;
+}
+
+int b200_stats_partials_count(int N, int C, long long voxels) {
+  (void)N;
+  if (C % 8 == 0) return ew_blocks(voxels, C);
+  long long p = (voxels + 8191) / 8192;
+  return (int)(p > 1024 ? 1024 : (p < 1 ? 1 : p));
+}
+int b200_stats_ncdhw_f32(const float* x, int N, int C, long long voxels, float* partials, b200_stream_t s) {
+  long long p = (voxels + 8191) / 8192;
+  int P = (int)(p > 1024 ? 1024 : (p < 1 ? 1 : p));
+  dim3 grid(P, N * C);
+  stats_ncdhw_f32_kernel<<<grid, 256, 0, ST(s)>>>(x, C, voxels, P, partials);
+  B200_CHECK_LAUNCH("stats_ncdhw_f32");
+  return 0;
+}
+int b200_stats_ncdhw_f32_partials_count(long long voxels) {
+  long long p = (voxels + 8191) / 8192;
+  return (int)(p > 1024 ? 1024 : (p < 1 ? 1 : p));
+}
+int b200_stats_ndhwc_bf16(const void* x, int N, int C, long long voxels, float* partials, b200_stream_t s) {
+  B200_CHECK_ARG(C % 8 == 0 && C <= 2048, "stats_ndhwc_bf16: C=%d must be a multiple of 8 and <= 2048", C);
+  int P = ew_blocks(voxels, C);
+  dim3 grid(P, N);
+  stats_ndhwc_bf16_kernel<<<grid, EW_THREADS, EW_THREADS * 16 * sizeof(float), ST(s)>>>((const bf16*)x, C, voxels, P, partials);
+  B200_CHECK_LAUNCH("stats_ndhwc_bf16");
+  return 0;
+}
+int b200_stats2_ndhwc_bf16(const void* a, const void* b, int N, int C, long long voxels, float* partials, b200_stream_t s) {
+  B200_CHECK_ARG(C % 8 == 0 && C <= 2048, "stats2_ndhwc_bf16: C=%d must be a multiple of 8 and <= 2048", C);
+  int P = ew_blocks(voxels, C);
+  dim3 grid(P, N);
+  stats2_ndhwc_bf16_kernel<<<grid, EW_THREADS, EW_THREADS * 16 * sizeof(float), ST(s)>>>((const bf16*)a, (const bf16*)b, C, voxels, P,
+                                                                                   partials);
+  B200_CHECK_LAUNCH("stats2_ndhwc_bf16");
+  return 0;
+}
+int b200_gn_bwd_sums_from_wgrad(const float* G, int S, const float* T, const float* W, int N, int Cin, int Cout, double* sums2,
+                                b200_stream_t s) {
+  dim3 grid(Cin, N);
+  gn_bwd_sums_from_wgrad_kernel<<<grid, 128, 0, ST(s)>>>(G, S, T, W, Cin, Cout, sums2);
+  B200_CHECK_LAUNCH("gn_bwd_sums_from_wgrad");
+  return 0;
+}
+int b200_partials_finalize(const float* partials, int N, int P, int C, double* sums, b200_stream_t s) {
+  dim3 grid(ceil_div(C * 2, 32), N), block(32, 32);
+  partials_finalize_kernel<<<grid, block, 0, ST(s)>>>(partials, P, C, sums);
+  B200_CHECK_LAUNCH("partials_finalize");
+  return 0;
+}
+int b200_reduce_rows(const float* partials, int P, int K, float* out, b200_stream_t s) {
+  dim3 grid(ceil_div(K, 32)), block(32, 32);
+  reduce_rows_kernel<<<grid, block, 0, ST(s)>>>(partials, P, K, out);
+  B200_CHECK_LAUNCH("reduce_rows");
+  return 0;
+}
+
+int b200_gn_coeffs(const double* sums, const float* gamma, const float* beta, int G, double count, int N, int C,
+                   float* mean_rstd, float* ab, b200_stream_t s) {
+  B200_CHECK_ARG(G > 0 && C % G == 0, "gn_coeffs: C=%d not divisible by G=%d", C, G);
+  gn_coeffs_kernel<<<N, 128, G * 2 * sizeof(float), ST(s)>>>(sums, gamma, beta, G, count, C, mean_rstd, ab);
+  B200_CHECK_LAUNCH("gn_coeffs");
+  return 0;
+}
+
+int b200_gn_fold(const double* sums, const float* gamma, const float* beta, int G, double count, const float* W,
+                 const float* conv_bias, int N, int Cin, int Cout, void* wf, float* biascls, float* mean_rstd, float* ab,
+                 b200_stream_t s) {
+  int n_w = 1;
+  const float* abp = nullptr;
+  if (sums) {
+    int rc = b200_gn_coeffs(sums, gamma, beta, G, count, N, Cin, mean_rstd, ab, s);
+    if (rc) return rc;
+    n_w = N;
+    abp = ab;
+  }
+  size_t total = (size_t)n_w * 27 * Cout * Cin;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 4096) blocks = 4096;
+  fold_weights_kernel<<<blocks, 256, 0, ST(s)>>>(W, abp, n_w, Cin, Cout, (bf16*)wf);
+  B200_CHECK_LAUNCH("fold_weights");
+  if (biascls && (abp || conv_bias)) {
+    dim3 grid(Cout, n_w);
+    fold_bias_kernel<<<grid, 128, 0, ST(s)>>>(W, abp, conv_bias, Cin, Cout, biascls);
+    B200_CHECK_LAUNCH("fold_bias");
+  }
+  return 0;
+}
+
+int b200_prep_dgrad_weights(const float* W, int Cin, int Cout, void* wd, b200_stream_t s) {
+  size_t total = (size_t)27 * Cin * Cout;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 4096) blocks = 4096;
+  prep_dgrad_weights_kernel<<<blocks, 256, 0, ST(s)>>>(W, Cin, Cout, (bf16*)wd);
+  B200_CHECK_LAUNCH("prep_dgrad_weights");
+  return 0;
+}
+
+int b200_gn_apply_act(const void* x, const float* ab, int N, int C, long long voxels, int act, float slope, void* y,
+                      float* partials, b200_stream_t s) {
+  B200_CHECK_ARG(C % 8 == 0 && C <= 2048, "gn_apply_act: C=%d must be a multiple of 8", C);
+  int P = ew_blocks(voxels, C);
+  dim3 grid(P, N);
+  gn_apply_act_kernel<<<grid, EW_THREADS, EW_THREADS * 16 * sizeof(float), ST(s)>>>((const bf16*)x, ab, C, voxels, P, act, slope,
+                                                                                  (bf16*)y, partials);
+  B200_CHECK_LAUNCH("gn_apply_act");
+  return 0;
+}
+
+int b200_gn_bwd_coeffs(const double* sums2, const float* gamma, const float* mean_rstd, int G, double count, int N, int C,
+                       float* coef, float* dgamma, float* dbeta, b200_stream_t s) {
+  gn_bwd_coeffs_kernel<<<1, 256, 0, ST(s)>>>(sums2, gamma, mean_rstd, G, count, N, C, coef, dgamma, dbeta);
+  B200_CHECK_LAUNCH("gn_bwd_coeffs");
+  return 0;
+}
+
+int b200_gn_bwd_apply(const void* dxhat, const void* x, const float* coef, int N, int C, long long voxels, int act, float slope,
+                      const void* gadd, void* out, b200_stream_t s) {
+  B200_CHECK_ARG(C % 8 == 0 && C <= 2048, "gn_bwd_apply: C=%d must be a multiple of 8", C);
+  int P = ew_blocks(voxels, C);
+  dim3 grid(P, N);
+  gn_bwd_apply_kernel<<<grid, EW_THREADS, 0, ST(s)>>>((const bf16*)dxhat, (const bf16*)x, coef, C, voxels, P, act, slope,
+                                                      (const bf16*)gadd, (bf16*)out);
+  B200_CHECK_LAUNCH("gn_bwd_apply");
+  return 0;
+}
+
+int b200_act_bwd(const void* g, int g_cs, int g_co, const void* y, int N, int C, long long voxels, int act, float slope,
+                 const void* gadd, void* out, b200_stream_t s) {
+  B200_CHECK_ARG(C % 8 == 0 && C <= 2048, "act_bwd: C=%d must be a multiple of 8", C);
+  B200_CHECK_ARG(g && g_cs % 8 == 0 && g_co % 8 == 0 && g_co + C <= g_cs, "act_bwd: bad gradient slice (cs=%d co=%d C=%d)", g_cs, g_co, C);
+  int P = ew_blocks(voxels, C);
+  dim3 grid(P, N);
+  act_bwd_kernel<<<grid, EW_THREADS, 0, ST(s)>>>((const bf16*)g, g_cs, g_co, (const bf16*)y, C, voxels, P, act, slope,
+                                                 (const bf16*)gadd, (bf16*)out);
+  B200_CHECK_LAUNCH("act_bwd");
+  return 0;
+}
+
+int b200_maxpool_partials_count(int N, int D, int H, int W, int C) {
+  (void)N;
+  return ew_blocks((long long)(D / 2) * (H / 2) * (W / 2), C);
+}
+int b200_maxpool_fwd(const void* x, int N, int D, int H, int W, int C, void* y, float* partials, b200_stream_t s) {
+  B200_CHECK_ARG(C % 8 == 0 && C <= 2048, "maxpool_fwd: C=%d must be a multiple of 8", C);
+  B200_CHECK_ARG(D >= 2 && H >= 2 && W >= 2, "maxpool_fwd: spatial size (%d,%d,%d) too small for MaxPool3d(2)", D, H, W);
+  int P = b200_maxpool_partials_count(N, D, H, W, C);
+  dim3 grid(P, N);
+  maxpool_fwd_kernel<<<grid, EW_THREADS, EW_THREADS * 16 * sizeof(float), ST(s)>>>((const bf16*)x, D, H, W, C, P, (bf16*)y,
+                                                                                 partials);
+  B200_CHECK_LAUNCH("maxpool_fwd");
+  return 0;
+}
+int b200_maxpool_bwd(const void* dpooled, const void* x_full, int N, int D, int H, int W, int C, int act, float slope,
+                     const void* gadd, void* dz_full, b200_stream_t s) {
+  B200_CHECK_ARG(C % 8 == 0 && C <= 2048, "maxpool_bwd: C=%d must be a multiple of 8", C);
+  long long cells = (long long)((D + 1) / 2) * ((H + 1) / 2) * ((W + 1) / 2);
+  int P = ew_blocks(cells, C);
+  dim3 grid(P, N);
+  maxpool_bwd_kernel<<<grid, EW_THREADS, 0, ST(s)>>>((const bf16*)dpooled, (const bf16*)x_full, D, H, W, C, P, act, slope,
+                                                     (const bf16*)gadd, (bf16*)dz_full);
+  B200_CHECK_LAUNCH("maxpool_bwd");
+  return 0;
+}
+
+int b200_upcat_partials_count(int N, int D, int H, int W, int C) {
+  (void)N;
+  return ew_blocks((long long)D * H * W, C);
+}
+int b200_upcat_fwd(const void* enc, int C0, const void* x, int C1, int N, int D, int H, int W, int d, int h, int w, void* cat,
+                   float* partials, b200_stream_t s) {
+  B200_CHECK_ARG(C0 % 8 == 0 && C1 % 8 == 0 && C0 + C1 <= 2048, "upcat_fwd: channel counts %d,%d must be multiples of 8", C0, C1);
+  int P = b200_upcat_partials_count(N, D, H, W, C0 + C1);
+  dim3 grid(P, N);
+  upcat_fwd_kernel<<<grid, EW_THREADS, EW_THREADS * 16 * sizeof(float), ST(s)>>>((const bf16*)enc, C0, (const bf16*)x, C1, D, H, W,
+                                                                               d, h, w, P, (bf16*)cat, partials);
+  B200_CHECK_LAUNCH("upcat_fwd");
+  return 0;
+}
+int b200_upcat_bwd(const void* dcat, int C0, int C1, const void* x_small, int N, int D, int H, int W, int d, int h, int w, int act,
+                   float slope, void* dx_small, b200_stream_t s) {
+  B200_CHECK_ARG(C0 % 8 == 0 && C1 % 8 == 0, "upcat_bwd: channel counts %d,%d must be multiples of 8", C0, C1);
+  int P = ew_blocks((long long)d * h * w, C1);
+  dim3 grid(P, N);
+  upcat_bwd_kernel<<<grid, EW_THREADS, 0, ST(s)>>>((const bf16*)dcat, C0, C1, (const bf16*)x_small, D, H, W, d, h, w, P, act, slope,
+                                                   (bf16*)dx_small);
+  B200_CHECK_LAUNCH("upcat_bwd");
+  return 0;
+}
+
+int b200_border_tap_sums_workspace(int N, int D, int H, int W, int C) {
+  // number of floats of scratch needed by b200_border_tap_sums
+  int P = ew_blocks((long long)D * H * W, 64);
+  return N * P * 64 * C;
+}
+int b200_border_tap_sums(const void* dz, int N, int D, int H, int W, int C, float* T, float* scratch, b200_stream_t s) {
+  B200_CHECK_ARG(C % 8 == 0, "border_tap_sums: C=%d must be a multiple of 8", C);
+  int P = ew_blocks((long long)D * H * W, 64);
+  dim3 grid(P, N, ceil_div(C, BT_CC));
+  border_class_sums_kernel<<<grid, EW_THREADS, 0, ST(s)>>>((const bf16*)dz, D, H, W, C, P, scratch);
+  B200_CHECK_LAUNCH("border_class_sums");
+  border_tap_from_class_kernel<<<N, 256, 0, ST(s)>>>(scratch, P, C, T);
+  B200_CHECK_LAUNCH("border_tap_from_class");
+  return 0;
+}
+
+int b200_wgrad_finalize(const float* G, int N, int S, int Cin, int Cout, const float* ab, const float* T, float* dW,
+                        b200_stream_t s) {
+  size_t total = (size_t)27 * Cin * Cout;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 4096) blocks = 4096;
+  wgrad_finalize_kernel<<<blocks, 256, 0, ST(s)>>>(G, N, S, Cin, Cout, ab, T, dW);
+  B200_CHECK_LAUNCH("wgrad_finalize");
+  return 0;
+}
+int b200_bias_grad_from_T(const float* T, int N, int C, float* db, b200_stream_t s) {
+  bias_grad_from_T_kernel<<<ceil_div(C, 128), 128, 0, ST(s)>>>(T, N, C, db);
+  B200_CHECK_LAUNCH("bias_grad_from_T");
+  return 0;
+}
+
+int b200_final_conv_fwd(const void* x, int N, long long voxels, int C, const float* W, const float* bias, int Cout,
+                        int final_act, float* logits, float* probs, b200_stream_t s) {
+  B200_CHECK_ARG(C % 8 == 0, "final_conv_fwd: C=%d must be a multiple of 8", C);
+  B200_CHECK_ARG(Cout >= 1 && Cout <= FC_MAXO, "final_conv_fwd: out_channels=%d unsupported (max %d)", Cout, FC_MAXO);
+  dim3 grid(ceil_div(voxels, 128), N);
+  size_t smem = ((size_t)Cout * C + Cout) * sizeof(float);
+  final_conv_fwd_kernel<<<grid, 128, smem, ST(s)>>>((const bf16*)x, voxels, C, W, bias, Cout, final_act, logits, probs);
+  B200_CHECK_LAUNCH("final_conv_fwd");
+  return 0;
+}
+int b200_final_conv_bwd_partials_count(int N, long long voxels, int C, int Cout) {
+  (void)N;
+  (void)Cout;
+  return ew_blocks(voxels, C);
+}
+int b200_final_conv_bwd(const float* dlogits, const void* x, int N, long long voxels, int C, const float* W, int Cout, int act,
+                        float slope, void* dz, float* partials, b200_stream_t s) {
+  B200_CHECK_ARG(C % 8 == 0 && C <= 2048, "final_conv_bwd: C=%d must be a multiple of 8", C);
+  int P = ew_blocks(voxels, C);
+  dim3 grid(P, N);
+  size_t smem = ((size_t)EW_THREADS * 16 + (size_t)Cout * C) * sizeof(float);
+  B200_CHECK_ARG(smem <= 48 * 1024, "final_conv_bwd: Cout*C=%d too large", Cout * C);
+  final_conv_bwd_kernel<<<grid, EW_THREADS, smem, ST(s)>>>(dlogits, (const bf16*)x, voxels, C, W, Cout, P, act, slope, (bf16*)dz,
+                                                          partials);
+  B200_CHECK_LAUNCH("final_conv_bwd");
+  return 0;
+}
+
+}  // extern "C"

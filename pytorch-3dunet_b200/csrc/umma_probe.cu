@@ -1,0 +1,98 @@
+// Hardware probe (test tooling, not on the product path): does tcgen05.mma accept a K-major SWIZZLE_128B A operand
+// whose start address is shifted by whole 128-byte rows (not a multiple of the 1024-byte swizzle pattern) and whose
+// 8-row groups sit at a stride that is not a multiple of 1024 bytes?  If the swizzle XOR is a pure function of the
+// shared-memory address bits (as it is for TMA writes), shifted views of ONE halo tile can serve all 27 filter taps.
+//   D[r][n] = sum_k A[row(r)][k] * B[n][k],  row(r) = shift + (r / 8) * group_rows + (r % 8)
+#include <string.h>
+
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace b200 {
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* t, uint64_t* bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                   smem_u32(dst)),
+               "l"(reinterpret_cast<uint64_t>(t)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(128) umma_probe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                                                         int rows, int shift, int group_rows, float* __restrict__ D) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar, done_bar;
+  __shared__ uint32_t tmem_slot;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;                                   // rows x 128 B
+  uint8_t* sB = smem + (((size_t)rows * 128 + 1023) & ~(size_t)1023);  // 16 x 128 B
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(&full_bar, 1);
+    mbar_init(&done_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, 32);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(&full_bar, (uint32_t)(rows * 128 + 16 * 128));
+    // TMA boxes are limited to 256 rows
+    tma_load_2d(sA, &tmA, &full_bar, 0, 0);
+    tma_load_2d(sB, &tmB, &full_bar, 0, 0);
+    mbar_wait(&full_bar, 0);
+    tc_fence_after();
+    const uint32_t idesc = umma_idesc_bf16(128, 16, 0, 0);
+    for (int k = 0; k < 4; ++k) {
+      const uint64_t adesc = umma_smem_desc(smem_u32(sA) + (uint32_t)(shift * 128 + k * 32), 16u, (uint32_t)(group_rows * 128), UMMA_LAYOUT_SW128);
+      const uint64_t bdesc = umma_smem_desc(smem_u32(sB) + (uint32_t)(k * 32), 16u, 1024u, UMMA_LAYOUT_SW128);
+      umma_bf16(tmem_base, adesc, bdesc, idesc, k != 0 ? 1u : 0u);
+    }
+    umma_commit(&done_bar);
+  }
+  mbar_wait(&done_bar, 0);
+  __syncwarp();
+  tc_fence_after();
+  uint32_t raw[16];
+  tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(warp * 32) << 16), raw);
+  tmem_ld_wait();
+  for (int i = 0; i < 16; ++i) D[(size_t)(warp * 32 + lane) * 16 + i] = __uint_as_float(raw[i]);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 32);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_tiled();
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_probe_umma_rowshift(const void* A, int rows, const void* B, int shift, int group_rows, float* D, b200_stream_t s) {
+  B200_CHECK_ARG(rows <= 256 && shift + 15 * group_rows + 8 <= rows, "probe: rows=%d too small for shift=%d group_rows=%d", rows, shift,
+                 group_rows);
+  EncodeTiledFn enc = get_encode_tiled();
+  B200_CHECK_ARG(enc, "cuTensorMapEncodeTiled entry point not available");
+  CUtensorMap tmA, tmB;
+  cuuint64_t dA[2] = {64, (cuuint64_t)rows}, dB[2] = {64, 16};
+  cuuint64_t st[1] = {128};
+  cuuint32_t bA[2] = {64, (cuuint32_t)rows}, bB[2] = {64, 16}, es[2] = {1, 1};
+  CUresult r1 = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(A), dA, st, bA, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r2 = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(B), dB, st, bB, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B200_CHECK_ARG(r1 == CUDA_SUCCESS && r2 == CUDA_SUCCESS, "probe: tensor map encode failed %d %d", (int)r1, (int)r2);
+  size_t smem = (((size_t)rows * 128 + 1023) & ~(size_t)1023) + 2048 + 1024;
+  cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  umma_probe_kernel<<<1, 128, smem, (cudaStream_t)s>>>(tmA, tmB, rows, shift, group_rows, D);
+  B200_CHECK_LAUNCH("umma_probe");
+  return 0;
+}

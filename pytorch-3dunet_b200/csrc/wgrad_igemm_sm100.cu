@@ -1,0 +1,262 @@
+// Weight gradient of the 3x3x3 convolution on the sm_100a tensor cores.
+//
+//   G[n][split][tap][ci][co] = sum over the voxels v of the split of  x[n, v+tap-1, ci] * dz[n, v, co]
+//
+// i.e. 27 GEMMs  D_tap[ci, co] = X_tap^T [ci, voxels] * dZ [voxels, co]  that share the dZ operand; the reduction
+// (GEMM-K) dimension is the voxel index.  Both operands are read exactly as they sit in HBM (NDHWC: one row per
+// voxel, channels contiguous), so they are "MN-major" UMMA operands: TMA box loads -> swizzled smem tiles
+// [128 voxels][AW channels], tcgen05.mma with a_major = b_major = MN, K = 16 voxels per instruction.
+// The zero padding of x is again the TMA out-of-bounds fill.  The GroupNorm scale/shift that the forward pass
+// folded into the weights is undone analytically in b200_wgrad_finalize (a[n,ci] * G + b[n,ci] * T).
+//
+// One CTA: (voxel split, sample, group of TG taps, 128-channel slice of C_in).  TMEM holds TG accumulators of
+// [128 x C_out] fp32 (TG * C_out <= 512 columns).  Warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..5 = epilogue.
+#include <string.h>
+
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace b200 {
+
+int make_act_tmap(CUtensorMap* tm, const void* ptr, int N, int D, int H, int W, int C, int kc, int bd, int bh, int bw);
+int choose_box(int D, int H, int W, int* bd, int* bh, int* bw);
+
+constexpr int WG_THREADS = 192;
+constexpr int WG_MAX_A_STAGES = 4;
+constexpr int WG_B_STAGES = 2;
+constexpr int WG_A_STAGE_BYTES = 128 * 128 * 2;  // 128 voxels x 128 channels bf16
+
+struct WgradParams {
+  int N, D, H, W, Cin, Cout;
+  int BD, BH, BW, tilesD, tilesH, tilesW, tiles;
+  int S, tiles_per_split;
+  int TG, ngroups, mchunks;
+  int AWa, AWb;  // channels per smem atom tile (64/32/16) on the x side and the dz side
+  int a_stages, b_stage_bytes;
+  int tmem_cols;
+  float* G;
+};
+
+__global__ void __launch_bounds__(WG_THREADS)
+conv3_wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ CUtensorMap tmapZ, const WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t a_full[WG_MAX_A_STAGES], a_empty[WG_MAX_A_STAGES];
+  __shared__ __align__(8) uint64_t b_full[WG_B_STAGES], b_empty[WG_B_STAGES];
+  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_slot;
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smemB = smem;                                           // WG_B_STAGES * b_stage_bytes
+  uint8_t* smemA = smem + (size_t)WG_B_STAGES * p.b_stage_bytes;   // a_stages * WG_A_STAGE_BYTES
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const int split = blockIdx.x % p.S;
+  const int n = blockIdx.x / p.S;
+  const int grp = blockIdx.y;
+  const int m0 = blockIdx.z * 128;
+  const int tap0 = grp * p.TG;
+  const int ntaps = min(p.TG, 27 - tap0);
+  const int t0 = split * p.tiles_per_split;
+  const int t1 = min(p.tiles, t0 + p.tiles_per_split);
+  const int m_real = min(128, p.Cin - m0);
+  const int natoms_a = m_real / p.AWa;
+  const int natoms_b = p.Cout / p.AWb;
+  const int a_atom_bytes = 128 * p.AWa * 2, b_atom_bytes = 128 * p.AWb * 2;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.a_stages; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < WG_B_STAGES; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    mbar_init(&tmem_full_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmapX);
+    tma_prefetch_desc(&tmapZ);
+  }
+  if (warp == 1) tmem_alloc(&tmem_slot, (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int ai = 0;  // running A-stage counter
+      for (int t = t0, bi = 0; t < t1; ++t, ++bi) {
+        int tt = t;
+        const int w0 = (tt % p.tilesW) * p.BW;
+        tt /= p.tilesW;
+        const int h0 = (tt % p.tilesH) * p.BH;
+        const int d0 = (tt / p.tilesH) * p.BD;
+        {
+          const int bs = bi % WG_B_STAGES;
+          mbar_wait(&b_empty[bs], ((uint32_t)(bi / WG_B_STAGES) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&b_full[bs], (uint32_t)(natoms_b * b_atom_bytes));
+          for (int j = 0; j < natoms_b; ++j)
+            tma_load_5d(smemB + (size_t)bs * p.b_stage_bytes + (size_t)j * b_atom_bytes, &tmapZ, &b_full[bs], j * p.AWb, w0, h0, d0, n);
+        }
+        for (int tp = 0; tp < ntaps; ++tp, ++ai) {
+          const int tap = tap0 + tp;
+          const int td = tap / 9, th = (tap / 3) % 3, tw = tap % 3;
+          const int as = ai % p.a_stages;
+          mbar_wait(&a_empty[as], ((uint32_t)(ai / p.a_stages) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&a_full[as], (uint32_t)(natoms_a * a_atom_bytes));
+          for (int j = 0; j < natoms_a; ++j)
+            tma_load_5d(smemA + (size_t)as * WG_A_STAGE_BYTES + (size_t)j * a_atom_bytes, &tmapX, &a_full[as], m0 + j * p.AWa,
+                        w0 + tw - 1, h0 + th - 1, d0 + td - 1, n);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, p.Cout, 1, 1);
+      const int rba = p.AWa * 2, rbb = p.AWb * 2;
+      const uint32_t la = umma_layout_for_row_bytes(rba), lb = umma_layout_for_row_bytes(rbb);
+      int ai = 0;
+      for (int t = t0, bi = 0; t < t1; ++t, ++bi) {
+        const int bs = bi % WG_B_STAGES;
+        mbar_wait(&b_full[bs], (uint32_t)(bi / WG_B_STAGES) & 1u);
+        const uint32_t sb = smem_u32(smemB + (size_t)bs * p.b_stage_bytes);
+        for (int tp = 0; tp < ntaps; ++tp, ++ai) {
+          const int as = ai % p.a_stages;
+          mbar_wait(&a_full[as], (uint32_t)(ai / p.a_stages) & 1u);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smemA + (size_t)as * WG_A_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {  // 128 voxels = 8 x K16
+            const uint64_t adesc = umma_smem_desc(sa + (uint32_t)(k * 16 * rba), (uint32_t)a_atom_bytes, (uint32_t)(8 * rba), la);
+            const uint64_t bdesc = umma_smem_desc(sb + (uint32_t)(k * 16 * rbb), (uint32_t)b_atom_bytes, (uint32_t)(8 * rbb), lb);
+            umma_bf16(tmem_base + (uint32_t)(tp * p.Cout), adesc, bdesc, idesc, (t > t0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&a_empty[as]);
+        }
+        umma_commit(&b_empty[bs]);
+      }
+      umma_commit(&tmem_full_bar);
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int ci = m0 + row;
+    const bool valid = row < m_real;
+    mbar_wait(&tmem_full_bar, 0);
+    __syncwarp();
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const bool have_work = t1 > t0;
+    for (int tp = 0; tp < ntaps; ++tp) {
+      float* grow = p.G + ((((size_t)n * p.S + split) * 27 + (tap0 + tp)) * p.Cin + (valid ? ci : 0)) * p.Cout;
+      for (int c0 = 0; c0 < p.Cout; c0 += 16) {
+        uint32_t raw[16];
+        tmem_ld_32x32b_x16(taddr + (uint32_t)(tp * p.Cout + c0), raw);
+        tmem_ld_wait();
+        if (valid) {
+          float4* o = reinterpret_cast<float4*>(grow + c0);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float4 f;
+            f.x = have_work ? __uint_as_float(raw[4 * i]) : 0.f;
+            f.y = have_work ? __uint_as_float(raw[4 * i + 1]) : 0.f;
+            f.z = have_work ? __uint_as_float(raw[4 * i + 2]) : 0.f;
+            f.w = have_work ? __uint_as_float(raw[4 * i + 3]) : 0.f;
+            o[i] = f;
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+static int atom_width(int C) { return (C % 64 == 0) ? 64 : (C % 32 == 0 ? 32 : 16); }
+
+static bool wgrad_supported(int N, int D, int H, int W, int Cin, int Cout) {
+  (void)N;
+  int bd, bh, bw;
+  if (Cin % 16 != 0 || Cout % 16 != 0 || Cout > 256) return false;
+  if (choose_box(D, H, W, &bd, &bh, &bw)) return false;
+  return true;
+}
+
+static void wgrad_plan(int N, int D, int H, int W, int Cin, int Cout, WgradParams& p) {
+  memset(&p, 0, sizeof(p));
+  p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
+  choose_box(D, H, W, &p.BD, &p.BH, &p.BW);
+  p.tilesD = (D + p.BD - 1) / p.BD;
+  p.tilesH = (H + p.BH - 1) / p.BH;
+  p.tilesW = (W + p.BW - 1) / p.BW;
+  p.tiles = p.tilesD * p.tilesH * p.tilesW;
+  int tgmax = 512 / Cout;
+  if (tgmax > 27) tgmax = 27;
+  p.ngroups = (27 + tgmax - 1) / tgmax;
+  p.TG = (27 + p.ngroups - 1) / p.ngroups;
+  p.ngroups = (27 + p.TG - 1) / p.TG;
+  p.mchunks = (Cin + 127) / 128;
+  int ctas_per_split = N * p.ngroups * p.mchunks;
+  int want = (2 * 148 + ctas_per_split - 1) / ctas_per_split;
+  if (want < 1) want = 1;
+  if (want > p.tiles) want = p.tiles;
+  p.tiles_per_split = (p.tiles + want - 1) / want;
+  p.S = (p.tiles + p.tiles_per_split - 1) / p.tiles_per_split;
+  p.AWa = atom_width(Cin);
+  p.AWb = atom_width(Cout);
+  p.b_stage_bytes = 128 * Cout * 2;
+  int budget = 200 * 1024 - WG_B_STAGES * p.b_stage_bytes;
+  p.a_stages = budget / WG_A_STAGE_BYTES;
+  if (p.a_stages > WG_MAX_A_STAGES) p.a_stages = WG_MAX_A_STAGES;
+  if (p.a_stages < 2) p.a_stages = 2;
+  int cols = 32;
+  while (cols < p.TG * Cout) cols <<= 1;
+  p.tmem_cols = cols;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+int b200_conv3_wgrad_igemm_supported(int N, int D, int H, int W, int Cin, int Cout) {
+  return wgrad_supported(N, D, H, W, Cin, Cout) ? 1 : 0;
+}
+
+int b200_conv3_wgrad_igemm_splits(int N, int D, int H, int W, int Cin, int Cout) {
+  if (!wgrad_supported(N, D, H, W, Cin, Cout)) return 0;
+  WgradParams p;
+  wgrad_plan(N, D, H, W, Cin, Cout, p);
+  return p.S;
+}
+
+int b200_conv3_wgrad_igemm(const void* x, const void* dz, int N, int D, int H, int W, int Cin, int Cout, float* G, b200_stream_t s) {
+  B200_CHECK_ARG(wgrad_supported(N, D, H, W, Cin, Cout), "conv3_wgrad_igemm: unsupported shape N=%d D=%d H=%d W=%d Cin=%d Cout=%d", N,
+                 D, H, W, Cin, Cout);
+  WgradParams p;
+  wgrad_plan(N, D, H, W, Cin, Cout, p);
+  p.G = G;
+  CUtensorMap tmX, tmZ;
+  int rc = make_act_tmap(&tmX, x, N, D, H, W, Cin, p.AWa, p.BD, p.BH, p.BW);
+  if (rc) return rc;
+  rc = make_act_tmap(&tmZ, dz, N, D, H, W, Cout, p.AWb, p.BD, p.BH, p.BW);
+  if (rc) return rc;
+  size_t smem = (size_t)WG_B_STAGES * p.b_stage_bytes + (size_t)p.a_stages * WG_A_STAGE_BYTES + 1024;
+  cudaError_t e = cudaFuncSetAttribute(conv3_wgrad_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  B200_CHECK_ARG(e == cudaSuccess, "conv3_wgrad_igemm: cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e));
+  dim3 grid((unsigned)(N * p.S), (unsigned)p.ngroups, (unsigned)p.mchunks);
+  conv3_wgrad_igemm_kernel<<<grid, WG_THREADS, smem, (cudaStream_t)s>>>(tmX, tmZ, p);
+  B200_CHECK_LAUNCH("conv3_wgrad_igemm");
+  return 0;
+}
+
+}  // extern "C"

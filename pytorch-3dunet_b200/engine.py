@@ -1,0 +1,454 @@
+"""Host-side driver of the B200 3D U-Net engine: sequences the C-ABI kernels of libb200unet.so for the
+forward pass and records a tape that replays the matching backward kernels.
+
+PyTorch is used here only for device memory (torch.empty on the caching allocator) and the current CUDA
+stream; no torch operator runs on the hot path.  Activations live as bf16 NDHWC tensors ("Act").
+
+Reference semantics implemented (file:line relative to the reference checkout):
+  SingleConv / create_conv      pytorch3dunet/unet3d/buildingblocks.py:10-135
+  Encoder (MaxPool3d(2))        buildingblocks.py:353-384
+  Decoder (nearest + concat)    buildingblocks.py:436-493, 598-614
+  final conv + activation       pytorch3dunet/unet3d/model.py:89-98, 141-147
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+
+from ._lib import B200Error, lib
+
+ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_ELU = 0, 1, 2, 3
+IMPL_AUTO, IMPL_DIRECT, IMPL_TCGEN05 = 0, 1, 2
+FINAL_NONE, FINAL_SIGMOID, FINAL_SOFTMAX = 0, 1, 2
+_ACT_OF = {"r": (ACT_RELU, 0.0), "l": (ACT_LEAKY, 0.01), "e": (ACT_ELU, 1.0)}
+
+
+# optional per-launch CUDA-event timing of selected entry points (bench.py roofline leg): list of
+# (name, flops, start_event, end_event) appended when enabled
+TIMING = None
+TIMED = {"b200_conv3_fwd", "b200_conv3_wgrad"}
+
+
+def default_impl() -> int:
+    return {"auto": IMPL_AUTO, "direct": IMPL_DIRECT, "tcgen05": IMPL_TCGEN05}[os.environ.get("B200UNET_CONV_IMPL", "auto")]
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+class Act:
+    """A bf16 NDHWC activation plus what the engine knows about it."""
+
+    __slots__ = ("t", "act", "slope", "partials", "P", "sums", "grad", "requires_grad")
+
+    def __init__(self, t, act=ACT_NONE, slope=0.0, partials=None, P=0, requires_grad=True):
+        self.t = t
+        self.act = act          # activation that produced this tensor (needed for the backward mask)
+        self.slope = slope
+        self.partials = partials  # float [N,P,C,2] partial (sum, sumsq) emitted by the producer, or None
+        self.P = P
+        self.sums = None        # double [N,C,2], finalised lazily
+        self.grad = None        # bf16 NDHWC, gradient w.r.t. the producer's PRE-activation output ("dz form")
+        self.requires_grad = requires_grad
+
+    @property
+    def dims(self):
+        n, d, h, w, c = self.t.shape
+        return n, d, h, w, c
+
+    @property
+    def voxels(self):
+        return self.t.shape[1] * self.t.shape[2] * self.t.shape[3]
+
+
+class InputF32:
+    """The network input kept in fp32 (reference: ToTensor -> float32, transforms.py:816-826), NDHWC view."""
+
+    __slots__ = ("t", "sums_src", "sums", "requires_grad", "grad", "act", "slope")
+
+    def __init__(self, t_ndhwc, ncdhw_src):
+        self.t = t_ndhwc
+        self.sums_src = ncdhw_src
+        self.sums = None
+        self.requires_grad = False
+        self.grad = None
+        self.act, self.slope = ACT_NONE, 0.0
+
+    @property
+    def dims(self):
+        n, d, h, w, c = self.t.shape
+        return n, d, h, w, c
+
+    @property
+    def voxels(self):
+        return self.t.shape[1] * self.t.shape[2] * self.t.shape[3]
+
+
+class Engine:
+    """One forward (+ optional backward) pass.  Not reusable across passes."""
+
+    def __init__(self, device, impl=None, record=True):
+        self.L = lib()
+        self.device = device
+        self.impl = default_impl() if impl is None else impl
+        self.record = record
+        self.tape = []
+        self.param_grads = {}
+        self.launches = 0
+        self.stream = torch.cuda.current_stream(device).cuda_stream
+
+    # ---------------------------------------------------------------- helpers
+    def empty(self, shape, dtype):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    def call(self, name, *args, launches=1, flops=0.0, tag=None):
+        if TIMING is not None and name in TIMED:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            self.L.call(name, *args, self.stream)
+            e1.record()
+            TIMING.append((tag or name, flops, e0, e1))
+        else:
+            self.L.call(name, *args, self.stream)
+        self.launches += launches
+
+    def _add_param_grad(self, name, g):
+        if name in self.param_grads:
+            self.param_grads[name] = self.param_grads[name] + g
+        else:
+            self.param_grads[name] = g
+
+    def sums_of(self, x):
+        """double [N,C,2] per-(sample, channel) (sum, sum of squares) of x."""
+        if x.sums is not None:
+            return x.sums
+        n, d, h, w, c = x.dims
+        vox = d * h * w
+        if isinstance(x, InputF32):
+            P = self.L.query("b200_stats_ncdhw_f32_partials_count", vox)
+            partials = self.empty((n, P, c, 2), torch.float32)
+            self.call("b200_stats_ncdhw_f32", _p(x.sums_src), n, c, vox, _p(partials))
+        elif x.partials is not None:
+            partials, P = x.partials, x.P
+        else:
+            P = self.L.query("b200_stats_partials_count", n, c, vox)
+            partials = self.empty((n, P, c, 2), torch.float32)
+            self.call("b200_stats_ndhwc_bf16", _p(x.t), n, c, vox, _p(partials))
+        sums = self.empty((n, c, 2), torch.float64)
+        self.call("b200_partials_finalize", _p(partials), n, P, c, _p(sums))
+        x.sums = sums
+        x.partials = None
+        return sums
+
+    def accumulate_grad(self, x, g):
+        """x.grad += g where g is already in x's dz form."""
+        if x.grad is None:
+            x.grad = g
+        else:
+            n, d, h, w, c = x.dims
+            self.call("b200_act_bwd", _p(g), c, 0, _p(x.t), n, c, d * h * w, ACT_NONE, 0.0, _p(x.grad), _p(x.grad))
+
+    # ---------------------------------------------------------------- input / output layout
+    def input_f32(self, x_ncdhw):
+        n, c, d, h, w = x_ncdhw.shape
+        x_ncdhw = x_ncdhw.contiguous()
+        if c == 1:
+            t = x_ncdhw.view(n, d, h, w, 1)
+        else:
+            t = self.empty((n, d, h, w, c), torch.float32)
+            self.call("b200_ncdhw_f32_to_ndhwc_f32", _p(x_ncdhw), _p(t), n, c, d, h, w)
+        return InputF32(t, x_ncdhw)
+
+    def input_bf16(self, x_ncdhw, requires_grad):
+        n, c, d, h, w = x_ncdhw.shape
+        if c % 8 != 0:
+            raise NotImplementedError(f"block-level input with C={c}: internal activations need C % 8 == 0")
+        x_ncdhw = x_ncdhw.contiguous()
+        t = self.empty((n, d, h, w, c), torch.bfloat16)
+        self.call("b200_ncdhw_f32_to_ndhwc_bf16", _p(x_ncdhw), _p(t), n, c, d, h, w)
+        return Act(t, ACT_NONE, 0.0, requires_grad=requires_grad)
+
+    def to_ncdhw_f32(self, t_ndhwc_bf16):
+        n, d, h, w, c = t_ndhwc_bf16.shape
+        out = self.empty((n, c, d, h, w), torch.float32)
+        self.call("b200_ndhwc_bf16_to_ncdhw_f32", _p(t_ndhwc_bf16), _p(out), n, c, d, h, w)
+        return out
+
+    def grad_from_ncdhw(self, y, g_ncdhw):
+        """seed y.grad from an external NCDHW fp32 gradient w.r.t. the (post-activation) output y."""
+        n, d, h, w, c = y.dims
+        g = self.empty((n, d, h, w, c), torch.bfloat16)
+        self.call("b200_ncdhw_f32_to_ndhwc_bf16", _p(g_ncdhw.contiguous()), _p(g), n, c, d, h, w)
+        gm = self.empty((n, d, h, w, c), torch.bfloat16)
+        self.call("b200_act_bwd", _p(g), c, 0, _p(y.t), n, c, d * h * w, y.act, y.slope, None, _p(gm))
+        self.accumulate_grad(y, gm)
+
+    # ---------------------------------------------------------------- conv
+    def conv3(self, x, W, bias, gn, name, act=(ACT_NONE, 0.0), want_stats=False, residual=None):
+        """[GroupNorm ->] Conv3d(3x3x3, pad 1) [-> + residual] [-> activation].
+
+        x: Act | InputF32; W: fp32 (Cout,Cin,3,3,3); bias: fp32 (Cout,) | None;
+        gn: None | (gamma, beta, num_groups, gamma_name, beta_name); name: parameter name prefix of the conv.
+        """
+        n, d, h, w, cin = x.dims
+        cout = W.shape[0]
+        assert W.shape == (cout, cin, 3, 3, 3), (tuple(W.shape), cin)
+        if cout % 8 != 0:
+            raise NotImplementedError(f"conv with C_out={cout}: the engine needs C_out % 8 == 0")
+        vox = d * h * w
+        is_f32 = isinstance(x, InputF32)
+        L = self.L
+        impl = L.query("b200_conv3_resolve_impl", self.impl, n, d, h, w, cin, cout, int(is_f32))
+        if impl < 0:
+            raise B200Error(f"tcgen05 conv requested but unsupported for shape N={n} {d}x{h}x{w} Cin={cin} Cout={cout}")
+        W = W.contiguous()
+        ab = mean_rstd = None
+        n_w = 1
+        if gn is not None:
+            gamma, beta, groups = gn[0].contiguous(), gn[1].contiguous(), gn[2]
+            sums = self.sums_of(x)
+            n_w = n
+            ab = self.empty((n, cin, 2), torch.float32)
+            mean_rstd = self.empty((n, groups, 2), torch.float32)
+        wf = self.empty((n_w, 27, cout, cin), torch.bfloat16)
+        n_b = n_w if (gn is not None or bias is not None) else 0
+        biascls = self.empty((n_b, 64, cout), torch.float32) if n_b else None
+        if gn is not None:
+            self.call("b200_gn_fold", _p(sums), _p(gamma), _p(beta), groups, float(vox), _p(W), _p(bias), n, cin, cout,
+                      _p(wf), _p(biascls), _p(mean_rstd), _p(ab), launches=3)
+        else:
+            self.call("b200_gn_fold", None, None, None, 1, float(vox), _p(W), _p(bias), n, cin, cout,
+                      _p(wf), _p(biascls), None, None, launches=2 if bias is not None else 1)
+        y = self.empty((n, d, h, w, cout), torch.bfloat16)
+        partials, P = None, 0
+        if want_stats:
+            P = L.query("b200_conv3_partials_count", impl, n, d, h, w, cin, cout)
+            partials = self.empty((n, P, cout, 2), torch.float32)
+        self.call("b200_conv3_fwd", impl, _p(x.t), int(is_f32), _p(wf), n_w, _p(biascls), n_b,
+                  _p(residual.t) if residual is not None else None, act[0], float(act[1]),
+                  n, d, h, w, cin, cout, _p(y), 1 if want_stats else 0, None, _p(partials),
+                  flops=2.0 * n * vox * 27 * cin * cout, tag=("fprop_tc" if impl == IMPL_TCGEN05 else "fprop_direct"))
+        out = Act(y, act[0], act[1], partials, P)
+
+        if self.record:
+            def backward():
+                dz = out.grad
+                if dz is None:
+                    return
+                need_T = gn is not None or bias is not None
+                T = None
+                if need_T:
+                    T = self.empty((n, 27, cout), torch.float32)
+                    scratch = self.empty((L.query("b200_border_tap_sums_workspace", n, d, h, w, cout),), torch.float32)
+                    self.call("b200_border_tap_sums", _p(dz), n, d, h, w, cout, _p(T), _p(scratch), launches=2)
+                wimpl = L.query("b200_conv3_wgrad_resolve_impl", self.impl, n, d, h, w, cin, cout, int(is_f32))
+                if wimpl < 0:
+                    raise B200Error("tcgen05 wgrad requested but unsupported for this shape")
+                S = L.query("b200_conv3_wgrad_splits", wimpl, n, d, h, w, cin, cout, int(is_f32))
+                G = self.empty((n, S, 27, cin, cout), torch.float32)
+                self.call("b200_conv3_wgrad", wimpl, _p(x.t), int(is_f32), _p(dz), n, d, h, w, cin, cout, _p(G),
+                          launches=1 if wimpl == IMPL_TCGEN05 else 2, flops=2.0 * n * vox * 27 * cin * cout,
+                          tag=("wgrad_tc" if wimpl == IMPL_TCGEN05 else "wgrad_direct"))
+                dW = torch.empty_like(W)
+                self.call("b200_wgrad_finalize", _p(G), n, S, cin, cout, _p(ab), _p(T) if ab is not None else None, _p(dW))
+                self._add_param_grad(name + "conv.weight", dW)
+                if bias is not None:
+                    db = torch.empty_like(bias)
+                    self.call("b200_bias_grad_from_T", _p(T), n, cout, _p(db))
+                    self._add_param_grad(name + "conv.bias", db)
+                coef = None
+                if gn is not None:
+                    sums2 = self.empty((n, cin, 2), torch.float64)
+                    self.call("b200_gn_bwd_sums_from_wgrad", _p(G), S, _p(T), _p(W), n, cin, cout, _p(sums2))
+                    coef = self.empty((n, cin, 3), torch.float32)
+                    dgamma, dbeta = torch.empty_like(gamma), torch.empty_like(beta)
+                    self.call("b200_gn_bwd_coeffs", _p(sums2), _p(gamma), _p(mean_rstd), groups, float(vox), n, cin,
+                              _p(coef), _p(dgamma), _p(dbeta))
+                    self._add_param_grad(gn[3], dgamma)
+                    self._add_param_grad(gn[4], dbeta)
+                if residual is not None and residual.requires_grad:
+                    g = self.empty(residual.t.shape, torch.bfloat16)
+                    self.call("b200_act_bwd", _p(dz), cout, 0, _p(residual.t), n, cout, vox, residual.act, residual.slope,
+                              _p(residual.grad), _p(g))
+                    residual.grad = g
+                if x.requires_grad:
+                    if is_f32:
+                        raise NotImplementedError("gradient w.r.t. the fp32 network input is not provided by the engine")
+                    wd = self.empty((27, cin, cout), torch.bfloat16)
+                    self.call("b200_prep_dgrad_weights", _p(W), cin, cout, _p(wd))
+                    dimpl = L.query("b200_conv3_resolve_impl", self.impl, n, d, h, w, cout, cin, 0)
+                    if dimpl < 0:
+                        raise B200Error("tcgen05 dgrad requested but unsupported for this shape")
+                    dxhat = self.empty((n, d, h, w, cin), torch.bfloat16)
+                    self.call("b200_conv3_fwd", dimpl, _p(dz), 0, _p(wd), 1, None, 0, None, ACT_NONE, 0.0,
+                              n, d, h, w, cout, cin, _p(dxhat), 0, None, None, flops=2.0 * n * vox * 27 * cin * cout,
+                              tag=("dgrad_tc" if dimpl == IMPL_TCGEN05 else "dgrad_direct"))
+                    if coef is not None:
+                        self.call("b200_gn_bwd_apply", _p(dxhat), _p(x.t), _p(coef), n, cin, vox, x.act, x.slope,
+                                  _p(x.grad), _p(dxhat))
+                    else:
+                        self.call("b200_act_bwd", _p(dxhat), cin, 0, _p(x.t), n, cin, vox, x.act, x.slope, _p(x.grad), _p(dxhat))
+                    x.grad = dxhat
+                out.grad = None
+            self.tape.append(backward)
+        return out
+
+    # ---------------------------------------------------------------- GroupNorm after the conv ('cg.', 'c.g')
+    def groupnorm_act(self, z, gamma, beta, groups, gname, bname, act=(ACT_NONE, 0.0), want_stats=False):
+        n, d, h, w, c = z.dims
+        vox = d * h * w
+        gamma, beta = gamma.contiguous(), beta.contiguous()
+        sums = self.sums_of(z)
+        ab = self.empty((n, c, 2), torch.float32)
+        mean_rstd = self.empty((n, groups, 2), torch.float32)
+        self.call("b200_gn_coeffs", _p(sums), _p(gamma), _p(beta), groups, float(vox), n, c, _p(mean_rstd), _p(ab))
+        y = self.empty(z.t.shape, torch.bfloat16)
+        partials, P = None, 0
+        if want_stats:
+            P = self.L.query("b200_stats_partials_count", n, c, vox)
+            partials = self.empty((n, P, c, 2), torch.float32)
+        self.call("b200_gn_apply_act", _p(z.t), _p(ab), n, c, vox, act[0], float(act[1]), _p(y), _p(partials))
+        out = Act(y, act[0], act[1], partials, P)
+        if self.record:
+            def backward():
+                du = out.grad
+                if du is None:
+                    return
+                P2 = self.L.query("b200_stats_partials_count", n, c, vox)
+                part2 = self.empty((n, P2, c, 2), torch.float32)
+                self.call("b200_stats2_ndhwc_bf16", _p(du), _p(z.t), n, c, vox, _p(part2))
+                sums2 = self.empty((n, c, 2), torch.float64)
+                self.call("b200_partials_finalize", _p(part2), n, P2, c, _p(sums2))
+                coef = self.empty((n, c, 3), torch.float32)
+                dgamma, dbeta = torch.empty_like(gamma), torch.empty_like(beta)
+                self.call("b200_gn_bwd_coeffs", _p(sums2), _p(gamma), _p(mean_rstd), groups, float(vox), n, c,
+                          _p(coef), _p(dgamma), _p(dbeta))
+                self._add_param_grad(gname, dgamma)
+                self._add_param_grad(bname, dbeta)
+                if z.requires_grad:
+                    g = self.empty(z.t.shape, torch.bfloat16)
+                    self.call("b200_gn_bwd_apply", _p(du), _p(z.t), _p(coef), n, c, vox, z.act, z.slope, _p(z.grad), _p(g))
+                    z.grad = g
+                out.grad = None
+            self.tape.append(backward)
+        return out
+
+    # ---------------------------------------------------------------- SingleConv (order string interpreter)
+    def single_conv(self, x, sd, prefix, order, num_groups, want_stats=False, residual=None, final_act=None):
+        """buildingblocks.py:10-135.  Supported orders: [g]c[r|l|e], c g [r|l|e], c [r|l|e] g.
+        `residual`/`final_act`: ResNetBlock fuses `out += residual; act` into its last conv (:285-286)."""
+        if any(ch in order for ch in "bdD"):
+            raise NotImplementedError(f"layer_order {order!r}: BatchNorm/Dropout layers are not implemented by the b200 engine")
+        ic = order.index("c")
+        pre, post = order[:ic], order[ic + 1:]
+        if pre not in ("", "g"):
+            raise NotImplementedError(f"layer_order {order!r} is not supported")
+        W = sd[prefix + "conv.weight"]
+        bias = sd.get(prefix + "conv.bias")
+        cin, cout = W.shape[1], W.shape[0]
+        gn_pre = None
+        if pre == "g":
+            g = 1 if cin < num_groups else num_groups
+            if cin % g != 0:
+                raise ValueError(f"GroupNorm: num_channels={cin} not divisible by num_groups={g}")
+            gn_pre = (sd[prefix + "groupnorm.weight"], sd[prefix + "groupnorm.bias"], g,
+                      prefix + "groupnorm.weight", prefix + "groupnorm.bias")
+        acts = [ch for ch in post if ch in _ACT_OF]
+        if len(acts) > 1 or post.count("g") > 1 or (pre == "g" and "g" in post):
+            raise NotImplementedError(f"layer_order {order!r} is not supported")
+        act = _ACT_OF[acts[0]] if acts else (ACT_NONE, 0.0)
+        if final_act is not None:
+            assert not acts
+            act = final_act
+        if "g" not in post:
+            return self.conv3(x, W, bias, gn_pre, prefix, act=act, want_stats=want_stats, residual=residual)
+        if residual is not None:
+            raise NotImplementedError("residual join after a post-conv GroupNorm (e.g. order 'cge') is not implemented")
+        g = 1 if cout < num_groups else num_groups
+        if cout % g != 0:
+            raise ValueError(f"GroupNorm: num_channels={cout} not divisible by num_groups={g}")
+        act_first = bool(acts) and post.index(acts[0]) < post.index("g")
+        z = self.conv3(x, W, bias, None, prefix, act=act if act_first else (ACT_NONE, 0.0), want_stats=True)
+        return self.groupnorm_act(z, sd[prefix + "groupnorm.weight"], sd[prefix + "groupnorm.bias"], g,
+                                  prefix + "groupnorm.weight", prefix + "groupnorm.bias",
+                                  act=(ACT_NONE, 0.0) if act_first else act, want_stats=want_stats)
+
+    # ---------------------------------------------------------------- pooling / upsample+concat
+    def maxpool(self, x, want_stats=True):
+        n, d, h, w, c = x.dims
+        y = self.empty((n, d // 2, h // 2, w // 2, c), torch.bfloat16)
+        P = self.L.query("b200_maxpool_partials_count", n, d, h, w, c)
+        partials = self.empty((n, P, c, 2), torch.float32) if want_stats else None
+        self.call("b200_maxpool_fwd", _p(x.t), n, d, h, w, c, _p(y), _p(partials))
+        out = Act(y, ACT_NONE, 0.0, partials, P)
+        if self.record:
+            def backward():
+                if out.grad is None or not x.requires_grad:
+                    return
+                g = x.grad if x.grad is not None else self.empty(x.t.shape, torch.bfloat16)
+                self.call("b200_maxpool_bwd", _p(out.grad), _p(x.t), n, d, h, w, c, x.act, x.slope, _p(x.grad), _p(g))
+                x.grad = g
+                out.grad = None
+            self.tape.append(backward)
+        return out
+
+    def upcat(self, enc, x, want_stats=True):
+        n, D, H, W, c0 = enc.dims
+        n2, d, h, w, c1 = x.dims
+        assert n == n2
+        cat = self.empty((n, D, H, W, c0 + c1), torch.bfloat16)
+        P = self.L.query("b200_upcat_partials_count", n, D, H, W, c0 + c1)
+        partials = self.empty((n, P, c0 + c1, 2), torch.float32) if want_stats else None
+        self.call("b200_upcat_fwd", _p(enc.t), c0, _p(x.t), c1, n, D, H, W, d, h, w, _p(cat), _p(partials))
+        out = Act(cat, ACT_NONE, 0.0, partials, P)
+        if self.record:
+            def backward():
+                dcat = out.grad
+                if dcat is None:
+                    return
+                if x.requires_grad:
+                    g = self.empty(x.t.shape, torch.bfloat16)
+                    self.call("b200_upcat_bwd", _p(dcat), c0, c1, _p(x.t), n, D, H, W, d, h, w, x.act, x.slope, _p(g))
+                    self.accumulate_grad(x, g)
+                if enc.requires_grad:
+                    ge = self.empty(enc.t.shape, torch.bfloat16)
+                    # ge = dcat[..., :c0] * act'(enc) + enc.grad (enc.grad, if any, is already in dz form)
+                    self.call("b200_act_bwd", _p(dcat), c0 + c1, 0, _p(enc.t), n, c0, D * H * W, enc.act, enc.slope,
+                              _p(enc.grad), _p(ge))
+                    enc.grad = ge
+                out.grad = None
+            self.tape.append(backward)
+        return out
+
+    # ---------------------------------------------------------------- final 1x1x1 conv + sigmoid/softmax
+    def final_conv(self, x, W, bias, final_act, wname, bname):
+        n, d, h, w, c = x.dims
+        vox = d * h * w
+        cout = W.shape[0]
+        W2 = W.reshape(cout, c).contiguous()
+        logits = self.empty((n, cout, d, h, w), torch.float32)
+        probs = self.empty((n, cout, d, h, w), torch.float32) if final_act != FINAL_NONE else None
+        self.call("b200_final_conv_fwd", _p(x.t), n, vox, c, _p(W2), _p(bias), cout, final_act, _p(logits), _p(probs))
+
+        def backward(dlogits):
+            dlogits = dlogits.contiguous()
+            P = self.L.query("b200_final_conv_bwd_partials_count", n, vox, c, cout)
+            K = cout * c + cout
+            partials = self.empty((n * P, K), torch.float32)
+            dz = self.empty(x.t.shape, torch.bfloat16)
+            self.call("b200_final_conv_bwd", _p(dlogits), _p(x.t), n, vox, c, _p(W2), cout, x.act, x.slope, _p(dz), _p(partials))
+            red = self.empty((K,), torch.float32)
+            self.call("b200_reduce_rows", _p(partials), n * P, K, _p(red))
+            self._add_param_grad(wname, red[: cout * c].reshape(W.shape))
+            if bias is not None:
+                self._add_param_grad(bname, red[cout * c:].clone())
+            self.accumulate_grad(x, dz)
+        return logits, probs, backward
+
+    # ---------------------------------------------------------------- backward driver
+    def run_backward(self):
+        for fn in reversed(self.tape):
+            fn()
+        self.tape = []

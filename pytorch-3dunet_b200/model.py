@@ -1,0 +1,398 @@
+"""nn.Module surface of the B200 3D U-Net engine -- the drop-in for `pytorch3dunet.unet3d.model`.
+
+Same constructor keywords, same parameter names / shapes (so reference checkpoints load with
+`load_state_dict`, reference utils.py:59-60) and the same `forward(x, return_logits=False)` contract as the
+reference (model.py:103-149), but every FLOP of forward and backward runs in libb200unet.so (hand-written
+sm_100a CUDA) through `engine.Engine`.  The torch modules below (`nn.Conv3d`, `nn.GroupNorm`, ...) are used as
+PARAMETER CONTAINERS only -- their own forward() is never called -- which also gives the reference's default
+initialisation and RNG consumption order for free.
+
+Reference constructors mirrored: UNet3D model.py:152-190, ResidualUNet3D :193-234, ResidualUNetSE3D :237-278,
+get_model :361-363; block wiring buildingblocks.py:138-227 (DoubleConv), :310-384 (Encoder), :387-493 (Decoder),
+:496-574 (create_encoders / create_decoders).
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from . import engine as E
+
+
+def number_of_features_per_level(init_channel_number, num_levels):
+    """reference utils.py:110-112"""
+    return [init_channel_number * 2 ** k for k in range(num_levels)]
+
+
+# ----------------------------------------------------------------------------------------------------
+# autograd bridge: one Function per call of a (sub)network; the engine's tape is the backward graph
+# ----------------------------------------------------------------------------------------------------
+class _EngineFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, program, n_inputs, names, *tensors):
+        inputs, params = tensors[:n_inputs], tensors[n_inputs:]
+        x0 = inputs[0]
+        if not x0.is_cuda:
+            raise RuntimeError("the b200 3D U-Net engine runs on CUDA tensors only (there is no CPU fallback)")
+        for t in tensors:
+            if t.dtype != torch.float32 or t.device != x0.device:
+                raise RuntimeError("b200 engine: inputs and parameters must be float32 tensors on one CUDA device")
+        needs_grad = any(ctx.needs_input_grad[3:])
+        with torch.cuda.device(x0.device):
+            eng = E.Engine(x0.device, record=needs_grad)
+            sd = dict(zip(names, params))
+            in_req = [bool(g) for g in ctx.needs_input_grad[3:3 + n_inputs]]
+            outs, seed, input_grads = program(eng, [t.detach() for t in inputs], sd, in_req)
+        ctx.eng, ctx.seed, ctx.input_grads = eng, seed, input_grads
+        ctx.names, ctx.n_inputs = names, n_inputs
+        ctx.param_meta = [(p.shape, p.dtype) for p in params]
+        ctx.set_materialize_grads(False)
+        ctx.device = x0.device
+        _EngineFn.last_launches = eng.launches
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *grad_outs):
+        eng = ctx.eng
+        if eng is None or not eng.record:
+            raise RuntimeError("b200 engine: backward called twice or without a recorded forward")
+        with torch.cuda.device(ctx.device):
+            eng.stream = torch.cuda.current_stream(ctx.device).cuda_stream
+            l0 = eng.launches
+            ctx.seed(eng, grad_outs)
+            eng.run_backward()
+            in_grads = ctx.input_grads(eng)
+            _EngineFn.last_launches_bwd = eng.launches - l0
+        pg = eng.param_grads
+        grads = []
+        for (shape, dtype), name in zip(ctx.param_meta, ctx.names):
+            g = pg.get(name)
+            grads.append(None if g is None else g.reshape(shape))
+        ctx.eng = None
+        return (None, None, None) + tuple(in_grads) + tuple(grads)
+
+
+_EngineFn.last_launches = 0
+_EngineFn.last_launches_bwd = 0
+
+
+def _run(module, program, inputs):
+    names, params = [], []
+    for k, p in module.named_parameters():
+        names.append(k)
+        params.append(p)
+    return _EngineFn.apply(program, len(inputs), tuple(names), *inputs, *params)
+
+
+def last_launch_counts():
+    """(forward, backward) number of engine kernels launched by the most recent call."""
+    return _EngineFn.last_launches, _EngineFn.last_launches_bwd
+
+
+# ----------------------------------------------------------------------------------------------------
+# engine programs for the blocks
+# ----------------------------------------------------------------------------------------------------
+def _has_pre_gn(order):
+    return "g" in order and order.index("g") < order.index("c")
+
+
+def run_double_conv(eng, x, sd, prefix, order, groups, out_stats):
+    h = eng.single_conv(x, sd, prefix + "SingleConv1.", order, groups, want_stats=_has_pre_gn(order))
+    return eng.single_conv(h, sd, prefix + "SingleConv2.", order, groups, want_stats=out_stats)
+
+
+def run_basic(eng, x, sd, prefix, spec, out_stats=False):
+    if spec["basic"] == "double":
+        return run_double_conv(eng, x, sd, prefix, spec["layer_order"], spec["num_groups"], out_stats)
+    raise NotImplementedError("ResNetBlock / ResNetBlockSE kernels (ResidualUNet3D, ResidualUNetSE3D) are not built yet "
+                              "in the b200 engine; there is deliberately no PyTorch fallback")
+
+
+def run_unet(eng, x, sd, spec):
+    """AbstractUNet._forward_logits, reference model.py:123-149."""
+    order = spec["layer_order"]
+    pre_gn = _has_pre_gn(order)
+    nlev = len(spec["f_maps"])
+    feats = []
+    for i in range(nlev):
+        if i > 0:
+            x = eng.maxpool(x, want_stats=pre_gn)
+        x = run_basic(eng, x, sd, f"encoders.{i}.basic_module.", spec)
+        feats.insert(0, x)
+    for i, enc in enumerate(feats[1:]):
+        if spec["upsample"] != "nearest" or not spec["concat"]:
+            raise NotImplementedError(f"decoder upsample={spec['upsample']!r} concat={spec['concat']} is not built yet in the b200 engine")
+        x = eng.upcat(enc, x, want_stats=pre_gn)
+        x = run_basic(eng, x, sd, f"decoders.{i}.basic_module.", spec)
+    final = E.FINAL_NONE
+    if spec["is_segmentation"]:
+        final = E.FINAL_SIGMOID if spec["final_sigmoid"] else E.FINAL_SOFTMAX
+    return eng.final_conv(x, sd["final_conv.weight"], sd.get("final_conv.bias"), final, "final_conv.weight", "final_conv.bias")
+
+
+# ----------------------------------------------------------------------------------------------------
+# parameter containers with the reference's names
+# ----------------------------------------------------------------------------------------------------
+def _conv_layers(in_channels, out_channels, order, num_groups, kernel_size=3, padding=1):
+    """(name, module) list with the names create_conv uses (buildingblocks.py:44-94); parameter-free layers
+    (activations) are kept so that printing the model reads like the reference's."""
+    assert "c" in order, "Conv layer MUST be present"
+    assert order[0] not in "rle", "Non-linearity cannot be the first operation in the layer"
+    out = []
+    for i, ch in enumerate(order):
+        if ch == "r":
+            out.append(("ReLU", nn.ReLU(inplace=True)))
+        elif ch == "l":
+            out.append(("LeakyReLU", nn.LeakyReLU(inplace=True)))
+        elif ch == "e":
+            out.append(("ELU", nn.ELU(inplace=True)))
+        elif ch == "c":
+            out.append(("conv", nn.Conv3d(in_channels, out_channels, kernel_size, padding=padding,
+                                          bias=not ("g" in order or "b" in order))))
+        elif ch == "g":
+            c = in_channels if i < order.index("c") else out_channels
+            g = 1 if c < num_groups else num_groups
+            assert c % g == 0, f"Expected number of channels in input to be divisible by num_groups. num_channels={c}, num_groups={g}"
+            out.append(("groupnorm", nn.GroupNorm(num_groups=g, num_channels=c)))
+        else:
+            raise NotImplementedError(f"layer type {ch!r} in layer_order={order!r} is not supported by the b200 engine "
+                                      "(supported: c, g, r, l, e)")
+    return out
+
+
+class _EngineModule(nn.Module):
+    """Block-level modules are callable on NCDHW fp32 tensors with C % 8 == 0 (parity tests, custom nets)."""
+
+    def _program(self):
+        raise NotImplementedError
+
+    def forward(self, *inputs):
+        prog = self._program()
+
+        def program(eng, ins, sd, in_req):
+            acts = [eng.input_bf16(t, r) for t, r in zip(ins, in_req)]
+            y = prog(eng, acts, sd)
+            out = eng.to_ncdhw_f32(y.t)
+
+            def seed(eng, grads):
+                if grads[0] is not None:
+                    eng.grad_from_ncdhw(y, grads[0])
+
+            def input_grads(eng):
+                res = []
+                for a, r in zip(acts, in_req):
+                    if r and a.grad is not None:
+                        res.append(eng.to_ncdhw_f32(a.grad))
+                    elif r:
+                        res.append(torch.zeros((a.t.shape[0], a.t.shape[4]) + tuple(a.t.shape[1:4]), device=a.t.device))
+                    else:
+                        res.append(None)
+                return res
+            return [out], seed, input_grads
+        return _run(self, program, list(inputs))[0]
+
+
+class SingleConv(_EngineModule):
+    def __init__(self, in_channels, out_channels, kernel_size=3, order="gcr", num_groups=8, padding=1, dropout_prob=0.1, is3d=True):
+        super().__init__()
+        if not is3d or kernel_size != 3 or padding != 1:
+            raise NotImplementedError("the b200 engine implements 3-D 3x3x3 convolutions with padding 1")
+        self.order, self.num_groups = order, num_groups
+        for name, m in _conv_layers(in_channels, out_channels, order, num_groups):
+            self.add_module(name, m)
+
+    def _program(self):
+        return lambda eng, acts, sd: eng.single_conv(acts[0], sd, "", self.order, self.num_groups)
+
+
+class DoubleConv(_EngineModule):
+    def __init__(self, in_channels, out_channels, encoder, kernel_size=3, order="gcr", num_groups=8, padding=1, upscale=2,
+                 dropout_prob=0.1, is3d=True):
+        super().__init__()
+        if encoder:
+            mid = out_channels if upscale == 1 else out_channels // 2
+            mid = max(mid, in_channels)
+        else:
+            mid = out_channels
+        self.order, self.num_groups = order, num_groups
+        self.SingleConv1 = SingleConv(in_channels, mid, kernel_size, order, num_groups, padding, is3d=is3d)
+        self.SingleConv2 = SingleConv(mid, out_channels, kernel_size, order, num_groups, padding, is3d=is3d)
+
+    def _program(self):
+        return lambda eng, acts, sd: run_double_conv(eng, acts[0], sd, "", self.order, self.num_groups, False)
+
+
+class _Marker(nn.Module):
+    """parameter-free placeholder so the module tree prints like the reference's (pooling / upsampling)."""
+
+    def __init__(self, text):
+        super().__init__()
+        self.text = text
+
+    def extra_repr(self):
+        return self.text
+
+
+class Encoder(_EngineModule):
+    def __init__(self, in_channels, out_channels, apply_pooling=True, basic="double", conv_layer_order="gcr", num_groups=8,
+                 upscale=2):
+        super().__init__()
+        self.pooling = _Marker("MaxPool3d(kernel_size=2) [fused b200 kernel]") if apply_pooling else None
+        self.spec = dict(basic=basic, layer_order=conv_layer_order, num_groups=num_groups)
+        self.basic_module = _make_basic(basic, in_channels, out_channels, True, conv_layer_order, num_groups, upscale)
+
+    def _program(self):
+        def prog(eng, acts, sd):
+            x = acts[0]
+            if self.pooling is not None:
+                x = eng.maxpool(x, want_stats=_has_pre_gn(self.spec["layer_order"]))
+            return run_basic(eng, x, sd, "basic_module.", self.spec)
+        return prog
+
+
+class Decoder(_EngineModule):
+    def __init__(self, in_channels, out_channels, basic="double", conv_layer_order="gcr", num_groups=8, upsample="nearest",
+                 concat=True):
+        super().__init__()
+        self.upsampling = _Marker(f"{upsample} to the encoder feature size [fused b200 kernel]")
+        self.spec = dict(basic=basic, layer_order=conv_layer_order, num_groups=num_groups, upsample=upsample, concat=concat)
+        self.basic_module = _make_basic(basic, in_channels, out_channels, False, conv_layer_order, num_groups, 2)
+
+    def forward(self, encoder_features, x):
+        return super().forward(encoder_features, x)
+
+    def _program(self):
+        def prog(eng, acts, sd):
+            if self.spec["upsample"] != "nearest" or not self.spec["concat"]:
+                raise NotImplementedError("only nearest-upsample + concat decoders are built so far")
+            cat = eng.upcat(acts[0], acts[1], want_stats=_has_pre_gn(self.spec["layer_order"]))
+            return run_basic(eng, cat, sd, "basic_module.", self.spec)
+        return prog
+
+
+def _make_basic(basic, cin, cout, encoder, order, groups, upscale):
+    if basic == "double":
+        return DoubleConv(cin, cout, encoder, order=order, num_groups=groups, upscale=upscale)
+    raise NotImplementedError("ResNetBlock / ResNetBlockSE are not built yet in the b200 engine (no PyTorch fallback on purpose)")
+
+
+# ----------------------------------------------------------------------------------------------------
+# models
+# ----------------------------------------------------------------------------------------------------
+class AbstractUNet(nn.Module):
+    """Same construction order as the reference (encoders, decoders, final_conv) => same default init under a seed."""
+
+    def __init__(self, in_channels, out_channels, final_sigmoid, basic, f_maps=64, layer_order="gcr", num_groups=8, num_levels=4,
+                 is_segmentation=True, conv_kernel_size=3, pool_kernel_size=2, conv_padding=1, conv_upscale=2, upsample="default",
+                 dropout_prob=0.1, is3d=True):
+        super().__init__()
+        if not is3d:
+            raise NotImplementedError("2-D models are out of scope of the b200 engine (SURVEY.md section 2, row 1)")
+        if conv_kernel_size != 3 or pool_kernel_size != 2 or conv_padding != 1:
+            raise NotImplementedError("the b200 engine implements conv 3x3x3 / padding 1 / pool 2 (what UNet3D & co. always use)")
+        if isinstance(f_maps, int):
+            f_maps = number_of_features_per_level(f_maps, num_levels=num_levels)
+        assert isinstance(f_maps, (list, tuple))
+        assert len(f_maps) > 1, "Required at least 2 levels in the U-Net"
+        if "g" in layer_order:
+            assert num_groups is not None, "num_groups must be specified if GroupNorm is used"
+        f_maps = list(f_maps)
+        concat = True
+        if upsample == "default":
+            if basic == "double":
+                upsample, concat = "nearest", True
+            else:
+                upsample, concat = "deconv", False
+        self.spec = dict(basic=basic, f_maps=f_maps, layer_order=layer_order, num_groups=num_groups, upsample=upsample,
+                         concat=concat, is_segmentation=is_segmentation, final_sigmoid=final_sigmoid,
+                         in_channels=in_channels, out_channels=out_channels)
+        self.encoders = nn.ModuleList(
+            Encoder(in_channels if i == 0 else f_maps[i - 1], f, apply_pooling=i > 0, basic=basic,
+                    conv_layer_order=layer_order, num_groups=num_groups, upscale=conv_upscale)
+            for i, f in enumerate(f_maps))
+        rf = f_maps[::-1]
+        decs = []
+        for i in range(len(rf) - 1):
+            cin = rf[i] + rf[i + 1] if (basic == "double" and upsample != "deconv") else rf[i]
+            decs.append(Decoder(cin, rf[i + 1], basic=basic, conv_layer_order=layer_order, num_groups=num_groups,
+                                upsample=upsample, concat=concat))
+        self.decoders = nn.ModuleList(decs)
+        self.final_conv = nn.Conv3d(f_maps[0], out_channels, 1)
+        if is_segmentation:
+            self.final_activation = nn.Sigmoid() if final_sigmoid else nn.Softmax(dim=1)
+        else:
+            self.final_activation = None
+
+    def forward(self, x, return_logits=False):
+        spec = self.spec
+        if x.dim() != 5 or x.shape[1] != spec["in_channels"]:
+            raise ValueError(f"expected input (N,{spec['in_channels']},D,H,W), got {tuple(x.shape)}")
+        if x.dtype != torch.float32:
+            x = x.float()
+
+        def program(eng, ins, sd, in_req):
+            if in_req[0]:
+                raise NotImplementedError("gradient w.r.t. the network input is not provided by the b200 engine")
+            xin = eng.input_f32(ins[0])
+            logits, probs, final_bwd = run_unet(eng, xin, sd, spec)
+            final = spec["is_segmentation"]
+
+            def seed(eng, grads):
+                g_logits = grads[0]
+                g_probs = grads[1] if final and len(grads) > 1 else None
+                if g_probs is not None:
+                    # chain rule through the final activation (tiny, C_out channels); only when the loss uses probabilities
+                    if spec["final_sigmoid"]:
+                        t = g_probs * probs * (1 - probs)
+                    else:
+                        t = probs * (g_probs - (g_probs * probs).sum(dim=1, keepdim=True))
+                    g_logits = t if g_logits is None else g_logits + t
+                if g_logits is not None:
+                    final_bwd(g_logits)
+            outs = [logits, probs] if final else [logits]
+            return outs, seed, lambda eng: [None]
+        res = _run(self, program, [x])
+        logits = res[0]
+        out = res[1] if spec["is_segmentation"] else logits
+        if return_logits:
+            return out, logits
+        return out
+
+
+class UNet3D(AbstractUNet):
+    def __init__(self, in_channels, out_channels, final_sigmoid=True, f_maps=64, layer_order="gcr", num_groups=8, num_levels=4,
+                 is_segmentation=True, conv_padding=1, conv_upscale=2, upsample="default", dropout_prob=0.1, **kwargs):
+        super().__init__(in_channels, out_channels, final_sigmoid, "double", f_maps=f_maps, layer_order=layer_order,
+                         num_groups=num_groups, num_levels=num_levels, is_segmentation=is_segmentation,
+                         conv_padding=conv_padding, conv_upscale=conv_upscale, upsample=upsample, dropout_prob=dropout_prob)
+
+
+class ResidualUNet3D(AbstractUNet):
+    def __init__(self, in_channels, out_channels, final_sigmoid=True, f_maps=64, layer_order="gcr", num_groups=8, num_levels=5,
+                 is_segmentation=True, conv_padding=1, conv_upscale=2, upsample="default", dropout_prob=0.1, **kwargs):
+        super().__init__(in_channels, out_channels, final_sigmoid, "res", f_maps=f_maps, layer_order=layer_order,
+                         num_groups=num_groups, num_levels=num_levels, is_segmentation=is_segmentation,
+                         conv_padding=conv_padding, conv_upscale=conv_upscale, upsample=upsample, dropout_prob=dropout_prob)
+
+
+class ResidualUNetSE3D(AbstractUNet):
+    def __init__(self, in_channels, out_channels, final_sigmoid=True, f_maps=64, layer_order="gcr", num_groups=8, num_levels=5,
+                 is_segmentation=True, conv_padding=1, conv_upscale=2, upsample="default", dropout_prob=0.1, **kwargs):
+        super().__init__(in_channels, out_channels, final_sigmoid, "res_se", f_maps=f_maps, layer_order=layer_order,
+                         num_groups=num_groups, num_levels=num_levels, is_segmentation=is_segmentation,
+                         conv_padding=conv_padding, conv_upscale=conv_upscale, upsample=upsample, dropout_prob=dropout_prob)
+
+
+_MODELS = {"UNet3D": UNet3D, "ResidualUNet3D": ResidualUNet3D, "ResidualUNetSE3D": ResidualUNetSE3D}
+
+
+def get_model(model_config):
+    """reference model.py:361-363: class by name, whole config dict splatted into the constructor."""
+    name = model_config["name"]
+    if name not in _MODELS:
+        raise NotImplementedError(f"model {name!r} is not provided by the b200 engine (3-D models only: {sorted(_MODELS)})")
+    return _MODELS[name](**model_config)
+
+
+def is_model_2d(model):
+    return False

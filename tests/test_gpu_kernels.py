@@ -1,0 +1,121 @@
+"""GPU: each conv kernel of libb200unet.so (through the C-ABI) against a plain PyTorch fp32 restatement of its
+contract, and the tcgen05 kernels against the direct CUDA-core kernels on identical operands."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-2  # north_star: within 1e-2 relative (fp32 reference), bf16 operands / fp32 accumulation
+
+
+def _mk(N, D, H, W, Cin, Cout, n_w, seed, bias=True):
+    from tests import gpu_util as U  # noqa
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = (torch.randn((N, D, H, W, Cin), device="cuda", generator=g) * 0.7 + 0.3).bfloat16()
+    wf = (torch.randn((n_w, 27, Cout, Cin), device="cuda", generator=g) * (2.0 / (27 * Cin)) ** 0.5).bfloat16()
+    b = torch.randn((n_w, 64, Cout), device="cuda", generator=g) * 0.2 if bias else None
+    return x, wf, b
+
+
+SHAPES = [
+    # N, D, H, W, Cin, Cout
+    (1, 8, 8, 8, 16, 32),
+    (2, 8, 8, 16, 32, 32),
+    (1, 8, 16, 8, 64, 64),
+    (2, 4, 8, 8, 96, 32),
+    (1, 8, 8, 8, 128, 128),
+    (1, 4, 8, 8, 128, 256),
+    (1, 4, 4, 8, 384, 128),
+    (1, 5, 9, 7, 32, 16),      # ragged: exercises TMA out-of-bounds fill and masked stores
+    (1, 16, 16, 16, 32, 64),
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_direct_conv_matches_torch(shape):
+    from tests import gpu_util as U
+    from pytorch3dunet_b200 import engine as E
+    N, D, H, W, Cin, Cout = shape
+    x, wf, b = _mk(N, D, H, W, Cin, Cout, N, 1)
+    y, sums = U.run_conv3(E.IMPL_DIRECT, x, wf, b, act=E.ACT_RELU, want_stats=True)
+    ref = U.conv3_contract_ref(x, wf, b, act=E.ACT_RELU)
+    torch.cuda.synchronize()
+    assert U.rel_l2(y, ref) < TOL
+    yf = y.double()
+    assert U.rel_l2(sums[..., 0], yf.sum(dim=(1, 2, 3))) < 1e-4
+    assert U.rel_l2(sums[..., 1], (yf * yf).sum(dim=(1, 2, 3))) < 1e-4
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_tcgen05_conv_matches_torch_and_direct(shape):
+    from tests import gpu_util as U
+    from pytorch3dunet_b200 import engine as E
+    N, D, H, W, Cin, Cout = shape
+    x, wf, b = _mk(N, D, H, W, Cin, Cout, N, 2)
+    y, sums = U.run_conv3(E.IMPL_TCGEN05, x, wf, b, act=E.ACT_RELU, want_stats=True)
+    torch.cuda.synchronize()
+    ref = U.conv3_contract_ref(x, wf, b, act=E.ACT_RELU)
+    yd, _ = U.run_conv3(E.IMPL_DIRECT, x, wf, b, act=E.ACT_RELU)
+    assert U.rel_l2(y, ref) < TOL
+    assert U.rel_l2(y, yd.float()) < 5e-3
+    yf = y.double()
+    assert U.rel_l2(sums[..., 0], yf.sum(dim=(1, 2, 3))) < 1e-4
+    assert U.rel_l2(sums[..., 1], (yf * yf).sum(dim=(1, 2, 3))) < 1e-4
+
+
+def test_tcgen05_conv_residual_no_bias_shared_weights():
+    from tests import gpu_util as U
+    from pytorch3dunet_b200 import engine as E
+    x, wf, _ = _mk(2, 8, 8, 8, 32, 32, 1, 3, bias=False)
+    res = torch.randn((2, 8, 8, 8, 32), device="cuda").bfloat16()
+    y, _ = U.run_conv3(E.IMPL_TCGEN05, x, wf, None, act=E.ACT_LEAKY, slope=0.1, residual=res)
+    ref = U.conv3_contract_ref(x, wf, None, act=E.ACT_LEAKY, slope=0.1, residual=res)
+    assert U.rel_l2(y, ref) < TOL
+
+
+WG_SHAPES = [(1, 8, 8, 8, 16, 32), (2, 8, 8, 8, 32, 32), (1, 8, 8, 8, 64, 64), (1, 4, 8, 8, 96, 32), (1, 8, 8, 8, 128, 128),
+             (1, 4, 8, 8, 192, 64), (1, 4, 4, 8, 384, 128), (1, 4, 4, 8, 128, 256), (1, 5, 9, 7, 32, 16), (1, 16, 16, 16, 32, 32)]
+
+
+@pytest.mark.parametrize("shape", WG_SHAPES)
+def test_direct_wgrad_matches_torch(shape):
+    from tests import gpu_util as U
+    from pytorch3dunet_b200 import engine as E
+    N, D, H, W, Cin, Cout = shape
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn((N, D, H, W, Cin), device="cuda", generator=g).bfloat16()
+    dz = torch.randn((N, D, H, W, Cout), device="cuda", generator=g).bfloat16()
+    G = U.run_wgrad(E.IMPL_DIRECT, x, dz)
+    assert U.rel_l2(G, U.wgrad_contract_ref(x, dz)) < 1e-3
+
+
+@pytest.mark.parametrize("shape", WG_SHAPES)
+def test_tcgen05_wgrad_matches_torch(shape):
+    from tests import gpu_util as U
+    from pytorch3dunet_b200 import engine as E
+    N, D, H, W, Cin, Cout = shape
+    g = torch.Generator(device="cuda").manual_seed(6)
+    x = torch.randn((N, D, H, W, Cin), device="cuda", generator=g).bfloat16()
+    dz = torch.randn((N, D, H, W, Cout), device="cuda", generator=g).bfloat16()
+    G = U.run_wgrad(E.IMPL_TCGEN05, x, dz)
+    torch.cuda.synchronize()
+    assert U.rel_l2(G, U.wgrad_contract_ref(x, dz)) < 1e-3
+
+
+@pytest.mark.parametrize("shift,group_rows", [(0, 8), (1, 8), (3, 8), (8, 8), (0, 10), (1, 10), (2, 10), (11, 10)])
+def test_probe_umma_row_shifted_swizzled_view(shift, group_rows):
+    """hardware fact the halo-reuse conv design depends on (see csrc/umma_probe.cu)"""
+    from tests import gpu_util as U
+    from pytorch3dunet_b200._lib import lib
+    rows = 200
+    g = torch.Generator(device="cuda").manual_seed(7)
+    A = torch.randn((rows, 64), device="cuda", generator=g).bfloat16()
+    B = torch.randn((16, 64), device="cuda", generator=g).bfloat16()
+    D = torch.zeros((128, 16), device="cuda")
+    lib().call("b200_probe_umma_rowshift", U.p(A), rows, U.p(B), shift, group_rows, U.p(D), U.stream())
+    torch.cuda.synchronize()
+    r = torch.arange(128, device="cuda")
+    idx = shift + (r // 8) * group_rows + (r % 8)
+    ref = A[idx].float() @ B.float().t()
+    print("probe shift", shift, "group_rows", group_rows, "rel", U.rel_l2(D, ref))
+    assert U.rel_l2(D, ref) < 1e-3
