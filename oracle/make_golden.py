@@ -106,7 +106,7 @@ def main():
     run_model_case("unet3d_f16_l3_odd", dict(name="UNet3D", in_channels=2, out_channels=3, f_maps=16, num_levels=3,
                                               final_sigmoid=False),
                    (1, 2, 9, 17, 13), "BCEDiceLoss", 2, model_mod, losses_mod)
-    run_model_case("unet3d_f8_l2_cgr", dict(name="UNet3D", in_channels=1, out_channels=1, f_maps=8, num_levels=2,
+    run_model_case("unet3d_f16_l2_cgr", dict(name="UNet3D", in_channels=1, out_channels=1, f_maps=16, num_levels=2,
                                              layer_order="cgr"),
                    (1, 1, 8, 8, 8), "BCEDiceLoss", 3, model_mod, losses_mod)
     run_model_case("resunet3d_f16_l3_s16", dict(name="ResidualUNet3D", in_channels=1, out_channels=1, f_maps=16, num_levels=3),

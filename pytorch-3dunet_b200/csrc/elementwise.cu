@@ -255,17 +255,26 @@ __global__ void fold_weights_kernel(const float* __restrict__ W, const float* __
   }
 }
 
-// biascls[n][cls][co] : grid (Cout, n_b), block 128
+// biascls[n][cls][co] : grid (Cout, n_b), block 128.
+// Besides the GroupNorm shift (W*b) the per-tap term carries the bf16 rounding residual of the folded weight times the
+// per-channel mean of x: sum_k (W*a - bf16(W*a)) * mean_x.  Without it the rounding error of W*a multiplies the MEAN of
+// the (un-normalised) activation and is amplified by mean/std relative to normalising first; with it only the centred
+// part of x sees the rounding error.
 __global__ void fold_bias_kernel(const float* __restrict__ W, const float* __restrict__ ab, const float* __restrict__ conv_bias,
-                                 int Cin, int Cout, float* __restrict__ biascls) {
+                                 const double* __restrict__ sums, double count, int Cin, int Cout, float* __restrict__ biascls) {
   __shared__ float bt[27];
   __shared__ float red[128];
   int co = blockIdx.x, n = blockIdx.y;
   for (int tap = 0; tap < 27; ++tap) {
     float acc = 0.f;
     if (ab)
-      for (int ci = threadIdx.x; ci < Cin; ci += blockDim.x)
-        acc += W[((size_t)co * Cin + ci) * 27 + tap] * ab[((size_t)n * Cin + ci) * 2 + 1];
+      for (int ci = threadIdx.x; ci < Cin; ci += blockDim.x) {
+        float w = W[((size_t)co * Cin + ci) * 27 + tap];
+        float wa = w * ab[((size_t)n * Cin + ci) * 2];
+        float resid = wa - __bfloat162float(__float2bfloat16_rn(wa));
+        float mean = sums ? (float)(sums[((size_t)n * Cin + ci) * 2] / count) : 0.f;
+        acc += w * ab[((size_t)n * Cin + ci) * 2 + 1] + resid * mean;
+      }
     red[threadIdx.x] = acc;
     __syncthreads();
     for (int o = 64; o; o >>= 1) {
@@ -996,7 +1005,7 @@ int b200_gn_fold(const double* sums, const float* gamma, const float* beta, int 
   B200_CHECK_LAUNCH("fold_weights");
   if (biascls && (abp || conv_bias)) {
     dim3 grid(Cout, n_w);
-    fold_bias_kernel<<<grid, 128, 0, ST(s)>>>(W, abp, conv_bias, Cin, Cout, biascls);
+    fold_bias_kernel<<<grid, 128, 0, ST(s)>>>(W, abp, conv_bias, sums, count, Cin, Cout, biascls);
     B200_CHECK_LAUNCH("fold_bias");
   }
   return 0;

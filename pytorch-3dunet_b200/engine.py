@@ -66,12 +66,13 @@ class Act:
 class InputF32:
     """The network input kept in fp32 (reference: ToTensor -> float32, transforms.py:816-826), NDHWC view."""
 
-    __slots__ = ("t", "sums_src", "sums", "requires_grad", "grad", "act", "slope")
+    __slots__ = ("t", "sums_src", "sums", "partials", "P", "requires_grad", "grad", "act", "slope")
 
     def __init__(self, t_ndhwc, ncdhw_src):
         self.t = t_ndhwc
         self.sums_src = ncdhw_src
         self.sums = None
+        self.partials, self.P = None, 0
         self.requires_grad = False
         self.grad = None
         self.act, self.slope = ACT_NONE, 0.0

@@ -54,20 +54,22 @@ def test_block_matches_reference_golden(name, impl, monkeypatch):
         y = mod(x)
     (y * rec["r"].cuda()).sum().backward()
     torch.cuda.synchronize()
-    assert_close_l2(y, rec["y"], BLOCK_TOL, msg="y")
-    assert_close_l2(x.grad, rec["grad_x"], GRAD_TOL, 1e-6, "grad_x")
+    report = {"y": rel_l2(y, rec["y"]), "grad_x": rel_l2(x.grad, rec["grad_x"])}
     if two_inputs:
-        assert_close_l2(enc.grad, rec["grad_enc"], GRAD_TOL, 1e-6, "grad_enc")
+        report["grad_enc"] = rel_l2(enc.grad, rec["grad_enc"])
     for k, p in mod.named_parameters():
         assert p.grad is not None, k
-        assert_close_l2(p.grad, grads[k], GRAD_TOL, 1e-5, k)
+        report[k] = rel_l2(p.grad, grads[k])
+    print(name, impl, {k: f"{v:.2e}" for k, v in report.items()})
+    bad = {k: v for k, v in report.items() if v > (BLOCK_TOL if k == "y" else GRAD_TOL)}
+    assert not bad, bad
 
 
 MODEL_CASES = {
     "unet3d_f16_l3_s16": (dict(name="UNet3D", in_channels=1, out_channels=1, f_maps=16, num_levels=3), "bce_dice_loss"),
     "unet3d_f16_l3_dice_b2": (dict(name="UNet3D", in_channels=1, out_channels=1, f_maps=16, num_levels=3), "dice_loss"),
     "unet3d_f16_l3_odd": (dict(name="UNet3D", in_channels=2, out_channels=3, f_maps=16, num_levels=3, final_sigmoid=False), "bce_dice_loss"),
-    "unet3d_f8_l2_cgr": (dict(name="UNet3D", in_channels=1, out_channels=1, f_maps=8, num_levels=2, layer_order="cgr"), "bce_dice_loss"),
+    "unet3d_f16_l2_cgr": (dict(name="UNet3D", in_channels=1, out_channels=1, f_maps=16, num_levels=2, layer_order="cgr"), "bce_dice_loss"),
 }
 
 

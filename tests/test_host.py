@@ -21,7 +21,7 @@ def test_library_exports_every_header_symbol():
 @pytest.mark.parametrize("golden,cfg", [
     ("unet3d_f16_l3_s16", dict(name="UNet3D", in_channels=1, out_channels=1, f_maps=16, num_levels=3)),
     ("unet3d_f16_l3_odd", dict(name="UNet3D", in_channels=2, out_channels=3, f_maps=16, num_levels=3, final_sigmoid=False)),
-    ("unet3d_f8_l2_cgr", dict(name="UNet3D", in_channels=1, out_channels=1, f_maps=8, num_levels=2, layer_order="cgr")),
+    ("unet3d_f16_l2_cgr", dict(name="UNet3D", in_channels=1, out_channels=1, f_maps=16, num_levels=2, layer_order="cgr")),
 ])
 def test_state_dict_contract_matches_reference(golden, cfg):
     import pytorch3dunet_b200 as P

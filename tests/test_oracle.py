@@ -12,7 +12,7 @@ MODEL_CASES = {
     "unet3d_f16_l3_s16": (dict(name="UNet3D", in_channels=1, out_channels=1, f_maps=16, num_levels=3), "bce_dice_loss"),
     "unet3d_f16_l3_dice_b2": (dict(name="UNet3D", in_channels=1, out_channels=1, f_maps=16, num_levels=3), "dice_loss"),
     "unet3d_f16_l3_odd": (dict(name="UNet3D", in_channels=2, out_channels=3, f_maps=16, num_levels=3, final_sigmoid=False), "bce_dice_loss"),
-    "unet3d_f8_l2_cgr": (dict(name="UNet3D", in_channels=1, out_channels=1, f_maps=8, num_levels=2, layer_order="cgr"), "bce_dice_loss"),
+    "unet3d_f16_l2_cgr": (dict(name="UNet3D", in_channels=1, out_channels=1, f_maps=16, num_levels=2, layer_order="cgr"), "bce_dice_loss"),
     "resunet3d_f16_l3_s16": (dict(name="ResidualUNet3D", in_channels=1, out_channels=1, f_maps=16, num_levels=3), "bce_dice_loss"),
     "resunetse3d_f16_l3_s16": (dict(name="ResidualUNetSE3D", in_channels=1, out_channels=1, f_maps=16, num_levels=3), "bce_dice_loss"),
 }
