@@ -83,8 +83,13 @@ def _groups(num_channels, num_groups):
     return 1 if num_channels < num_groups else num_groups
 
 
-def single_conv(x, sd, prefix, order, num_groups, padding=1):
-    """create_conv / SingleConv, buildingblocks.py:10-135.  `order` is walked left to right."""
+def single_conv(x, sd, prefix, order, num_groups, padding=1, masks=None):
+    """create_conv / SingleConv, buildingblocks.py:10-135.  `order` is walked left to right.
+
+    masks (tests only): {prefix: bool NCDHW tensor}.  When given, ReLU is evaluated with THAT activation pattern
+    (x * mask) instead of x > 0 -- lets a gradient parity test run the reference arithmetic at the activation
+    pattern of the implementation under test, so that bf16-induced flips of near-zero ReLU inputs (a
+    discontinuity, not an arithmetic error) do not dominate the comparison."""
     for ch in order:
         if ch == "c":
             x = F.conv3d(x, sd[prefix + "conv.weight"], sd.get(prefix + "conv.bias"), padding=padding)
@@ -92,7 +97,7 @@ def single_conv(x, sd, prefix, order, num_groups, padding=1):
             w = sd[prefix + "groupnorm.weight"]
             x = F.group_norm(x, _groups(w.numel(), num_groups), w, sd[prefix + "groupnorm.bias"], GN_EPS)
         elif ch == "r":
-            x = F.relu(x)
+            x = x * masks[prefix].to(x.dtype) if (masks is not None and prefix in masks) else F.relu(x)
         elif ch == "l":
             x = F.leaky_relu(x, 0.01)  # nn.LeakyReLU() default slope, buildingblocks.py:49
         elif ch == "e":
@@ -107,10 +112,10 @@ def single_conv(x, sd, prefix, order, num_groups, padding=1):
     return x
 
 
-def double_conv(x, sd, prefix, order, num_groups, padding=1):
+def double_conv(x, sd, prefix, order, num_groups, padding=1, masks=None):
     """DoubleConv.forward = SingleConv1 then SingleConv2 (nn.Sequential), buildingblocks.py:200-227."""
-    x = single_conv(x, sd, prefix + "SingleConv1.", order, num_groups, padding)
-    return single_conv(x, sd, prefix + "SingleConv2.", order, num_groups, padding)
+    x = single_conv(x, sd, prefix + "SingleConv1.", order, num_groups, padding, masks)
+    return single_conv(x, sd, prefix + "SingleConv2.", order, num_groups, padding, masks)
 
 
 def channel_se(x, sd, prefix):
@@ -150,9 +155,9 @@ def res_block(x, sd, prefix, order, num_groups, se=False):
     return out
 
 
-def basic_module(x, sd, prefix, cfg):
+def basic_module(x, sd, prefix, cfg, masks=None):
     if cfg["basic"] == "double":
-        return double_conv(x, sd, prefix, cfg["layer_order"], cfg["num_groups"], cfg["conv_padding"])
+        return double_conv(x, sd, prefix, cfg["layer_order"], cfg["num_groups"], cfg["conv_padding"], masks)
     return res_block(x, sd, prefix, cfg["layer_order"], cfg["num_groups"], se=cfg["basic"] == "res_se")
 
 
@@ -168,15 +173,15 @@ def decoder_mode(cfg):
     return up, concat
 
 
-def forward(sd, cfg, x):
-    """AbstractUNet._forward_logits, model.py:123-149.  Returns (output, logits)."""
+def forward(sd, cfg, x, masks=None):
+    """AbstractUNet._forward_logits, model.py:123-149.  Returns (output, logits).  `masks`: see single_conv."""
     cfg = normalize_config(cfg)
     nlev = len(cfg["f_maps"])
     feats = []
     for i in range(nlev):
         if i > 0:
             x = F.max_pool3d(x, 2)  # Encoder.forward :380-384, MaxPool3d(kernel_size=2) :356
-        x = basic_module(x, sd, f"encoders.{i}.basic_module.", cfg)
+        x = basic_module(x, sd, f"encoders.{i}.basic_module.", cfg, masks)
         feats.insert(0, x)
     feats = feats[1:]
     up, concat = decoder_mode(cfg)
@@ -192,7 +197,7 @@ def forward(sd, cfg, x):
         else:
             x = F.interpolate(x, size=size, mode=up)  # InterpolateUpsampling._interpolate :613-614
         x = torch.cat((enc, x), dim=1) if concat else enc + x  # Decoder._joining :488-493
-        x = basic_module(x, sd, f"decoders.{i}.basic_module.", cfg)
+        x = basic_module(x, sd, f"decoders.{i}.basic_module.", cfg, masks)
     logits = F.conv3d(x, sd["final_conv.weight"], sd["final_conv.bias"])  # model.py:89,141
     if cfg["is_segmentation"]:
         out = torch.sigmoid(logits) if cfg["final_sigmoid"] else torch.softmax(logits, dim=1)

@@ -691,19 +691,18 @@ __global__ void border_class_sums_kernel(const bf16* __restrict__ dz, int D, int
     Rp[(((size_t)n * P + p) * 64 + cls) * C + c0 + c] = bins[cls][c];
   }
 }
-// stage 2: T[n][tap][c] = sum_p sum_{cls: tap valid} Rp ; grid (N), block 256
-__global__ void border_tap_from_class_kernel(const float* __restrict__ Rp, int P, int C, float* __restrict__ T) {
-  int n = blockIdx.x;
-  for (int idx = threadIdx.x; idx < 27 * C; idx += blockDim.x) {
-    int tap = idx / C, c = idx % C;
-    int td = tap / 9, th = (tap / 3) % 3, tw = tap % 3;
-    double acc = 0.0;
-    for (int cls = 0; cls < 64; ++cls) {
-      if (!(tap_valid(cls >> 4, td) && tap_valid((cls >> 2) & 3, th) && tap_valid(cls & 3, tw))) continue;
-      for (int p = 0; p < P; ++p) acc += (double)Rp[(((size_t)n * P + p) * 64 + cls) * C + c];
-    }
-    T[((size_t)n * 27 + tap) * C + c] = (float)acc;
-  }
+// stage 2 (after the class sums were reduced over P by partials_finalize_kernel into R[n][cls][c], double):
+// T[n][tap][c] = sum_{cls: tap valid} R ; grid (ceil(27*C/256), N), block 256
+__global__ void border_tap_from_class_kernel(const double* __restrict__ R, int C, float* __restrict__ T) {
+  int n = blockIdx.y;
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 27 * C) return;
+  int tap = idx / C, c = idx % C;
+  int td = tap / 9, th = (tap / 3) % 3, tw = tap % 3;
+  double acc = 0.0;
+  for (int cls = 0; cls < 64; ++cls)
+    if (tap_valid(cls >> 4, td) && tap_valid((cls >> 2) & 3, th) && tap_valid(cls & 3, tw)) acc += R[((size_t)n * 64 + cls) * C + c];
+  T[((size_t)n * 27 + tap) * C + c] = (float)acc;
 }
 
 // dW[co][ci][tap] = sum_n ( a[n][ci] * sum_s G[n][s][tap][ci][co] + b[n][ci] * T[n][tap][co] )
@@ -1115,7 +1114,7 @@ int b200_upcat_bwd(const void* dcat, int C0, int C1, const void* x_small, int N,
 int b200_border_tap_sums_workspace(int N, int D, int H, int W, int C) {
   // number of floats of scratch needed by b200_border_tap_sums
   int P = ew_blocks((long long)D * H * W, 64);
-  return N * P * 64 * C;
+  return N * P * 64 * C + 2 * N * 64 * C;  // per-block class sums (float) + their reduction (double)
 }
 int b200_border_tap_sums(const void* dz, int N, int D, int H, int W, int C, float* T, float* scratch, b200_stream_t s) {
   B200_CHECK_ARG(C % 8 == 0, "border_tap_sums: C=%d must be a multiple of 8", C);
@@ -1123,7 +1122,15 @@ int b200_border_tap_sums(const void* dz, int N, int D, int H, int W, int C, floa
   dim3 grid(P, N, ceil_div(C, BT_CC));
   border_class_sums_kernel<<<grid, EW_THREADS, 0, ST(s)>>>((const bf16*)dz, D, H, W, C, P, scratch);
   B200_CHECK_LAUNCH("border_class_sums");
-  border_tap_from_class_kernel<<<N, 256, 0, ST(s)>>>(scratch, P, C, T);
+  double* R = reinterpret_cast<double*>(scratch + (size_t)N * P * 64 * C);
+  {
+    // [N][P][64*C] viewed as [N][P][C'][2] with C' = 32*C
+    dim3 g2(ceil_div(64 * C, 32), N), b2(32, 32);
+    partials_finalize_kernel<<<g2, b2, 0, ST(s)>>>(scratch, P, 32 * C, R);
+    B200_CHECK_LAUNCH("border_class_reduce");
+  }
+  dim3 g3(ceil_div(27 * C, 256), N);
+  border_tap_from_class_kernel<<<g3, 256, 0, ST(s)>>>(R, C, T);
   B200_CHECK_LAUNCH("border_tap_from_class");
   return 0;
 }

@@ -26,6 +26,7 @@ _ACT_OF = {"r": (ACT_RELU, 0.0), "l": (ACT_LEAKY, 0.01), "e": (ACT_ELU, 1.0)}
 
 # optional per-launch CUDA-event timing of selected entry points (bench.py roofline leg): list of
 # (name, flops, start_event, end_event) appended when enabled
+DEBUG = None   # dict: when set, backward closures stash clones of their intermediates (tools/debug_block.py)
 TIMING = None
 TIMED = {"b200_conv3_fwd", "b200_conv3_wgrad"}
 
@@ -181,7 +182,8 @@ class Engine:
         """seed y.grad from an external NCDHW fp32 gradient w.r.t. the (post-activation) output y."""
         n, d, h, w, c = y.dims
         g = self.empty((n, d, h, w, c), torch.bfloat16)
-        self.call("b200_ncdhw_f32_to_ndhwc_bf16", _p(g_ncdhw.contiguous()), _p(g), n, c, d, h, w)
+        g_src = g_ncdhw.contiguous()  # keep the (possible) copy alive until the kernel is enqueued
+        self.call("b200_ncdhw_f32_to_ndhwc_bf16", _p(g_src), _p(g), n, c, d, h, w)
         gm = self.empty((n, d, h, w, c), torch.bfloat16)
         self.call("b200_act_bwd", _p(g), c, 0, _p(y.t), n, c, d * h * w, y.act, y.slope, None, _p(gm))
         self.accumulate_grad(y, gm)
@@ -232,6 +234,8 @@ class Engine:
                   n, d, h, w, cin, cout, _p(y), 1 if want_stats else 0, None, _p(partials),
                   flops=2.0 * n * vox * 27 * cin * cout, tag=("fprop_tc" if impl == IMPL_TCGEN05 else "fprop_direct"))
         out = Act(y, act[0], act[1], partials, P)
+        if DEBUG is not None:
+            DEBUG.setdefault("fwd", {})[name] = y
 
         if self.record:
             def backward():
@@ -243,7 +247,7 @@ class Engine:
                 if need_T:
                     T = self.empty((n, 27, cout), torch.float32)
                     scratch = self.empty((L.query("b200_border_tap_sums_workspace", n, d, h, w, cout),), torch.float32)
-                    self.call("b200_border_tap_sums", _p(dz), n, d, h, w, cout, _p(T), _p(scratch), launches=2)
+                    self.call("b200_border_tap_sums", _p(dz), n, d, h, w, cout, _p(T), _p(scratch), launches=3)
                 wimpl = L.query("b200_conv3_wgrad_resolve_impl", self.impl, n, d, h, w, cin, cout, int(is_f32))
                 if wimpl < 0:
                     raise B200Error("tcgen05 wgrad requested but unsupported for this shape")
@@ -269,6 +273,11 @@ class Engine:
                               _p(coef), _p(dgamma), _p(dbeta))
                     self._add_param_grad(gn[3], dgamma)
                     self._add_param_grad(gn[4], dbeta)
+                if DEBUG is not None:
+                    DEBUG[name] = dict(dz=dz.clone(), T=None if T is None else T.clone(), G=G.clone(), dW=dW.clone(),
+                                       ab=None if ab is None else ab.clone(), x=x.t.clone(), y=out.t.clone(),
+                                       sums2=None if gn is None else sums2.clone(), coef=None if coef is None else coef.clone(),
+                                       mean_rstd=None if mean_rstd is None else mean_rstd.clone())
                 if residual is not None and residual.requires_grad:
                     g = self.empty(residual.t.shape, torch.bfloat16)
                     self.call("b200_act_bwd", _p(dz), cout, 0, _p(residual.t), n, cout, vox, residual.act, residual.slope,
@@ -292,6 +301,8 @@ class Engine:
                     else:
                         self.call("b200_act_bwd", _p(dxhat), cin, 0, _p(x.t), n, cin, vox, x.act, x.slope, _p(x.grad), _p(dxhat))
                     x.grad = dxhat
+                    if DEBUG is not None:
+                        DEBUG[name]["dx"] = dxhat.clone()
                 out.grad = None
             self.tape.append(backward)
         return out
@@ -312,6 +323,8 @@ class Engine:
             partials = self.empty((n, P, c, 2), torch.float32)
         self.call("b200_gn_apply_act", _p(z.t), _p(ab), n, c, vox, act[0], float(act[1]), _p(y), _p(partials))
         out = Act(y, act[0], act[1], partials, P)
+        if DEBUG is not None:
+            DEBUG.setdefault("fwd", {})[gname[: -len("groupnorm.weight")]] = y
         if self.record:
             def backward():
                 du = out.grad

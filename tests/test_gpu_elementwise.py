@@ -6,6 +6,10 @@ import torch.nn.functional as F
 pytestmark = pytest.mark.gpu
 
 
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
+
 def _ctx():
     from tests import gpu_util as U
     from pytorch3dunet_b200 import engine as E

@@ -4,6 +4,8 @@ import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
 
 TOL = 1e-2  # north_star: within 1e-2 relative (fp32 reference), bf16 operands / fp32 accumulation
 
