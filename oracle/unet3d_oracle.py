@@ -173,14 +173,22 @@ def decoder_mode(cfg):
     return up, concat
 
 
-def forward(sd, cfg, x, masks=None):
-    """AbstractUNet._forward_logits, model.py:123-149.  Returns (output, logits).  `masks`: see single_conv."""
+def max_pool_at(x, idx):
+    """MaxPool3d(2) whose selected element per window is given (tests only, same purpose as `masks`): the argmax of a
+    window with two nearly equal values is a discontinuity that bf16 rounding flips."""
+    return x.flatten(2).gather(2, idx.flatten(2)).view(idx.shape)
+
+
+def forward(sd, cfg, x, masks=None, pool_idx=None):
+    """AbstractUNet._forward_logits, model.py:123-149.  Returns (output, logits).  `masks`: see single_conv;
+    `pool_idx`: list of max-pool argmax index tensors (one per pooling level), see max_pool_at."""
     cfg = normalize_config(cfg)
     nlev = len(cfg["f_maps"])
     feats = []
     for i in range(nlev):
         if i > 0:
-            x = F.max_pool3d(x, 2)  # Encoder.forward :380-384, MaxPool3d(kernel_size=2) :356
+            # Encoder.forward :380-384, MaxPool3d(kernel_size=2) :356
+            x = max_pool_at(x, pool_idx[i - 1]) if pool_idx is not None else F.max_pool3d(x, 2)
         x = basic_module(x, sd, f"encoders.{i}.basic_module.", cfg, masks)
         feats.insert(0, x)
     feats = feats[1:]

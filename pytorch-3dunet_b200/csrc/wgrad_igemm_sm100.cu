@@ -22,9 +22,9 @@ int make_act_tmap(CUtensorMap* tm, const void* ptr, int N, int D, int H, int W, 
 int choose_box(int D, int H, int W, int* bd, int* bh, int* bw);
 
 constexpr int WG_THREADS = 192;
-constexpr int WG_MAX_A_STAGES = 4;
+constexpr int WG_MAX_A_STAGES = 8;
 constexpr int WG_B_STAGES = 2;
-constexpr int WG_A_STAGE_BYTES = 128 * 128 * 2;  // 128 voxels x 128 channels bf16
+constexpr int WG_A_FULL_BYTES = 128 * 128 * 2;  // an M=128 MMA reads up to 128 voxels x 128 channels past a stage base
 
 struct WgradParams {
   int N, D, H, W, Cin, Cout;
@@ -32,7 +32,7 @@ struct WgradParams {
   int S, tiles_per_split;
   int TG, ngroups, mchunks;
   int AWa, AWb;  // channels per smem atom tile (64/32/16) on the x side and the dz side
-  int a_stages, b_stage_bytes;
+  int a_stages, a_stage_bytes, b_stage_bytes;
   int tmem_cols;
   float* G;
 };
@@ -108,7 +108,7 @@ conv3_wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid
           mbar_wait(&a_empty[as], ((uint32_t)(ai / p.a_stages) & 1u) ^ 1u);
           mbar_arrive_expect_tx(&a_full[as], (uint32_t)(natoms_a * a_atom_bytes));
           for (int j = 0; j < natoms_a; ++j)
-            tma_load_5d(smemA + (size_t)as * WG_A_STAGE_BYTES + (size_t)j * a_atom_bytes, &tmapX, &a_full[as], m0 + j * p.AWa,
+            tma_load_5d(smemA + (size_t)as * p.a_stage_bytes + (size_t)j * a_atom_bytes, &tmapX, &a_full[as], m0 + j * p.AWa,
                         w0 + tw - 1, h0 + th - 1, d0 + td - 1, n);
         }
       }
@@ -127,7 +127,7 @@ conv3_wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid
           const int as = ai % p.a_stages;
           mbar_wait(&a_full[as], (uint32_t)(ai / p.a_stages) & 1u);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smemA + (size_t)as * WG_A_STAGE_BYTES);
+          const uint32_t sa = smem_u32(smemA + (size_t)as * p.a_stage_bytes);
 #pragma unroll
           for (int k = 0; k < 8; ++k) {  // 128 voxels = 8 x K16
             const uint64_t adesc = umma_smem_desc(sa + (uint32_t)(k * 16 * rba), (uint32_t)a_atom_bytes, (uint32_t)(8 * rba), la);
@@ -204,8 +204,9 @@ static void wgrad_plan(int N, int D, int H, int W, int Cin, int Cout, WgradParam
   p.TG = (27 + p.ngroups - 1) / p.ngroups;
   p.ngroups = (27 + p.TG - 1) / p.TG;
   p.mchunks = (Cin + 127) / 128;
+  // one CTA per SM (TMEM: TG*Cout columns, smem: deep A pipeline) -> size the split count for a single wave
   int ctas_per_split = N * p.ngroups * p.mchunks;
-  int want = (2 * 148 + ctas_per_split - 1) / ctas_per_split;
+  int want = 148 / ctas_per_split;
   if (want < 1) want = 1;
   if (want > p.tiles) want = p.tiles;
   p.tiles_per_split = (p.tiles + want - 1) / want;
@@ -213,8 +214,10 @@ static void wgrad_plan(int N, int D, int H, int W, int Cin, int Cout, WgradParam
   p.AWa = atom_width(Cin);
   p.AWb = atom_width(Cout);
   p.b_stage_bytes = 128 * Cout * 2;
-  int budget = 200 * 1024 - WG_B_STAGES * p.b_stage_bytes;
-  p.a_stages = budget / WG_A_STAGE_BYTES;
+  // an A stage only holds the channels that exist (garbage M rows of the MMA read past it, into the next stage or the tail pad)
+  p.a_stage_bytes = 128 * (Cin < 128 ? Cin : 128) * 2;
+  int budget = 190 * 1024 - WG_B_STAGES * p.b_stage_bytes - WG_A_FULL_BYTES;
+  p.a_stages = budget / p.a_stage_bytes;
   if (p.a_stages > WG_MAX_A_STAGES) p.a_stages = WG_MAX_A_STAGES;
   if (p.a_stages < 2) p.a_stages = 2;
   int cols = 32;
@@ -250,7 +253,7 @@ int b200_conv3_wgrad_igemm(const void* x, const void* dz, int N, int D, int H, i
   if (rc) return rc;
   rc = make_act_tmap(&tmZ, dz, N, D, H, W, Cout, p.AWb, p.BD, p.BH, p.BW);
   if (rc) return rc;
-  size_t smem = (size_t)WG_B_STAGES * p.b_stage_bytes + (size_t)p.a_stages * WG_A_STAGE_BYTES + 1024;
+  size_t smem = (size_t)WG_B_STAGES * p.b_stage_bytes + (size_t)p.a_stages * p.a_stage_bytes + WG_A_FULL_BYTES + 1024;
   cudaError_t e = cudaFuncSetAttribute(conv3_wgrad_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   B200_CHECK_ARG(e == cudaSuccess, "conv3_wgrad_igemm: cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e));
   dim3 grid((unsigned)(N * p.S), (unsigned)p.ngroups, (unsigned)p.mchunks);

@@ -397,6 +397,8 @@ class Engine:
         partials = self.empty((n, P, c, 2), torch.float32) if want_stats else None
         self.call("b200_maxpool_fwd", _p(x.t), n, d, h, w, c, _p(y), _p(partials))
         out = Act(y, ACT_NONE, 0.0, partials, P)
+        if DEBUG is not None:
+            DEBUG.setdefault("pool", []).append(x.t)
         if self.record:
             def backward():
                 if out.grad is None or not x.requires_grad:

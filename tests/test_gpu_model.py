@@ -21,6 +21,12 @@ def _engine_masks(E):
     return {k: (v.float() > 0).permute(0, 4, 1, 2, 3).cpu() for k, v in E.DEBUG["fwd"].items()}
 
 
+def _engine_pool_idx(E):
+    """argmax (flat D*H*W index, torch's first-max tie rule == the engine's) of every max-pool window of the last run"""
+    import torch.nn.functional as F
+    return [F.max_pool3d(t.float().permute(0, 4, 1, 2, 3), 2, return_indices=True)[1].cpu() for t in E.DEBUG.get("pool", [])]
+
+
 def _block(name):
     import pytorch3dunet_b200 as P
     from oracle import unet3d_oracle as O
@@ -34,7 +40,7 @@ def _block(name):
     if name == "block_doubleconv_dec_96_32":
         return P.DoubleConv(96, 32, encoder=False, order="gcr", num_groups=8), lambda sd, x, enc, m: O.double_conv(x, sd, "", "gcr", 8, masks=m)
     if name == "block_encoder_pool_32_64":
-        return P.Encoder(32, 64), lambda sd, x, enc, m: O.double_conv(F.max_pool3d(x, 2), sd, "basic_module.", "gcr", 8, masks=m)
+        return P.Encoder(32, 64), lambda sd, x, enc, m: O.double_conv(O.max_pool_at(x, m["__pool__"][0]), sd, "basic_module.", "gcr", 8, masks=m)
 
     def dec(sd, x, enc, m):
         u = F.interpolate(x, size=enc.shape[2:], mode="nearest")
@@ -73,13 +79,15 @@ def test_block_matches_reference_golden(name, impl, monkeypatch):
     (y * rec["r"].cuda()).sum().backward()
     torch.cuda.synchronize()
     masks = _engine_masks(E)
-    # oracle at the engine's activation pattern
+    masks["__pool__"] = _engine_pool_idx(E)
+    # oracle on IDENTICAL inputs (the block boundary rounds its fp32 input to bf16) at the engine's activation pattern
     osd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
-    ox = rec["x"].clone().requires_grad_(True)
-    oenc = rec["enc"].clone().requires_grad_(True) if two_inputs else None
+    ox = rec["x"].bfloat16().float().requires_grad_(True)
+    oenc = rec["enc"].bfloat16().float().requires_grad_(True) if two_inputs else None
     oy = ofn(osd, ox, oenc, masks)
     (oy * rec["r"]).sum().backward()
-    report = {"y": rel_l2(y, rec["y"]), "grad_x": rel_l2(x.grad, ox.grad), "grad_x_vs_golden(info)": rel_l2(x.grad, rec["grad_x"])}
+    report = {"y": rel_l2(y, oy), "y_vs_golden(info)": rel_l2(y, rec["y"]), "grad_x": rel_l2(x.grad, ox.grad),
+              "grad_x_vs_golden(info)": rel_l2(x.grad, rec["grad_x"])}
     if two_inputs:
         report["grad_enc"] = rel_l2(enc.grad, oenc.grad)
     for k, p in mod.named_parameters():
@@ -113,7 +121,7 @@ def _model_vs_oracle(cfg, loss_name, sd, x, target, monkeypatch, ref=None):
     torch.cuda.synchronize()
     masks = _engine_masks(E)
     osd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
-    o_out, o_logits = O.forward(osd, cfg, x, masks=masks)
+    o_out, o_logits = O.forward(osd, cfg, x, masks=masks, pool_idx=_engine_pool_idx(E))
     o_loss = getattr(O, loss_name)(o_logits, target)
     o_loss.backward()
     if ref is None:
