@@ -33,7 +33,8 @@ def main(path):
     for r in step:
         nm = r["Kernel Name"]
         if "igemm" in nm or "direct" in nm or "stem" in nm or "ring" in nm:
-            print(f"| {float(r['Metric Value'].replace(',', '')) / 1e3:.1f} | {r['Grid Size']} | `{re.sub(r'\\(.*', '', nm).replace('void ', '')[:60]}` |")
+            short = nm.split("(")[0].replace("void ", "")[:60]
+            print(f"| {float(r['Metric Value'].replace(',', '')) / 1e3:.1f} | {r['Grid Size']} | `{short}` |")
 
 
 if __name__ == "__main__":
