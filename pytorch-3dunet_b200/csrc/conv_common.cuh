@@ -1,0 +1,121 @@
+// Shared pieces of the tcgen05 convolution kernels: parameter block, the epilogue slab, host helpers.
+#pragma once
+#include <string.h>
+
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace b200 {
+
+constexpr int CONV_THREADS = 192;
+constexpr int CONV_MAX_STAGES = 8;
+constexpr int HALO_MAX_STAGES = 6;
+
+struct ConvParams {
+  int N, D, H, W, Cin, Cout;
+  int BD, BH, BW;
+  int tilesD, tilesH, tilesW;
+  int n_w, n_b;
+  int NT;       // output channels per CTA
+  int KC;       // channels per k-block (16/32/64)
+  int kchunks;  // Cin / KC
+  int stages;
+  int a_bytes, b_bytes;  // per-stage tile sizes (1024-aligned)
+  int tmem_cols;
+  int act;
+  float slope;
+  int pmode;
+  const float* biascls;
+  const bf16* residual;
+  const bf16* aux;
+  bf16* y;
+  float* partials;
+  // halo kernel only
+  int KCb;             // channels per resident-weight block (swizzle granule of B)
+  int a_stages;        // halo stages of KC channels each
+  int b_total_bytes;   // resident weights [Cin/KCb][27][NT][KCb]
+  int ctas_per_sample;
+};
+
+// one 32-/16-column slab of the accumulator tile for one thread (= one output voxel row)
+template <int CW>
+__device__ __forceinline__ void conv_epilogue_slab(const ConvParams& p, uint32_t taddr, int c0 /*col in tile*/, int n0, bool valid,
+                                                   size_t vox_off /* (n*vox+v) */, const float* bias_row /* or null */, int lane,
+                                                   float* scratch /* [NT][2] for this warp */) {
+  uint32_t raw[CW];
+  if constexpr (CW == 32) tmem_ld_32x32b_x32(taddr + c0, raw);
+  else tmem_ld_32x32b_x16(taddr + c0, raw);
+  tmem_ld_wait();
+  float v[CW];
+#pragma unroll
+  for (int i = 0; i < CW; ++i) v[i] = __uint_as_float(raw[i]);
+  const size_t goff = vox_off * p.Cout + n0 + c0;
+  if (valid) {
+    if (bias_row) {
+      const float4* bp = reinterpret_cast<const float4*>(bias_row + n0 + c0);
+#pragma unroll
+      for (int i = 0; i < CW / 4; ++i) {
+        float4 b = __ldg(bp + i);
+        v[4 * i] += b.x;
+        v[4 * i + 1] += b.y;
+        v[4 * i + 2] += b.z;
+        v[4 * i + 3] += b.w;
+      }
+    }
+    if (p.residual) {
+      const bf16x8* rp = reinterpret_cast<const bf16x8*>(p.residual + goff);
+#pragma unroll
+      for (int i = 0; i < CW / 8; ++i) {
+        float f[8];
+        unpack8(rp[i], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[8 * i + j] += f[j];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < CW; ++i) v[i] = bf16_round(act_fwd(v[i], p.act, p.slope));
+    bf16x8* op = reinterpret_cast<bf16x8*>(p.y + goff);
+#pragma unroll
+    for (int i = 0; i < CW / 8; ++i) op[i] = pack8(&v[8 * i]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < CW; ++i) v[i] = 0.f;
+  }
+  if (p.pmode) {
+    float w[CW];
+    if (p.pmode == 1) {
+#pragma unroll
+      for (int i = 0; i < CW; ++i) w[i] = v[i] * v[i];
+    } else {
+      if (valid) {
+        const bf16x8* ap = reinterpret_cast<const bf16x8*>(p.aux + goff);
+#pragma unroll
+        for (int i = 0; i < CW / 8; ++i) {
+          float f[8];
+          unpack8(ap[i], f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) w[8 * i + j] = v[8 * i + j] * f[j];
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < CW; ++i) w[i] = 0.f;
+      }
+    }
+    float s = warp_reduce_scatter<CW>(v, lane);
+    float q = warp_reduce_scatter<CW>(w, lane);
+    if (lane < CW) {
+      scratch[(c0 + lane) * 2] = s;
+      scratch[(c0 + lane) * 2 + 1] = q;
+    }
+  }
+}
+
+
+int make_act_tmap(CUtensorMap* tm, const void* ptr, int N, int D, int H, int W, int C, int kc, int bd, int bh, int bw);
+int make_w_tmap(CUtensorMap* tm, const void* ptr, int rows2, int rows1, int C, int kc, int nt, int ntaps_box = 1);
+int choose_box(int D, int H, int W, int* bd, int* bh, int* bw);
+bool conv_igemm_supported(int N, int D, int H, int W, int Cin, int Cout);
+bool conv_halo_plan(int N, int D, int H, int W, int Cin, int Cout, ConvParams* p);
+int conv_halo_launch(const void* x, const void* wf, ConvParams& p, cudaStream_t s);
+
+}  // namespace b200

@@ -1,0 +1,242 @@
+// 3x3x3 convolution for the small-channel / large-volume layers (where the plain tap-by-tap kernel is bound by
+// TMA latency and L2->SM traffic: 27 tile loads of 8-16 KB per 128 output voxels).
+//
+//   * persistent CTAs, one per SM; each walks output tiles of 1x16x8 voxels of ONE sample;
+//   * per tile and channel chunk ONE TMA box load brings the (3 x 18 x 10)-voxel halo into shared memory (4.2x the tile
+//     instead of 27x); every filter tap is then a row-shifted VIEW of that tile: the tcgen05 shared-memory descriptor
+//     starts at  halo_row((dd*18+dh)*10+dw)  with an 8-row-group stride of 10 rows.  That the 128/64/32-byte swizzle
+//     is a pure function of the shared-memory address (so such views stay consistent with what TMA wrote) is checked
+//     on hardware by tests/test_gpu_kernels.py::test_probe_umma_row_shifted_swizzled_view;
+//   * the (GroupNorm-folded, per-sample) weights of the CTA's sample stay RESIDENT in shared memory:
+//     [Cin/KCb][27][Cout][KCb], loaded once per CTA by 27*Cout-row TMA boxes;
+//   * two accumulator buffers in TMEM: the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Warp roles as in conv_igemm_sm100.cu: warp 0 TMA producer, warp 1 TMEM alloc + MMA issuer, warps 2..5 epilogue.
+#include <stdlib.h>
+
+#include "conv_common.cuh"
+
+namespace b200 {
+
+constexpr int HALO_BH = 16, HALO_BW = 8;
+constexpr int HALO_HD = 3, HALO_HH = HALO_BH + 2, HALO_HW = HALO_BW + 2;
+constexpr int HALO_ROWS = HALO_HD * HALO_HH * HALO_HW;  // 540
+
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+conv3_halo_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, const ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t a_full[HALO_MAX_STAGES], a_empty[HALO_MAX_STAGES];
+  __shared__ __align__(8) uint64_t b_full, tmem_full[2], tmem_empty[2];
+  __shared__ uint32_t tmem_slot;
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smemB = smem;
+  const int b_region = (p.b_total_bytes + 1023) & ~1023;
+  uint8_t* smemA = smem + b_region;
+  float* scratch_base = reinterpret_cast<float*>(smemA + (size_t)p.a_stages * p.a_bytes);  // [2][4][NT][2]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.y, cta = blockIdx.x, cps = gridDim.x;
+  const int tiles = p.tilesD * p.tilesH * p.tilesW;
+  const int nchunksA = p.Cin / p.KC;
+  const int rbA = p.KC * 2, rbB = p.KCb * 2;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.a_stages; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+    }
+    mbar_init(&b_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);  // one arrival per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmapA);
+    tma_prefetch_desc(&tmapB);
+  }
+  if (warp == 1) tmem_alloc(&tmem_slot, (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      const int wsample = p.n_w > 1 ? n : 0;
+      const int nchunksB = p.Cin / p.KCb;
+      mbar_arrive_expect_tx(&b_full, (uint32_t)p.b_total_bytes);
+      for (int cb = 0; cb < nchunksB; ++cb)
+        tma_load_3d(smemB + (size_t)cb * 27 * p.NT * rbB, &tmapB, &b_full, cb * p.KCb, 0, wsample * 27);
+      int it = 0;
+      for (int t = cta; t < tiles; t += cps) {
+        const int tw_i = t % p.tilesW;
+        const int r = t / p.tilesW;
+        const int th_i = r % p.tilesH, d0 = r / p.tilesH;
+        const int h0 = th_i * HALO_BH, w0 = tw_i * HALO_BW;
+        for (int j = 0; j < nchunksA; ++j, ++it) {
+          const int stage = it % p.a_stages;
+          mbar_wait(&a_empty[stage], ((uint32_t)(it / p.a_stages) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&a_full[stage], (uint32_t)(HALO_ROWS * rbA));
+          tma_load_5d(smemA + (size_t)stage * p.a_bytes, &tmapA, &a_full[stage], j * p.KC, w0 - 1, h0 - 1, d0 - 1, n);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, p.NT, 0, 0);
+      const uint32_t layA = umma_layout_for_row_bytes(rbA), layB = umma_layout_for_row_bytes(rbB);
+      const uint32_t sboA = (uint32_t)(HALO_HW * rbA), sboB = (uint32_t)(8 * rbB);
+      const uint32_t sB0 = smem_u32(smemB);
+      mbar_wait(&b_full, 0);
+      int it = 0, lt = 0;
+      for (int t = cta; t < tiles; t += cps, ++lt) {
+        const int buf = lt & 1;
+        mbar_wait(&tmem_empty[buf], ((uint32_t)(lt >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + (uint32_t)(buf * p.NT);
+        for (int j = 0; j < nchunksA; ++j, ++it) {
+          const int stage = it % p.a_stages;
+          mbar_wait(&a_full[stage], (uint32_t)(it / p.a_stages) & 1u);
+          tc_fence_after();
+          const uint32_t sA = smem_u32(smemA + (size_t)stage * p.a_bytes);
+          for (int tap = 0; tap < 27; ++tap) {
+            const int td = tap / 9, th = (tap / 3) % 3, tw = tap % 3;
+            const uint32_t a_tap = sA + (uint32_t)(((td * HALO_HH + th) * HALO_HW + tw) * rbA);
+            for (int k = 0; k < p.KC / 16; ++k) {
+              const int ch = j * p.KC + k * 16;  // first input channel of this K=16 slice
+              const int cb = ch / p.KCb, koff = (ch % p.KCb) * 2;
+              const uint32_t b_addr = sB0 + (uint32_t)((cb * 27 + tap) * p.NT * rbB + koff);
+              const uint64_t adesc = umma_smem_desc(a_tap + (uint32_t)(k * 32), 16u, sboA, layA);
+              const uint64_t bdesc = umma_smem_desc(b_addr, 16u, sboB, layB);
+              umma_bf16(tacc, adesc, bdesc, idesc, (j | tap | k) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(&a_empty[stage]);
+        }
+        umma_commit(&tmem_full[buf]);
+      }
+    }
+  } else {
+    // ================= epilogue (warps 2..5) =================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int bx = row % HALO_BW, by = row / HALO_BW;
+    const int n0 = 0;
+    int lt = 0;
+    for (int t = cta; t < tiles; t += cps, ++lt) {
+      const int buf = lt & 1;
+      const int tw_i = t % p.tilesW;
+      const int r = t / p.tilesW;
+      const int th_i = r % p.tilesH, xd = r / p.tilesH;
+      const int xh = th_i * HALO_BH + by, xw = tw_i * HALO_BW + bx;
+      const bool valid = xh < p.H && xw < p.W;
+      const size_t vox_off = (size_t)n * p.D * p.H * p.W + ((size_t)xd * p.H + xh) * p.W + xw;
+      const float* bias_row = nullptr;
+      if (p.n_b && valid) {
+        const int cls = (axis_cls(xd, p.D) << 4) | (axis_cls(xh, p.H) << 2) | axis_cls(xw, p.W);
+        bias_row = p.biascls + ((size_t)(p.n_b > 1 ? n : 0) * 64 + cls) * p.Cout;
+      }
+      mbar_wait(&tmem_full[buf], (uint32_t)(lt >> 1) & 1u);
+      __syncwarp();
+      tc_fence_after();
+      float* scratch_tile = scratch_base + (size_t)buf * 4 * p.NT * 2;
+      float* scratch = scratch_tile + (size_t)q * p.NT * 2;
+      const uint32_t taddr = tmem_base + (uint32_t)(buf * p.NT) + ((uint32_t)(q * 32) << 16);
+      int c0 = 0;
+      for (; c0 + 32 <= p.NT; c0 += 32) conv_epilogue_slab<32>(p, taddr, c0, n0, valid, vox_off, bias_row, lane, scratch);
+      if (c0 < p.NT) conv_epilogue_slab<16>(p, taddr, c0, n0, valid, vox_off, bias_row, lane, scratch);
+      // accumulator buffer drained -> hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+      if (p.pmode) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // the 4 epilogue warps only
+        const int et = threadIdx.x - 64;
+        float* out = p.partials + (((size_t)n * tiles + t) * p.Cout + n0) * 2;
+        for (int i = et; i < p.NT * 2; i += 128)
+          out[i] = scratch_tile[i] + scratch_tile[p.NT * 2 + i] + scratch_tile[p.NT * 4 + i] + scratch_tile[p.NT * 6 + i];
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+static int pow2_chunk(int C, int maxc) {
+  int c = maxc;
+  while (c > 16 && C % c != 0) c >>= 1;
+  return c;
+}
+
+// decides whether the halo kernel takes this layer and fills the plan
+bool conv_halo_plan(int N, int D, int H, int W, int Cin, int Cout, ConvParams* pp) {
+  ConvParams& p = *pp;
+  memset(&p, 0, sizeof(p));
+  if (Cin % 16 != 0 || Cout % 16 != 0 || Cout > 256) return false;
+  if (D < HALO_HD || H < HALO_HH || W < HALO_HW) return false;  // keep every TMA box inside the tensor extent
+  const char* dis = getenv("B200UNET_NO_HALO");
+  if (dis && dis[0] == '1') return false;
+  const int budget = 222 * 1024;
+  const int b_total = 27 * Cout * Cin * 2;
+  const int scratch = 2 * 4 * Cout * 2 * (int)sizeof(float);
+  int kca = 0, stages = 0, a_bytes = 0;
+  for (int kc = 64; kc >= 16; kc >>= 1) {
+    if (Cin % kc != 0) continue;
+    int ab = (HALO_ROWS * kc * 2 + 1023) & ~1023;
+    int st = (budget - ((b_total + 1023) & ~1023) - scratch - 1024) / ab;
+    if (st >= 3 || (st >= 2 && kc == 16)) {
+      kca = kc;
+      stages = st > HALO_MAX_STAGES ? HALO_MAX_STAGES : st;
+      a_bytes = ab;
+      break;
+    }
+  }
+  if (!kca) return false;
+  p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
+  p.BD = 1; p.BH = HALO_BH; p.BW = HALO_BW;
+  p.tilesD = D;
+  p.tilesH = (H + HALO_BH - 1) / HALO_BH;
+  p.tilesW = (W + HALO_BW - 1) / HALO_BW;
+  p.NT = Cout;
+  p.KC = kca;
+  p.kchunks = Cin / kca;
+  p.KCb = pow2_chunk(Cin, 64);
+  p.a_stages = stages;
+  p.a_bytes = a_bytes;
+  p.b_total_bytes = b_total;
+  int cols = 32;
+  while (cols < 2 * Cout) cols <<= 1;
+  p.tmem_cols = cols;
+  int tiles = p.tilesD * p.tilesH * p.tilesW;
+  int sms = 148;
+  int cps = sms / N;
+  if (cps < 1) cps = 1;
+  if (cps > tiles) cps = tiles;
+  p.ctas_per_sample = cps;
+  return true;
+}
+
+int conv_halo_launch(const void* x, const void* wf, ConvParams& p, cudaStream_t s) {
+  CUtensorMap tmA, tmB;
+  int rc = make_act_tmap(&tmA, x, p.N, p.D, p.H, p.W, p.Cin, p.KC, HALO_HD, HALO_HH, HALO_HW);
+  if (rc) return rc;
+  rc = make_w_tmap(&tmB, wf, 27 * p.n_w, p.Cout, p.Cin, p.KCb, p.NT, 27);
+  if (rc) return rc;
+  size_t smem = (size_t)((p.b_total_bytes + 1023) & ~1023) + (size_t)p.a_stages * p.a_bytes + (size_t)2 * 4 * p.NT * 2 * sizeof(float) + 1024;
+  cudaError_t e = cudaFuncSetAttribute(conv3_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  B200_CHECK_ARG(e == cudaSuccess, "conv3_halo: cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e));
+  dim3 grid((unsigned)p.ctas_per_sample, (unsigned)p.N);
+  conv3_halo_kernel<<<grid, CONV_THREADS, smem, s>>>(tmA, tmB, p);
+  B200_CHECK_LAUNCH("conv3_halo");
+  return 0;
+}
+
+}  // namespace b200

@@ -12,109 +12,9 @@
 //
 // The same kernel is the dgrad (input gradient): x := dz, weights := tap-flipped transposed weights.
 // Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
-#include <string.h>
-
-#include "common.cuh"
-#include "sm100_ptx.cuh"
+#include "conv_common.cuh"
 
 namespace b200 {
-
-constexpr int CONV_THREADS = 192;
-constexpr int CONV_MAX_STAGES = 8;
-
-struct ConvParams {
-  int N, D, H, W, Cin, Cout;
-  int BD, BH, BW;
-  int tilesD, tilesH, tilesW;
-  int n_w, n_b;
-  int NT;       // output channels per CTA
-  int KC;       // channels per k-block (16/32/64)
-  int kchunks;  // Cin / KC
-  int stages;
-  int a_bytes, b_bytes;  // per-stage tile sizes (1024-aligned)
-  int tmem_cols;
-  int act;
-  float slope;
-  int pmode;
-  const float* biascls;
-  const bf16* residual;
-  const bf16* aux;
-  bf16* y;
-  float* partials;
-};
-
-// one 32-/16-column slab of the accumulator tile for one thread (= one output voxel row)
-template <int CW>
-__device__ __forceinline__ void conv_epilogue_slab(const ConvParams& p, uint32_t taddr, int c0 /*col in tile*/, int n0, bool valid,
-                                                   size_t vox_off /* (n*vox+v) */, const float* bias_row /* or null */, int lane,
-                                                   float* scratch /* [NT][2] for this warp */) {
-  uint32_t raw[CW];
-  if constexpr (CW == 32) tmem_ld_32x32b_x32(taddr + c0, raw);
-  else tmem_ld_32x32b_x16(taddr + c0, raw);
-  tmem_ld_wait();
-  float v[CW];
-#pragma unroll
-  for (int i = 0; i < CW; ++i) v[i] = __uint_as_float(raw[i]);
-  const size_t goff = vox_off * p.Cout + n0 + c0;
-  if (valid) {
-    if (bias_row) {
-      const float4* bp = reinterpret_cast<const float4*>(bias_row + n0 + c0);
-#pragma unroll
-      for (int i = 0; i < CW / 4; ++i) {
-        float4 b = __ldg(bp + i);
-        v[4 * i] += b.x;
-        v[4 * i + 1] += b.y;
-        v[4 * i + 2] += b.z;
-        v[4 * i + 3] += b.w;
-      }
-    }
-    if (p.residual) {
-      const bf16x8* rp = reinterpret_cast<const bf16x8*>(p.residual + goff);
-#pragma unroll
-      for (int i = 0; i < CW / 8; ++i) {
-        float f[8];
-        unpack8(rp[i], f);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[8 * i + j] += f[j];
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < CW; ++i) v[i] = bf16_round(act_fwd(v[i], p.act, p.slope));
-    bf16x8* op = reinterpret_cast<bf16x8*>(p.y + goff);
-#pragma unroll
-    for (int i = 0; i < CW / 8; ++i) op[i] = pack8(&v[8 * i]);
-  } else {
-#pragma unroll
-    for (int i = 0; i < CW; ++i) v[i] = 0.f;
-  }
-  if (p.pmode) {
-    float w[CW];
-    if (p.pmode == 1) {
-#pragma unroll
-      for (int i = 0; i < CW; ++i) w[i] = v[i] * v[i];
-    } else {
-      if (valid) {
-        const bf16x8* ap = reinterpret_cast<const bf16x8*>(p.aux + goff);
-#pragma unroll
-        for (int i = 0; i < CW / 8; ++i) {
-          float f[8];
-          unpack8(ap[i], f);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) w[8 * i + j] = v[8 * i + j] * f[j];
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < CW; ++i) w[i] = 0.f;
-      }
-    }
-    float s = warp_reduce_scatter<CW>(v, lane);
-    float q = warp_reduce_scatter<CW>(w, lane);
-    if (lane < CW) {
-      scratch[(c0 + lane) * 2] = s;
-      scratch[(c0 + lane) * 2 + 1] = q;
-    }
-  }
-}
 
 __global__ void __launch_bounds__(CONV_THREADS)
 conv3_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, const ConvParams p) {
@@ -277,12 +177,12 @@ int make_act_tmap(CUtensorMap* tm, const void* ptr, int N, int D, int H, int W, 
   return 0;
 }
 // weights [rows2][rows1][C] bf16 viewed as rank-3 {C, rows1, rows2}; box {kc, nt, 1}
-int make_w_tmap(CUtensorMap* tm, const void* ptr, int rows2, int rows1, int C, int kc, int nt) {
+int make_w_tmap(CUtensorMap* tm, const void* ptr, int rows2, int rows1, int C, int kc, int nt, int ntaps_box) {
   EncodeTiledFn enc = get_encode_tiled();
   B200_CHECK_ARG(enc, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)rows1, (cuuint64_t)rows2};
   cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)rows1 * C * 2};
-  cuuint32_t box[3] = {(cuuint32_t)kc, (cuuint32_t)nt, 1};
+  cuuint32_t box[3] = {(cuuint32_t)kc, (cuuint32_t)nt, (cuuint32_t)ntaps_box};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_row_bytes(kc * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -343,6 +243,8 @@ int b200_conv3_igemm_partials_count(int N, int D, int H, int W, int Cin, int Cou
   (void)N;
   (void)Cin;
   (void)Cout;
+  ConvParams hp;
+  if (conv_halo_plan(N, D, H, W, Cin, Cout, &hp)) return hp.tilesD * hp.tilesH * hp.tilesW;
   int bd, bh, bw;
   if (choose_box(D, H, W, &bd, &bh, &bw)) return 0;
   return ((D + bd - 1) / bd) * ((H + bh - 1) / bh) * ((W + bw - 1) / bw);
@@ -354,6 +256,23 @@ int b200_conv3_igemm_fwd(const void* x, const void* wf, int n_w, const float* bi
   B200_CHECK_ARG(conv_igemm_supported(N, D, H, W, Cin, Cout), "conv3_igemm: unsupported shape N=%d D=%d H=%d W=%d Cin=%d Cout=%d", N, D,
                  H, W, Cin, Cout);
   ConvParams p;
+  memset(&p, 0, sizeof(p));
+  B200_CHECK_ARG(pmode == 0 || partials, "conv3_igemm: pmode=%d needs a partials buffer", pmode);
+  B200_CHECK_ARG(pmode != 2 || aux, "conv3_igemm: pmode=2 needs aux");
+  if (conv_halo_plan(N, D, H, W, Cin, Cout, &p)) {
+    // small-channel / large-volume layers: one halo tile in shared memory feeds all 27 taps, weights stay resident
+    p.n_w = n_w;
+    p.n_b = biascls ? n_b : 0;
+    p.act = act;
+    p.slope = slope;
+    p.pmode = pmode;
+    p.biascls = biascls;
+    p.residual = (const bf16*)residual;
+    p.aux = (const bf16*)aux;
+    p.y = (bf16*)y;
+    p.partials = partials;
+    return conv_halo_launch(x, wf, p, (cudaStream_t)s);
+  }
   memset(&p, 0, sizeof(p));
   p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
   choose_box(D, H, W, &p.BD, &p.BH, &p.BW);
@@ -383,8 +302,6 @@ int b200_conv3_igemm_fwd(const void* x, const void* wf, int n_w, const float* bi
   p.aux = (const bf16*)aux;
   p.y = (bf16*)y;
   p.partials = partials;
-  B200_CHECK_ARG(pmode == 0 || partials, "conv3_igemm: pmode=%d needs a partials buffer", pmode);
-  B200_CHECK_ARG(pmode != 2 || aux, "conv3_igemm: pmode=2 needs aux");
 
   CUtensorMap tmA, tmB;
   int rc = make_act_tmap(&tmA, x, N, D, H, W, Cin, p.KC, p.BD, p.BH, p.BW);

@@ -30,6 +30,14 @@ SHAPES = [
     (1, 4, 4, 8, 384, 128),
     (1, 5, 9, 7, 32, 16),      # ragged: exercises TMA out-of-bounds fill and masked stores
     (1, 16, 16, 16, 32, 64),
+    # large enough for the halo kernel (D>=3, H>=18, W>=10): resident weights + shifted halo views
+    (2, 3, 18, 10, 16, 32),
+    (1, 4, 20, 12, 32, 32),
+    (1, 5, 33, 17, 96, 32),    # ragged, three weight blocks, 16-channel halo chunks
+    (1, 4, 32, 16, 32, 96),
+    (1, 4, 20, 12, 64, 32),
+    (1, 4, 20, 12, 32, 64),
+    (2, 6, 24, 24, 32, 16),
 ]
 
 
