@@ -169,6 +169,11 @@ int b200_conv3_wgrad_igemm(const void* x, const void* dz, int N, int D, int H, i
 /* hardware probe (test tooling): tcgen05.mma on a row-shifted / odd-strided view of a SWIZZLE_128B tile.
  * A: [rows][64] bf16, B: [16][64] bf16, D: [128][16] f32 with D[r][n] = sum_k A[shift + (r/8)*group_rows + r%8][k] * B[n][k] */
 int b200_probe_umma_rowshift(const void* A, int rows, const void* B, int shift, int group_rows, float* D, b200_stream_t s);
+/* hardware probe: cycles to issue / complete iters*4 tcgen05.mma (M=128,N,K=16) spread over n_acc accumulators;
+ * out[0] = issue cycles, out[1] = cycles until all completed */
+/* test tooling: per-CTA wait-cycle counters of the halo kernel (8 x int64 per CTA); NULL disables */
+int b200_set_debug_buffer(void* buf);
+int b200_probe_umma_issue(int N, int n_acc, int iters, long long* out, b200_stream_t s);
 
 #ifdef __cplusplus
 }

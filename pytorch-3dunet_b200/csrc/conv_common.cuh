@@ -35,6 +35,7 @@ struct ConvParams {
   int a_stages;        // halo stages of KC channels each
   int b_total_bytes;   // resident weights [Cin/KCb][27][NT][KCb]
   int ctas_per_sample;
+  long long* dbg;      // optional per-CTA wait-cycle counters (b200_set_debug_buffer), NULL in production
 };
 
 // one 32-/16-column slab of the accumulator tile for one thread (= one output voxel row)
@@ -55,7 +56,7 @@ __device__ __forceinline__ void conv_epilogue_slab(const ConvParams& p, uint32_t
       const float4* bp = reinterpret_cast<const float4*>(bias_row + n0 + c0);
 #pragma unroll
       for (int i = 0; i < CW / 4; ++i) {
-        float4 b = __ldg(bp + i);
+        float4 b = bp[i];  // generic load: bias_row may live in shared memory (halo kernel) or global
         v[4 * i] += b.x;
         v[4 * i + 1] += b.y;
         v[4 * i + 2] += b.z;

@@ -21,8 +21,9 @@ namespace b200 {
 constexpr int HALO_BH = 16, HALO_BW = 8;
 constexpr int HALO_HD = 3, HALO_HH = HALO_BH + 2, HALO_HW = HALO_BW + 2;
 constexpr int HALO_ROWS = HALO_HD * HALO_HH * HALO_HW;  // 540
+constexpr int HALO_THREADS = 64 + 2 * 128;  // producer warp, MMA warp, two epilogue warpgroups (even / odd tiles)
 
-__global__ void __launch_bounds__(CONV_THREADS, 1)
+__global__ void __launch_bounds__(HALO_THREADS, 1)
 conv3_halo_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, const ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[HALO_MAX_STAGES], a_empty[HALO_MAX_STAGES];
@@ -33,7 +34,8 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
   uint8_t* smemB = smem;
   const int b_region = (p.b_total_bytes + 1023) & ~1023;
   uint8_t* smemA = smem + b_region;
-  float* scratch_base = reinterpret_cast<float*>(smemA + (size_t)p.a_stages * p.a_bytes);  // [2][4][NT][2]
+  float* scratch_base = reinterpret_cast<float*>(smemA + (size_t)p.a_stages * p.a_bytes);  // [2 groups][2 alternating][4 warps][NT][2]
+  float* bias_interior = scratch_base + 4 * 4 * p.NT * 2;                                    // [NT]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = blockIdx.y, cta = blockIdx.x, cps = gridDim.x;
   const int tiles = p.tilesD * p.tilesH * p.tilesW;
@@ -57,6 +59,10 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     tma_prefetch_desc(&tmapB);
   }
   if (warp == 1) tmem_alloc(&tmem_slot, (uint32_t)p.tmem_cols);
+  constexpr int kInteriorCls = (1 << 4) | (1 << 2) | 1;
+  if (p.n_b)
+    for (int i = threadIdx.x; i < p.NT; i += HALO_THREADS)
+      bias_interior[i] = p.biascls[((size_t)(p.n_b > 1 ? n : 0) * 64 + kInteriorCls) * p.Cout + i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -71,6 +77,7 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       for (int cb = 0; cb < nchunksB; ++cb)
         tma_load_3d(smemB + (size_t)cb * 27 * p.NT * rbB, &tmapB, &b_full, cb * p.KCb, 0, wsample * 27);
       int it = 0;
+      long long w_prod = 0, t_begin = clock64();
       for (int t = cta; t < tiles; t += cps) {
         const int tw_i = t % p.tilesW;
         const int r = t / p.tilesW;
@@ -78,10 +85,17 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
         const int h0 = th_i * HALO_BH, w0 = tw_i * HALO_BW;
         for (int j = 0; j < nchunksA; ++j, ++it) {
           const int stage = it % p.a_stages;
+          long long c0 = clock64();
           mbar_wait(&a_empty[stage], ((uint32_t)(it / p.a_stages) & 1u) ^ 1u);
+          w_prod += clock64() - c0;
           mbar_arrive_expect_tx(&a_full[stage], (uint32_t)(HALO_ROWS * rbA));
           tma_load_5d(smemA + (size_t)stage * p.a_bytes, &tmapA, &a_full[stage], j * p.KC, w0 - 1, h0 - 1, d0 - 1, n);
         }
+      }
+      if (p.dbg) {
+        long long* o = p.dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8;
+        o[0] = w_prod;
+        o[1] = clock64() - t_begin;
       }
     }
   } else if (warp == 1) {
@@ -89,46 +103,76 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(128, p.NT, 0, 0);
       const uint32_t layA = umma_layout_for_row_bytes(rbA), layB = umma_layout_for_row_bytes(rbB);
-      const uint32_t sboA = (uint32_t)(HALO_HW * rbA), sboB = (uint32_t)(8 * rbB);
+      // descriptors = constant high word (SBO, version, layout) + low word (start address >> 4 | LBO): only the low
+      // word changes inside the loop, by plain adds -- the single issuing thread must stay far below the ~56-cycle
+      // dispatch floor of tcgen05.mma (measured, tools/probe_umma_issue.py), so no divisions / rebuilds in here.
+      const uint64_t hiA = umma_smem_desc(0, 16u, (uint32_t)(HALO_HW * rbA), layA) & 0xFFFFFFFF00000000ull;
+      const uint64_t hiB = umma_smem_desc(0, 16u, (uint32_t)(8 * rbB), layB) & 0xFFFFFFFF00000000ull;
+      const uint32_t lo_lbo = 1u << 16;
       const uint32_t sB0 = smem_u32(smemB);
+      const uint32_t a_row = (uint32_t)rbA >> 4;                    // one halo row, in 16-byte units
+      const uint32_t a_line = (uint32_t)(HALO_HW * rbA) >> 4;       // one halo line (dh)
+      const uint32_t a_slice = (uint32_t)(HALO_HH * HALO_HW * rbA) >> 4;  // one halo slice (dd)
+      const uint32_t b_tap = (uint32_t)(p.NT * rbB) >> 4;           // one tap of the resident weights
+      const int ksteps = p.KC / 16;
       mbar_wait(&b_full, 0);
       int it = 0, lt = 0;
+      long long w_afull = 0, w_tempty = 0, t_begin = clock64();
       for (int t = cta; t < tiles; t += cps, ++lt) {
         const int buf = lt & 1;
+        long long c0 = clock64();
         mbar_wait(&tmem_empty[buf], ((uint32_t)(lt >> 1) & 1u) ^ 1u);
+        w_tempty += clock64() - c0;
         tc_fence_after();
         const uint32_t tacc = tmem_base + (uint32_t)(buf * p.NT);
+        uint32_t accum = 0;
         for (int j = 0; j < nchunksA; ++j, ++it) {
           const int stage = it % p.a_stages;
+          long long c1 = clock64();
           mbar_wait(&a_full[stage], (uint32_t)(it / p.a_stages) & 1u);
+          w_afull += clock64() - c1;
           tc_fence_after();
-          const uint32_t sA = smem_u32(smemA + (size_t)stage * p.a_bytes);
-          for (int tap = 0; tap < 27; ++tap) {
-            const int td = tap / 9, th = (tap / 3) % 3, tw = tap % 3;
-            const uint32_t a_tap = sA + (uint32_t)(((td * HALO_HH + th) * HALO_HW + tw) * rbA);
-            for (int k = 0; k < p.KC / 16; ++k) {
-              const int ch = j * p.KC + k * 16;  // first input channel of this K=16 slice
-              const int cb = ch / p.KCb, koff = (ch % p.KCb) * 2;
-              const uint32_t b_addr = sB0 + (uint32_t)((cb * 27 + tap) * p.NT * rbB + koff);
-              const uint64_t adesc = umma_smem_desc(a_tap + (uint32_t)(k * 32), 16u, sboA, layA);
-              const uint64_t bdesc = umma_smem_desc(b_addr, 16u, sboB, layB);
-              umma_bf16(tacc, adesc, bdesc, idesc, (j | tap | k) != 0 ? 1u : 0u);
+          const int ch0 = j * p.KC;
+          const uint32_t a_lo0 = ((smem_u32(smemA + (size_t)stage * p.a_bytes) >> 4) & 0x3FFFu) | lo_lbo;
+          uint32_t b_lo = (((sB0 + (uint32_t)((ch0 / p.KCb) * 27 * p.NT * rbB + (ch0 % p.KCb) * 2)) >> 4) & 0x3FFFu) | lo_lbo;
+          uint32_t a_d = a_lo0;
+#pragma unroll 1
+          for (int td = 0; td < 3; ++td, a_d += a_slice) {
+            uint32_t a_h = a_d;
+#pragma unroll 1
+            for (int th = 0; th < 3; ++th, a_h += a_line) {
+              uint32_t a_w = a_h;
+#pragma unroll
+              for (int tw = 0; tw < 3; ++tw, a_w += a_row, b_lo += b_tap) {
+                for (int k = 0; k < ksteps; ++k) {
+                  umma_bf16(tacc, hiA | (uint64_t)(a_w + 2u * k), hiB | (uint64_t)(b_lo + 2u * k), idesc, accum);
+                  accum = 1u;
+                }
+              }
             }
           }
           umma_commit(&a_empty[stage]);
         }
         umma_commit(&tmem_full[buf]);
       }
+      if (p.dbg) {
+        long long* o = p.dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8;
+        o[2] = w_afull;
+        o[3] = w_tempty;
+        o[4] = clock64() - t_begin;
+      }
     }
   } else {
-    // ================= epilogue (warps 2..5) =================
+    // ================= epilogue: warps 2..5 take even tiles (TMEM buffer 0), warps 6..9 odd tiles (buffer 1) =========
     const int q = warp & 3;
+    const int grp = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const int bx = row % HALO_BW, by = row / HALO_BW;
     const int n0 = 0;
-    int lt = 0;
-    for (int t = cta; t < tiles; t += cps, ++lt) {
-      const int buf = lt & 1;
+    int lt = grp;
+    long long w_tfull = 0, t_begin = clock64();
+    for (int t = cta + grp * cps; t < tiles; t += 2 * cps, lt += 2) {
+      const int buf = grp;
       const int tw_i = t % p.tilesW;
       const int r = t / p.tilesW;
       const int th_i = r % p.tilesH, xd = r / p.tilesH;
@@ -138,12 +182,14 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       const float* bias_row = nullptr;
       if (p.n_b && valid) {
         const int cls = (axis_cls(xd, p.D) << 4) | (axis_cls(xh, p.H) << 2) | axis_cls(xw, p.W);
-        bias_row = p.biascls + ((size_t)(p.n_b > 1 ? n : 0) * 64 + cls) * p.Cout;
+        bias_row = cls == kInteriorCls ? bias_interior : p.biascls + ((size_t)(p.n_b > 1 ? n : 0) * 64 + cls) * p.Cout;
       }
+      long long cw = clock64();
       mbar_wait(&tmem_full[buf], (uint32_t)(lt >> 1) & 1u);
+      w_tfull += clock64() - cw;
       __syncwarp();
       tc_fence_after();
-      float* scratch_tile = scratch_base + (size_t)buf * 4 * p.NT * 2;
+      float* scratch_tile = scratch_base + (size_t)(grp * 2 + ((lt >> 1) & 1)) * 4 * p.NT * 2;  // alternate: see bar.sync below
       float* scratch = scratch_tile + (size_t)q * p.NT * 2;
       const uint32_t taddr = tmem_base + (uint32_t)(buf * p.NT) + ((uint32_t)(q * 32) << 16);
       int c0 = 0;
@@ -154,12 +200,19 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[buf]);
       if (p.pmode) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // the 4 epilogue warps only
-        const int et = threadIdx.x - 64;
+        if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");  // the 4 warps of this epilogue group only
+        else asm volatile("bar.sync 2, 128;" ::: "memory");
+        const int et = (threadIdx.x - 64) & 127;
         float* out = p.partials + (((size_t)n * tiles + t) * p.Cout + n0) * 2;
         for (int i = et; i < p.NT * 2; i += 128)
           out[i] = scratch_tile[i] + scratch_tile[p.NT * 2 + i] + scratch_tile[p.NT * 4 + i] + scratch_tile[p.NT * 6 + i];
       }
+    }
+    if (p.dbg && threadIdx.x == 64) {  // group 0 only
+      long long* o = p.dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8;
+      o[5] = w_tfull;
+      o[6] = clock64() - t_begin;
+      o[7] = (tiles - cta + cps - 1) / cps;
     }
   }
   __syncthreads();
@@ -186,7 +239,7 @@ bool conv_halo_plan(int N, int D, int H, int W, int Cin, int Cout, ConvParams* p
   if (dis && dis[0] == '1') return false;
   const int budget = 222 * 1024;
   const int b_total = 27 * Cout * Cin * 2;
-  const int scratch = 2 * 4 * Cout * 2 * (int)sizeof(float);
+  const int scratch = (4 * 4 * Cout * 2 + Cout) * (int)sizeof(float);
   int kca = 0, stages = 0, a_bytes = 0;
   for (int kc = 64; kc >= 16; kc >>= 1) {
     if (Cin % kc != 0) continue;
@@ -224,19 +277,28 @@ bool conv_halo_plan(int N, int D, int H, int W, int Cin, int Cout, ConvParams* p
   return true;
 }
 
+static long long* g_dbg = nullptr;
+void set_debug_buffer(long long* p) { g_dbg = p; }
+
 int conv_halo_launch(const void* x, const void* wf, ConvParams& p, cudaStream_t s) {
+  p.dbg = g_dbg;
   CUtensorMap tmA, tmB;
   int rc = make_act_tmap(&tmA, x, p.N, p.D, p.H, p.W, p.Cin, p.KC, HALO_HD, HALO_HH, HALO_HW);
   if (rc) return rc;
   rc = make_w_tmap(&tmB, wf, 27 * p.n_w, p.Cout, p.Cin, p.KCb, p.NT, 27);
   if (rc) return rc;
-  size_t smem = (size_t)((p.b_total_bytes + 1023) & ~1023) + (size_t)p.a_stages * p.a_bytes + (size_t)2 * 4 * p.NT * 2 * sizeof(float) + 1024;
+  size_t smem = (size_t)((p.b_total_bytes + 1023) & ~1023) + (size_t)p.a_stages * p.a_bytes + (size_t)(4 * 4 * p.NT * 2 + p.NT) * sizeof(float) + 1024;
   cudaError_t e = cudaFuncSetAttribute(conv3_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   B200_CHECK_ARG(e == cudaSuccess, "conv3_halo: cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e));
   dim3 grid((unsigned)p.ctas_per_sample, (unsigned)p.N);
-  conv3_halo_kernel<<<grid, CONV_THREADS, smem, s>>>(tmA, tmB, p);
+  conv3_halo_kernel<<<grid, HALO_THREADS, smem, s>>>(tmA, tmB, p);
   B200_CHECK_LAUNCH("conv3_halo");
   return 0;
 }
 
 }  // namespace b200
+
+extern "C" int b200_set_debug_buffer(void* buf) {
+  b200::set_debug_buffer(reinterpret_cast<long long*>(buf));
+  return 0;
+}

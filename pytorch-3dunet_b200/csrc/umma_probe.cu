@@ -96,3 +96,67 @@ extern "C" int b200_probe_umma_rowshift(const void* A, int rows, const void* B, 
   B200_CHECK_LAUNCH("umma_probe");
   return 0;
 }
+
+// ---- probe 2: tcgen05.mma issue/accumulate throughput -----------------------------------------------------------
+// cycles per MMA (M=128, N, K=16, bf16) when `iters*4` MMAs are spread round-robin over `n_acc` independent
+// accumulators (TMEM column ranges).  n_acc=1 exposes the latency of the accumulate dependency chain.
+namespace b200 {
+__global__ void __launch_bounds__(128) umma_issue_probe_kernel(int N, int n_acc, int iters, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t done_bar;
+  __shared__ uint32_t tmem_slot;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;               // 128 x 128 B
+  uint8_t* sB = smem + 16384;       // N x 128 B
+  for (int i = threadIdx.x; i < (16384 + N * 128) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    mbar_init(&done_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, 512);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = umma_idesc_bf16(128, N, 0, 0);
+    uint64_t ad[4], bd[4];
+    for (int k = 0; k < 4; ++k) {
+      ad[k] = umma_smem_desc(smem_u32(sA) + k * 32, 16u, 1024u, UMMA_LAYOUT_SW128);
+      bd[k] = umma_smem_desc(smem_u32(sB) + k * 32, 16u, 1024u, UMMA_LAYOUT_SW128);
+    }
+    long long t0 = clock64();
+    int a = 0;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        umma_bf16(tmem_base + (uint32_t)(a * N), ad[k], bd[k], idesc, 1u);
+        a = (a + 1 == n_acc) ? 0 : a + 1;
+      }
+    }
+    long long t1 = clock64();
+    umma_commit(&done_bar);
+    mbar_wait(&done_bar, 0);
+    long long t2 = clock64();
+    out[0] = t1 - t0;  // issue time
+    out[1] = t2 - t0;  // until all complete
+  }
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+}  // namespace b200
+
+extern "C" int b200_probe_umma_issue(int N, int n_acc, int iters, long long* out, b200_stream_t s) {
+  B200_CHECK_ARG(N % 16 == 0 && N >= 16 && N <= 256 && n_acc >= 1 && n_acc * N <= 512, "probe: bad N=%d n_acc=%d", N, n_acc);
+  size_t smem = 16384 + (size_t)N * 128 + 2048;
+  cudaFuncSetAttribute(umma_issue_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  umma_issue_probe_kernel<<<1, 128, smem, (cudaStream_t)s>>>(N, n_acc, iters, out);
+  B200_CHECK_LAUNCH("umma_issue_probe");
+  return 0;
+}
