@@ -171,9 +171,11 @@ int b200_conv3_wgrad_igemm(const void* x, const void* dz, int N, int D, int H, i
 int b200_probe_umma_rowshift(const void* A, int rows, const void* B, int shift, int group_rows, float* D, b200_stream_t s);
 /* hardware probe: cycles to issue / complete iters*4 tcgen05.mma (M=128,N,K=16) spread over n_acc accumulators;
  * out[0] = issue cycles, out[1] = cycles until all completed */
+/* hardware probe: cycles for ld_iters tcgen05.ld (4 warps, 32 columns each) while mma_iters*4 MMAs (N columns) run; out[0] ld cycles, out[1] mma cycles */
+int b200_probe_tmem_ld_contention(int N, int mma_iters, int ld_iters, long long* out, b200_stream_t s);
 /* test tooling: per-CTA wait-cycle counters of the halo kernel (8 x int64 per CTA); NULL disables */
 int b200_set_debug_buffer(void* buf);
-int b200_probe_umma_issue(int N, int n_acc, int iters, long long* out, b200_stream_t s);
+int b200_probe_umma_issue(int N, int n_acc, int iters, int rb, int group_rows, int shift, long long* out, b200_stream_t s);
 
 #ifdef __cplusplus
 }

@@ -30,22 +30,32 @@ void set_error(const char* fmt, ...);
 
 typedef __nv_bfloat16 bf16;
 
+// 8 bf16 = one 16-byte vector.  Held as a uint4 so that every copy / dereference is ONE 128-bit load or store
+// (a struct of four __nv_bfloat162 members is copied member-wise: four 32-bit accesses).
 struct alignas(16) bf16x8 {
-  __nv_bfloat162 v[4];
+  uint4 u;
 };
 
 __device__ __forceinline__ void unpack8(const bf16x8& p, float f[8]) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float2 t = __bfloat1622float2(p.v[i]);
-    f[2 * i] = t.x;
-    f[2 * i + 1] = t.y;
-  }
+  f[0] = __uint_as_float(p.u.x << 16);
+  f[1] = __uint_as_float(p.u.x & 0xffff0000u);
+  f[2] = __uint_as_float(p.u.y << 16);
+  f[3] = __uint_as_float(p.u.y & 0xffff0000u);
+  f[4] = __uint_as_float(p.u.z << 16);
+  f[5] = __uint_as_float(p.u.z & 0xffff0000u);
+  f[6] = __uint_as_float(p.u.w << 16);
+  f[7] = __uint_as_float(p.u.w & 0xffff0000u);
+}
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);  // .x (low half) = lo
+  return *reinterpret_cast<uint32_t*>(&t);
 }
 __device__ __forceinline__ bf16x8 pack8(const float f[8]) {
   bf16x8 p;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  p.u.x = pack2(f[0], f[1]);
+  p.u.y = pack2(f[2], f[3]);
+  p.u.z = pack2(f[4], f[5]);
+  p.u.w = pack2(f[6], f[7]);
   return p;
 }
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }

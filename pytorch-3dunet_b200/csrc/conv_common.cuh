@@ -42,11 +42,13 @@ struct ConvParams {
 template <int CW>
 __device__ __forceinline__ void conv_epilogue_slab(const ConvParams& p, uint32_t taddr, int c0 /*col in tile*/, int n0, bool valid,
                                                    size_t vox_off /* (n*vox+v) */, const float* bias_row /* or null */, int lane,
-                                                   float* scratch /* [NT][2] for this warp */) {
+                                                   float* scratch /* [NT][2] for this warp */, long long* tim = nullptr) {
   uint32_t raw[CW];
+  long long t0 = tim ? clock64() : 0;
   if constexpr (CW == 32) tmem_ld_32x32b_x32(taddr + c0, raw);
   else tmem_ld_32x32b_x16(taddr + c0, raw);
   tmem_ld_wait();
+  long long t1 = tim ? clock64() : 0;
   float v[CW];
 #pragma unroll
   for (int i = 0; i < CW; ++i) v[i] = __uint_as_float(raw[i]);
@@ -82,6 +84,7 @@ __device__ __forceinline__ void conv_epilogue_slab(const ConvParams& p, uint32_t
 #pragma unroll
     for (int i = 0; i < CW; ++i) v[i] = 0.f;
   }
+  long long t2 = tim ? clock64() : 0;
   if (p.pmode) {
     float w[CW];
     if (p.pmode == 1) {
@@ -108,6 +111,12 @@ __device__ __forceinline__ void conv_epilogue_slab(const ConvParams& p, uint32_t
       scratch[(c0 + lane) * 2] = s;
       scratch[(c0 + lane) * 2 + 1] = q;
     }
+  }
+  if (tim) {
+    long long t3 = clock64();
+    tim[0] += t1 - t0;
+    tim[1] += t2 - t1;
+    tim[2] += t3 - t2;
   }
 }
 

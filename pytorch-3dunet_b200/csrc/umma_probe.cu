@@ -101,14 +101,14 @@ extern "C" int b200_probe_umma_rowshift(const void* A, int rows, const void* B, 
 // cycles per MMA (M=128, N, K=16, bf16) when `iters*4` MMAs are spread round-robin over `n_acc` independent
 // accumulators (TMEM column ranges).  n_acc=1 exposes the latency of the accumulate dependency chain.
 namespace b200 {
-__global__ void __launch_bounds__(128) umma_issue_probe_kernel(int N, int n_acc, int iters, long long* out) {
+__global__ void __launch_bounds__(128) umma_issue_probe_kernel(int N, int n_acc, int iters, int rb, int group_rows, int shift, long long* out) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t done_bar;
   __shared__ uint32_t tmem_slot;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* sA = smem;               // 128 x 128 B
-  uint8_t* sB = smem + 16384;       // N x 128 B
-  for (int i = threadIdx.x; i < (16384 + N * 128) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  uint8_t* sA = smem;               // up to 256 rows x 128 B
+  uint8_t* sB = smem + 32768;       // N x 128 B
+  for (int i = threadIdx.x; i < (32768 + N * 128) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
     mbar_init(&done_bar, 1);
@@ -123,9 +123,11 @@ __global__ void __launch_bounds__(128) umma_issue_probe_kernel(int N, int n_acc,
   if (threadIdx.x == 0) {
     const uint32_t idesc = umma_idesc_bf16(128, N, 0, 0);
     uint64_t ad[4], bd[4];
+    const uint32_t lay = umma_layout_for_row_bytes(rb);
+    const int ksl = rb / 32;  // K=16 slices available per row
     for (int k = 0; k < 4; ++k) {
-      ad[k] = umma_smem_desc(smem_u32(sA) + k * 32, 16u, 1024u, UMMA_LAYOUT_SW128);
-      bd[k] = umma_smem_desc(smem_u32(sB) + k * 32, 16u, 1024u, UMMA_LAYOUT_SW128);
+      ad[k] = umma_smem_desc(smem_u32(sA) + shift * rb + (k % ksl) * 32, 16u, (uint32_t)(group_rows * rb), lay);
+      bd[k] = umma_smem_desc(smem_u32(sB) + (k % ksl) * 32, 16u, (uint32_t)(8 * rb), lay);
     }
     long long t0 = clock64();
     int a = 0;
@@ -152,11 +154,85 @@ __global__ void __launch_bounds__(128) umma_issue_probe_kernel(int N, int n_acc,
 }
 }  // namespace b200
 
-extern "C" int b200_probe_umma_issue(int N, int n_acc, int iters, long long* out, b200_stream_t s) {
+extern "C" int b200_probe_umma_issue(int N, int n_acc, int iters, int rb, int group_rows, int shift, long long* out, b200_stream_t s) {
   B200_CHECK_ARG(N % 16 == 0 && N >= 16 && N <= 256 && n_acc >= 1 && n_acc * N <= 512, "probe: bad N=%d n_acc=%d", N, n_acc);
-  size_t smem = 16384 + (size_t)N * 128 + 2048;
+  B200_CHECK_ARG((rb == 32 || rb == 64 || rb == 128) && (shift + 15 * group_rows + 8) * rb <= 32768, "probe: bad view");
+  size_t smem = 32768 + (size_t)N * 128 + 2048;
   cudaFuncSetAttribute(umma_issue_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  umma_issue_probe_kernel<<<1, 128, smem, (cudaStream_t)s>>>(N, n_acc, iters, out);
+  umma_issue_probe_kernel<<<1, 128, smem, (cudaStream_t)s>>>(N, n_acc, iters, rb, group_rows, shift, out);
   B200_CHECK_LAUNCH("umma_issue_probe");
+  return 0;
+}
+
+// ---- probe 3: does a stream of tcgen05.mma starve tcgen05.ld of another TMEM column range? ----------------------
+// warp 0 (one lane) issues `mma_iters*4` MMAs (N columns at column 0); warps 4..7 time `ld_iters` x (tcgen05.ld 32x32b.x32 +
+// wait) of columns [256, 288).  out[0] = cycles per ld with the MMA stream running (mma_iters > 0) or idle (mma_iters == 0).
+namespace b200 {
+__global__ void __launch_bounds__(256) tmem_ld_contention_kernel(int N, int mma_iters, int ld_iters, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t done_bar;
+  __shared__ uint32_t tmem_slot;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + 16384;
+  for (int i = threadIdx.x; i < (16384 + N * 128) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(&done_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, 512);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  if (warp == 0) {
+    if (lane == 0 && mma_iters > 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, N, 0, 0);
+      uint64_t ad[4], bd[4];
+      for (int k = 0; k < 4; ++k) {
+        ad[k] = umma_smem_desc(smem_u32(sA) + k * 32, 16u, 1024u, UMMA_LAYOUT_SW128);
+        bd[k] = umma_smem_desc(smem_u32(sB) + k * 32, 16u, 1024u, UMMA_LAYOUT_SW128);
+      }
+      long long t0 = clock64();
+      for (int it = 0; it < mma_iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, ad[k], bd[k], idesc, 1u);
+      }
+      umma_commit(&done_bar);
+      mbar_wait(&done_bar, 0);
+      out[1] = (clock64() - t0);
+    }
+  } else if (warp >= 4) {
+    const uint32_t taddr = tmem_base + 256 + ((uint32_t)((warp & 3) * 32) << 16);
+    uint32_t raw[32];
+    float acc = 0.f;
+    __syncwarp();
+    long long t0 = clock64();
+    for (int i = 0; i < ld_iters; ++i) {
+      tmem_ld_32x32b_x32(taddr, raw);
+      tmem_ld_wait();
+      acc += __uint_as_float(raw[i & 31]);
+    }
+    long long t1 = clock64();
+    if (threadIdx.x == 128) out[0] = t1 - t0;
+    if (acc == 123.456f) out[2] = 1;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+}  // namespace b200
+
+extern "C" int b200_probe_tmem_ld_contention(int N, int mma_iters, int ld_iters, long long* out, b200_stream_t s) {
+  size_t smem = 16384 + (size_t)N * 128 + 2048;
+  cudaFuncSetAttribute(b200::tmem_ld_contention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  b200::tmem_ld_contention_kernel<<<1, 256, smem, (cudaStream_t)s>>>(N, mma_iters, ld_iters, out);
+  B200_CHECK_LAUNCH("tmem_ld_contention");
   return 0;
 }
