@@ -20,6 +20,8 @@ namespace b200 {
 
 int make_act_tmap(CUtensorMap* tm, const void* ptr, int N, int D, int H, int W, int C, int kc, int bd, int bh, int bw);
 int choose_box(int D, int H, int W, int* bd, int* bh, int* bw);
+int wgrad_halo_splits(int N, int D, int H, int W, int Cin, int Cout);
+int wgrad_halo_run(const void* x, const void* dz, int N, int D, int H, int W, int Cin, int Cout, float* G, cudaStream_t s);
 
 constexpr int WG_THREADS = 192;
 constexpr int WG_MAX_A_STAGES = 8;
@@ -237,6 +239,8 @@ int b200_conv3_wgrad_igemm_supported(int N, int D, int H, int W, int Cin, int Co
 
 int b200_conv3_wgrad_igemm_splits(int N, int D, int H, int W, int Cin, int Cout) {
   if (!wgrad_supported(N, D, H, W, Cin, Cout)) return 0;
+  int hs = wgrad_halo_splits(N, D, H, W, Cin, Cout);
+  if (hs > 0) return hs;
   WgradParams p;
   wgrad_plan(N, D, H, W, Cin, Cout, p);
   return p.S;
@@ -245,6 +249,7 @@ int b200_conv3_wgrad_igemm_splits(int N, int D, int H, int W, int Cin, int Cout)
 int b200_conv3_wgrad_igemm(const void* x, const void* dz, int N, int D, int H, int W, int Cin, int Cout, float* G, b200_stream_t s) {
   B200_CHECK_ARG(wgrad_supported(N, D, H, W, Cin, Cout), "conv3_wgrad_igemm: unsupported shape N=%d D=%d H=%d W=%d Cin=%d Cout=%d", N,
                  D, H, W, Cin, Cout);
+  if (wgrad_halo_splits(N, D, H, W, Cin, Cout) > 0) return wgrad_halo_run(x, dz, N, D, H, W, Cin, Cout, G, (cudaStream_t)s);
   WgradParams p;
   wgrad_plan(N, D, H, W, Cin, Cout, p);
   p.G = G;

@@ -84,7 +84,10 @@ def test_tcgen05_conv_residual_no_bias_shared_weights():
 
 
 WG_SHAPES = [(1, 8, 8, 8, 16, 32), (2, 8, 8, 8, 32, 32), (1, 8, 8, 8, 64, 64), (1, 4, 8, 8, 96, 32), (1, 8, 8, 8, 128, 128),
-             (1, 4, 8, 8, 192, 64), (1, 4, 4, 8, 384, 128), (1, 4, 4, 8, 128, 256), (1, 5, 9, 7, 32, 16), (1, 16, 16, 16, 32, 32)]
+             (1, 4, 8, 8, 192, 64), (1, 4, 4, 8, 384, 128), (1, 4, 4, 8, 128, 256), (1, 5, 9, 7, 32, 16), (1, 16, 16, 16, 32, 32),
+             # large enough for the halo / stacked-tap wgrad kernel (D>=3, H>=18, W>=10)
+             (2, 3, 18, 10, 16, 32), (1, 4, 20, 12, 32, 32), (1, 5, 33, 17, 96, 32), (1, 4, 32, 16, 32, 96), (1, 4, 20, 12, 64, 64),
+             (1, 3, 18, 10, 128, 128), (1, 3, 20, 10, 32, 256), (2, 6, 24, 24, 32, 16)]
 
 
 @pytest.mark.parametrize("shape", WG_SHAPES)
