@@ -226,57 +226,102 @@ __global__ void __launch_bounds__(256, 2) stem_conv_fwd_kernel(const float* __re
   }
 }
 
-// stem weight gradient: G[n][0][tap][ci][co] += sum_{v in chunk} dz[v,co] * x[v+tap-1,ci]   (fp32 x, C_in <= 4)
-// thread = (co, voxel lane); 27 register accumulators per input channel; block reduce, one atomicAdd per output.
-constexpr int STEM_WG_CHUNK = 4096;
+// stem weight gradient: G[n][0][tap][ci][co] += sum_v dz[v,co] * x[v+tap-1,ci]   (fp32 x, C_in <= 4).
+// Shared-memory tiled: a block walks tiles of 2x8x32 voxels; per tile the fp32 x halo (4x10x34) and the dz tile (as fp32)
+// are staged in shared memory; a thread owns one (dd,dh) tap row x 8 output channels = 24 accumulators (3 dw taps) and
+// strides over the tile's voxels: 2 LDS.128 + 3 LDS per 24 FMA.  One block-level reduction + atomicAdd at the very end.
+constexpr int SW_TD = 2, SW_TH = 8, SW_TW = 32, SW_VOX = SW_TD * SW_TH * SW_TW;
+constexpr int SW_HD = SW_TD + 2, SW_HH = SW_TH + 2, SW_HW = SW_TW + 2, SW_HALO = SW_HD * SW_HH * SW_HW;
 template <int COUT>
 __global__ void __launch_bounds__(256, 2) stem_wgrad_kernel(const float* __restrict__ x, const bf16* __restrict__ dz, int D, int H, int W, int Cin,
-                                                         float* __restrict__ G) {
-  __shared__ float red[256 / COUT][27][COUT + 1];
+                                                            int tiles_per_block, float* __restrict__ G) {
+  extern __shared__ float sm[];
+  float* xs = sm;                 // [SW_HALO]
+  float* dzs = sm + SW_HALO;  // [SW_VOX][COUT]
+  static_assert(SW_HALO % 4 == 0, "dz tile must stay 16-byte aligned");
+  constexpr int GROUPS = 9 * (COUT / 8);
+  constexpr int LANES = 256 / GROUPS;
   const int n = blockIdx.y;
+  const int tD = (D + SW_TD - 1) / SW_TD, tH = (H + SW_TH - 1) / SW_TH, tW = (W + SW_TW - 1) / SW_TW;
+  const int ntiles = tD * tH * tW;
+  const int t_begin = blockIdx.x * tiles_per_block;
+  const int t_end = min(ntiles, t_begin + tiles_per_block);
   const long long vox = (long long)D * H * W;
-  long long v0 = (long long)blockIdx.x * STEM_WG_CHUNK, v1 = v0 + STEM_WG_CHUNK;
-  if (v1 > vox) v1 = vox;
-  constexpr int VL = 256 / COUT;
-  const int co = threadIdx.x % COUT, vl = threadIdx.x / COUT;
-  const float* xn = x + (size_t)n * vox * Cin;
-  const bf16* dn = dz + (size_t)n * vox * COUT;
+  const int grp = threadIdx.x % GROUPS, lane = threadIdx.x / GROUPS;
+  const int oct = grp % (COUT / 8), trow = grp / (COUT / 8);  // output-channel octet, (dd,dh) tap row
+  const int tdd = trow / 3, tdh = trow % 3;
+  const bool active = lane < LANES;
   for (int ci = 0; ci < Cin; ++ci) {
-    float acc[27];
+    float acc[3][8];
 #pragma unroll
-    for (int t = 0; t < 27; ++t) acc[t] = 0.f;
-    for (long long v = v0 + vl; v < v1; v += VL) {
-      float g = __bfloat162float(dn[(size_t)v * COUT + co]);
-      int xw = (int)(v % W);
-      long long r = v / W;
-      int xh = (int)(r % H), xd = (int)(r / H);
+    for (int a = 0; a < 3; ++a)
 #pragma unroll
-      for (int td = 0; td < 3; ++td) {
-        int zd = xd + td - 1;
-        bool okd = zd >= 0 && zd < D;
+      for (int j = 0; j < 8; ++j) acc[a][j] = 0.f;
+    for (int t = t_begin; t < t_end; ++t) {
+      const int w0 = (t % tW) * SW_TW;
+      const int r = t / tW;
+      const int h0 = (r % tH) * SW_TH, d0 = (r / tH) * SW_TD;
+      __syncthreads();
+      for (int i = threadIdx.x; i < SW_HALO; i += 256) {
+        int hx = i % SW_HW, rr = i / SW_HW, hy = rr % SW_HH, hz = rr / SW_HH;
+        int gz = d0 + hz - 1, gy = h0 + hy - 1, gx = w0 + hx - 1;
+        float v = 0.f;
+        if (gz >= 0 && gz < D && gy >= 0 && gy < H && gx >= 0 && gx < W)
+          v = __ldg(x + ((size_t)n * vox + ((size_t)gz * H + gy) * W + gx) * Cin + ci);
+        xs[i] = v;
+      }
+      for (int i = threadIdx.x; i < SW_VOX * (COUT / 8); i += 256) {
+        int o8 = i % (COUT / 8), v = i / (COUT / 8);
+        int vx = v % SW_TW, vy = (v / SW_TW) % SW_TH, vz = v / (SW_TW * SW_TH);
+        int gz = d0 + vz, gy = h0 + vy, gx = w0 + vx;
+        float f[8];
+        if (gz < D && gy < H && gx < W) {
+          unpack8(*reinterpret_cast<const bf16x8*>(dz + ((size_t)n * vox + ((size_t)gz * H + gy) * W + gx) * COUT + o8 * 8), f);
+        } else {
 #pragma unroll
-        for (int th = 0; th < 3; ++th) {
-          int zh = xh + th - 1;
-          bool okh = okd && zh >= 0 && zh < H;
+          for (int j = 0; j < 8; ++j) f[j] = 0.f;
+        }
+        float4* dst = reinterpret_cast<float4*>(dzs + (size_t)v * COUT + o8 * 8);
+        dst[0] = make_float4(f[0], f[1], f[2], f[3]);
+        dst[1] = make_float4(f[4], f[5], f[6], f[7]);
+      }
+      __syncthreads();
+      if (active) {
+        for (int v = lane; v < SW_VOX; v += LANES) {
+          const int vx = v % SW_TW, vy = (v / SW_TW) % SW_TH, vz = v / (SW_TW * SW_TH);
+          const float* xp = xs + ((vz + tdd) * SW_HH + (vy + tdh)) * SW_HW + vx;
+          const float x0 = xp[0], x1 = xp[1], x2 = xp[2];
+          const float4* dp = reinterpret_cast<const float4*>(dzs + (size_t)v * COUT + oct * 8);
+          const float4 g0 = dp[0], g1 = dp[1];
+          const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
-          for (int tw = 0; tw < 3; ++tw) {
-            int zw = xw + tw - 1;
-            float xv = (okh && zw >= 0 && zw < W) ? __ldg(xn + (((size_t)zd * H + zh) * W + zw) * Cin + ci) : 0.f;
-            acc[(td * 3 + th) * 3 + tw] = fmaf(g, xv, acc[(td * 3 + th) * 3 + tw]);
+          for (int j = 0; j < 8; ++j) {
+            acc[0][j] = fmaf(x0, g[j], acc[0][j]);
+            acc[1][j] = fmaf(x1, g[j], acc[1][j]);
+            acc[2][j] = fmaf(x2, g[j], acc[2][j]);
           }
         }
       }
     }
-#pragma unroll
-    for (int t = 0; t < 27; ++t) red[vl][t][co] = acc[t];
+    // block reduction over the voxel lanes, then one atomic per output
     __syncthreads();
-    for (int i = threadIdx.x; i < 27 * COUT; i += 256) {
-      int t = i / COUT, c = i % COUT;
-      float a = 0.f;
-      for (int l = 0; l < VL; ++l) a += red[l][t][c];
-      atomicAdd(&G[(((size_t)n * 27 + t) * Cin + ci) * COUT + c], a);
+    float* red = dzs;  // [LANES][GROUPS][24]
+    if (active) {
+      float* rp = red + ((size_t)lane * GROUPS + grp) * 24;
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) rp[a * 8 + j] = acc[a][j];
     }
     __syncthreads();
+    for (int i = threadIdx.x; i < GROUPS * 24; i += 256) {
+      float sum = 0.f;
+      for (int l = 0; l < LANES; ++l) sum += red[(size_t)l * GROUPS * 24 + i];
+      const int g = i / 24, a = (i % 24) / 8, j = i % 8;
+      const int o8 = g % (COUT / 8), tr = g / (COUT / 8);
+      const int tap = tr * 3 + a;
+      atomicAdd(&G[(((size_t)n * 27 + tap) * Cin + ci) * COUT + o8 * 8 + j], sum);
+    }
   }
 }
 
@@ -331,10 +376,23 @@ int b200_conv3_direct_wgrad(const void* x, int x_is_f32, const void* dz, int N, 
   long long vox = (long long)D * H * W;
   int total = 27 * Cin * Cout;
   if (x_is_f32 && Cin <= 4 && (Cout == 8 || Cout == 16 || Cout == 32)) {
-    dim3 g2(ceil_div(vox, STEM_WG_CHUNK), N);
-    if (Cout == 8) stem_wgrad_kernel<8><<<g2, 256, 0, ST(s)>>>((const float*)x, (const bf16*)dz, D, H, W, Cin, G);
-    else if (Cout == 16) stem_wgrad_kernel<16><<<g2, 256, 0, ST(s)>>>((const float*)x, (const bf16*)dz, D, H, W, Cin, G);
-    else stem_wgrad_kernel<32><<<g2, 256, 0, ST(s)>>>((const float*)x, (const bf16*)dz, D, H, W, Cin, G);
+    int ntiles = ceil_div(D, SW_TD) * ceil_div(H, SW_TH) * ceil_div(W, SW_TW);
+    int tpb = ceil_div(ntiles, 4 * 148 / (N > 0 ? N : 1) > 0 ? 4 * 148 / N : 1);  // ~4 blocks per SM in total
+    if (tpb < 1) tpb = 1;
+    dim3 g2(ceil_div(ntiles, tpb), N);
+    size_t red_floats = (size_t)(256 / (9 * (Cout / 8))) * 9 * (Cout / 8) * 24;
+    size_t dz_floats = (size_t)SW_VOX * Cout;
+    size_t sm2 = (SW_HALO + (dz_floats > red_floats ? dz_floats : red_floats)) * sizeof(float);
+    if (Cout == 8) {
+      cudaFuncSetAttribute(stem_wgrad_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
+      stem_wgrad_kernel<8><<<g2, 256, sm2, ST(s)>>>((const float*)x, (const bf16*)dz, D, H, W, Cin, tpb, G);
+    } else if (Cout == 16) {
+      cudaFuncSetAttribute(stem_wgrad_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
+      stem_wgrad_kernel<16><<<g2, 256, sm2, ST(s)>>>((const float*)x, (const bf16*)dz, D, H, W, Cin, tpb, G);
+    } else {
+      cudaFuncSetAttribute(stem_wgrad_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
+      stem_wgrad_kernel<32><<<g2, 256, sm2, ST(s)>>>((const float*)x, (const bf16*)dz, D, H, W, Cin, tpb, G);
+    }
     B200_CHECK_LAUNCH("stem_wgrad");
     return 0;
   }

@@ -77,27 +77,28 @@ conv3_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_const
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
+    // ================= MMA issuer (whole warp converged, one elected lane issues) =================
+    {
       const uint32_t idesc = umma_idesc_bf16(128, p.NT, 0, 0);
       const int rb = p.KC * 2;
-      const uint32_t layout = umma_layout_for_row_bytes(rb);
-      const uint32_t sbo = 8u * (uint32_t)rb;
+      const uint64_t hi = umma_smem_desc(0, 16u, 8u * (uint32_t)rb, umma_layout_for_row_bytes(rb)) & 0xFFFFFFFF00000000ull;
+      const int ksteps = p.KC / 16;
+      uint32_t accum = 0;
       for (int kb = 0; kb < numK; ++kb) {
         const int stage = kb % p.stages;
         const uint32_t phase = (uint32_t)(kb / p.stages) & 1u;
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-        const uint32_t sb = sa + (uint32_t)p.a_bytes;
-        for (int k = 0; k < p.KC / 16; ++k) {
-          const uint64_t adesc = umma_smem_desc(sa + (uint32_t)k * 32u, 16u, sbo, layout);
-          const uint64_t bdesc = umma_smem_desc(sb + (uint32_t)k * 32u, 16u, sbo, layout);
-          umma_bf16(tmem_base, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+        const uint32_t a_lo = ((sa >> 4) & 0x3FFFu) | (1u << 16);
+        const uint32_t b_lo = (((sa + (uint32_t)p.a_bytes) >> 4) & 0x3FFFu) | (1u << 16);
+        for (int k = 0; k < ksteps; ++k) {
+          umma_bf16_elect(tmem_base, hi | (uint64_t)(a_lo + 2u * k), hi | (uint64_t)(b_lo + 2u * k), idesc, accum);
+          accum = 1u;
         }
-        umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+        umma_commit_elect(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
       }
-      umma_commit(&tmem_full_bar);  // accumulator complete
+      umma_commit_elect(&tmem_full_bar);  // accumulator complete
     }
   } else {
     // ================= epilogue (warps 2..5) =================

@@ -667,10 +667,13 @@ __global__ void border_class_sums_kernel(const bf16* __restrict__ dz, int D, int
   const int interior = (1 << 4) | (1 << 2) | 1;
   float acc[8] = {0};
   if (vl < VL) {
-    for (long long v = v0 + vl; v < v1; v += VL) {
-      int xw = (int)(v % W);
-      long long r = v / W;
-      int xh = (int)(r % H), xd = (int)(r / H);
+    // coordinates advance incrementally (one division per thread, not per voxel)
+    long long v = v0 + vl;
+    int xw = (int)(v % W);
+    long long r = v / W;
+    int xh = (int)(r % H), xd = (int)(r / H);
+    const int stepw = VL % W, steph = (VL / W) % H, stepd = VL / (W * H);
+    for (; v < v1; v += VL) {
       int cls = (axis_cls(xd, D) << 4) | (axis_cls(xh, H) << 2) | axis_cls(xw, W);
       float f[8];
       unpack8(*reinterpret_cast<const bf16x8*>(dz + ((size_t)n * vox + v) * C + c0 + cg * 8), f);
@@ -680,6 +683,17 @@ __global__ void border_class_sums_kernel(const bf16* __restrict__ dz, int D, int
       } else {
 #pragma unroll
         for (int i = 0; i < 8; ++i) atomicAdd(&bins[cls][cg * 8 + i], f[i]);
+      }
+      xw += stepw;
+      xh += steph;
+      xd += stepd;
+      if (xw >= W) {
+        xw -= W;
+        ++xh;
+      }
+      if (xh >= H) {
+        xh -= H;
+        ++xd;
       }
     }
 #pragma unroll

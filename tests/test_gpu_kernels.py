@@ -132,3 +132,24 @@ def test_probe_umma_row_shifted_swizzled_view(shift, group_rows):
     ref = A[idx].float() @ B.float().t()
     print("probe shift", shift, "group_rows", group_rows, "rel", U.rel_l2(D, ref))
     assert U.rel_l2(D, ref) < 1e-3
+
+
+@pytest.mark.parametrize("shape", [(2, 6, 9, 35, 1, 16), (1, 5, 8, 40, 2, 8), (1, 4, 17, 33, 1, 32), (1, 16, 16, 16, 3, 16)])
+def test_stem_kernels_fp32_input(shape):
+    """network stem: fp32 NDHWC input with C_in <= 4 (dedicated CUDA-core kernels, HBM-bound)"""
+    from tests import gpu_util as U
+    from pytorch3dunet_b200 import engine as E
+    N, D, H, W, Cin, Cout = shape
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.rand((N, D, H, W, Cin), device="cuda", generator=g)
+    wf = (torch.randn((N, 27, Cout, Cin), device="cuda", generator=g) * 0.2).bfloat16()
+    b = torch.randn((N, 64, Cout), device="cuda", generator=g) * 0.2
+    y, sums = U.run_conv3(E.IMPL_AUTO, x, wf, b, act=E.ACT_RELU, want_stats=True)
+    ref = U.conv3_contract_ref(x, wf, b, act=E.ACT_RELU)
+    assert U.rel_l2(y, ref) < 5e-3
+    yf = y.double()
+    assert U.rel_l2(sums[..., 0], yf.sum(dim=(1, 2, 3))) < 1e-4
+    assert U.rel_l2(sums[..., 1], (yf * yf).sum(dim=(1, 2, 3))) < 1e-4
+    dz = torch.randn((N, D, H, W, Cout), device="cuda", generator=g).bfloat16()
+    G = U.run_wgrad(E.IMPL_AUTO, x, dz)
+    assert U.rel_l2(G, U.wgrad_contract_ref(x, dz)) < 1e-4
