@@ -100,9 +100,10 @@ int b200_conv3_wgrad(int impl, const void* x, int x_is_f32, const void* dz,
  * scratch: b200_border_tap_sums_workspace(...) floats */
 int b200_border_tap_sums_workspace(int N, int D, int H, int W, int C);
 int b200_border_tap_sums(const void* dz, int N, int D, int H, int W, int C, float* T, float* scratch, b200_stream_t s);
-/* dW[co][ci][tap] = sum_n ( a[n][ci] * sum_split G + b[n][ci] * T[n][tap][co] ); ab == NULL -> a=1,b=0 */
+/* dW[co][ci][tap] = sum_n ( a[n][ci] * sum_split G + b[n][ci] * T[n][tap][co] ); ab == NULL -> a=1,b=0.
+ * Gsum (optional) [N][27][Cin][Cout] receives sum_split G for b200_gn_bwd_sums_from_wgrad (then called with S = 1) */
 int b200_wgrad_finalize(const float* G, int N, int S, int Cin, int Cout, const float* ab, const float* T,
-                        float* dW, b200_stream_t s);
+                        float* dW, float* Gsum, b200_stream_t s);
 /* bias gradient for convs that have one: db[co] = sum_{n,tap=center...}: simply sum_n,v dz = T[n][13][co] summed */
 int b200_bias_grad_from_T(const float* T, int N, int C, float* db, b200_stream_t s);
 

@@ -651,7 +651,10 @@ __global__ void upcat_bwd_kernel(const bf16* __restrict__ dcat, int C0, int C1, 
 // ------------------------------------------------------------------------------------------------
 // border tap sums: T[n][tap][c] = sum_{v : v+tap-1 in bounds} dz[n,v,c]
 // ------------------------------------------------------------------------------------------------
-// stage 1: class sums R partials [N][P][64][C]; grid (P, N, C/CC) ; interior class accumulated in registers
+// stage 1a: per-channel TOTAL sums of dz: stats_ndhwc_bf16_kernel (a branch-free streaming pass at HBM speed).
+// stage 1b: class sums of the BORDER voxels only (4-5 % of a 128^3 volume); the interior class is total - sum(border).
+// grid (P, N, C/BT_CC): a block owns a range of (d,h) lines; full lines when the line lies on a d/h face, else only its two
+// end voxels.  Partials Rp [N][P][64][C] (interior slot left 0).
 constexpr int BT_CC = 64;
 __global__ void border_class_sums_kernel(const bf16* __restrict__ dz, int D, int H, int W, int C, int P, float* __restrict__ Rp) {
   __shared__ float bins[64][BT_CC];
@@ -662,42 +665,26 @@ __global__ void border_class_sums_kernel(const bf16* __restrict__ dz, int D, int
   int cg = threadIdx.x % CG, vl = threadIdx.x / CG;
   for (int i = threadIdx.x; i < 64 * BT_CC; i += EW_THREADS) (&bins[0][0])[i] = 0.f;
   __syncthreads();
-  long long vox = (long long)D * H * W, v0, v1;
-  ew_range(vox, p, P, v0, v1);
-  const int interior = (1 << 4) | (1 << 2) | 1;
-  float acc[8] = {0};
+  const long long lines = (long long)D * H;
+  long long l0, l1;
+  ew_range(lines, p, P, l0, l1);
+  const long long vox = (long long)D * H * W;
   if (vl < VL) {
-    // coordinates advance incrementally (one division per thread, not per voxel)
-    long long v = v0 + vl;
-    int xw = (int)(v % W);
-    long long r = v / W;
-    int xh = (int)(r % H), xd = (int)(r / H);
-    const int stepw = VL % W, steph = (VL / W) % H, stepd = VL / (W * H);
-    for (; v < v1; v += VL) {
-      int cls = (axis_cls(xd, D) << 4) | (axis_cls(xh, H) << 2) | axis_cls(xw, W);
-      float f[8];
-      unpack8(*reinterpret_cast<const bf16x8*>(dz + ((size_t)n * vox + v) * C + c0 + cg * 8), f);
-      if (cls == interior) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] += f[i];
-      } else {
+    for (long long l = l0; l < l1; ++l) {
+      const int xh = (int)(l % H), xd = (int)(l / H);
+      const int cdh = (axis_cls(xd, D) << 4) | (axis_cls(xh, H) << 2);
+      const bool face = (cdh != ((1 << 4) | (1 << 2)));
+      // voxels of this line that are border voxels: all W (face line) or the two ends
+      const int cnt = face ? W : (W > 1 ? 2 : 1);
+      for (int k = vl; k < cnt; k += VL) {
+        const int xw = face ? k : (k == 0 ? 0 : W - 1);
+        const int cls = cdh | axis_cls(xw, W);
+        float f[8];
+        unpack8(*reinterpret_cast<const bf16x8*>(dz + ((size_t)n * vox + (size_t)l * W + xw) * C + c0 + cg * 8), f);
 #pragma unroll
         for (int i = 0; i < 8; ++i) atomicAdd(&bins[cls][cg * 8 + i], f[i]);
       }
-      xw += stepw;
-      xh += steph;
-      xd += stepd;
-      if (xw >= W) {
-        xw -= W;
-        ++xh;
-      }
-      if (xh >= H) {
-        xh -= H;
-        ++xd;
-      }
     }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) atomicAdd(&bins[interior][cg * 8 + i], acc[i]);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 64 * CC; i += EW_THREADS) {
@@ -705,23 +692,29 @@ __global__ void border_class_sums_kernel(const bf16* __restrict__ dz, int D, int
     Rp[(((size_t)n * P + p) * 64 + cls) * C + c0 + c] = bins[cls][c];
   }
 }
-// stage 2 (after the class sums were reduced over P by partials_finalize_kernel into R[n][cls][c], double):
-// T[n][tap][c] = sum_{cls: tap valid} R ; grid (ceil(27*C/256), N), block 256
-__global__ void border_tap_from_class_kernel(const double* __restrict__ R, int C, float* __restrict__ T) {
+// stage 2 (after the border class sums were reduced over P into R[n][cls][c] and the totals into tot[n][c][2], double):
+// T[n][tap][c] = sum_{cls: tap valid} R, with R[interior] = total - sum(border classes); grid (ceil(27*C/256), N), block 256
+__global__ void border_tap_from_class_kernel(const double* __restrict__ R, const double* __restrict__ tot, int C, float* __restrict__ T) {
   int n = blockIdx.y;
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= 27 * C) return;
   int tap = idx / C, c = idx % C;
   int td = tap / 9, th = (tap / 3) % 3, tw = tap % 3;
-  double acc = 0.0;
-  for (int cls = 0; cls < 64; ++cls)
-    if (tap_valid(cls >> 4, td) && tap_valid((cls >> 2) & 3, th) && tap_valid(cls & 3, tw)) acc += R[((size_t)n * 64 + cls) * C + c];
+  const int interior = (1 << 4) | (1 << 2) | 1;
+  double border_all = 0.0, acc = 0.0;
+  for (int cls = 0; cls < 64; ++cls) {
+    if (cls == interior) continue;
+    double r = R[((size_t)n * 64 + cls) * C + c];
+    border_all += r;
+    if (tap_valid(cls >> 4, td) && tap_valid((cls >> 2) & 3, th) && tap_valid(cls & 3, tw)) acc += r;
+  }
+  acc += tot[((size_t)n * C + c) * 2] - border_all;  // every tap is valid for interior voxels
   T[((size_t)n * 27 + tap) * C + c] = (float)acc;
 }
 
 // dW[co][ci][tap] = sum_n ( a[n][ci] * sum_s G[n][s][tap][ci][co] + b[n][ci] * T[n][tap][co] )
 __global__ void wgrad_finalize_kernel(const float* __restrict__ G, int N, int S, int Cin, int Cout, const float* __restrict__ ab,
-                                      const float* __restrict__ T, float* __restrict__ dW) {
+                                      const float* __restrict__ T, float* __restrict__ dW, float* __restrict__ Gsum) {
   size_t total = (size_t)27 * Cin * Cout;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     int co = (int)(i % Cout);
@@ -732,6 +725,7 @@ __global__ void wgrad_finalize_kernel(const float* __restrict__ G, int N, int S,
     for (int n = 0; n < N; ++n) {
       double g = 0.0;
       for (int s = 0; s < S; ++s) g += (double)G[((((size_t)n * S + s) * 27 + tap) * Cin + ci) * Cout + co];
+      if (Gsum) Gsum[(((size_t)n * 27 + tap) * Cin + ci) * Cout + co] = (float)g;  // split-reduced raw wgrad, reused by GN backward
       if (ab) {
         acc += (double)ab[((size_t)n * Cin + ci) * 2] * g;
         if (T) acc += (double)ab[((size_t)n * Cin + ci) * 2 + 1] * (double)T[((size_t)n * 27 + tap) * Cout + co];
@@ -1125,36 +1119,58 @@ int b200_upcat_bwd(const void* dcat, int C0, int C1, const void* x_small, int N,
   return 0;
 }
 
+static int border_blocks(int D, int H) {
+  long long lines = (long long)D * H;
+  long long p = (lines + 15) / 16;
+  return (int)(p > 512 ? 512 : (p < 1 ? 1 : p));
+}
 int b200_border_tap_sums_workspace(int N, int D, int H, int W, int C) {
-  // number of floats of scratch needed by b200_border_tap_sums
-  int P = ew_blocks((long long)D * H * W, 64);
-  return N * P * 64 * C + 2 * N * 64 * C;  // per-block class sums (float) + their reduction (double)
+  // floats: border class partials [N][P][64][C] | totals partials [N][P2][C][2] | (doubles) R [N][64][C] | tot [N][C][2]
+  int P = border_blocks(D, H);
+  int P2 = ew_blocks((long long)D * H * W, C);
+  size_t f = (size_t)N * P * 64 * C + (size_t)N * P2 * C * 2;
+  f += f & 1;
+  return (int)(f + 2 * ((size_t)N * 64 * C + (size_t)N * C * 2));
 }
 int b200_border_tap_sums(const void* dz, int N, int D, int H, int W, int C, float* T, float* scratch, b200_stream_t s) {
-  B200_CHECK_ARG(C % 8 == 0, "border_tap_sums: C=%d must be a multiple of 8", C);
-  int P = ew_blocks((long long)D * H * W, 64);
-  dim3 grid(P, N, ceil_div(C, BT_CC));
-  border_class_sums_kernel<<<grid, EW_THREADS, 0, ST(s)>>>((const bf16*)dz, D, H, W, C, P, scratch);
-  B200_CHECK_LAUNCH("border_class_sums");
-  double* R = reinterpret_cast<double*>(scratch + (size_t)N * P * 64 * C);
+  B200_CHECK_ARG(C % 8 == 0 && C <= 2048, "border_tap_sums: C=%d must be a multiple of 8", C);
+  const long long vox = (long long)D * H * W;
+  int P = border_blocks(D, H);
+  int P2 = ew_blocks(vox, C);
+  float* Rp = scratch;
+  float* totp = scratch + (size_t)N * P * 64 * C;
+  size_t f = (size_t)N * P * 64 * C + (size_t)N * P2 * C * 2;
+  f += f & 1;
+  double* R = reinterpret_cast<double*>(scratch + f);
+  double* tot = R + (size_t)N * 64 * C;
   {
-    // [N][P][64*C] viewed as [N][P][C'][2] with C' = 32*C
-    dim3 g2(ceil_div(64 * C, 32), N), b2(32, 32);
-    partials_finalize_kernel<<<g2, b2, 0, ST(s)>>>(scratch, P, 32 * C, R);
+    dim3 grid(P2, N);
+    stats_ndhwc_bf16_kernel<<<grid, EW_THREADS, EW_THREADS * 16 * sizeof(float), ST(s)>>>((const bf16*)dz, C, vox, P2, totp);
+    B200_CHECK_LAUNCH("border_totals");
+    dim3 g2(ceil_div(C * 2, 32), N), b2(32, 32);
+    partials_finalize_kernel<<<g2, b2, 0, ST(s)>>>(totp, P2, C, tot);
+    B200_CHECK_LAUNCH("border_totals_reduce");
+  }
+  {
+    dim3 grid(P, N, ceil_div(C, BT_CC));
+    border_class_sums_kernel<<<grid, EW_THREADS, 0, ST(s)>>>((const bf16*)dz, D, H, W, C, P, Rp);
+    B200_CHECK_LAUNCH("border_class_sums");
+    dim3 g2(ceil_div(64 * C, 32), N), b2(32, 32);  // [N][P][64*C] viewed as [N][P][C'][2] with C' = 32*C
+    partials_finalize_kernel<<<g2, b2, 0, ST(s)>>>(Rp, P, 32 * C, R);
     B200_CHECK_LAUNCH("border_class_reduce");
   }
   dim3 g3(ceil_div(27 * C, 256), N);
-  border_tap_from_class_kernel<<<g3, 256, 0, ST(s)>>>(R, C, T);
+  border_tap_from_class_kernel<<<g3, 256, 0, ST(s)>>>(R, tot, C, T);
   B200_CHECK_LAUNCH("border_tap_from_class");
   return 0;
 }
 
-int b200_wgrad_finalize(const float* G, int N, int S, int Cin, int Cout, const float* ab, const float* T, float* dW,
+int b200_wgrad_finalize(const float* G, int N, int S, int Cin, int Cout, const float* ab, const float* T, float* dW, float* Gsum,
                         b200_stream_t s) {
   size_t total = (size_t)27 * Cin * Cout;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 4096) blocks = 4096;
-  wgrad_finalize_kernel<<<blocks, 256, 0, ST(s)>>>(G, N, S, Cin, Cout, ab, T, dW);
+  wgrad_finalize_kernel<<<blocks, 256, 0, ST(s)>>>(G, N, S, Cin, Cout, ab, T, dW, Gsum);
   B200_CHECK_LAUNCH("wgrad_finalize");
   return 0;
 }

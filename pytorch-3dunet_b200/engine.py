@@ -247,7 +247,7 @@ class Engine:
                 if need_T:
                     T = self.empty((n, 27, cout), torch.float32)
                     scratch = self.empty((L.query("b200_border_tap_sums_workspace", n, d, h, w, cout),), torch.float32)
-                    self.call("b200_border_tap_sums", _p(dz), n, d, h, w, cout, _p(T), _p(scratch), launches=3)
+                    self.call("b200_border_tap_sums", _p(dz), n, d, h, w, cout, _p(T), _p(scratch), launches=5)
                 wimpl = L.query("b200_conv3_wgrad_resolve_impl", self.impl, n, d, h, w, cin, cout, int(is_f32))
                 if wimpl < 0:
                     raise B200Error("tcgen05 wgrad requested but unsupported for this shape")
@@ -257,7 +257,8 @@ class Engine:
                           launches=1 if wimpl == IMPL_TCGEN05 else 2, flops=2.0 * n * vox * 27 * cin * cout,
                           tag=("wgrad_tc" if wimpl == IMPL_TCGEN05 else "wgrad_direct"))
                 dW = torch.empty_like(W)
-                self.call("b200_wgrad_finalize", _p(G), n, S, cin, cout, _p(ab), _p(T) if ab is not None else None, _p(dW))
+                Gsum = self.empty((n, 1, 27, cin, cout), torch.float32) if gn is not None else None
+                self.call("b200_wgrad_finalize", _p(G), n, S, cin, cout, _p(ab), _p(T) if ab is not None else None, _p(dW), _p(Gsum))
                 self._add_param_grad(name + "conv.weight", dW)
                 if bias is not None:
                     db = torch.empty_like(bias)
@@ -266,7 +267,7 @@ class Engine:
                 coef = None
                 if gn is not None:
                     sums2 = self.empty((n, cin, 2), torch.float64)
-                    self.call("b200_gn_bwd_sums_from_wgrad", _p(G), S, _p(T), _p(W), n, cin, cout, _p(sums2))
+                    self.call("b200_gn_bwd_sums_from_wgrad", _p(Gsum), 1, _p(T), _p(W), n, cin, cout, _p(sums2))
                     coef = self.empty((n, cin, 3), torch.float32)
                     dgamma, dbeta = torch.empty_like(gamma), torch.empty_like(beta)
                     self.call("b200_gn_bwd_coeffs", _p(sums2), _p(gamma), _p(mean_rstd), groups, float(vox), n, cin,

@@ -101,7 +101,9 @@ def test_border_tap_sums_and_gn_bwd_sums():
     # wgrad finalize with a,b
     ab = torch.rand((N, Cin, 2), device="cuda") + 0.5
     dW = torch.empty_like(Wt)
-    L.call("b200_wgrad_finalize", U.p(Gf), N, 1, Cin, Cout, U.p(ab), U.p(T), U.p(dW), U.stream())
+    Gsum = torch.full((N, 27, Cin, Cout), float("nan"), device="cuda")
+    L.call("b200_wgrad_finalize", U.p(Gf), N, 1, Cin, Cout, U.p(ab), U.p(T), U.p(dW), U.p(Gsum), U.stream())
+    assert U.rel_l2(Gsum, Gd) < 1e-6
     ref = torch.einsum("nc,ntco->oct", ab[..., 0].double(), Gd) + torch.einsum("nc,nto->oct", ab[..., 1].double(), Tref)
     assert U.rel_l2(dW.reshape(Cout, Cin, 27), ref) < 1e-4
 
