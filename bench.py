@@ -159,7 +159,8 @@ def main():
     x_host = torch.rand(B, 1, S, S, S).pin_memory()
     t_host = (torch.rand(B, 1, S, S, S) > 0.5).float().pin_memory()
     x_dev, t_dev = x_host.to(dev), t_host.to(dev)
-    flat = torch.empty(sum(p.numel() for p in params), device=dev) if world > 1 else None
+    from pytorch3dunet_b200.parallel import GradAllReducer
+    reducer = GradAllReducer(params, world)
 
     def step(x, t):
         for p in params:
@@ -167,14 +168,7 @@ def main():
         out, logits = model(x, return_logits=True)
         loss = P.losses.bce_dice_loss(logits, t)
         loss.backward()
-        if world > 1:  # one gradient allreduce per step over NVLink (replaces DataParallel's reduce-to-GPU-0, trainer.py:203-204)
-            torch.cat([p.grad.reshape(-1) for p in params], out=flat)
-            dist.all_reduce(flat)
-            flat.div_(world)
-            off = 0
-            for p in params:
-                p.grad.copy_(flat[off:off + p.numel()].view_as(p))
-                off += p.numel()
+        reducer()  # one gradient allreduce per step over NVLink (replaces DataParallel's reduce-to-GPU-0, trainer.py:203-204)
         return loss
 
     def barrier():

@@ -167,6 +167,42 @@ int b200_conv3_wgrad_igemm_splits(int N, int D, int H, int W, int Cin, int Cout)
 int b200_conv3_wgrad_igemm(const void* x, const void* dz, int N, int D, int H, int W, int Cin, int Cout, float* G, b200_stream_t s);
 
 
+/* ---- residual family: 1x1x1 conv with bias (ResNetBlock.conv1, buildingblocks.py:251) ------------------------------
+ * y[v,co] = sum_ci W[co][ci] x[v,ci] + bias[co]; transposed=1 reads W as [Cin][Cout]^T (input gradient). partials of y. */
+int b200_pointwise_partials_count(int N, long long voxels, int Cout);
+int b200_pointwise_fwd(const void* x, int x_is_f32, const float* W, int transposed, const float* bias, int N, long long voxels,
+                       int Cin, int Cout, void* y, float* partials, b200_stream_t s);
+/* partial rows [N*P][Cout*Cin + Cout] of dW, db; reduce with b200_reduce_rows */
+int b200_pointwise_wgrad_partials_count(int N, long long voxels);
+int b200_pointwise_wgrad(const void* x, int x_is_f32, const void* dy, int N, long long voxels, int Cin, int Cout, float* partials,
+                         b200_stream_t s);
+/* ---- ConvTranspose3d(k3,s2,p1,bias=False) + nearest resize to the encoder size + sum-join
+ * (TransposeConvUpsampling buildingblocks.py:617-664, Decoder._joining :493).  Wt: fp32 (Cin,Cout,3,3,3) */
+int b200_deconv_prep_weights(const float* Wt, int Cin, int Cout, void* wt /*[27][Cout][Cin]*/, void* wtb /*[27][Cin][Cout]*/, b200_stream_t s);
+int b200_deconv_up_add_partials_count(int N, int D, int H, int W, int Cout);
+int b200_deconv_up_add_fwd(const void* x, const void* wt, const void* enc, int N, int d, int h, int w, int D, int H, int W, int Cin,
+                           int Cout, void* out, float* partials, b200_stream_t s);
+/* dT[N,2d-1,2h-1,2w-1,C] = adjoint of the nearest resize applied to dout[N,D,H,W,C] */
+int b200_deconv_gather(const void* dout, int N, int d, int h, int w, int D, int H, int W, int C, void* dT, b200_stream_t s);
+int b200_deconv_dgrad(const void* dT, const void* wtb, const void* x, int N, int d, int h, int w, int Cin, int Cout, int act, float slope,
+                      const void* gadd, void* out, b200_stream_t s);
+int b200_deconv_wgrad(const void* x, const void* dT, int N, int d, int h, int w, int Cin, int Cout, float* dWt, b200_stream_t s);
+
+/* ---- scSE, reduction_ratio 1 (ChannelSpatialSELayer3D se.py:96-114; cSE :18-51, sSE :54-93) ----------------------------
+ * gates: smean[N][C] = channel means (from the producer's partial sums), h = relu(W1 s + b1), g = sigmoid(W2 h + b2) */
+int b200_se_gates_fwd(const double* sums, double count, const float* W1, const float* b1, const float* W2, const float* b2, int N, int C,
+                      float* smean, float* h, float* g, b200_stream_t s);
+int b200_scse_partials_count(int N, long long voxels, int C);
+/* q[n,v] = sigmoid(ws . y[v,:] + bs) (saved for backward); out = max(y*g, y*q) */
+int b200_scse_apply_fwd(const void* y, const float* g, const float* ws, float bs, int N, long long voxels, int C, void* out, float* q,
+                        b200_stream_t s);
+/* tmp = d out/d y without the channel-mean path; partials [N][P][C][2] = (d g, d ws per sample); dbs_part [N][P] */
+int b200_scse_bwd1(const void* dout, const void* y, const float* g, const float* q, const float* ws, int N, long long voxels, int C, void* tmp,
+                   float* partials, float* dbs_part, b200_stream_t s);
+/* gate MLP backward; coef[N][C][3] = (1, 0, ds/V) feeds b200_gn_bwd_apply(tmp, y, coef) to finish d y. scratch: 2*N*C floats */
+int b200_se_gates_bwd(const double* sums2, const float* smean, const float* h, const float* g, const float* W1, const float* W2, int N, int C,
+                      double count, float* coef, float* dW1, float* db1, float* dW2, float* db2, float* dws, float* scratch, b200_stream_t s);
+
 /* hardware probe (test tooling): tcgen05.mma on a row-shifted / odd-strided view of a SWIZZLE_128B tile.
  * A: [rows][64] bf16, B: [16][64] bf16, D: [128][16] f32 with D[r][n] = sum_k A[shift + (r/8)*group_rows + r%8][k] * B[n][k] */
 int b200_probe_umma_rowshift(const void* A, int rows, const void* B, int shift, int group_rows, float* D, b200_stream_t s);

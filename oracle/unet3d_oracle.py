@@ -133,20 +133,23 @@ def spatial_se(x, sd, prefix):
     return x * g
 
 
-def res_block(x, sd, prefix, order, num_groups, se=False):
-    """ResNetBlock.forward buildingblocks.py:277-288 (+ ResNetBlockSE :304-307)."""
+def res_block(x, sd, prefix, order, num_groups, se=False, masks=None):
+    """ResNetBlock.forward buildingblocks.py:277-288 (+ ResNetBlockSE :304-307).  `masks`: see single_conv; the block's
+    final ReLU (after the residual add) is keyed by the conv3 prefix."""
     if (prefix + "conv1.weight") in sd:
         residual = F.conv3d(x, sd[prefix + "conv1.weight"], sd[prefix + "conv1.bias"])
     else:
         residual = x
-    out = single_conv(residual, sd, prefix + "conv2.", order, num_groups)
+    out = single_conv(residual, sd, prefix + "conv2.", order, num_groups, masks=masks)
     n_order = order.replace("r", "").replace("e", "").replace("l", "")
-    out = single_conv(out, sd, prefix + "conv3.", n_order, num_groups)
+    out = single_conv(out, sd, prefix + "conv3.", n_order, num_groups, masks=masks)
     out = out + residual
     if "l" in order:
         out = F.leaky_relu(out, 0.1)  # buildingblocks.py:271 : slope 0.1 here, not 0.01
     elif "e" in order:
         out = F.elu(out)
+    elif masks is not None and (prefix + "conv3.") in masks:
+        out = out * masks[prefix + "conv3."].to(out.dtype)
     else:
         out = F.relu(out)
     if se:
@@ -158,7 +161,7 @@ def res_block(x, sd, prefix, order, num_groups, se=False):
 def basic_module(x, sd, prefix, cfg, masks=None):
     if cfg["basic"] == "double":
         return double_conv(x, sd, prefix, cfg["layer_order"], cfg["num_groups"], cfg["conv_padding"], masks)
-    return res_block(x, sd, prefix, cfg["layer_order"], cfg["num_groups"], se=cfg["basic"] == "res_se")
+    return res_block(x, sd, prefix, cfg["layer_order"], cfg["num_groups"], se=cfg["basic"] == "res_se", masks=masks)
 
 
 def decoder_mode(cfg):

@@ -6,7 +6,8 @@
     pytorch3dunet_b200.install()                        # rebinds get_model & the model classes inside an installed
                                                         # reference package so train3dunet / predict3dunet use the engine
 """
-from .model import (AbstractUNet, Decoder, DoubleConv, Encoder, ResidualUNet3D, ResidualUNetSE3D, SingleConv, UNet3D,  # noqa: F401
+from .model import (AbstractUNet, Decoder, DoubleConv, Encoder, ResidualUNet3D, ResidualUNetSE3D, ResNetBlock, ResNetBlockSE,  # noqa: F401
+                    SingleConv, UNet3D,
                     get_model, is_model_2d, last_launch_counts, number_of_features_per_level)
 from .install import install  # noqa: F401
 from . import losses  # noqa: F401

@@ -669,20 +669,46 @@ __global__ void border_class_sums_kernel(const bf16* __restrict__ dz, int D, int
   long long l0, l1;
   ew_range(lines, p, P, l0, l1);
   const long long vox = (long long)D * H * W;
+  const int lane = threadIdx.x & 31;
   if (vl < VL) {
     for (long long l = l0; l < l1; ++l) {
       const int xh = (int)(l % H), xd = (int)(l / H);
       const int cdh = (axis_cls(xd, D) << 4) | (axis_cls(xh, H) << 2);
       const bool face = (cdh != ((1 << 4) | (1 << 2)));
-      // voxels of this line that are border voxels: all W (face line) or the two ends
-      const int cnt = face ? W : (W > 1 ? 2 : 1);
-      for (int k = vl; k < cnt; k += VL) {
-        const int xw = face ? k : (k == 0 ? 0 : W - 1);
-        const int cls = cdh | axis_cls(xw, W);
-        float f[8];
-        unpack8(*reinterpret_cast<const bf16x8*>(dz + ((size_t)n * vox + (size_t)l * W + xw) * C + c0 + cg * 8), f);
+      const bf16* line = dz + ((size_t)n * vox + (size_t)l * W) * C + c0 + cg * 8;
+      // the two end voxels of the line (their w-class differs): lanes vl == 0 / 1
+      if (vl < 2 && vl < W) {
+        const int xw = vl == 0 ? 0 : W - 1;
+        if (!(vl == 1 && W == 1)) {
+          float f[8];
+          unpack8(*reinterpret_cast<const bf16x8*>(line + (size_t)xw * C), f);
+          const int cls = cdh | axis_cls(xw, W);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) atomicAdd(&bins[cls][cg * 8 + i], f[i]);
+          for (int i = 0; i < 8; ++i) atomicAdd(&bins[cls][cg * 8 + i], f[i]);
+        }
+      }
+      // the middle of a line that lies on a d/h face: one class for all of it -> registers, one reduction per warp
+      if (face && W > 2) {
+        float acc[8] = {0};
+        for (int xw = 1 + vl; xw < W - 1; xw += VL) {
+          float f[8];
+          unpack8(*reinterpret_cast<const bf16x8*>(line + (size_t)xw * C), f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] += f[i];
+        }
+        // lanes of a warp that share cg differ by multiples of CG (CG <= 8 here, a power of two or 1..8)
+        if ((32 % CG) == 0) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            for (int o = CG; o < 32; o <<= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+          if (lane < CG) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) atomicAdd(&bins[cdh | 1][cg * 8 + i], acc[i]);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) atomicAdd(&bins[cdh | 1][cg * 8 + i], acc[i]);
+        }
       }
     }
   }

@@ -1,0 +1,727 @@
+// Kernels that only the residual model family needs (ResidualUNet3D / ResidualUNetSE3D):
+//   * 1x1x1 convolution with bias (ResNetBlock.conv1, buildingblocks.py:251) forward / dgrad / wgrad
+//   * ConvTranspose3d(k=3, stride=2, padding=1, bias=False) + nearest resize to the encoder size + sum-join
+//     (TransposeConvUpsampling buildingblocks.py:617-664, Decoder._joining :493) forward / backward
+// These carry ~1/27 (pointwise) resp. a few % (deconv) of the model's FLOPs; they are CUDA-core kernels in this
+// round (the 3x3x3 convolutions of the residual blocks run on the tcgen05 kernels with the residual add + activation
+// fused into the epilogue).
+#include "common.cuh"
+#include "ew.cuh"
+
+namespace b200 {
+
+template <typename T>
+__device__ __forceinline__ float ldv(const T* p);
+template <>
+__device__ __forceinline__ float ldv<float>(const float* p) {
+  return *p;
+}
+template <>
+__device__ __forceinline__ float ldv<bf16>(const bf16* p) {
+  return __bfloat162float(*p);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// y[v,co] = sum_ci Wq[co][ci] * x[v,ci] + bias[co]      (Wq: fp32 [Cout][Cin] or, transposed=1, [Cin_w][Cout_w] read as W^T)
+// grid (P, N, ceil(Cout/64)); a block keeps its 64 x Cin weight slab in shared memory.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int PW_CO = 64;
+template <typename InT>
+__global__ void pointwise_fwd_kernel(const InT* __restrict__ x, const float* __restrict__ Wq, int transposed, const float* __restrict__ bias,
+                                     long long vox, int Cin, int Cout, int P, bf16* __restrict__ y, float* __restrict__ partials) {
+  extern __shared__ float sm[];  // w[CC][Cin] | red[EW_THREADS*16]
+  const int p = blockIdx.x, n = blockIdx.y, c0 = blockIdx.z * PW_CO;
+  const int CC = min(PW_CO, Cout - c0);
+  float* wsm = sm;
+  float* red = sm + (size_t)PW_CO * Cin;
+  for (int i = threadIdx.x; i < CC * Cin; i += EW_THREADS) {
+    int co = i / Cin, ci = i % Cin;
+    wsm[i] = transposed ? Wq[(size_t)ci * Cout + c0 + co] : Wq[(size_t)(c0 + co) * Cin + ci];
+  }
+  __syncthreads();
+  const int CG = CC >> 3, VL = EW_THREADS / CG;
+  const int cg = threadIdx.x % CG, vl = threadIdx.x / CG;
+  long long v0, v1;
+  ew_range(vox, p, P, v0, v1);
+  float s[8] = {0}, q[8] = {0};
+  if (vl < VL) {
+    float b8[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) b8[i] = bias ? bias[c0 + cg * 8 + i] : 0.f;
+    const InT* xn = x + (size_t)n * vox * Cin;
+    for (long long v = v0 + vl; v < v1; v += VL) {
+      float acc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = b8[i];
+      const InT* xp = xn + (size_t)v * Cin;
+      const float* wp = wsm + (size_t)cg * 8 * Cin;
+      for (int ci = 0; ci < Cin; ++ci) {
+        float xv = ldv<InT>(xp + ci);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(xv, wp[i * Cin + ci], acc[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        acc[i] = bf16_round(acc[i]);
+        s[i] += acc[i];
+        q[i] += acc[i] * acc[i];
+      }
+      *reinterpret_cast<bf16x8*>(y + ((size_t)n * vox + v) * Cout + c0 + cg * 8) = pack8(acc);
+    }
+  }
+  if (partials) {
+    // per-channel partial sums of this block's channel slab: [N][P][Cout][2]
+    EwMap m;
+    m.CG = CG; m.VL = VL; m.cg = cg; m.vl = vl; m.active = vl < VL;
+    ew_write_partials(s, q, m, partials + (((size_t)n * P + p) * Cout + c0) * 2, red);
+  }
+}
+
+// dW[co][ci] = sum_v dy[v,co] * x[v,ci], db[co] = sum_v dy[v,co]; partial rows [N*P][Cout*Cin + Cout]; grid (P, N, tiles of 16x16 (co,ci))
+template <typename InT>
+__global__ void pointwise_wgrad_kernel(const InT* __restrict__ x, const bf16* __restrict__ dy, long long vox, int Cin, int Cout, int P,
+                                       float* __restrict__ partials) {
+  __shared__ float xs[64][17], ds[64][17];
+  const int p = blockIdx.x, n = blockIdx.y;
+  const int tiles_ci = (Cin + 15) / 16;
+  const int co0 = (blockIdx.z / tiles_ci) * 16, ci0 = (blockIdx.z % tiles_ci) * 16;
+  const int tco = threadIdx.x / 16, tci = threadIdx.x % 16;  // 256 threads = 16 x 16 outputs
+  long long v0, v1;
+  ew_range(vox, p, P, v0, v1);
+  float acc = 0.f, accb = 0.f;
+  for (long long vb = v0; vb < v1; vb += 64) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+      int vv = i / 16, c = i % 16;
+      long long v = vb + vv;
+      bool ok = v < v1;
+      xs[vv][c] = (ok && ci0 + c < Cin) ? ldv<InT>(x + ((size_t)n * vox + v) * Cin + ci0 + c) : 0.f;
+      ds[vv][c] = (ok && co0 + c < Cout) ? __bfloat162float(dy[((size_t)n * vox + v) * Cout + co0 + c]) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 16
+    for (int vv = 0; vv < 64; ++vv) {
+      acc = fmaf(ds[vv][tco], xs[vv][tci], acc);
+      accb += ds[vv][tco];
+    }
+  }
+  float* row = partials + ((size_t)n * P + p) * ((size_t)Cout * Cin + Cout);
+  if (co0 + tco < Cout && ci0 + tci < Cin) row[(size_t)(co0 + tco) * Cin + ci0 + tci] = acc;
+  if (ci0 == 0 && tci == 0 && co0 + tco < Cout) row[(size_t)Cout * Cin + co0 + tco] = accb;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// transposed conv (k3, s2, p1) evaluated at the nearest-resized position + encoder features:
+//   out[o,co] = enc[o,co] + sum_{k valid at s(o)} sum_ci x[i(s,k),ci] * Wt[ci][co][k],   s = nearest_src(o; 2n-1 -> size of enc)
+// per axis: s even -> k=1, i=s/2 ; s odd -> k=0,i=(s+1)/2 and k=2,i=(s-1)/2.  wt: bf16 [27][Cout][Cin].
+// grid (P, N); thread = one output voxel x 8 output channels.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int nearest_src_i(int dst, int in, int out) {
+  float scale = (float)in / (float)out;
+  int s = (int)floorf((float)dst * scale);
+  return s < in - 1 ? s : in - 1;
+}
+__device__ __forceinline__ int axis_taps(int s, int k[2], int i[2]) {
+  if ((s & 1) == 0) {
+    k[0] = 1;
+    i[0] = s >> 1;
+    return 1;
+  }
+  k[0] = 0;
+  i[0] = (s + 1) >> 1;
+  k[1] = 2;
+  i[1] = (s - 1) >> 1;
+  return 2;
+}
+
+__global__ void deconv_up_add_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ wt, const bf16* __restrict__ enc, int d, int h, int w,
+                                         int D, int H, int W, int Cin, int Cout, int P, bf16* __restrict__ out, float* __restrict__ partials) {
+  extern __shared__ float red[];
+  const int p = blockIdx.x, n = blockIdx.y;
+  EwMap m = ew_map(Cout);
+  const long long vox = (long long)D * H * W, svox = (long long)d * h * w;
+  long long v0, v1;
+  ew_range(vox, p, P, v0, v1);
+  float s[8] = {0}, q[8] = {0};
+  if (m.active) {
+    const bf16* xn = x + (size_t)n * svox * Cin;
+    for (long long v = v0 + m.vl; v < v1; v += m.VL) {
+      const int ow = (int)(v % W);
+      const long long r = v / W;
+      const int oh = (int)(r % H), od = (int)(r / H);
+      int kd[2], id[2], kh[2], ih[2], kw[2], iw[2];
+      const int nd = axis_taps(nearest_src_i(od, 2 * d - 1, D), kd, id);
+      const int nh = axis_taps(nearest_src_i(oh, 2 * h - 1, H), kh, ih);
+      const int nw = axis_taps(nearest_src_i(ow, 2 * w - 1, W), kw, iw);
+      float acc[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(enc + ((size_t)n * vox + v) * Cout + m.cg * 8), acc);
+      for (int a = 0; a < nd; ++a)
+        for (int b = 0; b < nh; ++b)
+          for (int c = 0; c < nw; ++c) {
+            const int tap = (kd[a] * 3 + kh[b]) * 3 + kw[c];
+            const bf16* xp = xn + (((size_t)id[a] * h + ih[b]) * w + iw[c]) * Cin;
+            const bf16* wp = wt + ((size_t)tap * Cout + m.cg * 8) * Cin;
+            for (int ci = 0; ci < Cin; ++ci) {
+              const float xv = __bfloat162float(xp[ci]);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) acc[i] = fmaf(xv, __bfloat162float(wp[(size_t)i * Cin + ci]), acc[i]);
+            }
+          }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        acc[i] = bf16_round(acc[i]);
+        s[i] += acc[i];
+        q[i] += acc[i] * acc[i];
+      }
+      *reinterpret_cast<bf16x8*>(out + ((size_t)n * vox + v) * Cout + m.cg * 8) = pack8(acc);
+    }
+  }
+  if (partials) ew_write_partials(s, q, m, partials + ((size_t)n * P + p) * Cout * 2, red);
+}
+
+// dT[s,co] = sum over destination voxels o with s(o) == s of dout[o,co]   (adjoint of the nearest resize 2n-1 -> size);
+// grid (P, N) over the (2d-1)(2h-1)(2w-1) deconv grid
+__device__ __forceinline__ void dst_range(int s, int in, int out, int& lo, int& hi) {
+  float inv = (float)out / (float)in;
+  int a = (int)floorf((float)s * inv) - 2, b = (int)ceilf((float)(s + 1) * inv) + 2;
+  if (a < 0) a = 0;
+  if (b > out - 1) b = out - 1;
+  lo = out;
+  hi = -1;
+  for (int t = a; t <= b; ++t)
+    if (nearest_src_i(t, in, out) == s) {
+      if (t < lo) lo = t;
+      if (t > hi) hi = t;
+    }
+}
+__global__ void deconv_gather_kernel(const bf16* __restrict__ dout, int sd, int sh, int sw, int D, int H, int W, int C, int P,
+                                     bf16* __restrict__ dT) {
+  const int p = blockIdx.x, n = blockIdx.y;
+  EwMap m = ew_map(C);
+  const long long svox = (long long)sd * sh * sw, vox = (long long)D * H * W;
+  long long v0, v1;
+  ew_range(svox, p, P, v0, v1);
+  if (!m.active) return;
+  for (long long v = v0 + m.vl; v < v1; v += m.VL) {
+    const int xw = (int)(v % sw);
+    const long long r = v / sw;
+    const int xh = (int)(r % sh), xd = (int)(r / sh);
+    int d0, d1, h0, h1, w0, w1;
+    dst_range(xd, sd, D, d0, d1);
+    dst_range(xh, sh, H, h0, h1);
+    dst_range(xw, sw, W, w0, w1);
+    float acc[8] = {0};
+    for (int z = d0; z <= d1; ++z)
+      for (int y = h0; y <= h1; ++y)
+        for (int xx = w0; xx <= w1; ++xx) {
+          float f[8];
+          unpack8(*reinterpret_cast<const bf16x8*>(dout + ((size_t)n * vox + ((size_t)z * H + y) * W + xx) * C + m.cg * 8), f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] += f[i];
+        }
+    *reinterpret_cast<bf16x8*>(dT + ((size_t)n * svox + v) * C + m.cg * 8) = pack8(acc);
+  }
+}
+
+// dx[i,ci] = (sum_k sum_co Wt[ci][co][k] * dT[2i+k-1,co]) * act'(x[i,ci]) [+ gadd]; wtb: bf16 [27][Cin][Cout]; grid (P, N)
+__global__ void deconv_dgrad_kernel(const bf16* __restrict__ dT, const bf16* __restrict__ wtb, const bf16* __restrict__ x, int d, int h, int w, int Cin,
+                                    int Cout, int P, int act, float slope, const bf16* gadd, bf16* out) {
+  const int p = blockIdx.x, n = blockIdx.y;
+  EwMap m = ew_map(Cin);
+  const int sd = 2 * d - 1, sh = 2 * h - 1, sw = 2 * w - 1;
+  const long long vox = (long long)d * h * w, svox = (long long)sd * sh * sw;
+  long long v0, v1;
+  ew_range(vox, p, P, v0, v1);
+  if (!m.active) return;
+  const bf16* tn = dT + (size_t)n * svox * Cout;
+  for (long long v = v0 + m.vl; v < v1; v += m.VL) {
+    const int iw = (int)(v % w);
+    const long long r = v / w;
+    const int ih = (int)(r % h), id = (int)(r / h);
+    float acc[8] = {0};
+    for (int kd = 0; kd < 3; ++kd) {
+      const int zd = 2 * id + kd - 1;
+      if (zd < 0 || zd >= sd) continue;
+      for (int kh = 0; kh < 3; ++kh) {
+        const int zh = 2 * ih + kh - 1;
+        if (zh < 0 || zh >= sh) continue;
+        for (int kw = 0; kw < 3; ++kw) {
+          const int zw = 2 * iw + kw - 1;
+          if (zw < 0 || zw >= sw) continue;
+          const bf16* tp = tn + (((size_t)zd * sh + zh) * sw + zw) * Cout;
+          const bf16* wp = wtb + ((size_t)((kd * 3 + kh) * 3 + kw) * Cin + m.cg * 8) * Cout;
+          for (int co = 0; co < Cout; ++co) {
+            const float g = __bfloat162float(tp[co]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = fmaf(g, __bfloat162float(wp[(size_t)i * Cout + co]), acc[i]);
+          }
+        }
+      }
+    }
+    const size_t o = ((size_t)n * vox + v) * Cin + m.cg * 8;
+    float xv[8], ga[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(x + o), xv);
+    if (gadd) unpack8(*reinterpret_cast<const bf16x8*>(gadd + o), ga);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      acc[i] *= act_grad_from_out(xv[i], act, slope);
+      if (gadd) acc[i] += ga[i];
+    }
+    *reinterpret_cast<bf16x8*>(out + o) = pack8(acc);
+  }
+}
+
+// dWt[ci][co][k] += sum_i x[i,ci] * dT[2i+k-1,co]; one thread per (k,ci,co) output and voxel chunk, atomicAdd; grid (chunks, N, outputs/256)
+constexpr int DC_CHUNK = 1024;
+__global__ void deconv_wgrad_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dT, int d, int h, int w, int Cin, int Cout,
+                                    float* __restrict__ dWt) {
+  const int n = blockIdx.y;
+  const int total = 27 * Cin * Cout;
+  const int o = blockIdx.z * blockDim.x + threadIdx.x;
+  if (o >= total) return;
+  const int co = o % Cout;
+  const int r0 = o / Cout;
+  const int ci = r0 % Cin, tap = r0 / Cin;
+  const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
+  const int sd = 2 * d - 1, sh = 2 * h - 1, sw = 2 * w - 1;
+  const long long vox = (long long)d * h * w, svox = (long long)sd * sh * sw;
+  long long v0 = (long long)blockIdx.x * DC_CHUNK, v1 = v0 + DC_CHUNK;
+  if (v1 > vox) v1 = vox;
+  const bf16* xn = x + (size_t)n * vox * Cin;
+  const bf16* tn = dT + (size_t)n * svox * Cout;
+  float acc = 0.f;
+  for (long long v = v0; v < v1; ++v) {
+    const int iw = (int)(v % w);
+    const long long r = v / w;
+    const int ih = (int)(r % h), id = (int)(r / h);
+    const int zd = 2 * id + kd - 1, zh = 2 * ih + kh - 1, zw = 2 * iw + kw - 1;
+    if (zd < 0 || zd >= sd || zh < 0 || zh >= sh || zw < 0 || zw >= sw) continue;
+    acc += __bfloat162float(xn[(size_t)v * Cin + ci]) * __bfloat162float(tn[(((size_t)zd * sh + zh) * sw + zw) * Cout + co]);
+  }
+  atomicAdd(&dWt[((size_t)ci * Cout + co) * 27 + tap], acc);
+}
+
+// wt[k][co][ci] = bf16(Wt[ci][co][k]) and wtb[k][ci][co] = bf16(Wt[ci][co][k])
+__global__ void deconv_prep_weights_kernel(const float* __restrict__ Wt, int Cin, int Cout, bf16* __restrict__ wt, bf16* __restrict__ wtb) {
+  size_t total = (size_t)27 * Cin * Cout;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int k = (int)(i % 27);
+    size_t r = i / 27;
+    int co = (int)(r % Cout), ci = (int)(r / Cout);
+    bf16 v = __float2bfloat16_rn(Wt[i]);
+    if (wt) wt[((size_t)k * Cout + co) * Cin + ci] = v;
+    if (wtb) wtb[((size_t)k * Cin + ci) * Cout + co] = v;
+  }
+}
+
+}  // namespace b200
+
+using namespace b200;
+#define ST(s) ((cudaStream_t)(s))
+
+extern "C" {
+
+int b200_pointwise_partials_count(int N, long long voxels, int Cout) {
+  (void)N;
+  return ew_blocks(voxels, Cout < PW_CO ? Cout : PW_CO);
+}
+
+int b200_pointwise_fwd(const void* x, int x_is_f32, const float* W, int transposed, const float* bias, int N, long long voxels, int Cin,
+                       int Cout, void* y, float* partials, b200_stream_t s) {
+  B200_CHECK_ARG(Cout % 8 == 0 && Cout <= 4096, "pointwise_fwd: Cout=%d must be a multiple of 8", Cout);
+  int P = b200_pointwise_partials_count(N, voxels, Cout);
+  dim3 grid(P, N, ceil_div(Cout, PW_CO));
+  size_t smem = ((size_t)PW_CO * Cin + EW_THREADS * 16) * sizeof(float);
+  B200_CHECK_ARG(smem <= 200 * 1024, "pointwise_fwd: Cin=%d too large", Cin);
+  if (x_is_f32) {
+    cudaFuncSetAttribute(pointwise_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    pointwise_fwd_kernel<float><<<grid, EW_THREADS, smem, ST(s)>>>((const float*)x, W, transposed, bias, voxels, Cin, Cout, P, (bf16*)y, partials);
+  } else {
+    cudaFuncSetAttribute(pointwise_fwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    pointwise_fwd_kernel<bf16><<<grid, EW_THREADS, smem, ST(s)>>>((const bf16*)x, W, transposed, bias, voxels, Cin, Cout, P, (bf16*)y, partials);
+  }
+  B200_CHECK_LAUNCH("pointwise_fwd");
+  return 0;
+}
+
+int b200_pointwise_wgrad_partials_count(int N, long long voxels) {
+  (void)N;
+  long long p = (voxels + 4095) / 4096;
+  return (int)(p > 64 ? 64 : (p < 1 ? 1 : p));
+}
+int b200_pointwise_wgrad(const void* x, int x_is_f32, const void* dy, int N, long long voxels, int Cin, int Cout, float* partials,
+                         b200_stream_t s) {
+  int P = b200_pointwise_wgrad_partials_count(N, voxels);
+  dim3 grid(P, N, ceil_div(Cout, 16) * ceil_div(Cin, 16));
+  if (x_is_f32) pointwise_wgrad_kernel<float><<<grid, 256, 0, ST(s)>>>((const float*)x, (const bf16*)dy, voxels, Cin, Cout, P, partials);
+  else pointwise_wgrad_kernel<bf16><<<grid, 256, 0, ST(s)>>>((const bf16*)x, (const bf16*)dy, voxels, Cin, Cout, P, partials);
+  B200_CHECK_LAUNCH("pointwise_wgrad");
+  return 0;
+}
+
+int b200_deconv_prep_weights(const float* Wt, int Cin, int Cout, void* wt, void* wtb, b200_stream_t s) {
+  size_t total = (size_t)27 * Cin * Cout;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 4096) blocks = 4096;
+  deconv_prep_weights_kernel<<<blocks, 256, 0, ST(s)>>>(Wt, Cin, Cout, (bf16*)wt, (bf16*)wtb);
+  B200_CHECK_LAUNCH("deconv_prep_weights");
+  return 0;
+}
+
+int b200_deconv_up_add_partials_count(int N, int D, int H, int W, int Cout) {
+  (void)N;
+  return ew_blocks((long long)D * H * W, Cout);
+}
+int b200_deconv_up_add_fwd(const void* x, const void* wt, const void* enc, int N, int d, int h, int w, int D, int H, int W, int Cin, int Cout,
+                           void* out, float* partials, b200_stream_t s) {
+  B200_CHECK_ARG(Cin % 8 == 0 && Cout % 8 == 0 && Cout <= 2048, "deconv_up_add_fwd: channels %d,%d must be multiples of 8", Cin, Cout);
+  int P = b200_deconv_up_add_partials_count(N, D, H, W, Cout);
+  dim3 grid(P, N);
+  deconv_up_add_fwd_kernel<<<grid, EW_THREADS, EW_THREADS * 16 * sizeof(float), ST(s)>>>((const bf16*)x, (const bf16*)wt, (const bf16*)enc, d, h, w, D, H,
+                                                                                     W, Cin, Cout, P, (bf16*)out, partials);
+  B200_CHECK_LAUNCH("deconv_up_add_fwd");
+  return 0;
+}
+
+int b200_deconv_gather(const void* dout, int N, int d, int h, int w, int D, int H, int W, int C, void* dT, b200_stream_t s) {
+  B200_CHECK_ARG(C % 8 == 0 && C <= 2048, "deconv_gather: C=%d must be a multiple of 8", C);
+  int sd = 2 * d - 1, sh = 2 * h - 1, sw = 2 * w - 1;
+  int P = ew_blocks((long long)sd * sh * sw, C);
+  dim3 grid(P, N);
+  deconv_gather_kernel<<<grid, EW_THREADS, 0, ST(s)>>>((const bf16*)dout, sd, sh, sw, D, H, W, C, P, (bf16*)dT);
+  B200_CHECK_LAUNCH("deconv_gather");
+  return 0;
+}
+
+int b200_deconv_dgrad(const void* dT, const void* wtb, const void* x, int N, int d, int h, int w, int Cin, int Cout, int act, float slope,
+                      const void* gadd, void* out, b200_stream_t s) {
+  B200_CHECK_ARG(Cin % 8 == 0 && Cin <= 2048, "deconv_dgrad: Cin=%d must be a multiple of 8", Cin);
+  int P = ew_blocks((long long)d * h * w, Cin);
+  dim3 grid(P, N);
+  deconv_dgrad_kernel<<<grid, EW_THREADS, 0, ST(s)>>>((const bf16*)dT, (const bf16*)wtb, (const bf16*)x, d, h, w, Cin, Cout, P, act, slope,
+                                                      (const bf16*)gadd, (bf16*)out);
+  B200_CHECK_LAUNCH("deconv_dgrad");
+  return 0;
+}
+
+int b200_deconv_wgrad(const void* x, const void* dT, int N, int d, int h, int w, int Cin, int Cout, float* dWt, b200_stream_t s) {
+  size_t bytes = (size_t)27 * Cin * Cout * sizeof(float);
+  cudaError_t e = cudaMemsetAsync(dWt, 0, bytes, ST(s));
+  B200_CHECK_ARG(e == cudaSuccess, "deconv_wgrad: memset failed: %s", cudaGetErrorString(e));
+  long long vox = (long long)d * h * w;
+  dim3 grid(ceil_div(vox, DC_CHUNK), N, ceil_div(27 * Cin * Cout, 256));
+  deconv_wgrad_kernel<<<grid, 256, 0, ST(s)>>>((const bf16*)x, (const bf16*)dT, d, h, w, Cin, Cout, dWt);
+  B200_CHECK_LAUNCH("deconv_wgrad");
+  return 0;
+}
+
+}  // extern "C"
+
+// =================================================================================================================
+// Concurrent spatial + channel squeeze-and-excitation (ChannelSpatialSELayer3D, reduction_ratio = 1; se.py:18-114):
+//   s = mean_v y;  h = relu(W1 s + b1);  g = sigmoid(W2 h + b2)                  (cSE gates, per sample & channel)
+//   q[v] = sigmoid(sum_c ws[c] y[v,c] + bs)                                      (sSE gate, per voxel)
+//   out[v,c] = max(y[v,c]*g[c], y[v,c]*q[v])
+// The channel means come for free from the (sum y) partials the producing conv's epilogue already emits.  The apply
+// pass is one read of y and one write of out (the reference makes 9 full-tensor passes).
+// =================================================================================================================
+namespace b200 {
+
+// grid N, block 256.  sums: double [N][C][2]; h,g: float [N][C]
+__global__ void se_gates_fwd_kernel(const double* __restrict__ sums, double count, const float* __restrict__ W1, const float* __restrict__ b1,
+                                    const float* __restrict__ W2, const float* __restrict__ b2, int C, float* __restrict__ sm_out,
+                                    float* __restrict__ h, float* __restrict__ g) {
+  extern __shared__ float sh[];  // s[C] | h[C]
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float m = (float)(sums[((size_t)n * C + c) * 2] / count);
+    sh[c] = m;
+    sm_out[(size_t)n * C + c] = m;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < C; j += blockDim.x) {
+    float acc = b1[j];
+    for (int c = 0; c < C; ++c) acc = fmaf(W1[(size_t)j * C + c], sh[c], acc);
+    acc = acc > 0.f ? acc : 0.f;
+    sh[C + j] = acc;
+    h[(size_t)n * C + j] = acc;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < C; j += blockDim.x) {
+    float acc = b2[j];
+    for (int c = 0; c < C; ++c) acc = fmaf(W2[(size_t)j * C + c], sh[C + c], acc);
+    g[(size_t)n * C + j] = 1.f / (1.f + expf(-acc));
+  }
+}
+
+// lane mapping shared by the apply / backward kernels: a warp handles VPW voxels, each by GL = min(CG,32) lanes that own
+// CPL = ceil(CG/32) 16-byte channel chunks each; dot products over channels reduce with xor shuffles inside the GL lanes.
+struct SeMap {
+  int CG, GL, VPW, CPL, sub, gl;
+};
+__device__ __forceinline__ SeMap se_map(int C, int lane) {
+  SeMap m;
+  m.CG = C >> 3;
+  m.GL = m.CG < 32 ? m.CG : 32;
+  m.VPW = 32 / m.GL;
+  m.CPL = (m.CG + 31) / 32;
+  m.sub = lane / m.GL;
+  m.gl = lane % m.GL;
+  return m;
+}
+__device__ __forceinline__ float se_group_sum(float v, int GL) {
+  for (int o = GL >> 1; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+constexpr int SE_MAX_CPL = 4;  // C <= 1024
+
+// grid (P, N), block 256 (8 warps).  q: float [N][V]
+__global__ void scse_apply_fwd_kernel(const bf16* __restrict__ y, const float* __restrict__ g, const float* __restrict__ ws, float bs, int C,
+                                      long long vox, int P, bf16* __restrict__ out, float* __restrict__ q) {
+  const int p = blockIdx.x, n = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const SeMap m = se_map(C, lane);
+  long long v0, v1;
+  ew_range(vox, p, P, v0, v1);
+  float gg[SE_MAX_CPL][8], ww[SE_MAX_CPL][8];
+#pragma unroll
+  for (int k = 0; k < SE_MAX_CPL; ++k) {
+    const int cg = m.gl + 32 * k;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const bool ok = k < m.CPL && cg < m.CG;
+      gg[k][i] = ok ? g[(size_t)n * C + cg * 8 + i] : 0.f;
+      ww[k][i] = ok ? ws[cg * 8 + i] : 0.f;
+    }
+  }
+  const int vstep = 8 * m.VPW;
+  for (long long vb = v0 + warp * m.VPW; vb < v1; vb += vstep) {
+    const long long v = vb + m.sub;
+    const bool okv = v < v1;
+    float f[SE_MAX_CPL][8];
+    float dot = 0.f;
+#pragma unroll
+    for (int k = 0; k < SE_MAX_CPL; ++k) {
+      const int cg = m.gl + 32 * k;
+      if (k < m.CPL && cg < m.CG && okv) {
+        unpack8(*reinterpret_cast<const bf16x8*>(y + ((size_t)n * vox + v) * C + cg * 8), f[k]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dot = fmaf(f[k][i], ww[k][i], dot);
+      }
+    }
+    dot = se_group_sum(dot, m.GL);
+    const float qv = 1.f / (1.f + expf(-(dot + bs)));
+    if (okv && m.gl == 0) q[(size_t)n * vox + v] = qv;
+#pragma unroll
+    for (int k = 0; k < SE_MAX_CPL; ++k) {
+      const int cg = m.gl + 32 * k;
+      if (k < m.CPL && cg < m.CG && okv) {
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = fmaxf(f[k][i] * gg[k][i], f[k][i] * qv);
+        *reinterpret_cast<bf16x8*>(out + ((size_t)n * vox + v) * C + cg * 8) = pack8(o);
+      }
+    }
+  }
+}
+
+// backward pass 1.  tmp[v,c] = dout*(sel_c*g + sel_s*q) + dlogit*ws ;  partials [N][P][C][2] = (sum dout*y*sel_c, sum dlogit*y);
+// dbs partial [N][P] = sum dlogit.   sel_c = (y*g > y*q) + 0.5*(y*g == y*q)   (torch.max splits the gradient at ties)
+__global__ void scse_bwd1_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ y, const float* __restrict__ g, const float* __restrict__ q,
+                                 const float* __restrict__ ws, int C, long long vox, int P, bf16* __restrict__ tmp, float* __restrict__ partials,
+                                 float* __restrict__ dbs_part) {
+  extern __shared__ float red[];  // [8 warps][C][2] + [8]
+  const int p = blockIdx.x, n = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const SeMap m = se_map(C, lane);
+  long long v0, v1;
+  ew_range(vox, p, P, v0, v1);
+  float gg[SE_MAX_CPL][8], ww[SE_MAX_CPL][8], adg[SE_MAX_CPL][8], adw[SE_MAX_CPL][8];
+  float adb = 0.f;
+#pragma unroll
+  for (int k = 0; k < SE_MAX_CPL; ++k) {
+    const int cg = m.gl + 32 * k;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const bool ok = k < m.CPL && cg < m.CG;
+      gg[k][i] = ok ? g[(size_t)n * C + cg * 8 + i] : 0.f;
+      ww[k][i] = ok ? ws[cg * 8 + i] : 0.f;
+      adg[k][i] = 0.f;
+      adw[k][i] = 0.f;
+    }
+  }
+  const int vstep = 8 * m.VPW;
+  for (long long vb = v0 + warp * m.VPW; vb < v1; vb += vstep) {
+    const long long v = vb + m.sub;
+    const bool okv = v < v1;
+    const float qv = okv ? q[(size_t)n * vox + v] : 0.f;
+    float fy[SE_MAX_CPL][8], fd[SE_MAX_CPL][8], sc[SE_MAX_CPL][8];
+    float dq = 0.f;
+#pragma unroll
+    for (int k = 0; k < SE_MAX_CPL; ++k) {
+      const int cg = m.gl + 32 * k;
+      if (k < m.CPL && cg < m.CG && okv) {
+        const size_t o = ((size_t)n * vox + v) * C + cg * 8;
+        unpack8(*reinterpret_cast<const bf16x8*>(y + o), fy[k]);
+        unpack8(*reinterpret_cast<const bf16x8*>(dout + o), fd[k]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float a = fy[k][i] * gg[k][i], b = fy[k][i] * qv;
+          sc[k][i] = a > b ? 1.f : (a == b ? 0.5f : 0.f);
+          dq = fmaf(fd[k][i] * fy[k][i], 1.f - sc[k][i], dq);
+        }
+      }
+    }
+    dq = se_group_sum(dq, m.GL);
+    const float dl = dq * qv * (1.f - qv);
+    if (okv && m.gl == 0) adb += dl;
+#pragma unroll
+    for (int k = 0; k < SE_MAX_CPL; ++k) {
+      const int cg = m.gl + 32 * k;
+      if (k < m.CPL && cg < m.CG && okv) {
+        float o8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          o8[i] = fd[k][i] * (sc[k][i] * gg[k][i] + (1.f - sc[k][i]) * qv) + dl * ww[k][i];
+          adg[k][i] = fmaf(fd[k][i] * fy[k][i], sc[k][i], adg[k][i]);
+          adw[k][i] = fmaf(dl, fy[k][i], adw[k][i]);
+        }
+        *reinterpret_cast<bf16x8*>(tmp + ((size_t)n * vox + v) * C + cg * 8) = pack8(o8);
+      }
+    }
+  }
+  // reduce over the voxel sub-groups of the warp (lanes with equal gl), then over the 8 warps through shared memory
+#pragma unroll
+  for (int k = 0; k < SE_MAX_CPL; ++k)
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      for (int o = m.GL; o < 32; o <<= 1) {
+        adg[k][i] += __shfl_xor_sync(0xffffffffu, adg[k][i], o);
+        adw[k][i] += __shfl_xor_sync(0xffffffffu, adw[k][i], o);
+      }
+  for (int o = 16; o; o >>= 1) adb += __shfl_xor_sync(0xffffffffu, adb, o);
+  float* rw = red + (size_t)warp * C * 2;
+  if (m.sub == 0) {
+#pragma unroll
+    for (int k = 0; k < SE_MAX_CPL; ++k) {
+      const int cg = m.gl + 32 * k;
+      if (k < m.CPL && cg < m.CG)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          rw[(cg * 8 + i) * 2] = adg[k][i];
+          rw[(cg * 8 + i) * 2 + 1] = adw[k][i];
+        }
+    }
+  }
+  float* rb = red + (size_t)8 * C * 2;
+  if (lane == 0) rb[warp] = adb;
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * 2; i += blockDim.x) {
+    float a = 0.f;
+    for (int wv = 0; wv < 8; ++wv) a += red[(size_t)wv * C * 2 + i];
+    partials[((size_t)n * P + p) * C * 2 + i] = a;
+  }
+  if (threadIdx.x == 0) {
+    float a = 0.f;
+    for (int wv = 0; wv < 8; ++wv) a += rb[wv];
+    dbs_part[(size_t)n * P + p] = a;
+  }
+}
+
+// gates backward, grid 1 block 256: sums2 double [N][C][2] = (dg, dws_n).  Outputs: coef[N][C][3] = (1, 0, ds/V) for
+// b200_gn_bwd_apply, dW1,db1,dW2,db2, dws[C] (summed over n)
+__global__ void se_gates_bwd_kernel(const double* __restrict__ sums2, const float* __restrict__ sm, const float* __restrict__ h,
+                                    const float* __restrict__ g, const float* __restrict__ W1, const float* __restrict__ W2, int N, int C,
+                                    double count, float* __restrict__ coef, float* __restrict__ dW1, float* __restrict__ db1,
+                                    float* __restrict__ dW2, float* __restrict__ db2, float* __restrict__ dws, float* __restrict__ scratch /*[N][2][C]*/) {
+  // dl2[n][j] = dg*g*(1-g); dh[n][c] = sum_j W2[j][c] dl2[n][j]; dl1[n][c] = dh * (h>0)
+  for (int i = threadIdx.x; i < N * C; i += blockDim.x) {
+    const int n = i / C, j = i % C;
+    const float gv = g[i];
+    scratch[((size_t)n * 2) * C + j] = (float)sums2[(size_t)i * 2] * gv * (1.f - gv);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < N * C; i += blockDim.x) {
+    const int n = i / C, c = i % C;
+    float acc = 0.f;
+    for (int j = 0; j < C; ++j) acc = fmaf(W2[(size_t)j * C + c], scratch[((size_t)n * 2) * C + j], acc);
+    scratch[((size_t)n * 2 + 1) * C + c] = h[i] > 0.f ? acc : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * C; i += blockDim.x) {
+    const int j = i / C, c = i % C;
+    float a2 = 0.f, a1 = 0.f;
+    for (int n = 0; n < N; ++n) {
+      a2 = fmaf(scratch[((size_t)n * 2) * C + j], h[(size_t)n * C + c], a2);        // dW2[j][c] = sum_n dl2[n][j] h[n][c]
+      a1 = fmaf(scratch[((size_t)n * 2 + 1) * C + j], sm[(size_t)n * C + c], a1);  // dW1[j][c] = sum_n dl1[n][j] s[n][c]
+    }
+    dW2[i] = a2;
+    dW1[i] = a1;
+  }
+  for (int j = threadIdx.x; j < C; j += blockDim.x) {
+    float a2 = 0.f, a1 = 0.f, aw = 0.f;
+    for (int n = 0; n < N; ++n) {
+      a2 += scratch[((size_t)n * 2) * C + j];
+      a1 += scratch[((size_t)n * 2 + 1) * C + j];
+      aw += (float)sums2[((size_t)n * C + j) * 2 + 1];
+    }
+    db2[j] = a2;
+    db1[j] = a1;
+    dws[j] = aw;
+  }
+  for (int i = threadIdx.x; i < N * C; i += blockDim.x) {
+    const int n = i / C, k = i % C;
+    float acc = 0.f;
+    for (int c = 0; c < C; ++c) acc = fmaf(W1[(size_t)c * C + k], scratch[((size_t)n * 2 + 1) * C + c], acc);  // ds[n][k]
+    coef[(size_t)i * 3] = 1.f;
+    coef[(size_t)i * 3 + 1] = 0.f;
+    coef[(size_t)i * 3 + 2] = (float)(acc / count);
+  }
+}
+
+}  // namespace b200
+
+extern "C" {
+
+int b200_se_gates_fwd(const double* sums, double count, const float* W1, const float* b1, const float* W2, const float* b2, int N, int C,
+                      float* smean, float* h, float* g, b200_stream_t s) {
+  b200::se_gates_fwd_kernel<<<N, 256, 2 * C * sizeof(float), ST(s)>>>(sums, count, W1, b1, W2, b2, C, smean, h, g);
+  B200_CHECK_LAUNCH("se_gates_fwd");
+  return 0;
+}
+int b200_scse_partials_count(int N, long long voxels, int C) {
+  (void)N;
+  (void)C;
+  long long p = (voxels + 2047) / 2048;
+  return (int)(p > 1024 ? 1024 : (p < 1 ? 1 : p));
+}
+int b200_scse_apply_fwd(const void* y, const float* g, const float* ws, float bs, int N, long long voxels, int C, void* out, float* q,
+                        b200_stream_t s) {
+  int CG = C / 8;
+  B200_CHECK_ARG(C % 8 == 0 && C <= 1024 && (CG & (CG - 1)) == 0, "scse_apply_fwd: C=%d must be 8 * a power of two, <= 1024", C);
+  int P = b200_scse_partials_count(N, voxels, C);
+  dim3 grid(P, N);
+  b200::scse_apply_fwd_kernel<<<grid, 256, 0, ST(s)>>>((const bf16*)y, g, ws, bs, C, voxels, P, (bf16*)out, q);
+  B200_CHECK_LAUNCH("scse_apply_fwd");
+  return 0;
+}
+int b200_scse_bwd1(const void* dout, const void* y, const float* g, const float* q, const float* ws, int N, long long voxels, int C, void* tmp,
+                   float* partials, float* dbs_part, b200_stream_t s) {
+  int CG = C / 8;
+  B200_CHECK_ARG(C % 8 == 0 && C <= 1024 && (CG & (CG - 1)) == 0, "scse_bwd1: C=%d must be 8 * a power of two, <= 1024", C);
+  int P = b200_scse_partials_count(N, voxels, C);
+  dim3 grid(P, N);
+  size_t smem = ((size_t)8 * C * 2 + 8) * sizeof(float);
+  cudaFuncSetAttribute(b200::scse_bwd1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  b200::scse_bwd1_kernel<<<grid, 256, smem, ST(s)>>>((const bf16*)dout, (const bf16*)y, g, q, ws, C, voxels, P, (bf16*)tmp, partials, dbs_part);
+  B200_CHECK_LAUNCH("scse_bwd1");
+  return 0;
+}
+int b200_se_gates_bwd(const double* sums2, const float* smean, const float* h, const float* g, const float* W1, const float* W2, int N, int C,
+                      double count, float* coef, float* dW1, float* db1, float* dW2, float* db2, float* dws, float* scratch, b200_stream_t s) {
+  b200::se_gates_bwd_kernel<<<1, 256, 0, ST(s)>>>(sums2, smean, h, g, W1, W2, N, C, count, coef, dW1, db1, dW2, db2, dws, scratch);
+  B200_CHECK_LAUNCH("se_gates_bwd");
+  return 0;
+}
+
+}  // extern "C"

@@ -439,6 +439,141 @@ class Engine:
             self.tape.append(backward)
         return out
 
+    # ---------------------------------------------------------------- 1x1x1 conv with bias (ResNetBlock.conv1, buildingblocks.py:251)
+    def pointwise(self, x, W, bias, wname, bname, want_stats=True):
+        n, d, h, w, cin = x.dims
+        vox = d * h * w
+        cout = W.shape[0]
+        if cout % 8 != 0:
+            raise NotImplementedError(f"1x1x1 conv with C_out={cout}: the engine needs C_out % 8 == 0")
+        is_f32 = isinstance(x, InputF32)
+        W2 = W.reshape(cout, cin).contiguous()
+        y = self.empty((n, d, h, w, cout), torch.bfloat16)
+        P = self.L.query("b200_pointwise_partials_count", n, vox, cout)
+        partials = self.empty((n, P, cout, 2), torch.float32) if want_stats else None
+        self.call("b200_pointwise_fwd", _p(x.t), int(is_f32), _p(W2), 0, _p(bias), n, vox, cin, cout, _p(y), _p(partials))
+        out = Act(y, ACT_NONE, 0.0, partials, P)
+        if self.record:
+            def backward():
+                dy = out.grad
+                if dy is None:
+                    return
+                Pw = self.L.query("b200_pointwise_wgrad_partials_count", n, vox)
+                K = cout * cin + cout
+                part = self.empty((n * Pw, K), torch.float32)
+                self.call("b200_pointwise_wgrad", _p(x.t), int(is_f32), _p(dy), n, vox, cin, cout, _p(part))
+                red = self.empty((K,), torch.float32)
+                self.call("b200_reduce_rows", _p(part), n * Pw, K, _p(red))
+                self._add_param_grad(wname, red[: cout * cin].reshape(W.shape))
+                if bias is not None:
+                    self._add_param_grad(bname, red[cout * cin:].clone())
+                if x.requires_grad:
+                    if is_f32:
+                        raise NotImplementedError("gradient w.r.t. the fp32 network input is not provided by the engine")
+                    g = self.empty(x.t.shape, torch.bfloat16)
+                    self.call("b200_pointwise_fwd", _p(dy), 0, _p(W2), 1, None, n, vox, cout, cin, _p(g), None)
+                    self.call("b200_act_bwd", _p(g), cin, 0, _p(x.t), n, cin, vox, x.act, x.slope, _p(x.grad), _p(g))
+                    x.grad = g
+                out.grad = None
+            self.tape.append(backward)
+        return out
+
+    # ---------------------------------------------------------------- ConvTranspose3d(k3,s2,p1) + nearest resize + sum-join
+    def deconv_up_add(self, enc, x, Wt, wname, want_stats=True):
+        """TransposeConvUpsampling (buildingblocks.py:617-664) followed by Decoder._joining(concat=False) (:493):
+        out = enc + interpolate(conv_transpose3d(x), size=enc.shape[2:])"""
+        n, D, H, W_, cout = enc.dims
+        n2, d, h, w, cin = x.dims
+        assert n == n2 and tuple(Wt.shape) == (cin, cout, 3, 3, 3), (tuple(Wt.shape), cin, cout)
+        Wt = Wt.contiguous()
+        wt = self.empty((27, cout, cin), torch.bfloat16)
+        self.call("b200_deconv_prep_weights", _p(Wt), cin, cout, _p(wt), None)
+        out_t = self.empty((n, D, H, W_, cout), torch.bfloat16)
+        P = self.L.query("b200_deconv_up_add_partials_count", n, D, H, W_, cout)
+        partials = self.empty((n, P, cout, 2), torch.float32) if want_stats else None
+        self.call("b200_deconv_up_add_fwd", _p(x.t), _p(wt), _p(enc.t), n, d, h, w, D, H, W_, cin, cout, _p(out_t), _p(partials))
+        out = Act(out_t, ACT_NONE, 0.0, partials, P)
+        if self.record:
+            def backward():
+                g = out.grad
+                if g is None:
+                    return
+                sd, sh, sw = 2 * d - 1, 2 * h - 1, 2 * w - 1
+                dT = self.empty((n, sd, sh, sw, cout), torch.bfloat16)
+                self.call("b200_deconv_gather", _p(g), n, d, h, w, D, H, W_, cout, _p(dT))
+                dWt = torch.empty_like(Wt)
+                self.call("b200_deconv_wgrad", _p(x.t), _p(dT), n, d, h, w, cin, cout, _p(dWt), launches=2)
+                self._add_param_grad(wname, dWt)
+                if x.requires_grad:
+                    wtb = self.empty((27, cin, cout), torch.bfloat16)
+                    self.call("b200_deconv_prep_weights", _p(Wt), cin, cout, None, _p(wtb))
+                    gx = self.empty(x.t.shape, torch.bfloat16)
+                    self.call("b200_deconv_dgrad", _p(dT), _p(wtb), _p(x.t), n, d, h, w, cin, cout, x.act, x.slope, _p(x.grad), _p(gx))
+                    x.grad = gx
+                if enc.requires_grad:
+                    ge = self.empty(enc.t.shape, torch.bfloat16)
+                    self.call("b200_act_bwd", _p(g), cout, 0, _p(enc.t), n, cout, D * H * W_, enc.act, enc.slope, _p(enc.grad), _p(ge))
+                    enc.grad = ge
+                out.grad = None
+            self.tape.append(backward)
+        return out
+
+    # ---------------------------------------------------------------- scSE (ChannelSpatialSELayer3D, se.py:96-114)
+    def scse(self, y, sd, prefix):
+        """out = max(cSE(y), sSE(y)) with reduction_ratio 1 (ResNetBlockSE, buildingblocks.py:291-307)."""
+        n, d, h, w, c = y.dims
+        vox = d * h * w
+        W1, b1 = sd[prefix + "cSE.fc1.weight"].contiguous(), sd[prefix + "cSE.fc1.bias"].contiguous()
+        W2, b2 = sd[prefix + "cSE.fc2.weight"].contiguous(), sd[prefix + "cSE.fc2.bias"].contiguous()
+        ws = sd[prefix + "sSE.conv.weight"].reshape(-1).contiguous()
+        bs_t = sd[prefix + "sSE.conv.bias"]
+        if W1.shape != (c, c) or W2.shape != (c, c):
+            raise NotImplementedError("the b200 engine implements scSE with reduction_ratio=1 (what ResNetBlockSE uses)")
+        sums = self.sums_of(y)
+        smean = self.empty((n, c), torch.float32)
+        hh = self.empty((n, c), torch.float32)
+        g = self.empty((n, c), torch.float32)
+        self.call("b200_se_gates_fwd", _p(sums), float(vox), _p(W1), _p(b1), _p(W2), _p(b2), n, c, _p(smean), _p(hh), _p(g))
+        out_t = self.empty(y.t.shape, torch.bfloat16)
+        q = self.empty((n, vox), torch.float32)
+        bs = float(bs_t.item())  # 1-element parameter passed by value (one small D2H per SE block per forward)
+        self.call("b200_scse_apply_fwd", _p(y.t), _p(g), _p(ws), bs, n, vox, c, _p(out_t), _p(q))
+        out = Act(out_t, ACT_NONE, 0.0)
+        if self.record:
+            def backward():
+                dout = out.grad
+                if dout is None:
+                    return
+                P = self.L.query("b200_scse_partials_count", n, vox, c)
+                tmp = self.empty(y.t.shape, torch.bfloat16)
+                part = self.empty((n, P, c, 2), torch.float32)
+                dbs_part = self.empty((n * P, 1), torch.float32)
+                self.call("b200_scse_bwd1", _p(dout), _p(y.t), _p(g), _p(q), _p(ws), n, vox, c, _p(tmp), _p(part), _p(dbs_part))
+                sums2 = self.empty((n, c, 2), torch.float64)
+                self.call("b200_partials_finalize", _p(part), n, P, c, _p(sums2))
+                dbs = self.empty((1,), torch.float32)
+                self.call("b200_reduce_rows", _p(dbs_part), n * P, 1, _p(dbs))
+                coef = self.empty((n, c, 3), torch.float32)
+                dW1, db1 = torch.empty_like(W1), torch.empty_like(b1)
+                dW2, db2 = torch.empty_like(W2), torch.empty_like(b2)
+                dws = self.empty((c,), torch.float32)
+                scratch = self.empty((n, 2, c), torch.float32)
+                self.call("b200_se_gates_bwd", _p(sums2), _p(smean), _p(hh), _p(g), _p(W1), _p(W2), n, c, float(vox),
+                          _p(coef), _p(dW1), _p(db1), _p(dW2), _p(db2), _p(dws), _p(scratch))
+                self._add_param_grad(prefix + "cSE.fc1.weight", dW1)
+                self._add_param_grad(prefix + "cSE.fc1.bias", db1)
+                self._add_param_grad(prefix + "cSE.fc2.weight", dW2)
+                self._add_param_grad(prefix + "cSE.fc2.bias", db2)
+                self._add_param_grad(prefix + "sSE.conv.weight", dws.reshape(sd[prefix + "sSE.conv.weight"].shape))
+                self._add_param_grad(prefix + "sSE.conv.bias", dbs)
+                if y.requires_grad:
+                    gy = self.empty(y.t.shape, torch.bfloat16)
+                    self.call("b200_gn_bwd_apply", _p(tmp), _p(y.t), _p(coef), n, c, vox, y.act, y.slope, _p(y.grad), _p(gy))
+                    y.grad = gy
+                out.grad = None
+            self.tape.append(backward)
+        return out
+
     # ---------------------------------------------------------------- final 1x1x1 conv + sigmoid/softmax
     def final_conv(self, x, W, bias, final_act, wname, bname):
         n, d, h, w, c = x.dims

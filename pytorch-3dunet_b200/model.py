@@ -101,11 +101,50 @@ def run_double_conv(eng, x, sd, prefix, order, groups, out_stats):
     return eng.single_conv(h, sd, prefix + "SingleConv2.", order, groups, want_stats=out_stats)
 
 
+def run_res_block(eng, x, sd, prefix, order, groups, out_stats):
+    """ResNetBlock.forward, reference buildingblocks.py:277-288: conv1 (1x1x1 + bias, or Identity) -> conv2 (order) ->
+    conv3 (order without the non-linearity) -> += residual -> non-linearity.  The add + activation are the epilogue of
+    conv3's tensor-core kernel."""
+    pre_gn = _has_pre_gn(order)
+    if (prefix + "conv1.weight") in sd:
+        residual = eng.pointwise(x, sd[prefix + "conv1.weight"], sd.get(prefix + "conv1.bias"), prefix + "conv1.weight",
+                                 prefix + "conv1.bias", want_stats=pre_gn)
+    else:
+        if isinstance(x, E.InputF32):
+            raise NotImplementedError("ResNetBlock with in_channels == out_channels directly on the fp32 network input")
+        residual = x
+    n_order = order.replace("r", "").replace("e", "").replace("l", "")
+    if "l" in order:
+        block_act = (E.ACT_LEAKY, 0.1)   # buildingblocks.py:271: slope 0.1 here (create_conv's LeakyReLU uses 0.01)
+    elif "e" in order:
+        block_act = (E.ACT_ELU, 1.0)
+    else:
+        block_act = (E.ACT_RELU, 0.0)
+    h = eng.single_conv(residual, sd, prefix + "conv2.", order, groups, want_stats=_has_pre_gn(n_order))
+    return eng.single_conv(h, sd, prefix + "conv3.", n_order, groups, want_stats=out_stats, residual=residual, final_act=block_act)
+
+
 def run_basic(eng, x, sd, prefix, spec, out_stats=False):
     if spec["basic"] == "double":
         return run_double_conv(eng, x, sd, prefix, spec["layer_order"], spec["num_groups"], out_stats)
-    raise NotImplementedError("ResNetBlock / ResNetBlockSE kernels (ResidualUNet3D, ResidualUNetSE3D) are not built yet "
-                              "in the b200 engine; there is deliberately no PyTorch fallback")
+    if spec["basic"] == "res":
+        return run_res_block(eng, x, sd, prefix, spec["layer_order"], spec["num_groups"], out_stats)
+    if spec["basic"] == "res_se":
+        # ResNetBlockSE.forward (buildingblocks.py:304-307): ResNetBlock then scSE; the SE means reuse the block output's partial sums
+        y = run_res_block(eng, x, sd, prefix, spec["layer_order"], spec["num_groups"], True)
+        return eng.scse(y, sd, prefix + "se_module.")
+    raise NotImplementedError(f"basic module {spec['basic']!r}")
+
+
+def run_join(eng, enc, x, sd, prefix, spec, want_stats):
+    """Decoder.forward up to the basic module, reference buildingblocks.py:482-493"""
+    if spec["upsample"] == "nearest" and spec["concat"]:
+        return eng.upcat(enc, x, want_stats=want_stats)
+    if spec["upsample"] == "deconv" and not spec["concat"]:
+        return eng.deconv_up_add(enc, x, sd[prefix + "upsampling.upsample.conv_transposed.weight"],
+                                 prefix + "upsampling.upsample.conv_transposed.weight", want_stats=want_stats)
+    raise NotImplementedError(f"decoder upsample={spec['upsample']!r} concat={spec['concat']} is not built in the b200 engine "
+                              "(built: nearest+concat, deconv+sum)")
 
 
 def run_unet(eng, x, sd, spec):
@@ -120,9 +159,7 @@ def run_unet(eng, x, sd, spec):
         x = run_basic(eng, x, sd, f"encoders.{i}.basic_module.", spec)
         feats.insert(0, x)
     for i, enc in enumerate(feats[1:]):
-        if spec["upsample"] != "nearest" or not spec["concat"]:
-            raise NotImplementedError(f"decoder upsample={spec['upsample']!r} concat={spec['concat']} is not built yet in the b200 engine")
-        x = eng.upcat(enc, x, want_stats=pre_gn)
+        x = run_join(eng, enc, x, sd, f"decoders.{i}.", spec, pre_gn)
         x = run_basic(eng, x, sd, f"decoders.{i}.basic_module.", spec)
     final = E.FINAL_NONE
     if spec["is_segmentation"]:
@@ -254,7 +291,12 @@ class Decoder(_EngineModule):
     def __init__(self, in_channels, out_channels, basic="double", conv_layer_order="gcr", num_groups=8, upsample="nearest",
                  concat=True):
         super().__init__()
-        self.upsampling = _Marker(f"{upsample} to the encoder feature size [fused b200 kernel]")
+        if upsample == "deconv":
+            self.upsampling = _DeconvHolder(in_channels, out_channels)
+            if not concat:
+                in_channels = out_channels  # adapt_channels, reference buildingblocks.py:466-468
+        else:
+            self.upsampling = _Marker(f"{upsample} to the encoder feature size [fused b200 kernel]")
         self.spec = dict(basic=basic, layer_order=conv_layer_order, num_groups=num_groups, upsample=upsample, concat=concat)
         self.basic_module = _make_basic(basic, in_channels, out_channels, False, conv_layer_order, num_groups, 2)
 
@@ -263,17 +305,85 @@ class Decoder(_EngineModule):
 
     def _program(self):
         def prog(eng, acts, sd):
-            if self.spec["upsample"] != "nearest" or not self.spec["concat"]:
-                raise NotImplementedError("only nearest-upsample + concat decoders are built so far")
-            cat = eng.upcat(acts[0], acts[1], want_stats=_has_pre_gn(self.spec["layer_order"]))
-            return run_basic(eng, cat, sd, "basic_module.", self.spec)
+            j = run_join(eng, acts[0], acts[1], sd, "", self.spec, _has_pre_gn(self.spec["layer_order"]))
+            return run_basic(eng, j, sd, "basic_module.", self.spec)
         return prog
+
+
+class ResNetBlock(_EngineModule):
+    """parameter names of the reference's ResNetBlock (buildingblocks.py:230-275): conv1 (1x1x1 or Identity), conv2, conv3"""
+
+    def __init__(self, in_channels, out_channels, kernel_size=3, order="cge", num_groups=8, is3d=True, **kwargs):
+        super().__init__()
+        self.conv1 = nn.Conv3d(in_channels, out_channels, 1) if in_channels != out_channels else nn.Identity()
+        self.order, self.num_groups = order, num_groups
+        self.conv2 = SingleConv(out_channels, out_channels, kernel_size=kernel_size, order=order, num_groups=num_groups, is3d=is3d)
+        n_order = order.replace("r", "").replace("e", "").replace("l", "")
+        self.conv3 = SingleConv(out_channels, out_channels, kernel_size=kernel_size, order=n_order, num_groups=num_groups, is3d=is3d)
+        if "l" in order:
+            self.non_linearity = nn.LeakyReLU(negative_slope=0.1, inplace=True)
+        elif "e" in order:
+            self.non_linearity = nn.ELU(inplace=True)
+        else:
+            self.non_linearity = nn.ReLU(inplace=True)
+
+    def _program(self):
+        return lambda eng, acts, sd: run_res_block(eng, acts[0], sd, "", self.order, self.num_groups, False)
+
+
+class _ChannelSE(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.fc1 = nn.Linear(c, c, bias=True)
+        self.fc2 = nn.Linear(c, c, bias=True)
+
+
+class _SpatialSE(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.conv = nn.Conv3d(c, 1, 1)
+
+
+class _SCSE(nn.Module):
+    """parameters of ChannelSpatialSELayer3D(num_channels, reduction_ratio=1) (se.py:96-111), same creation order"""
+
+    def __init__(self, c):
+        super().__init__()
+        self.cSE = _ChannelSE(c)
+        self.sSE = _SpatialSE(c)
+
+
+class ResNetBlockSE(ResNetBlock):
+    def __init__(self, in_channels, out_channels, kernel_size=3, order="cge", num_groups=8, se_module="scse", **kwargs):
+        super().__init__(in_channels, out_channels, kernel_size=kernel_size, order=order, num_groups=num_groups)
+        if se_module != "scse":
+            raise NotImplementedError("only se_module='scse' (the ResNetBlockSE default) is built in the b200 engine")
+        self.se_module = _SCSE(out_channels)
+
+    def _program(self):
+        def prog(eng, acts, sd):
+            y = run_res_block(eng, acts[0], sd, "", self.order, self.num_groups, True)
+            return eng.scse(y, sd, "se_module.")
+        return prog
+
+
+class _DeconvHolder(nn.Module):
+    """`upsampling.upsample.conv_transposed.weight` (TransposeConvUpsampling.Upsample, buildingblocks.py:633-664)"""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.upsample = nn.Module()
+        self.upsample.conv_transposed = nn.ConvTranspose3d(in_channels, out_channels, kernel_size=3, stride=2, padding=1, bias=False)
 
 
 def _make_basic(basic, cin, cout, encoder, order, groups, upscale):
     if basic == "double":
         return DoubleConv(cin, cout, encoder, order=order, num_groups=groups, upscale=upscale)
-    raise NotImplementedError("ResNetBlock / ResNetBlockSE are not built yet in the b200 engine (no PyTorch fallback on purpose)")
+    if basic == "res":
+        return ResNetBlock(cin, cout, order=order, num_groups=groups)
+    if basic == "res_se":
+        return ResNetBlockSE(cin, cout, order=order, num_groups=groups)
+    raise NotImplementedError(f"basic module {basic!r}")
 
 
 # ----------------------------------------------------------------------------------------------------

@@ -49,11 +49,23 @@ def _block(name):
         return P.Decoder(96, 32), dec
     if name == "block_decoder_cat_odd":
         return P.Decoder(48, 16), dec
+    if name == "block_resnet_16_32":
+        return P.model.ResNetBlock(16, 32, order="gcr", num_groups=8), lambda sd, x, enc, m: O.res_block(x, sd, "", "gcr", 8, masks=m)
+
+    def dec_res(sd, x, enc, m):
+        u = F.conv_transpose3d(x, sd["upsampling.upsample.conv_transposed.weight"], None, stride=2, padding=1)
+        u = F.interpolate(u, size=enc.shape[2:])
+        return O.res_block(enc + u, sd, "basic_module.", "gcr", 8, masks=m)
+    if name == "block_decoder_deconv_32_16":
+        return P.Decoder(32, 16, basic="res", upsample="deconv", concat=False), dec_res
+    if name == "block_resnetse_32_32":
+        return P.ResNetBlockSE(32, 32, order="gcr", num_groups=8), lambda sd, x, enc, m: O.res_block(x, sd, "", "gcr", 8, se=True, masks=m)
     raise KeyError(name)
 
 
 BLOCKS = ["block_singleconv_gcr_16_32", "block_singleconv_cr_16_16", "block_doubleconv_enc_32_64", "block_doubleconv_dec_96_32",
-          "block_encoder_pool_32_64", "block_decoder_cat_64_32", "block_decoder_cat_odd"]
+          "block_encoder_pool_32_64", "block_decoder_cat_64_32", "block_decoder_cat_odd", "block_resnet_16_32",
+          "block_decoder_deconv_32_16", "block_resnetse_32_32"]
 
 
 @pytest.mark.parametrize("impl", ["direct", "auto"])
@@ -103,6 +115,8 @@ MODEL_CASES = {
     "unet3d_f16_l3_dice_b2": (dict(name="UNet3D", in_channels=1, out_channels=1, f_maps=16, num_levels=3), "dice_loss"),
     "unet3d_f16_l3_odd": (dict(name="UNet3D", in_channels=2, out_channels=3, f_maps=16, num_levels=3, final_sigmoid=False), "bce_dice_loss"),
     "unet3d_f16_l2_cgr": (dict(name="UNet3D", in_channels=1, out_channels=1, f_maps=16, num_levels=2, layer_order="cgr"), "bce_dice_loss"),
+    "resunet3d_f16_l3_s16": (dict(name="ResidualUNet3D", in_channels=1, out_channels=1, f_maps=16, num_levels=3), "bce_dice_loss"),
+    "resunetse3d_f16_l3_s16": (dict(name="ResidualUNetSE3D", in_channels=1, out_channels=1, f_maps=16, num_levels=3), "bce_dice_loss"),
 }
 
 
