@@ -153,8 +153,15 @@ def res_block(x, sd, prefix, order, num_groups, se=False, masks=None):
     else:
         out = F.relu(out)
     if se:
-        out = torch.max(channel_se(out, sd, prefix + "se_module.cSE."),
-                        spatial_se(out, sd, prefix + "se_module.sSE."))  # se.py:113
+        cse = channel_se(out, sd, prefix + "se_module.cSE.")
+        sse = spatial_se(out, sd, prefix + "se_module.sSE.")
+        key = prefix + "se_module.#select"
+        if masks is not None and key in masks:
+            # tests only: which branch of the element-wise max wins is a discontinuity for the gate-parameter gradients
+            # (g ~ q ~ 0.5 at initialisation, so bf16 noise flips many selections); evaluate at the given selection
+            out = torch.where(masks[key], cse, sse)
+        else:
+            out = torch.max(cse, sse)  # se.py:113
     return out
 
 

@@ -539,6 +539,8 @@ class Engine:
         bs = float(bs_t.item())  # 1-element parameter passed by value (one small D2H per SE block per forward)
         self.call("b200_scse_apply_fwd", _p(y.t), _p(g), _p(ws), bs, n, vox, c, _p(out_t), _p(q))
         out = Act(out_t, ACT_NONE, 0.0)
+        if DEBUG is not None:
+            DEBUG.setdefault("se", {})[prefix] = (y.t, g, q)
         if self.record:
             def backward():
                 dout = out.grad

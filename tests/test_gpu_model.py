@@ -17,8 +17,15 @@ E2E_GRAD_TOL = 8e-2  # worst parameter gradient of a whole model (max-pool argma
 
 
 def _engine_masks(E):
-    """{conv prefix: bool NCDHW cpu tensor} activation pattern (y > 0) of every SingleConv output of the last engine run"""
-    return {k: (v.float() > 0).permute(0, 4, 1, 2, 3).cpu() for k, v in E.DEBUG["fwd"].items()}
+    """{conv prefix: bool NCDHW cpu tensor} activation pattern (y > 0) of every SingleConv output of the last engine run,
+    plus, per scSE module, which branch of max(cSE, sSE) the engine selected ("<prefix>#select")"""
+    m = {k: (v.float() > 0).permute(0, 4, 1, 2, 3).cpu() for k, v in E.DEBUG["fwd"].items()}
+    for k, (y, g, q) in E.DEBUG.get("se", {}).items():
+        yf = y.float()
+        n, d, h, w, c = yf.shape
+        sel = (yf * g.view(n, 1, 1, 1, c)) >= (yf * q.view(n, d, h, w, 1))
+        m[k + "#select"] = sel.permute(0, 4, 1, 2, 3).cpu()
+    return m
 
 
 def _engine_pool_idx(E):
