@@ -229,8 +229,17 @@ def main():
     tc_ms = sum(v[1] for v in tc.values())
     achieved = tc_flops / (tc_ms / 1e3) / 1e12 if tc_ms > 0 else 0.0
     peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
-    roofline = {"bound": "tensor", "kernel": "conv3_igemm_kernel + conv3_wgrad_igemm_kernel (tcgen05)", "achieved": achieved, "peak": peak,
-                "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": None, "peak_source": pk_src + " sustained bf16",
+    traffic = None
+    try:  # dram bytes of one launch of the largest-share kernel, from the committed ncu --set full capture
+        prof = json.load(open(os.path.join(ROOT, "profiles", "ncu_r01_full_summary.json")))["wgrad_halo_kernel"]
+        traffic = (float(prof["dram__bytes_read.sum"]["value"]) + float(prof["dram__bytes_write.sum"]["value"])) * 1e6
+    except Exception:
+        pass
+    roofline = {"bound": "tensor", "kernel": "tcgen05 conv kernels: conv3_halo_kernel / conv3_igemm_kernel (fprop+dgrad), wgrad_halo_kernel / conv3_wgrad_igemm_kernel",
+                "achieved": achieved, "peak": peak,
+                "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": traffic,
+                "traffic_note": "dram read+write bytes of ONE wgrad_halo_kernel<32> launch (32->32 @ 2x128^3; algorithmic 537 MB: x + dz), profiles/ncu_r01_full_summary.md",
+                "peak_source": pk_src + " sustained bf16",
                 "share_of_step": tc_ms / ms if ms else None,
                 "per_kernel": {k: {"tflops": v[0] / (v[1] / 1e3) / 1e12 if v[1] else None, "ms_per_step": v[1] / args.steps, "launches_per_step": v[2] / args.steps}
                                for k, v in by.items()}}
