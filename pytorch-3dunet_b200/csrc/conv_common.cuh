@@ -36,6 +36,7 @@ struct ConvParams {
   int b_total_bytes;   // resident weights [Cin/KCb][27][NT][KCb]
   int ctas_per_sample;
   long long* dbg;      // optional per-CTA wait-cycle counters (b200_set_debug_buffer), NULL in production
+  int dbg_flags;       // experiments only (env B200UNET_DBG_FLAGS): 1 = skip the global stores, 2 = skip the bias add
 };
 
 // one 32-/16-column slab of the accumulator tile for one thread (= one output voxel row)
@@ -54,7 +55,7 @@ __device__ __forceinline__ void conv_epilogue_slab(const ConvParams& p, uint32_t
   for (int i = 0; i < CW; ++i) v[i] = __uint_as_float(raw[i]);
   const size_t goff = vox_off * p.Cout + n0 + c0;
   if (valid) {
-    if (bias_row) {
+    if (bias_row && !(p.dbg_flags & 2)) {
       const float4* bp = reinterpret_cast<const float4*>(bias_row + n0 + c0);
 #pragma unroll
       for (int i = 0; i < CW / 4; ++i) {
@@ -90,8 +91,10 @@ __device__ __forceinline__ void conv_epilogue_slab(const ConvParams& p, uint32_t
 #pragma unroll
     for (int i = 0; i < CW; ++i) v[i] = bf16_round(v[i]);
     bf16x8* op = reinterpret_cast<bf16x8*>(p.y + goff);
+    if (!(p.dbg_flags & 1)) {
 #pragma unroll
-    for (int i = 0; i < CW / 8; ++i) op[i] = pack8(&v[8 * i]);
+      for (int i = 0; i < CW / 8; ++i) op[i] = pack8(&v[8 * i]);
+    }
   } else {
 #pragma unroll
     for (int i = 0; i < CW; ++i) v[i] = 0.f;

@@ -104,10 +104,10 @@ __global__ void conv3_direct_wgrad_kernel(const InT* __restrict__ x, const bf16*
                                           float* __restrict__ G) {
   int n = blockIdx.y;
   long long vox = (long long)D * H * W;
-  long long v0 = (long long)blockIdx.x * WG_CHUNK, v1 = v0 + WG_CHUNK;
+  long long v0 = (long long)blockIdx.z * WG_CHUNK, v1 = v0 + WG_CHUNK;
   if (v1 > vox) v1 = vox;
   int total = 27 * Cin * Cout;
-  int o = blockIdx.z * blockDim.x + threadIdx.x;
+  int o = blockIdx.x * blockDim.x + threadIdx.x;
   if (o >= total) return;
   int co = o % Cout;
   int r = o / Cout;
@@ -396,7 +396,8 @@ int b200_conv3_direct_wgrad(const void* x, int x_is_f32, const void* dz, int N, 
     B200_CHECK_LAUNCH("stem_wgrad");
     return 0;
   }
-  dim3 grid(ceil_div(vox, WG_CHUNK), N, ceil_div(total, 256));
+  dim3 grid(ceil_div(total, 256), N, ceil_div(vox, WG_CHUNK));  // outputs on x (no 65535 limit), voxel chunks on z
+  B200_CHECK_ARG(grid.z <= 65535, "conv3_direct_wgrad: volume too large for the fallback kernel (%lld voxels)", vox);
   if (x_is_f32)
     conv3_direct_wgrad_kernel<float><<<grid, 256, 0, ST(s)>>>((const float*)x, (const bf16*)dz, D, H, W, Cin, Cout, G);
   else

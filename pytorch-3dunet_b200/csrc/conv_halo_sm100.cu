@@ -296,6 +296,8 @@ void set_debug_buffer(long long* p) { g_dbg = p; }
 
 int conv_halo_launch(const void* x, const void* wf, ConvParams& p, cudaStream_t s) {
   p.dbg = g_dbg;
+  const char* fl = getenv("B200UNET_DBG_FLAGS");
+  p.dbg_flags = fl ? atoi(fl) : 0;
   CUtensorMap tmA, tmB;
   int rc = make_act_tmap(&tmA, x, p.N, p.D, p.H, p.W, p.Cin, p.KC, HALO_HD, HALO_HH, HALO_HW);
   if (rc) return rc;

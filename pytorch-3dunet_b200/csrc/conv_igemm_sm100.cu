@@ -200,14 +200,18 @@ int choose_box(int D, int H, int W, int* bd, int* bh, int* bw) {
                                 {32, 2, 2}, {2, 32, 2}, {2, 64, 1}, {4, 16, 2}, {4, 32, 1}, {8, 16, 1}, {16, 1, 8}, {8, 1, 16},
                                 {4, 1, 32}, {2, 1, 64}, {32, 1, 4}, {64, 1, 2}};
   long long best = -1;
-  for (auto& c : cand) {
-    if (c[0] > D || c[1] > H || c[2] > W) continue;
-    long long padded = (long long)((D + c[0] - 1) / c[0]) * c[0] * ((H + c[1] - 1) / c[1]) * c[1] * ((W + c[2] - 1) / c[2]) * c[2];
-    if (best < 0 || padded < best) {
-      best = padded;
-      *bd = c[0];
-      *bh = c[1];
-      *bw = c[2];
+  // pass 0: boxes that fit inside the volume; pass 1 (tiny volumes, e.g. the 6^3 bottom level of a 5-level net): any box --
+  // the part of a TMA box that lies outside the tensor is zero-filled on load and masked on store like any ragged border
+  for (int pass = 0; pass < 2 && best < 0; ++pass) {
+    for (auto& c : cand) {
+      if (pass == 0 && (c[0] > D || c[1] > H || c[2] > W)) continue;
+      long long padded = (long long)((D + c[0] - 1) / c[0]) * c[0] * ((H + c[1] - 1) / c[1]) * c[1] * ((W + c[2] - 1) / c[2]) * c[2];
+      if (best < 0 || padded < best) {
+        best = padded;
+        *bd = c[0];
+        *bh = c[1];
+        *bw = c[2];
+      }
     }
   }
   return best < 0 ? 1 : 0;

@@ -277,7 +277,7 @@ __global__ void deconv_wgrad_kernel(const bf16* __restrict__ x, const bf16* __re
                                     float* __restrict__ dWt) {
   const int n = blockIdx.y;
   const int total = 27 * Cin * Cout;
-  const int o = blockIdx.z * blockDim.x + threadIdx.x;
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
   if (o >= total) return;
   const int co = o % Cout;
   const int r0 = o / Cout;
@@ -285,7 +285,7 @@ __global__ void deconv_wgrad_kernel(const bf16* __restrict__ x, const bf16* __re
   const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
   const int sd = 2 * d - 1, sh = 2 * h - 1, sw = 2 * w - 1;
   const long long vox = (long long)d * h * w, svox = (long long)sd * sh * sw;
-  long long v0 = (long long)blockIdx.x * DC_CHUNK, v1 = v0 + DC_CHUNK;
+  long long v0 = (long long)blockIdx.z * DC_CHUNK, v1 = v0 + DC_CHUNK;
   if (v1 > vox) v1 = vox;
   const bf16* xn = x + (size_t)n * vox * Cin;
   const bf16* tn = dT + (size_t)n * svox * Cout;
@@ -409,7 +409,8 @@ int b200_deconv_wgrad(const void* x, const void* dT, int N, int d, int h, int w,
   cudaError_t e = cudaMemsetAsync(dWt, 0, bytes, ST(s));
   B200_CHECK_ARG(e == cudaSuccess, "deconv_wgrad: memset failed: %s", cudaGetErrorString(e));
   long long vox = (long long)d * h * w;
-  dim3 grid(ceil_div(vox, DC_CHUNK), N, ceil_div(27 * Cin * Cout, 256));
+  dim3 grid(ceil_div(27 * Cin * Cout, 256), N, ceil_div(vox, DC_CHUNK));
+  B200_CHECK_ARG(grid.z <= 65535, "deconv_wgrad: volume too large (%lld voxels)", vox);
   deconv_wgrad_kernel<<<grid, 256, 0, ST(s)>>>((const bf16*)x, (const bf16*)dT, d, h, w, Cin, Cout, dWt);
   B200_CHECK_LAUNCH("deconv_wgrad");
   return 0;

@@ -30,6 +30,8 @@ SHAPES = [
     (1, 4, 4, 8, 384, 128),
     (1, 5, 9, 7, 32, 16),      # ragged: exercises TMA out-of-bounds fill and masked stores
     (1, 16, 16, 16, 32, 64),
+    (2, 4, 4, 4, 64, 64),      # volume smaller than any 128-voxel box: the TMA box overhangs the tensor
+    (1, 6, 6, 6, 128, 128),
     # large enough for the halo kernel (D>=3, H>=18, W>=10): resident weights + shifted halo views
     (2, 3, 18, 10, 16, 32),
     (1, 4, 20, 12, 32, 32),
@@ -85,6 +87,7 @@ def test_tcgen05_conv_residual_no_bias_shared_weights():
 
 WG_SHAPES = [(1, 8, 8, 8, 16, 32), (2, 8, 8, 8, 32, 32), (1, 8, 8, 8, 64, 64), (1, 4, 8, 8, 96, 32), (1, 8, 8, 8, 128, 128),
              (1, 4, 8, 8, 192, 64), (1, 4, 4, 8, 384, 128), (1, 4, 4, 8, 128, 256), (1, 5, 9, 7, 32, 16), (1, 16, 16, 16, 32, 32),
+             (2, 4, 4, 4, 64, 64), (1, 6, 6, 6, 128, 128),
              # large enough for the halo / stacked-tap wgrad kernel (D>=3, H>=18, W>=10)
              (2, 3, 18, 10, 16, 32), (1, 4, 20, 12, 32, 32), (1, 5, 33, 17, 96, 32), (1, 4, 32, 16, 32, 96), (1, 4, 20, 12, 64, 64),
              (1, 3, 18, 10, 128, 128), (1, 3, 20, 10, 32, 256), (2, 6, 24, 24, 32, 16)]

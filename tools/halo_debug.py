@@ -6,7 +6,7 @@ from pytorch3dunet_b200 import engine as E
 from pytorch3dunet_b200._lib import lib
 from tests import gpu_util as U
 L = lib()
-for (Cin, Cout) in [(32, 32), (16, 32), (96, 32), (32, 96)]:
+for (Cin, Cout) in [(32, 32), (32, 96)]:
     N, D, H, W = 2, 128, 128, 128
     x = torch.randn((N, D, H, W, Cin), device="cuda").bfloat16()
     wf = (torch.randn((N, 27, Cout, Cin), device="cuda") * 0.05).bfloat16()
