@@ -25,10 +25,14 @@ __device__ __forceinline__ float ldv<bf16>(const bf16* p) {
 // y[v,co] = sum_ci Wq[co][ci] * x[v,ci] + bias[co]      (Wq: fp32 [Cout][Cin] or, transposed=1, [Cin_w][Cout_w] read as W^T)
 // grid (P, N, ceil(Cout/64)); a block keeps its 64 x Cin weight slab in shared memory.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int PW_CO = 64;
+static int pw_co_chunk(int Cin) {  // output channels per block: the fp32 weight slab [chunk][Cin] must fit in shared memory
+  int c = 64;
+  while (c > 8 && (size_t)c * Cin * sizeof(float) > 160 * 1024) c >>= 1;
+  return c;
+}
 template <typename InT>
 __global__ void pointwise_fwd_kernel(const InT* __restrict__ x, const float* __restrict__ Wq, int transposed, const float* __restrict__ bias,
-                                     long long vox, int Cin, int Cout, int P, bf16* __restrict__ y, float* __restrict__ partials) {
+                                     long long vox, int Cin, int Cout, int P, int PW_CO, bf16* __restrict__ y, float* __restrict__ partials) {
   extern __shared__ float sm[];  // w[CC][Cin] | red[EW_THREADS*16]
   const int p = blockIdx.x, n = blockIdx.y, c0 = blockIdx.z * PW_CO;
   const int CC = min(PW_CO, Cout - c0);
@@ -323,22 +327,25 @@ extern "C" {
 
 int b200_pointwise_partials_count(int N, long long voxels, int Cout) {
   (void)N;
-  return ew_blocks(voxels, Cout < PW_CO ? Cout : PW_CO);
+  return ew_blocks(voxels, Cout < 8 ? 8 : (Cout < 64 ? Cout : 64));
 }
 
 int b200_pointwise_fwd(const void* x, int x_is_f32, const float* W, int transposed, const float* bias, int N, long long voxels, int Cin,
                        int Cout, void* y, float* partials, b200_stream_t s) {
   B200_CHECK_ARG(Cout % 8 == 0 && Cout <= 4096, "pointwise_fwd: Cout=%d must be a multiple of 8", Cout);
   int P = b200_pointwise_partials_count(N, voxels, Cout);
+  const int PW_CO = pw_co_chunk(Cin);
   dim3 grid(P, N, ceil_div(Cout, PW_CO));
   size_t smem = ((size_t)PW_CO * Cin + EW_THREADS * 16) * sizeof(float);
   B200_CHECK_ARG(smem <= 200 * 1024, "pointwise_fwd: Cin=%d too large", Cin);
   if (x_is_f32) {
     cudaFuncSetAttribute(pointwise_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    pointwise_fwd_kernel<float><<<grid, EW_THREADS, smem, ST(s)>>>((const float*)x, W, transposed, bias, voxels, Cin, Cout, P, (bf16*)y, partials);
+    pointwise_fwd_kernel<float><<<grid, EW_THREADS, smem, ST(s)>>>((const float*)x, W, transposed, bias, voxels, Cin, Cout, P, PW_CO, (bf16*)y,
+                                                                  partials);
   } else {
     cudaFuncSetAttribute(pointwise_fwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    pointwise_fwd_kernel<bf16><<<grid, EW_THREADS, smem, ST(s)>>>((const bf16*)x, W, transposed, bias, voxels, Cin, Cout, P, (bf16*)y, partials);
+    pointwise_fwd_kernel<bf16><<<grid, EW_THREADS, smem, ST(s)>>>((const bf16*)x, W, transposed, bias, voxels, Cin, Cout, P, PW_CO, (bf16*)y,
+                                                                 partials);
   }
   B200_CHECK_LAUNCH("pointwise_fwd");
   return 0;
