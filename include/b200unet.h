@@ -177,16 +177,19 @@ int b200_pointwise_wgrad_partials_count(int N, long long voxels);
 int b200_pointwise_wgrad(const void* x, int x_is_f32, const void* dy, int N, long long voxels, int Cin, int Cout, float* partials,
                          b200_stream_t s);
 /* ---- ConvTranspose3d(k3,s2,p1,bias=False) + nearest resize to the encoder size + sum-join
- * (TransposeConvUpsampling buildingblocks.py:617-664, Decoder._joining :493).  Wt: fp32 (Cin,Cout,3,3,3) */
-int b200_deconv_prep_weights(const float* Wt, int Cin, int Cout, void* wt /*[27][Cout][Cin]*/, void* wtb /*[27][Cin][Cout]*/, b200_stream_t s);
-int b200_deconv_up_add_partials_count(int N, int D, int H, int W, int Cout);
-int b200_deconv_up_add_fwd(const void* x, const void* wt, const void* enc, int N, int d, int h, int w, int D, int H, int W, int Cin,
-                           int Cout, void* out, float* partials, b200_stream_t s);
+ * (TransposeConvUpsampling buildingblocks.py:617-664, Decoder._joining :493), built from the tensor-core 3x3x3 conv:
+ *   conv_transpose3d(x, Wt) == conv3d(zero_insert(x), Wc, padding 1),  Wc[co][ci][k] = Wt[ci][co][26-k]  (Wt: (Cin,Cout,3,3,3)) */
+int b200_zero_insert(const void* x, int N, int d, int h, int w, int C, void* xz /* [N,2d-1,2h-1,2w-1,C] */, b200_stream_t s);
+int b200_subsample2_bwd(const void* dxz, const void* x, int N, int d, int h, int w, int C, int act, float slope, const void* gadd, void* out,
+                        b200_stream_t s);
+int b200_resize_add_partials_count(int N, int D, int H, int W, int C);
+/* out[o] = enc[o] + T[nearest_src(o)], T on the (sd,sh,sw) grid; partials of out */
+int b200_resize_add_fwd(const void* T, const void* enc, int N, int sd, int sh, int sw, int D, int H, int W, int C, void* out, float* partials,
+                        b200_stream_t s);
 /* dT[N,2d-1,2h-1,2w-1,C] = adjoint of the nearest resize applied to dout[N,D,H,W,C] */
 int b200_deconv_gather(const void* dout, int N, int d, int h, int w, int D, int H, int W, int C, void* dT, b200_stream_t s);
-int b200_deconv_dgrad(const void* dT, const void* wtb, const void* x, int N, int d, int h, int w, int Cin, int Cout, int act, float slope,
-                      const void* gadd, void* out, b200_stream_t s);
-int b200_deconv_wgrad(const void* x, const void* dT, int N, int d, int h, int w, int Cin, int Cout, float* dWt, b200_stream_t s);
+/* to_conv=1: Wc[co][ci][k] = Wt[ci][co][26-k]; to_conv=0: dWt[ci][co][k] = dWc[co][ci][26-k] */
+int b200_deconv_weight_permute(const float* src, int Cin, int Cout, int to_conv, float* dst, b200_stream_t s);
 
 /* ---- scSE, reduction_ratio 1 (ChannelSpatialSELayer3D se.py:96-114; cSE :18-51, sSE :54-93) ----------------------------
  * gates: smean[N][C] = channel means (from the producer's partial sums), h = relu(W1 s + b1), g = sigmoid(W2 h + b2) */

@@ -138,51 +138,6 @@ __device__ __forceinline__ int axis_taps(int s, int k[2], int i[2]) {
   return 2;
 }
 
-__global__ void deconv_up_add_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ wt, const bf16* __restrict__ enc, int d, int h, int w,
-                                         int D, int H, int W, int Cin, int Cout, int P, bf16* __restrict__ out, float* __restrict__ partials) {
-  extern __shared__ float red[];
-  const int p = blockIdx.x, n = blockIdx.y;
-  EwMap m = ew_map(Cout);
-  const long long vox = (long long)D * H * W, svox = (long long)d * h * w;
-  long long v0, v1;
-  ew_range(vox, p, P, v0, v1);
-  float s[8] = {0}, q[8] = {0};
-  if (m.active) {
-    const bf16* xn = x + (size_t)n * svox * Cin;
-    for (long long v = v0 + m.vl; v < v1; v += m.VL) {
-      const int ow = (int)(v % W);
-      const long long r = v / W;
-      const int oh = (int)(r % H), od = (int)(r / H);
-      int kd[2], id[2], kh[2], ih[2], kw[2], iw[2];
-      const int nd = axis_taps(nearest_src_i(od, 2 * d - 1, D), kd, id);
-      const int nh = axis_taps(nearest_src_i(oh, 2 * h - 1, H), kh, ih);
-      const int nw = axis_taps(nearest_src_i(ow, 2 * w - 1, W), kw, iw);
-      float acc[8];
-      unpack8(*reinterpret_cast<const bf16x8*>(enc + ((size_t)n * vox + v) * Cout + m.cg * 8), acc);
-      for (int a = 0; a < nd; ++a)
-        for (int b = 0; b < nh; ++b)
-          for (int c = 0; c < nw; ++c) {
-            const int tap = (kd[a] * 3 + kh[b]) * 3 + kw[c];
-            const bf16* xp = xn + (((size_t)id[a] * h + ih[b]) * w + iw[c]) * Cin;
-            const bf16* wp = wt + ((size_t)tap * Cout + m.cg * 8) * Cin;
-            for (int ci = 0; ci < Cin; ++ci) {
-              const float xv = __bfloat162float(xp[ci]);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) acc[i] = fmaf(xv, __bfloat162float(wp[(size_t)i * Cin + ci]), acc[i]);
-            }
-          }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        acc[i] = bf16_round(acc[i]);
-        s[i] += acc[i];
-        q[i] += acc[i] * acc[i];
-      }
-      *reinterpret_cast<bf16x8*>(out + ((size_t)n * vox + v) * Cout + m.cg * 8) = pack8(acc);
-    }
-  }
-  if (partials) ew_write_partials(s, q, m, partials + ((size_t)n * P + p) * Cout * 2, red);
-}
-
 // dT[s,co] = sum over destination voxels o with s(o) == s of dout[o,co]   (adjoint of the nearest resize 2n-1 -> size);
 // grid (P, N) over the (2d-1)(2h-1)(2w-1) deconv grid
 __device__ __forceinline__ void dst_range(int s, int in, int out, int& lo, int& hi) {
@@ -227,94 +182,103 @@ __global__ void deconv_gather_kernel(const bf16* __restrict__ dout, int sd, int 
   }
 }
 
-// dx[i,ci] = (sum_k sum_co Wt[ci][co][k] * dT[2i+k-1,co]) * act'(x[i,ci]) [+ gadd]; wtb: bf16 [27][Cin][Cout]; grid (P, N)
-__global__ void deconv_dgrad_kernel(const bf16* __restrict__ dT, const bf16* __restrict__ wtb, const bf16* __restrict__ x, int d, int h, int w, int Cin,
-                                    int Cout, int P, int act, float slope, const bf16* gadd, bf16* out) {
+// ---- transposed conv as a tensor-core 3x3x3 conv over the zero-inserted input -------------------------------------------------
+// conv_transpose3d(x, Wt, stride 2, padding 1) == conv3d(zero_insert(x), Wc, padding 1) with Wc[co][ci][k] = Wt[ci][co][26-k];
+// zero_insert(x)[2i] = x[i] on the (2d-1, 2h-1, 2w-1) grid.  7/8 of that tensor is zeros (8x redundant FLOPs), but the
+// convolution, its dgrad and its wgrad then run on the tcgen05 kernels (two orders of magnitude faster than the CUDA-core
+// gather formulation this replaced).
+
+// xz[s] = (s all even) ? x[s/2] : 0 ; grid (P, N) over the (2d-1)(2h-1)(2w-1) grid
+__global__ void zero_insert_kernel(const bf16* __restrict__ x, int d, int h, int w, int C, int P, bf16* __restrict__ xz) {
   const int p = blockIdx.x, n = blockIdx.y;
-  EwMap m = ew_map(Cin);
+  EwMap m = ew_map(C);
   const int sd = 2 * d - 1, sh = 2 * h - 1, sw = 2 * w - 1;
-  const long long vox = (long long)d * h * w, svox = (long long)sd * sh * sw;
+  const long long svox = (long long)sd * sh * sw, vox = (long long)d * h * w;
+  long long v0, v1;
+  ew_range(svox, p, P, v0, v1);
+  if (!m.active) return;
+  bf16x8 zero;
+  zero.u = make_uint4(0, 0, 0, 0);
+  for (long long v = v0 + m.vl; v < v1; v += m.VL) {
+    const int xw = (int)(v % sw);
+    const long long r = v / sw;
+    const int xh = (int)(r % sh), xd = (int)(r / sh);
+    bf16x8 val = zero;
+    if (!((xw | xh | xd) & 1))
+      val = *reinterpret_cast<const bf16x8*>(x + ((size_t)n * vox + ((size_t)(xd >> 1) * h + (xh >> 1)) * w + (xw >> 1)) * C + m.cg * 8);
+    *reinterpret_cast<bf16x8*>(xz + ((size_t)n * svox + v) * C + m.cg * 8) = val;
+  }
+}
+// out[i] = dxz[2i] * act'(x[i]) [+ gadd]
+__global__ void subsample2_bwd_kernel(const bf16* __restrict__ dxz, const bf16* __restrict__ x, int d, int h, int w, int C, int P, int act,
+                                      float slope, const bf16* gadd, bf16* out) {
+  const int p = blockIdx.x, n = blockIdx.y;
+  EwMap m = ew_map(C);
+  const int sh = 2 * h - 1, sw = 2 * w - 1;
+  const long long svox = (long long)(2 * d - 1) * sh * sw, vox = (long long)d * h * w;
   long long v0, v1;
   ew_range(vox, p, P, v0, v1);
   if (!m.active) return;
-  const bf16* tn = dT + (size_t)n * svox * Cout;
   for (long long v = v0 + m.vl; v < v1; v += m.VL) {
     const int iw = (int)(v % w);
     const long long r = v / w;
     const int ih = (int)(r % h), id = (int)(r / h);
-    float acc[8] = {0};
-    for (int kd = 0; kd < 3; ++kd) {
-      const int zd = 2 * id + kd - 1;
-      if (zd < 0 || zd >= sd) continue;
-      for (int kh = 0; kh < 3; ++kh) {
-        const int zh = 2 * ih + kh - 1;
-        if (zh < 0 || zh >= sh) continue;
-        for (int kw = 0; kw < 3; ++kw) {
-          const int zw = 2 * iw + kw - 1;
-          if (zw < 0 || zw >= sw) continue;
-          const bf16* tp = tn + (((size_t)zd * sh + zh) * sw + zw) * Cout;
-          const bf16* wp = wtb + ((size_t)((kd * 3 + kh) * 3 + kw) * Cin + m.cg * 8) * Cout;
-          for (int co = 0; co < Cout; ++co) {
-            const float g = __bfloat162float(tp[co]);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) acc[i] = fmaf(g, __bfloat162float(wp[(size_t)i * Cout + co]), acc[i]);
-          }
-        }
-      }
-    }
-    const size_t o = ((size_t)n * vox + v) * Cin + m.cg * 8;
-    float xv[8], ga[8];
+    float g[8], xv[8], ga[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(dxz + ((size_t)n * svox + ((size_t)(2 * id) * sh + 2 * ih) * sw + 2 * iw) * C + m.cg * 8), g);
+    const size_t o = ((size_t)n * vox + v) * C + m.cg * 8;
     unpack8(*reinterpret_cast<const bf16x8*>(x + o), xv);
     if (gadd) unpack8(*reinterpret_cast<const bf16x8*>(gadd + o), ga);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      acc[i] *= act_grad_from_out(xv[i], act, slope);
-      if (gadd) acc[i] += ga[i];
+      g[i] *= act_grad_from_out(xv[i], act, slope);
+      if (gadd) g[i] += ga[i];
     }
-    *reinterpret_cast<bf16x8*>(out + o) = pack8(acc);
+    *reinterpret_cast<bf16x8*>(out + o) = pack8(g);
   }
 }
-
-// dWt[ci][co][k] += sum_i x[i,ci] * dT[2i+k-1,co]; one thread per (k,ci,co) output and voxel chunk, atomicAdd; grid (chunks, N, outputs/256)
-constexpr int DC_CHUNK = 1024;
-__global__ void deconv_wgrad_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dT, int d, int h, int w, int Cin, int Cout,
-                                    float* __restrict__ dWt) {
-  const int n = blockIdx.y;
-  const int total = 27 * Cin * Cout;
-  const int o = blockIdx.x * blockDim.x + threadIdx.x;
-  if (o >= total) return;
-  const int co = o % Cout;
-  const int r0 = o / Cout;
-  const int ci = r0 % Cin, tap = r0 / Cin;
-  const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
-  const int sd = 2 * d - 1, sh = 2 * h - 1, sw = 2 * w - 1;
-  const long long vox = (long long)d * h * w, svox = (long long)sd * sh * sw;
-  long long v0 = (long long)blockIdx.z * DC_CHUNK, v1 = v0 + DC_CHUNK;
-  if (v1 > vox) v1 = vox;
-  const bf16* xn = x + (size_t)n * vox * Cin;
-  const bf16* tn = dT + (size_t)n * svox * Cout;
-  float acc = 0.f;
-  for (long long v = v0; v < v1; ++v) {
-    const int iw = (int)(v % w);
-    const long long r = v / w;
-    const int ih = (int)(r % h), id = (int)(r / h);
-    const int zd = 2 * id + kd - 1, zh = 2 * ih + kh - 1, zw = 2 * iw + kw - 1;
-    if (zd < 0 || zd >= sd || zh < 0 || zh >= sh || zw < 0 || zw >= sw) continue;
-    acc += __bfloat162float(xn[(size_t)v * Cin + ci]) * __bfloat162float(tn[(((size_t)zd * sh + zh) * sw + zw) * Cout + co]);
+// out[o] = enc[o] + T[nearest_src(o)] (+ partial sums of out for the next GroupNorm); T on the (sd,sh,sw) grid
+__global__ void resize_add_fwd_kernel(const bf16* __restrict__ T, const bf16* __restrict__ enc, int sd, int sh, int sw, int D, int H, int W, int C,
+                                      int P, bf16* __restrict__ out, float* __restrict__ partials) {
+  extern __shared__ float red[];
+  const int p = blockIdx.x, n = blockIdx.y;
+  EwMap m = ew_map(C);
+  const long long vox = (long long)D * H * W, svox = (long long)sd * sh * sw;
+  long long v0, v1;
+  ew_range(vox, p, P, v0, v1);
+  float s[8] = {0}, q[8] = {0};
+  if (m.active) {
+    for (long long v = v0 + m.vl; v < v1; v += m.VL) {
+      const int ow = (int)(v % W);
+      const long long r = v / W;
+      const int oh = (int)(r % H), od = (int)(r / H);
+      const size_t sv = ((size_t)nearest_src_i(od, sd, D) * sh + nearest_src_i(oh, sh, H)) * sw + nearest_src_i(ow, sw, W);
+      float a[8], b[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(enc + ((size_t)n * vox + v) * C + m.cg * 8), a);
+      unpack8(*reinterpret_cast<const bf16x8*>(T + ((size_t)n * svox + sv) * C + m.cg * 8), b);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        a[i] = bf16_round(a[i] + b[i]);
+        s[i] += a[i];
+        q[i] += a[i] * a[i];
+      }
+      *reinterpret_cast<bf16x8*>(out + ((size_t)n * vox + v) * C + m.cg * 8) = pack8(a);
+    }
   }
-  atomicAdd(&dWt[((size_t)ci * Cout + co) * 27 + tap], acc);
+  if (partials) ew_write_partials(s, q, m, partials + ((size_t)n * P + p) * C * 2, red);
 }
-
-// wt[k][co][ci] = bf16(Wt[ci][co][k]) and wtb[k][ci][co] = bf16(Wt[ci][co][k])
-__global__ void deconv_prep_weights_kernel(const float* __restrict__ Wt, int Cin, int Cout, bf16* __restrict__ wt, bf16* __restrict__ wtb) {
+// Wc[co][ci][k] = Wt[ci][co][26-k]  (to_conv = 1)   or   dWt[ci][co][k] = dWc[co][ci][26-k]  (to_conv = 0)
+__global__ void deconv_weight_permute_kernel(const float* __restrict__ src, int Cin, int Cout, int to_conv, float* __restrict__ dst) {
   size_t total = (size_t)27 * Cin * Cout;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     int k = (int)(i % 27);
     size_t r = i / 27;
-    int co = (int)(r % Cout), ci = (int)(r / Cout);
-    bf16 v = __float2bfloat16_rn(Wt[i]);
-    if (wt) wt[((size_t)k * Cout + co) * Cin + ci] = v;
-    if (wtb) wtb[((size_t)k * Cin + ci) * Cout + co] = v;
+    if (to_conv) {  // i indexes Wc[co][ci][k]
+      int ci = (int)(r % Cin), co = (int)(r / Cin);
+      dst[i] = src[((size_t)ci * Cout + co) * 27 + (26 - k)];
+    } else {  // i indexes dWt[ci][co][k]
+      int co = (int)(r % Cout), ci = (int)(r / Cout);
+      dst[i] = src[((size_t)co * Cin + ci) * 27 + (26 - k)];
+    }
   }
 }
 
@@ -366,30 +330,6 @@ int b200_pointwise_wgrad(const void* x, int x_is_f32, const void* dy, int N, lon
   return 0;
 }
 
-int b200_deconv_prep_weights(const float* Wt, int Cin, int Cout, void* wt, void* wtb, b200_stream_t s) {
-  size_t total = (size_t)27 * Cin * Cout;
-  int blocks = (int)((total + 255) / 256);
-  if (blocks > 4096) blocks = 4096;
-  deconv_prep_weights_kernel<<<blocks, 256, 0, ST(s)>>>(Wt, Cin, Cout, (bf16*)wt, (bf16*)wtb);
-  B200_CHECK_LAUNCH("deconv_prep_weights");
-  return 0;
-}
-
-int b200_deconv_up_add_partials_count(int N, int D, int H, int W, int Cout) {
-  (void)N;
-  return ew_blocks((long long)D * H * W, Cout);
-}
-int b200_deconv_up_add_fwd(const void* x, const void* wt, const void* enc, int N, int d, int h, int w, int D, int H, int W, int Cin, int Cout,
-                           void* out, float* partials, b200_stream_t s) {
-  B200_CHECK_ARG(Cin % 8 == 0 && Cout % 8 == 0 && Cout <= 2048, "deconv_up_add_fwd: channels %d,%d must be multiples of 8", Cin, Cout);
-  int P = b200_deconv_up_add_partials_count(N, D, H, W, Cout);
-  dim3 grid(P, N);
-  deconv_up_add_fwd_kernel<<<grid, EW_THREADS, EW_THREADS * 16 * sizeof(float), ST(s)>>>((const bf16*)x, (const bf16*)wt, (const bf16*)enc, d, h, w, D, H,
-                                                                                     W, Cin, Cout, P, (bf16*)out, partials);
-  B200_CHECK_LAUNCH("deconv_up_add_fwd");
-  return 0;
-}
-
 int b200_deconv_gather(const void* dout, int N, int d, int h, int w, int D, int H, int W, int C, void* dT, b200_stream_t s) {
   B200_CHECK_ARG(C % 8 == 0 && C <= 2048, "deconv_gather: C=%d must be a multiple of 8", C);
   int sd = 2 * d - 1, sh = 2 * h - 1, sw = 2 * w - 1;
@@ -400,26 +340,43 @@ int b200_deconv_gather(const void* dout, int N, int d, int h, int w, int D, int 
   return 0;
 }
 
-int b200_deconv_dgrad(const void* dT, const void* wtb, const void* x, int N, int d, int h, int w, int Cin, int Cout, int act, float slope,
-                      const void* gadd, void* out, b200_stream_t s) {
-  B200_CHECK_ARG(Cin % 8 == 0 && Cin <= 2048, "deconv_dgrad: Cin=%d must be a multiple of 8", Cin);
-  int P = ew_blocks((long long)d * h * w, Cin);
+int b200_zero_insert(const void* x, int N, int d, int h, int w, int C, void* xz, b200_stream_t s) {
+  B200_CHECK_ARG(C % 8 == 0 && C <= 2048, "zero_insert: C=%d must be a multiple of 8", C);
+  int P = ew_blocks((long long)(2 * d - 1) * (2 * h - 1) * (2 * w - 1), C);
   dim3 grid(P, N);
-  deconv_dgrad_kernel<<<grid, EW_THREADS, 0, ST(s)>>>((const bf16*)dT, (const bf16*)wtb, (const bf16*)x, d, h, w, Cin, Cout, P, act, slope,
-                                                      (const bf16*)gadd, (bf16*)out);
-  B200_CHECK_LAUNCH("deconv_dgrad");
+  zero_insert_kernel<<<grid, EW_THREADS, 0, ST(s)>>>((const bf16*)x, d, h, w, C, P, (bf16*)xz);
+  B200_CHECK_LAUNCH("zero_insert");
   return 0;
 }
-
-int b200_deconv_wgrad(const void* x, const void* dT, int N, int d, int h, int w, int Cin, int Cout, float* dWt, b200_stream_t s) {
-  size_t bytes = (size_t)27 * Cin * Cout * sizeof(float);
-  cudaError_t e = cudaMemsetAsync(dWt, 0, bytes, ST(s));
-  B200_CHECK_ARG(e == cudaSuccess, "deconv_wgrad: memset failed: %s", cudaGetErrorString(e));
-  long long vox = (long long)d * h * w;
-  dim3 grid(ceil_div(27 * Cin * Cout, 256), N, ceil_div(vox, DC_CHUNK));
-  B200_CHECK_ARG(grid.z <= 65535, "deconv_wgrad: volume too large (%lld voxels)", vox);
-  deconv_wgrad_kernel<<<grid, 256, 0, ST(s)>>>((const bf16*)x, (const bf16*)dT, d, h, w, Cin, Cout, dWt);
-  B200_CHECK_LAUNCH("deconv_wgrad");
+int b200_subsample2_bwd(const void* dxz, const void* x, int N, int d, int h, int w, int C, int act, float slope, const void* gadd, void* out,
+                        b200_stream_t s) {
+  B200_CHECK_ARG(C % 8 == 0 && C <= 2048, "subsample2_bwd: C=%d must be a multiple of 8", C);
+  int P = ew_blocks((long long)d * h * w, C);
+  dim3 grid(P, N);
+  subsample2_bwd_kernel<<<grid, EW_THREADS, 0, ST(s)>>>((const bf16*)dxz, (const bf16*)x, d, h, w, C, P, act, slope, (const bf16*)gadd, (bf16*)out);
+  B200_CHECK_LAUNCH("subsample2_bwd");
+  return 0;
+}
+int b200_resize_add_partials_count(int N, int D, int H, int W, int C) {
+  (void)N;
+  return ew_blocks((long long)D * H * W, C);
+}
+int b200_resize_add_fwd(const void* T, const void* enc, int N, int sd, int sh, int sw, int D, int H, int W, int C, void* out, float* partials,
+                        b200_stream_t s) {
+  B200_CHECK_ARG(C % 8 == 0 && C <= 2048, "resize_add_fwd: C=%d must be a multiple of 8", C);
+  int P = b200_resize_add_partials_count(N, D, H, W, C);
+  dim3 grid(P, N);
+  resize_add_fwd_kernel<<<grid, EW_THREADS, EW_THREADS * 16 * sizeof(float), ST(s)>>>((const bf16*)T, (const bf16*)enc, sd, sh, sw, D, H, W, C, P,
+                                                                                  (bf16*)out, partials);
+  B200_CHECK_LAUNCH("resize_add_fwd");
+  return 0;
+}
+int b200_deconv_weight_permute(const float* src, int Cin, int Cout, int to_conv, float* dst, b200_stream_t s) {
+  size_t total = (size_t)27 * Cin * Cout;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 4096) blocks = 4096;
+  deconv_weight_permute_kernel<<<blocks, 256, 0, ST(s)>>>(src, Cin, Cout, to_conv, dst);
+  B200_CHECK_LAUNCH("deconv_weight_permute");
   return 0;
 }
 

@@ -36,6 +36,7 @@ struct WgradHaloParams {
   int AWb;      // dz atom width (channels)
   int a_stages, b_stages, a_bytes, b_bytes;
   int tmem_cols;
+  int co0, CoutTotal;  // slice [co0, co0 + Cout) of a wider C_out
   float* G;
 };
 
@@ -91,7 +92,7 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_consta
         mbar_wait(&b_empty[bs], ((uint32_t)(it / p.b_stages) & 1u) ^ 1u);
         mbar_arrive_expect_tx(&b_full[bs], (uint32_t)(natoms_b * b_atom_bytes));
         for (int j = 0; j < natoms_b; ++j)
-          tma_load_5d(smemB + (size_t)bs * p.b_bytes + (size_t)j * b_atom_bytes, &tmapZ, &b_full[bs], j * p.AWb, w0, h0, d0, n);
+          tma_load_5d(smemB + (size_t)bs * p.b_bytes + (size_t)j * b_atom_bytes, &tmapZ, &b_full[bs], p.co0 + j * p.AWb, w0, h0, d0, n);
         mbar_wait(&a_empty[as], ((uint32_t)(it / p.a_stages) & 1u) ^ 1u);
         mbar_arrive_expect_tx(&a_full[as], (uint32_t)(WH_ROWS * rbA));
         tma_load_5d(smemA + (size_t)as * p.a_bytes, &tmapX, &a_full[as], slice * CA, w0 - 1, h0 - 1, d0 - 1, n);
@@ -143,7 +144,7 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_consta
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
     for (int g = 0; g < p.PG; ++g) {
       const int tap = (pg0 + g) * 3 + (valid ? dw : 0);
-      float* grow = p.G + ((((size_t)n * p.S + split) * 27 + tap) * p.Cin + ci) * p.Cout;
+      float* grow = p.G + ((((size_t)n * p.S + split) * 27 + tap) * p.Cin + ci) * p.CoutTotal + p.co0;
       for (int c0 = 0; c0 < p.Cout; c0 += 16) {
         uint32_t raw[16];
         tmem_ld_32x32b_x16(taddr + (uint32_t)(g * p.Cout + c0), raw);
@@ -210,7 +211,7 @@ int wgrad_halo_launch(const void* x, const void* dz, WgradHaloParams& p, cudaStr
   CUtensorMap tmX, tmZ;
   int rc = make_act_tmap(&tmX, x, p.N, p.D, p.H, p.W, p.Cin, p.CA, WH_HD, WH_HH, WH_HW);
   if (rc) return rc;
-  rc = make_act_tmap(&tmZ, dz, p.N, p.D, p.H, p.W, p.Cout, p.AWb, 1, WH_BH, WH_BW);
+  rc = make_act_tmap(&tmZ, dz, p.N, p.D, p.H, p.W, p.CoutTotal, p.AWb, 1, WH_BH, WH_BW);
   if (rc) return rc;
   size_t smem = (size_t)p.a_stages * p.a_bytes + (size_t)p.b_stages * p.b_bytes + 1024;
   auto kern = p.CA == 32 ? wgrad_halo_kernel<32> : wgrad_halo_kernel<16>;
@@ -227,10 +228,13 @@ int wgrad_halo_splits(int N, int D, int H, int W, int Cin, int Cout) {
   return wgrad_halo_plan(N, D, H, W, Cin, Cout, &p) ? p.S : 0;
 }
 
-int wgrad_halo_run(const void* x, const void* dz, int N, int D, int H, int W, int Cin, int Cout, float* G, cudaStream_t s) {
+int wgrad_halo_run(const void* x, const void* dz, int N, int D, int H, int W, int Cin, int Cout, int co0, int CoutTotal, float* G,
+                   cudaStream_t s) {
   WgradHaloParams p;
   if (!wgrad_halo_plan(N, D, H, W, Cin, Cout, &p)) return -1;
   p.G = G;
+  p.co0 = co0;
+  p.CoutTotal = CoutTotal;
   return wgrad_halo_launch(x, dz, p, s);
 }
 

@@ -21,7 +21,7 @@ namespace b200 {
 int make_act_tmap(CUtensorMap* tm, const void* ptr, int N, int D, int H, int W, int C, int kc, int bd, int bh, int bw);
 int choose_box(int D, int H, int W, int* bd, int* bh, int* bw);
 int wgrad_halo_splits(int N, int D, int H, int W, int Cin, int Cout);
-int wgrad_halo_run(const void* x, const void* dz, int N, int D, int H, int W, int Cin, int Cout, float* G, cudaStream_t s);
+int wgrad_halo_run(const void* x, const void* dz, int N, int D, int H, int W, int Cin, int Cout, int co0, int CoutTotal, float* G, cudaStream_t s);
 
 constexpr int WG_THREADS = 192;
 constexpr int WG_MAX_A_STAGES = 8;
@@ -36,6 +36,7 @@ struct WgradParams {
   int AWa, AWb;  // channels per smem atom tile (64/32/16) on the x side and the dz side
   int a_stages, a_stage_bytes, b_stage_bytes;
   int tmem_cols;
+  int co0, CoutTotal;  // this launch covers output channels [co0, co0 + Cout) of CoutTotal (C_out > 256 is processed in slices)
   float* G;
 };
 
@@ -101,7 +102,7 @@ conv3_wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid
           mbar_wait(&b_empty[bs], ((uint32_t)(bi / WG_B_STAGES) & 1u) ^ 1u);
           mbar_arrive_expect_tx(&b_full[bs], (uint32_t)(natoms_b * b_atom_bytes));
           for (int j = 0; j < natoms_b; ++j)
-            tma_load_5d(smemB + (size_t)bs * p.b_stage_bytes + (size_t)j * b_atom_bytes, &tmapZ, &b_full[bs], j * p.AWb, w0, h0, d0, n);
+            tma_load_5d(smemB + (size_t)bs * p.b_stage_bytes + (size_t)j * b_atom_bytes, &tmapZ, &b_full[bs], p.co0 + j * p.AWb, w0, h0, d0, n);
         }
         for (int tp = 0; tp < ntaps; ++tp, ++ai) {
           const int tap = tap0 + tp;
@@ -153,7 +154,7 @@ conv3_wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
     const bool have_work = t1 > t0;
     for (int tp = 0; tp < ntaps; ++tp) {
-      float* grow = p.G + ((((size_t)n * p.S + split) * 27 + (tap0 + tp)) * p.Cin + (valid ? ci : 0)) * p.Cout;
+      float* grow = p.G + ((((size_t)n * p.S + split) * 27 + (tap0 + tp)) * p.Cin + (valid ? ci : 0)) * p.CoutTotal + p.co0;
       for (int c0 = 0; c0 < p.Cout; c0 += 16) {
         uint32_t raw[16];
         tmem_ld_32x32b_x16(taddr + (uint32_t)(tp * p.Cout + c0), raw);
@@ -184,10 +185,14 @@ conv3_wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid
 
 static int atom_width(int C) { return (C % 64 == 0) ? 64 : (C % 32 == 0 ? 32 : 16); }
 
+static int cout_slice(int Cout) {  // C_out per launch (N dimension of the MMA <= 256)
+  if (Cout <= 256) return Cout;
+  return Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : (Cout % 64 == 0 ? 64 : (Cout % 32 == 0 ? 32 : 16)));
+}
 static bool wgrad_supported(int N, int D, int H, int W, int Cin, int Cout) {
   (void)N;
   int bd, bh, bw;
-  if (Cin % 16 != 0 || Cout % 16 != 0 || Cout > 256) return false;
+  if (Cin % 16 != 0 || Cout % 16 != 0) return false;
   if (choose_box(D, H, W, &bd, &bh, &bw)) return false;
   return true;
 }
@@ -239,20 +244,29 @@ int b200_conv3_wgrad_igemm_supported(int N, int D, int H, int W, int Cin, int Co
 
 int b200_conv3_wgrad_igemm_splits(int N, int D, int H, int W, int Cin, int Cout) {
   if (!wgrad_supported(N, D, H, W, Cin, Cout)) return 0;
-  int hs = wgrad_halo_splits(N, D, H, W, Cin, Cout);
+  const int cs = cout_slice(Cout);
+  int hs = wgrad_halo_splits(N, D, H, W, Cin, cs);
   if (hs > 0) return hs;
   WgradParams p;
-  wgrad_plan(N, D, H, W, Cin, Cout, p);
+  wgrad_plan(N, D, H, W, Cin, cs, p);
   return p.S;
 }
 
 int b200_conv3_wgrad_igemm(const void* x, const void* dz, int N, int D, int H, int W, int Cin, int Cout, float* G, b200_stream_t s) {
   B200_CHECK_ARG(wgrad_supported(N, D, H, W, Cin, Cout), "conv3_wgrad_igemm: unsupported shape N=%d D=%d H=%d W=%d Cin=%d Cout=%d", N,
                  D, H, W, Cin, Cout);
-  if (wgrad_halo_splits(N, D, H, W, Cin, Cout) > 0) return wgrad_halo_run(x, dz, N, D, H, W, Cin, Cout, G, (cudaStream_t)s);
+  const int cs = cout_slice(Cout);
+  if (wgrad_halo_splits(N, D, H, W, Cin, cs) > 0) {
+    for (int co0 = 0; co0 < Cout; co0 += cs) {
+      int rc = wgrad_halo_run(x, dz, N, D, H, W, Cin, cs, co0, Cout, G, (cudaStream_t)s);
+      if (rc) return rc;
+    }
+    return 0;
+  }
   WgradParams p;
-  wgrad_plan(N, D, H, W, Cin, Cout, p);
+  wgrad_plan(N, D, H, W, Cin, cs, p);
   p.G = G;
+  p.CoutTotal = Cout;
   CUtensorMap tmX, tmZ;
   int rc = make_act_tmap(&tmX, x, N, D, H, W, Cin, p.AWa, p.BD, p.BH, p.BW);
   if (rc) return rc;
@@ -262,8 +276,11 @@ int b200_conv3_wgrad_igemm(const void* x, const void* dz, int N, int D, int H, i
   cudaError_t e = cudaFuncSetAttribute(conv3_wgrad_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   B200_CHECK_ARG(e == cudaSuccess, "conv3_wgrad_igemm: cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e));
   dim3 grid((unsigned)(N * p.S), (unsigned)p.ngroups, (unsigned)p.mchunks);
-  conv3_wgrad_igemm_kernel<<<grid, WG_THREADS, smem, (cudaStream_t)s>>>(tmX, tmZ, p);
-  B200_CHECK_LAUNCH("conv3_wgrad_igemm");
+  for (int co0 = 0; co0 < Cout; co0 += cs) {
+    p.co0 = co0;
+    conv3_wgrad_igemm_kernel<<<grid, WG_THREADS, smem, (cudaStream_t)s>>>(tmX, tmZ, p);
+    B200_CHECK_LAUNCH("conv3_wgrad_igemm");
+  }
   return 0;
 }
 

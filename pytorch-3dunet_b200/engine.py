@@ -189,7 +189,7 @@ class Engine:
         self.accumulate_grad(y, gm)
 
     # ---------------------------------------------------------------- conv
-    def conv3(self, x, W, bias, gn, name, act=(ACT_NONE, 0.0), want_stats=False, residual=None):
+    def conv3(self, x, W, bias, gn, name, act=(ACT_NONE, 0.0), want_stats=False, residual=None, grad_sink=None):
         """[GroupNorm ->] Conv3d(3x3x3, pad 1) [-> + residual] [-> activation].
 
         x: Act | InputF32; W: fp32 (Cout,Cin,3,3,3); bias: fp32 (Cout,) | None;
@@ -259,7 +259,10 @@ class Engine:
                 dW = torch.empty_like(W)
                 Gsum = self.empty((n, 1, 27, cin, cout), torch.float32) if gn is not None else None
                 self.call("b200_wgrad_finalize", _p(G), n, S, cin, cout, _p(ab), _p(T) if ab is not None else None, _p(dW), _p(Gsum))
-                self._add_param_grad(name + "conv.weight", dW)
+                if grad_sink is not None:
+                    grad_sink(dW)  # the weight is a derived tensor (e.g. the conv form of a ConvTranspose3d weight)
+                else:
+                    self._add_param_grad(name + "conv.weight", dW)
                 if bias is not None:
                     db = torch.empty_like(bias)
                     self.call("b200_bias_grad_from_T", _p(T), n, cout, _p(db))
@@ -299,7 +302,7 @@ class Engine:
                     if coef is not None:
                         self.call("b200_gn_bwd_apply", _p(dxhat), _p(x.t), _p(coef), n, cin, vox, x.act, x.slope,
                                   _p(x.grad), _p(dxhat))
-                    else:
+                    elif x.act != ACT_NONE or x.grad is not None:
                         self.call("b200_act_bwd", _p(dxhat), cin, 0, _p(x.t), n, cin, vox, x.act, x.slope, _p(x.grad), _p(dxhat))
                     x.grad = dxhat
                     if DEBUG is not None:
@@ -481,35 +484,48 @@ class Engine:
     # ---------------------------------------------------------------- ConvTranspose3d(k3,s2,p1) + nearest resize + sum-join
     def deconv_up_add(self, enc, x, Wt, wname, want_stats=True):
         """TransposeConvUpsampling (buildingblocks.py:617-664) followed by Decoder._joining(concat=False) (:493):
-        out = enc + interpolate(conv_transpose3d(x), size=enc.shape[2:])"""
+        out = enc + interpolate(conv_transpose3d(x), size=enc.shape[2:]).
+
+        conv_transpose3d(x, Wt, stride 2, pad 1) == conv3d(zero_insert(x), Wc, pad 1) with Wc[co][ci][k] = Wt[ci][co][26-k], so the
+        transposed conv, its input gradient and its weight gradient all run on the tcgen05 3x3x3 kernels (conv3)."""
         n, D, H, W_, cout = enc.dims
         n2, d, h, w, cin = x.dims
         assert n == n2 and tuple(Wt.shape) == (cin, cout, 3, 3, 3), (tuple(Wt.shape), cin, cout)
         Wt = Wt.contiguous()
-        wt = self.empty((27, cout, cin), torch.bfloat16)
-        self.call("b200_deconv_prep_weights", _p(Wt), cin, cout, _p(wt), None)
+        sd_, sh_, sw_ = 2 * d - 1, 2 * h - 1, 2 * w - 1
+        Wc = self.empty((cout, cin, 3, 3, 3), torch.float32)
+        self.call("b200_deconv_weight_permute", _p(Wt), cin, cout, 1, _p(Wc))
+        xz_t = self.empty((n, sd_, sh_, sw_, cin), torch.bfloat16)
+        self.call("b200_zero_insert", _p(x.t), n, d, h, w, cin, _p(xz_t))
+        xz = Act(xz_t, ACT_NONE, 0.0, requires_grad=x.requires_grad)
+        if self.record:
+            def backward_zero_insert():
+                if xz.grad is None or not x.requires_grad:
+                    return
+                gx = self.empty(x.t.shape, torch.bfloat16)
+                self.call("b200_subsample2_bwd", _p(xz.grad), _p(x.t), n, d, h, w, cin, x.act, x.slope, _p(x.grad), _p(gx))
+                x.grad = gx
+                xz.grad = None
+            self.tape.append(backward_zero_insert)
+
+        def sink(dWc):
+            dWt = torch.empty_like(Wt)
+            self.call("b200_deconv_weight_permute", _p(dWc), cin, cout, 0, _p(dWt))
+            self._add_param_grad(wname, dWt)
+        T = self.conv3(xz, Wc, None, None, wname + "#conv.", want_stats=False, grad_sink=sink)
         out_t = self.empty((n, D, H, W_, cout), torch.bfloat16)
-        P = self.L.query("b200_deconv_up_add_partials_count", n, D, H, W_, cout)
+        P = self.L.query("b200_resize_add_partials_count", n, D, H, W_, cout)
         partials = self.empty((n, P, cout, 2), torch.float32) if want_stats else None
-        self.call("b200_deconv_up_add_fwd", _p(x.t), _p(wt), _p(enc.t), n, d, h, w, D, H, W_, cin, cout, _p(out_t), _p(partials))
+        self.call("b200_resize_add_fwd", _p(T.t), _p(enc.t), n, sd_, sh_, sw_, D, H, W_, cout, _p(out_t), _p(partials))
         out = Act(out_t, ACT_NONE, 0.0, partials, P)
         if self.record:
             def backward():
                 g = out.grad
                 if g is None:
                     return
-                sd, sh, sw = 2 * d - 1, 2 * h - 1, 2 * w - 1
-                dT = self.empty((n, sd, sh, sw, cout), torch.bfloat16)
+                dT = self.empty(T.t.shape, torch.bfloat16)
                 self.call("b200_deconv_gather", _p(g), n, d, h, w, D, H, W_, cout, _p(dT))
-                dWt = torch.empty_like(Wt)
-                self.call("b200_deconv_wgrad", _p(x.t), _p(dT), n, d, h, w, cin, cout, _p(dWt), launches=2)
-                self._add_param_grad(wname, dWt)
-                if x.requires_grad:
-                    wtb = self.empty((27, cin, cout), torch.bfloat16)
-                    self.call("b200_deconv_prep_weights", _p(Wt), cin, cout, None, _p(wtb))
-                    gx = self.empty(x.t.shape, torch.bfloat16)
-                    self.call("b200_deconv_dgrad", _p(dT), _p(wtb), _p(x.t), n, d, h, w, cin, cout, x.act, x.slope, _p(x.grad), _p(gx))
-                    x.grad = gx
+                self.accumulate_grad(T, dT)
                 if enc.requires_grad:
                     ge = self.empty(enc.t.shape, torch.bfloat16)
                     self.call("b200_act_bwd", _p(g), cout, 0, _p(enc.t), n, cout, D * H * W_, enc.act, enc.slope, _p(enc.grad), _p(ge))

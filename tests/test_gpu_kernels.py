@@ -90,7 +90,9 @@ WG_SHAPES = [(1, 8, 8, 8, 16, 32), (2, 8, 8, 8, 32, 32), (1, 8, 8, 8, 64, 64), (
              (2, 4, 4, 4, 64, 64), (1, 6, 6, 6, 128, 128),
              # large enough for the halo / stacked-tap wgrad kernel (D>=3, H>=18, W>=10)
              (2, 3, 18, 10, 16, 32), (1, 4, 20, 12, 32, 32), (1, 5, 33, 17, 96, 32), (1, 4, 32, 16, 32, 96), (1, 4, 20, 12, 64, 64),
-             (1, 3, 18, 10, 128, 128), (1, 3, 20, 10, 32, 256), (2, 6, 24, 24, 32, 16)]
+             (1, 3, 18, 10, 128, 128), (1, 3, 20, 10, 32, 256), (2, 6, 24, 24, 32, 16),
+             # C_out > 256: processed in output-channel slices (plain and stacked-tap kernels)
+             (1, 6, 6, 6, 256, 512), (1, 4, 4, 8, 64, 320), (1, 3, 18, 10, 32, 512), (2, 6, 6, 6, 512, 512)]
 
 
 @pytest.mark.parametrize("shape", WG_SHAPES)

@@ -55,38 +55,90 @@ def test_pointwise_fwd_dgrad_wgrad(cin, cout, f32):
 
 
 @pytest.mark.parametrize("small,big,cin,cout", [((4, 4, 4), (8, 8, 8), 32, 16), ((3, 5, 4), (5, 9, 7), 16, 8), ((2, 2, 2), (4, 4, 4), 64, 32)])
-def test_deconv_up_add_fwd_bwd(small, big, cin, cout):
+def test_deconv_pieces(small, big, cin, cout):
+    """zero-insert / weight permute / resize+add / gather / subsample: each against its torch restatement (bit-exact data movement)."""
+    U, E, L = _ctx()
+    N = 2
+    (d, h, w), (D, H, W) = small, big
+    sd, sh, sw = 2 * d - 1, 2 * h - 1, 2 * w - 1
+    x = F.relu(_rand((N, d, h, w, cin), 4).float()).bfloat16()
+    xz = torch.full((N, sd, sh, sw, cin), float("nan"), dtype=torch.bfloat16, device="cuda")
+    L.call("b200_zero_insert", U.p(x), N, d, h, w, cin, U.p(xz), U.stream())
+    ref = torch.zeros_like(xz)
+    ref[:, ::2, ::2, ::2] = x
+    assert torch.equal(xz, ref)
+    g = torch.Generator(device="cuda").manual_seed(6)
+    Wt = torch.randn((cin, cout, 3, 3, 3), device="cuda", generator=g) * 0.1
+    Wc = torch.empty((cout, cin, 3, 3, 3), device="cuda")
+    L.call("b200_deconv_weight_permute", U.p(Wt), cin, cout, 1, U.p(Wc), U.stream())
+    assert torch.equal(Wc, Wt.flip(2, 3, 4).transpose(0, 1).contiguous())
+    back = torch.empty_like(Wt)
+    L.call("b200_deconv_weight_permute", U.p(Wc), cin, cout, 0, U.p(back), U.stream())
+    assert torch.equal(back, Wt)
+    # the identity the engine relies on
+    xr = x.float().permute(0, 4, 1, 2, 3)
+    t_ref = F.conv_transpose3d(xr, Wt, None, stride=2, padding=1)
+    t_conv = F.conv3d(xz.float().permute(0, 4, 1, 2, 3), Wc, None, padding=1)
+    assert U.rel_l2(t_conv, t_ref) < 1e-5
+    # resize (nearest) + add + statistics
+    T = _rand((N, sd, sh, sw, cout), 11)
+    enc = _rand((N, D, H, W, cout), 5)
+    out = torch.empty((N, D, H, W, cout), dtype=torch.bfloat16, device="cuda")
+    P = L.query("b200_resize_add_partials_count", N, D, H, W, cout)
+    part = torch.full((N, P, cout, 2), float("nan"), device="cuda")
+    L.call("b200_resize_add_fwd", U.p(T), U.p(enc), N, sd, sh, sw, D, H, W, cout, U.p(out), U.p(part), U.stream())
+    Tr = T.float().permute(0, 4, 1, 2, 3).requires_grad_(True)
+    ref = enc.float().permute(0, 4, 1, 2, 3) + F.interpolate(Tr, size=(D, H, W))
+    assert torch.equal(out, ref.permute(0, 2, 3, 4, 1).bfloat16())
+    od = out.double()
+    assert U.rel_l2(part.double().sum(1)[..., 0], od.sum((1, 2, 3))) < 1e-4
+    assert U.rel_l2(part.double().sum(1)[..., 1], (od * od).sum((1, 2, 3))) < 1e-4
+    dout = _rand((N, D, H, W, cout), 7)
+    ref.backward(dout.float().permute(0, 4, 1, 2, 3))
+    dT = torch.empty((N, sd, sh, sw, cout), dtype=torch.bfloat16, device="cuda")
+    L.call("b200_deconv_gather", U.p(dout), N, d, h, w, D, H, W, cout, U.p(dT), U.stream())
+    assert U.rel_l2(dT, Tr.grad.permute(0, 2, 3, 4, 1)) < 4e-3
+    # subsample of the zero-inserted gradient, masked by the producer's ReLU, plus an existing gradient
+    dxz = _rand((N, sd, sh, sw, cin), 12)
+    gadd = _rand((N, d, h, w, cin), 13)
+    gx = torch.empty_like(x)
+    L.call("b200_subsample2_bwd", U.p(dxz), U.p(x), N, d, h, w, cin, E.ACT_RELU, 0.0, U.p(gadd), U.p(gx), U.stream())
+    want = dxz[:, ::2, ::2, ::2].float() * (x.float() > 0) + gadd.float()
+    assert U.rel_l2(gx, want) < 4e-3
+    L.call("b200_subsample2_bwd", U.p(dxz), U.p(x), N, d, h, w, cin, E.ACT_NONE, 0.0, None, U.p(gx), U.stream())
+    assert torch.equal(gx, dxz[:, ::2, ::2, ::2])
+
+
+@pytest.mark.parametrize("small,big,cin,cout", [((4, 4, 4), (8, 8, 8), 32, 16), ((3, 5, 4), (5, 9, 7), 16, 16), ((6, 6, 6), (12, 12, 12), 128, 64)])
+def test_deconv_up_add_engine(small, big, cin, cout):
+    """Engine.deconv_up_add (zero-insert -> tcgen05 conv -> resize+add) and its backward against
+    conv_transpose3d + interpolate + add in fp32 torch (buildingblocks.py:617-664, :493)."""
     U, E, L = _ctx()
     N = 2
     (d, h, w), (D, H, W) = small, big
     x = F.relu(_rand((N, d, h, w, cin), 4).float()).bfloat16()
-    enc = _rand((N, D, H, W, cout), 5)
+    enc = F.relu(_rand((N, D, H, W, cout), 5).float()).bfloat16()
     g = torch.Generator(device="cuda").manual_seed(6)
     Wt = torch.randn((cin, cout, 3, 3, 3), device="cuda", generator=g) * 0.1
-    wt = torch.empty((27, cout, cin), dtype=torch.bfloat16, device="cuda")
-    wtb = torch.empty((27, cin, cout), dtype=torch.bfloat16, device="cuda")
-    L.call("b200_deconv_prep_weights", U.p(Wt), cin, cout, U.p(wt), U.p(wtb), U.stream())
-    out = torch.empty((N, D, H, W, cout), dtype=torch.bfloat16, device="cuda")
-    P = L.query("b200_deconv_up_add_partials_count", N, D, H, W, cout)
-    part = torch.full((N, P, cout, 2), float("nan"), device="cuda")
-    L.call("b200_deconv_up_add_fwd", U.p(x), U.p(wt), U.p(enc), N, d, h, w, D, H, W, cin, cout, U.p(out), U.p(part), U.stream())
+    eng = E.Engine(torch.device("cuda"), record=True)
+    xa = E.Act(x, E.ACT_RELU, 0.0, requires_grad=True)
+    ea = E.Act(enc, E.ACT_RELU, 0.0, requires_grad=True)
+    out = eng.deconv_up_add(ea, xa, Wt, "up.weight", want_stats=True)
     xr = x.float().permute(0, 4, 1, 2, 3).requires_grad_(True)
+    er = enc.float().permute(0, 4, 1, 2, 3).requires_grad_(True)
     Wr = Wt.bfloat16().float().requires_grad_(True)
-    t = F.conv_transpose3d(xr, Wr, None, stride=2, padding=1)
-    ref = enc.float().permute(0, 4, 1, 2, 3) + F.interpolate(t, size=(D, H, W))
-    assert U.rel_l2(out, ref.permute(0, 2, 3, 4, 1)) < 5e-3
-    od = out.double()
-    assert U.rel_l2(part.double().sum(1)[..., 0], od.sum((1, 2, 3))) < 1e-4
+    ref = er + F.interpolate(F.conv_transpose3d(xr, Wr, None, stride=2, padding=1), size=(D, H, W))
+    assert U.rel_l2(out.t, ref.permute(0, 2, 3, 4, 1)) < 5e-3
+    od = out.t.double()
+    sums = eng.sums_of(out)
+    assert U.rel_l2(sums[..., 0], od.sum((1, 2, 3))) < 1e-4
     dout = _rand((N, D, H, W, cout), 7)
     ref.backward(dout.float().permute(0, 4, 1, 2, 3))
-    dT = torch.empty((N, 2 * d - 1, 2 * h - 1, 2 * w - 1, cout), dtype=torch.bfloat16, device="cuda")
-    L.call("b200_deconv_gather", U.p(dout), N, d, h, w, D, H, W, cout, U.p(dT), U.stream())
-    gx = torch.empty_like(x)
-    L.call("b200_deconv_dgrad", U.p(dT), U.p(wtb), U.p(x), N, d, h, w, cin, cout, E.ACT_RELU, 0.0, None, U.p(gx), U.stream())
-    assert U.rel_l2(gx, xr.grad.permute(0, 2, 3, 4, 1) * (x.float() > 0)) < 1e-2
-    dWt = torch.empty_like(Wt)
-    L.call("b200_deconv_wgrad", U.p(x), U.p(dT), N, d, h, w, cin, cout, U.p(dWt), U.stream())
-    assert U.rel_l2(dWt, Wr.grad) < 1e-2
+    out.grad = dout
+    eng.run_backward()
+    assert U.rel_l2(xa.grad, xr.grad.permute(0, 2, 3, 4, 1) * (x.float() > 0)) < 1e-2
+    assert U.rel_l2(ea.grad, er.grad.permute(0, 2, 3, 4, 1) * (enc.float() > 0)) < 1e-2
+    assert U.rel_l2(eng.param_grads["up.weight"], Wr.grad) < 1e-2
 
 
 @pytest.mark.parametrize("C", [32, 64, 256, 512])
