@@ -173,6 +173,16 @@ int b200_pointwise_partials_count(int N, long long voxels, int Cout);
 int b200_pointwise_fwd(const void* x, int x_is_f32, const float* W, int transposed, const float* bias, int N, long long voxels,
                        int Cin, int Cout, void* y, float* partials, b200_stream_t s);
 /* partial rows [N*P][Cout*Cin + Cout] of dW, db; reduce with b200_reduce_rows */
+/* 1x1x1 conv on the tensor cores (C_in, C_out multiples of 16; bf16 input): the tcgen05 conv / wgrad kernels over a flat voxel list.
+ * wq: bf16 [Cout][Cin] from b200_pointwise_prep_weights (transposed=1 gives the dgrad operand [Cin][Cout]); bias fp32 [Cout] or NULL;
+ * partials [N][P][Cout][2] (P = b200_pointwise_tc_partials_count) or NULL; G [N][S][Cin][Cout] fp32 (S = ..._wgrad_splits). */
+int b200_pointwise_prep_weights(const float* W, int Cin, int Cout, int transposed, void* wq, b200_stream_t s);
+int b200_pointwise_tc_supported(int N, long long vox, int Cin, int Cout);
+int b200_pointwise_tc_partials_count(int N, long long vox);
+int b200_pointwise_tc_fwd(const void* x, const void* wq, const float* bias, int N, long long vox, int Cin, int Cout, void* y,
+                          float* partials, b200_stream_t s);
+int b200_pointwise_tc_wgrad_splits(int N, long long vox, int Cin, int Cout);
+int b200_pointwise_tc_wgrad(const void* x, const void* dy, int N, long long vox, int Cin, int Cout, float* G, b200_stream_t s);
 int b200_pointwise_wgrad_partials_count(int N, long long voxels);
 int b200_pointwise_wgrad(const void* x, int x_is_f32, const void* dy, int N, long long voxels, int Cin, int Cout, float* partials,
                          b200_stream_t s);
@@ -196,8 +206,8 @@ int b200_deconv_weight_permute(const float* src, int Cin, int Cout, int to_conv,
 int b200_se_gates_fwd(const double* sums, double count, const float* W1, const float* b1, const float* W2, const float* b2, int N, int C,
                       float* smean, float* h, float* g, b200_stream_t s);
 int b200_scse_partials_count(int N, long long voxels, int C);
-/* q[n,v] = sigmoid(ws . y[v,:] + bs) (saved for backward); out = max(y*g, y*q) */
-int b200_scse_apply_fwd(const void* y, const float* g, const float* ws, float bs, int N, long long voxels, int C, void* out, float* q,
+/* q[n,v] = sigmoid(ws . y[v,:] + bs[0]) (saved for backward); out = max(y*g, y*q); bs: device pointer to the 1-element conv bias */
+int b200_scse_apply_fwd(const void* y, const float* g, const float* ws, const float* bs, int N, long long voxels, int C, void* out, float* q,
                         b200_stream_t s);
 /* tmp = d out/d y without the channel-mean path; partials [N][P][C][2] = (d g, d ws per sample); dbs_part [N][P] */
 int b200_scse_bwd1(const void* dout, const void* y, const float* g, const float* q, const float* ws, int N, long long voxels, int C, void* tmp,
@@ -213,6 +223,8 @@ int b200_probe_umma_rowshift(const void* A, int rows, const void* B, int shift, 
  * out[0] = issue cycles, out[1] = cycles until all completed */
 /* hardware probe: cycles for ld_iters tcgen05.ld (4 warps, 32 columns each) while mma_iters*4 MMAs (N columns) run; out[0] ld cycles, out[1] mma cycles */
 int b200_probe_tmem_ld_contention(int N, int mma_iters, int ld_iters, long long* out, b200_stream_t s);
+/* out[cta*4 + w] = cycles until issuing warp w's iters*4 MMAs (own accumulator) completed; grid CTAs, 256 TMEM columns each */
+int b200_probe_umma_multi_issue(int N, int n_issuers, int iters, int grid, long long* out, b200_stream_t s);
 /* test tooling: per-CTA wait-cycle counters of the halo kernel (8 x int64 per CTA); NULL disables */
 int b200_set_debug_buffer(void* buf);
 int b200_probe_umma_issue(int N, int n_acc, int iters, int rb, int group_rows, int shift, long long* out, b200_stream_t s);

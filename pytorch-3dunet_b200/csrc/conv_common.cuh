@@ -16,6 +16,7 @@ struct ConvParams {
   int BD, BH, BW;
   int tilesD, tilesH, tilesW;
   int n_w, n_b;
+  int ntaps;    // 27 (3x3x3) or 1 (1x1x1 conv: centre tap only, bias row 0 for every voxel) -- plain igemm kernel only
   int NT;       // output channels per CTA
   int KC;       // channels per k-block (16/32/64)
   int kchunks;  // Cin / KC

@@ -39,7 +39,7 @@ conv3_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_const
   const int tile_in_sample = blockIdx.x - n * (p.tilesD * p.tilesH * p.tilesW);
   const int d0 = td_i * p.BD, h0 = th_i * p.BH, w0 = tw_i * p.BW;
   const int n0 = blockIdx.y * p.NT;
-  const int numK = 27 * p.kchunks;
+  const int numK = p.ntaps * p.kchunks;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.stages; ++i) {
@@ -68,12 +68,12 @@ conv3_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_const
         const uint32_t phase = (uint32_t)(kb / p.stages) & 1u;
         mbar_wait(&empty_bar[stage], phase ^ 1u);
         const int tap = kb / p.kchunks, kc = kb - tap * p.kchunks;
-        const int td = tap / 9, th = (tap / 3) % 3, tw = tap % 3;
+        const int td = p.ntaps == 1 ? 1 : tap / 9, th = p.ntaps == 1 ? 1 : (tap / 3) % 3, tw = p.ntaps == 1 ? 1 : tap % 3;
         uint8_t* sa = smem + (size_t)stage * stage_bytes;
         uint8_t* sb = sa + p.a_bytes;
         mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(128 * p.KC * 2 + p.NT * p.KC * 2));
         tma_load_5d(sa, &tmapA, &full_bar[stage], kc * p.KC, w0 + tw - 1, h0 + th - 1, d0 + td - 1, n);
-        tma_load_3d(sb, &tmapB, &full_bar[stage], kc * p.KC, n0, wsample * 27 + tap);
+        tma_load_3d(sb, &tmapB, &full_bar[stage], kc * p.KC, n0, wsample * p.ntaps + tap);
       }
     }
   } else if (warp == 1) {
@@ -110,7 +110,7 @@ conv3_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_const
     const size_t vox_off = (size_t)n * p.D * p.H * p.W + ((size_t)xd * p.H + xh) * p.W + xw;
     const float* bias_row = nullptr;
     if (p.n_b && valid) {
-      const int cls = (axis_cls(xd, p.D) << 4) | (axis_cls(xh, p.H) << 2) | axis_cls(xw, p.W);
+      const int cls = p.ntaps == 1 ? 0 : ((axis_cls(xd, p.D) << 4) | (axis_cls(xh, p.H) << 2) | axis_cls(xw, p.W));
       bias_row = p.biascls + ((size_t)(p.n_b > 1 ? n : 0) * 64 + cls) * p.Cout;
     }
     mbar_wait(&tmem_full_bar, 0);
@@ -236,6 +236,62 @@ static int pick_nt(int Cout) {
 
 }  // namespace b200
 
+namespace b200 {
+// plain (tap-loop) kernel launch; ntaps = 27: 3x3x3 conv over (D,H,W); ntaps = 1: 1x1x1 conv (wf [n_w][1][Cout][Cin], biascls [n_b][Cout])
+static int conv_igemm_plain_launch(const void* x, const void* wf, int n_w, const float* biascls, int n_b, const void* residual, int act,
+                                   float slope, int N, int D, int H, int W, int Cin, int Cout, void* y, int pmode, const void* aux,
+                                   float* partials, int ntaps, cudaStream_t s) {
+  ConvParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
+  p.ntaps = ntaps;
+  choose_box(D, H, W, &p.BD, &p.BH, &p.BW);
+  p.tilesD = (D + p.BD - 1) / p.BD;
+  p.tilesH = (H + p.BH - 1) / p.BH;
+  p.tilesW = (W + p.BW - 1) / p.BW;
+  p.n_w = n_w;
+  p.n_b = biascls ? n_b : 0;
+  p.NT = pick_nt(Cout);
+  p.KC = (Cin % 64 == 0) ? 64 : (Cin % 32 == 0 ? 32 : 16);
+  p.kchunks = Cin / p.KC;
+  p.a_bytes = (128 * p.KC * 2 + 1023) & ~1023;
+  p.b_bytes = (p.NT * p.KC * 2 + 1023) & ~1023;
+  const int stage_bytes = p.a_bytes + p.b_bytes;
+  int stages = (96 * 1024) / stage_bytes;
+  if (ntaps == 1 && stages > p.kchunks) stages = p.kchunks;  // short K loop: keep the CTA small so several fit on an SM
+  if (stages < 3) stages = ntaps == 1 ? (stages < 1 ? 1 : stages) : 3;
+  if (stages > CONV_MAX_STAGES) stages = CONV_MAX_STAGES;
+  p.stages = stages;
+  int cols = 32;
+  while (cols < p.NT) cols <<= 1;
+  p.tmem_cols = cols;
+  p.act = act;
+  p.slope = slope;
+  p.pmode = pmode;
+  p.biascls = biascls;
+  p.residual = (const bf16*)residual;
+  p.aux = (const bf16*)aux;
+  p.y = (bf16*)y;
+  p.partials = partials;
+
+  CUtensorMap tmA, tmB;
+  int rc = make_act_tmap(&tmA, x, N, D, H, W, Cin, p.KC, p.BD, p.BH, p.BW);
+  if (rc) return rc;
+  rc = make_w_tmap(&tmB, wf, ntaps * n_w, Cout, Cin, p.KC, p.NT, 1);
+  if (rc) return rc;
+
+  size_t smem = (size_t)stages * stage_bytes + 1024;
+  size_t scratch = (size_t)4 * p.NT * 2 * sizeof(float);
+  if (smem < scratch + 1024) smem = scratch + 1024;
+  cudaError_t e = cudaFuncSetAttribute(conv3_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  B200_CHECK_ARG(e == cudaSuccess, "conv3_igemm: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+  dim3 grid((unsigned)(N * p.tilesD * p.tilesH * p.tilesW), (unsigned)(Cout / p.NT));
+  conv3_igemm_kernel<<<grid, CONV_THREADS, smem, s>>>(tmA, tmB, p);
+  B200_CHECK_LAUNCH("conv3_igemm");
+  return 0;
+}
+}  // namespace b200
+
 using namespace b200;
 
 extern "C" {
@@ -278,51 +334,25 @@ int b200_conv3_igemm_fwd(const void* x, const void* wf, int n_w, const float* bi
     p.partials = partials;
     return conv_halo_launch(x, wf, p, (cudaStream_t)s);
   }
-  memset(&p, 0, sizeof(p));
-  p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
-  choose_box(D, H, W, &p.BD, &p.BH, &p.BW);
-  p.tilesD = (D + p.BD - 1) / p.BD;
-  p.tilesH = (H + p.BH - 1) / p.BH;
-  p.tilesW = (W + p.BW - 1) / p.BW;
-  p.n_w = n_w;
-  p.n_b = biascls ? n_b : 0;
-  p.NT = pick_nt(Cout);
-  p.KC = (Cin % 64 == 0) ? 64 : (Cin % 32 == 0 ? 32 : 16);
-  p.kchunks = Cin / p.KC;
-  p.a_bytes = (128 * p.KC * 2 + 1023) & ~1023;
-  p.b_bytes = (p.NT * p.KC * 2 + 1023) & ~1023;
-  const int stage_bytes = p.a_bytes + p.b_bytes;
-  int stages = (96 * 1024) / stage_bytes;
-  if (stages < 3) stages = 3;
-  if (stages > CONV_MAX_STAGES) stages = CONV_MAX_STAGES;
-  p.stages = stages;
-  int cols = 32;
-  while (cols < p.NT) cols <<= 1;
-  p.tmem_cols = cols;
-  p.act = act;
-  p.slope = slope;
-  p.pmode = pmode;
-  p.biascls = biascls;
-  p.residual = (const bf16*)residual;
-  p.aux = (const bf16*)aux;
-  p.y = (bf16*)y;
-  p.partials = partials;
+  return conv_igemm_plain_launch(x, wf, n_w, biascls, n_b, residual, act, slope, N, D, H, W, Cin, Cout, y, pmode, aux, partials, 27,
+                                 (cudaStream_t)s);
+}
 
-  CUtensorMap tmA, tmB;
-  int rc = make_act_tmap(&tmA, x, N, D, H, W, Cin, p.KC, p.BD, p.BH, p.BW);
-  if (rc) return rc;
-  rc = make_w_tmap(&tmB, wf, 27 * n_w, Cout, Cin, p.KC, p.NT);
-  if (rc) return rc;
-
-  size_t smem = (size_t)stages * stage_bytes + 1024;
-  size_t scratch = (size_t)4 * p.NT * 2 * sizeof(float);
-  if (smem < scratch + 1024) smem = scratch + 1024;
-  cudaError_t e = cudaFuncSetAttribute(conv3_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  B200_CHECK_ARG(e == cudaSuccess, "conv3_igemm: cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e));
-  dim3 grid((unsigned)(N * p.tilesD * p.tilesH * p.tilesW), (unsigned)(Cout / p.NT));
-  conv3_igemm_kernel<<<grid, CONV_THREADS, smem, (cudaStream_t)s>>>(tmA, tmB, p);
-  B200_CHECK_LAUNCH("conv3_igemm");
-  return 0;
+// ---- 1x1x1 convolution (ResNetBlock.conv1, buildingblocks.py:203) on the same kernel: the volume is a flat list of voxels
+int b200_pointwise_tc_supported(int N, long long vox, int Cin, int Cout) {
+  (void)N;
+  return (Cin % 16 == 0 && Cout % 16 == 0 && vox >= 1 && vox < (1ll << 31)) ? 1 : 0;
+}
+int b200_pointwise_tc_partials_count(int N, long long vox) {
+  (void)N;
+  return (int)((vox + 127) / 128);
+}
+int b200_pointwise_tc_fwd(const void* x, const void* wq, const float* bias, int N, long long vox, int Cin, int Cout, void* y,
+                          float* partials, b200_stream_t s) {
+  B200_CHECK_ARG(b200_pointwise_tc_supported(N, vox, Cin, Cout), "pointwise_tc: unsupported N=%d vox=%lld Cin=%d Cout=%d", N, vox, Cin,
+                 Cout);
+  return conv_igemm_plain_launch(x, wq, 1, bias, bias ? 1 : 0, nullptr, B200_ACT_NONE, 0.f, N, 1, 1, (int)vox, Cin, Cout, y, partials ? 1 : 0,
+                                 nullptr, partials, 1, (cudaStream_t)s);
 }
 
 }  // extern "C"

@@ -491,62 +491,69 @@ __global__ void maxpool_fwd_kernel(const bf16* __restrict__ x, int D, int H, int
 // iterates over 2x2x2 cells of the FULL-resolution grid (ceil), so ragged borders still get gadd*mask (or 0)
 __global__ void maxpool_bwd_kernel(const bf16* __restrict__ dpooled, const bf16* __restrict__ xf, int D, int H, int W, int C, int P,
                                    int act, float slope, const bf16* gadd, bf16* out) {
-  int p = blockIdx.x, n = blockIdx.y;
-  int oD = D / 2, oH = H / 2, oW = W / 2;
-  int cD = (D + 1) / 2, cH = (H + 1) / 2, cW = (W + 1) / 2;
-  long long cells = (long long)cD * cH * cW;
-  EwMap m = ew_map(C);
-  long long v0, v1;
-  ew_range(cells, p, P, v0, v1);
-  if (!m.active) return;
-  size_t fvox = (size_t)D * H * W;
-  const bf16x8* xp = reinterpret_cast<const bf16x8*>(xf + (size_t)n * fvox * C);
-  const bf16x8* dp = reinterpret_cast<const bf16x8*>(dpooled + (size_t)n * oD * oH * oW * C);
-  bf16x8* op = reinterpret_cast<bf16x8*>(out + (size_t)n * fvox * C);
-  for (long long v = v0 + m.vl; v < v1; v += m.VL) {
-    int cw = (int)(v % cW);
-    long long r = v / cW;
-    int ch = (int)(r % cH), cd = (int)(r / cH);
-    bool pooled = cd < oD && ch < oH && cw < oW;
-    float xv[8][8];
-    bool inb[8];
-    int arg[8];
-    float mx[8];
+  const int p = blockIdx.x, n = blockIdx.y;
+  const int oD = D / 2, oH = H / 2, oW = W / 2;
+  const int cD = (D + 1) / 2, cH = (H + 1) / 2, cW = (W + 1) / 2;
+  const EwMap m = ew_map(C);
+  const LineMap lm = line_map(m, cW);
+  int l0, l1;
+  ew_range_i(cD * cH, p, P, l0, l1);
+  if (!lm.active) return;
+  const size_t fvox = (size_t)D * H * W;
+  const bf16x8* xp = reinterpret_cast<const bf16x8*>(xf + (size_t)n * fvox * C) + m.cg;
+  const bf16x8* dp = reinterpret_cast<const bf16x8*>(dpooled + (size_t)n * oD * oH * oW * C) + m.cg;
+  const bf16x8* gp = gadd ? reinterpret_cast<const bf16x8*>(gadd + (size_t)n * fvox * C) + m.cg : nullptr;
+  bf16x8* op = reinterpret_cast<bf16x8*>(out + (size_t)n * fvox * C) + m.cg;
+  for (int l = l0 + lm.ls; l < l1; l += lm.LPB) {
+    const int ch = l % cH, cd = l / cH;
+    const bool pooled_dh = cd < oD && ch < oH;
+    for (int cw = lm.lw; cw < cW; cw += lm.lpl) {
+      const bool pooled = pooled_dh && cw < oW;
+      bf16x8 xr[8];
+      bool inb[8];
+      int arg[8];
+      float mx[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      mx[i] = -INFINITY;
-      arg[i] = 0;
-    }
+      for (int i = 0; i < 8; ++i) {
+        mx[i] = -INFINITY;
+        arg[i] = 0;
+      }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      int z = 2 * cd + (k >> 2), yy = 2 * ch + ((k >> 1) & 1), xx = 2 * cw + (k & 1);
-      inb[k] = z < D && yy < H && xx < W;
-      if (inb[k]) {
-        unpack8(xp[(((size_t)z * H + yy) * W + xx) * m.CG + m.cg], xv[k]);
+      for (int k = 0; k < 8; ++k) {
+        const int z = 2 * cd + (k >> 2), yy = 2 * ch + ((k >> 1) & 1), xx = 2 * cw + (k & 1);
+        inb[k] = z < D && yy < H && xx < W;
+        if (inb[k]) xr[k] = xp[(((size_t)z * H + yy) * W + xx) * m.CG];
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (!inb[k]) continue;
+        float f[8];
+        unpack8(xr[k], f);
 #pragma unroll
         for (int i = 0; i < 8; ++i)
-          if (xv[k][i] > mx[i]) {  // strict '>' : first maximum in (d,h,w) scan order wins, as max_pool3d_with_indices
-            mx[i] = xv[k][i];
+          if (f[i] > mx[i]) {  // strict '>' : first maximum in (d,h,w) scan order wins, as max_pool3d_with_indices
+            mx[i] = f[i];
             arg[i] = k;
           }
       }
-    }
-    float g[8] = {0};
-    if (pooled) unpack8(dp[(((size_t)cd * oH + ch) * oW + cw) * m.CG + m.cg], g);
+      float g[8] = {0};
+      if (pooled) unpack8(dp[(((size_t)cd * oH + ch) * oW + cw) * m.CG], g);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      if (!inb[k]) continue;
-      int z = 2 * cd + (k >> 2), yy = 2 * ch + ((k >> 1) & 1), xx = 2 * cw + (k & 1);
-      size_t iv = ((size_t)z * H + yy) * W + xx;
-      float ga[8], o[8];
-      if (gadd) unpack8(*reinterpret_cast<const bf16x8*>(gadd + ((size_t)n * fvox + iv) * C + m.cg * 8), ga);
+      for (int k = 0; k < 8; ++k) {
+        if (!inb[k]) continue;
+        const int z = 2 * cd + (k >> 2), yy = 2 * ch + ((k >> 1) & 1), xx = 2 * cw + (k & 1);
+        const size_t iv = (((size_t)z * H + yy) * W + xx) * m.CG;
+        float ga[8], o[8], f[8];
+        unpack8(xr[k], f);
+        if (gp) unpack8(gp[iv], ga);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float t = (pooled && arg[i] == k) ? g[i] * act_grad_from_out(xv[k][i], act, slope) : 0.f;
-        if (gadd) t += ga[i];
-        o[i] = t;
+        for (int i = 0; i < 8; ++i) {
+          float t = (pooled && arg[i] == k) ? g[i] * act_grad_from_out(f[i], act, slope) : 0.f;
+          if (gp) t += ga[i];
+          o[i] = t;
+        }
+        op[iv] = pack8(o);
       }
-      op[iv * m.CG + m.cg] = pack8(o);
     }
   }
 }
@@ -564,34 +571,38 @@ __device__ __forceinline__ int nearest_src(int dst, int in, int out) {
 __global__ void upcat_fwd_kernel(const bf16* __restrict__ enc, int C0, const bf16* __restrict__ x, int C1, int D, int H, int W, int d,
                                  int h, int w, int P, bf16* __restrict__ cat, float* __restrict__ partials) {
   extern __shared__ float red[];
-  int p = blockIdx.x, n = blockIdx.y;
-  int C = C0 + C1;
-  long long vox = (long long)D * H * W;
-  EwMap m = ew_map(C);
-  long long v0, v1;
-  ew_range(vox, p, P, v0, v1);
+  const int p = blockIdx.x, n = blockIdx.y;
+  const int C = C0 + C1;
+  const size_t vox = (size_t)D * H * W;
+  const EwMap m = ew_map(C);
+  const LineMap lm = line_map(m, W);
+  int l0, l1;
+  ew_range_i(D * H, p, P, l0, l1);
   float s[8] = {0}, q[8] = {0};
-  if (m.active) {
-    int c = m.cg * 8;
-    bf16x8* op = reinterpret_cast<bf16x8*>(cat + (size_t)n * vox * C);
-    for (long long v = v0 + m.vl; v < v1; v += m.VL) {
-      bf16x8 val;
-      if (c < C0) {
-        val = *reinterpret_cast<const bf16x8*>(enc + ((size_t)n * vox + v) * C0 + c);
-      } else {
-        int xw = (int)(v % W);
-        long long r = v / W;
-        int xh = (int)(r % H), xd = (int)(r / H);
-        size_t sv = ((size_t)nearest_src(xd, d, D) * h + nearest_src(xh, h, H)) * w + nearest_src(xw, w, W);
-        val = *reinterpret_cast<const bf16x8*>(x + ((size_t)n * d * h * w + sv) * C1 + (c - C0));
-      }
-      op[v * m.CG + m.cg] = val;
-      float f[8];
-      unpack8(val, f);
+  if (lm.active) {
+    const int c = m.cg * 8;
+    const bool from_enc = c < C0;
+    const bf16* encp = enc + (size_t)n * vox * C0 + c;
+    const bf16* xp = x + (size_t)n * d * h * w * C1 + (c - C0);
+    bf16x8* op = reinterpret_cast<bf16x8*>(cat + (size_t)n * vox * C) + m.cg;
+    for (int l = l0 + lm.ls; l < l1; l += lm.LPB) {
+      const int xh = l % H, xd = l / H;
+      const size_t srow = ((size_t)nearest_src(xd, d, D) * h + nearest_src(xh, h, H)) * w;
+      for (int xw = lm.lw; xw < W; xw += lm.lpl) {
+        const size_t v = (size_t)l * W + xw;
+        bf16x8 val;
+        if (from_enc)
+          val = *reinterpret_cast<const bf16x8*>(encp + v * C0);
+        else
+          val = *reinterpret_cast<const bf16x8*>(xp + (srow + nearest_src(xw, w, W)) * C1);
+        op[v * m.CG] = val;
+        float f[8];
+        unpack8(val, f);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        s[i] += f[i];
-        q[i] += f[i] * f[i];
+        for (int i = 0; i < 8; ++i) {
+          s[i] += f[i];
+          q[i] += f[i] * f[i];
+        }
       }
     }
   }
@@ -600,6 +611,11 @@ __global__ void upcat_fwd_kernel(const bf16* __restrict__ enc, int C0, const bf1
 
 // destination index range [lo,hi] along one axis that maps to source index s (empty if lo>hi)
 __device__ __forceinline__ void nearest_dst_range(int s, int in, int out, int& lo, int& hi) {
+  if (out == 2 * in) {  // the usual case: exact 2x
+    lo = 2 * s;
+    hi = 2 * s + 1;
+    return;
+  }
   float inv = (float)out / (float)in;
   int a = (int)floorf((float)s * inv) - 2, b = (int)ceilf((float)(s + 1) * inv) + 2;
   if (a < 0) a = 0;
@@ -615,36 +631,40 @@ __device__ __forceinline__ void nearest_dst_range(int s, int in, int out, int& l
 
 __global__ void upcat_bwd_kernel(const bf16* __restrict__ dcat, int C0, int C1, const bf16* __restrict__ xs, int D, int H, int W, int d,
                                  int h, int w, int P, int act, float slope, bf16* __restrict__ out) {
-  int p = blockIdx.x, n = blockIdx.y;
-  int C = C0 + C1;
-  long long svox = (long long)d * h * w, vox = (long long)D * H * W;
-  EwMap m = ew_map(C1);
-  long long v0, v1;
-  ew_range(svox, p, P, v0, v1);
-  if (!m.active) return;
-  for (long long v = v0 + m.vl; v < v1; v += m.VL) {
-    int sw = (int)(v % w);
-    long long r = v / w;
-    int sh = (int)(r % h), sd = (int)(r / h);
-    int d0, d1, h0, h1, w0, w1;
+  const int p = blockIdx.x, n = blockIdx.y;
+  const int C = C0 + C1;
+  const size_t svox = (size_t)d * h * w, vox = (size_t)D * H * W;
+  const EwMap m = ew_map(C1);
+  const LineMap lm = line_map(m, w);
+  int l0, l1;
+  ew_range_i(d * h, p, P, l0, l1);
+  if (!lm.active) return;
+  const bf16* gp = dcat + (size_t)n * vox * C + C0 + m.cg * 8;
+  for (int l = l0 + lm.ls; l < l1; l += lm.LPB) {
+    const int sh = l % h, sd = l / h;
+    int d0, d1, h0, h1;
     nearest_dst_range(sd, d, D, d0, d1);
     nearest_dst_range(sh, h, H, h0, h1);
-    nearest_dst_range(sw, w, W, w0, w1);
-    float acc[8] = {0};
-    for (int z = d0; z <= d1; ++z)
-      for (int y = h0; y <= h1; ++y)
-        for (int x = w0; x <= w1; ++x) {
-          size_t dv = ((size_t)z * H + y) * W + x;
-          float f[8];
-          unpack8(*reinterpret_cast<const bf16x8*>(dcat + ((size_t)n * vox + dv) * C + C0 + m.cg * 8), f);
+    for (int sw = lm.lw; sw < w; sw += lm.lpl) {
+      int w0, w1;
+      nearest_dst_range(sw, w, W, w0, w1);
+      float acc[8] = {0};
+      for (int z = d0; z <= d1; ++z)
+        for (int y = h0; y <= h1; ++y)
+          for (int x = w0; x <= w1; ++x) {
+            const size_t dv = ((size_t)z * H + y) * W + x;
+            float f[8];
+            unpack8(*reinterpret_cast<const bf16x8*>(gp + dv * C), f);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) acc[i] += f[i];
-        }
-    float xv[8];
-    unpack8(*reinterpret_cast<const bf16x8*>(xs + ((size_t)n * svox + v) * C1 + m.cg * 8), xv);
+            for (int i = 0; i < 8; ++i) acc[i] += f[i];
+          }
+      const size_t v = (size_t)l * w + sw;
+      float xv[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(xs + ((size_t)n * svox + v) * C1 + m.cg * 8), xv);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] *= act_grad_from_out(xv[i], act, slope);
-    *reinterpret_cast<bf16x8*>(out + ((size_t)n * svox + v) * C1 + m.cg * 8) = pack8(acc);
+      for (int i = 0; i < 8; ++i) acc[i] *= act_grad_from_out(xv[i], act, slope);
+      *reinterpret_cast<bf16x8*>(out + ((size_t)n * svox + v) * C1 + m.cg * 8) = pack8(acc);
+    }
   }
 }
 
@@ -653,63 +673,91 @@ __global__ void upcat_bwd_kernel(const bf16* __restrict__ dcat, int C0, int C1, 
 // ------------------------------------------------------------------------------------------------
 // stage 1a: per-channel TOTAL sums of dz: stats_ndhwc_bf16_kernel (a branch-free streaming pass at HBM speed).
 // stage 1b: class sums of the BORDER voxels only (4-5 % of a 128^3 volume); the interior class is total - sum(border).
-// grid (P, N, C/BT_CC): a block owns a range of (d,h) lines; full lines when the line lies on a d/h face, else only its two
-// end voxels.  Partials Rp [N][P][64][C] (interior slot left 0).
+// grid (P, N, C/BT_CC).  Two evenly distributed phases per block:
+//   A  the middles (w = 1..W-2) of the lines that lie on a d/h face, dealt round-robin over the blocks (one class per line:
+//      registers -> one shuffle reduction -> shared-memory bins);
+//   B  the two end voxels (w = 0, W-1) of a contiguous range of ALL lines, one (line, end, channel group) item per thread per
+//      pass; lines off the d/h faces (almost all) accumulate in registers, face lines go straight to the bins.
+// Partials Rp [N][P][64][C] (interior slot left 0).
 constexpr int BT_CC = 64;
 __global__ void border_class_sums_kernel(const bf16* __restrict__ dz, int D, int H, int W, int C, int P, float* __restrict__ Rp) {
   __shared__ float bins[64][BT_CC];
-  int p = blockIdx.x, n = blockIdx.y, c0 = blockIdx.z * BT_CC;
-  int CC = min(BT_CC, C - c0);
-  int CG = CC >> 3;
-  int VL = EW_THREADS / CG;
-  int cg = threadIdx.x % CG, vl = threadIdx.x / CG;
+  const int p = blockIdx.x, n = blockIdx.y, c0 = blockIdx.z * BT_CC;
+  const int CC = min(BT_CC, C - c0);
+  const int CG = CC >> 3;
   for (int i = threadIdx.x; i < 64 * BT_CC; i += EW_THREADS) (&bins[0][0])[i] = 0.f;
   __syncthreads();
-  const long long lines = (long long)D * H;
-  long long l0, l1;
-  ew_range(lines, p, P, l0, l1);
-  const long long vox = (long long)D * H * W;
+  const size_t vox = (size_t)D * H * W;
+  const bf16* base = dz + (size_t)n * vox * C + c0;
   const int lane = threadIdx.x & 31;
-  if (vl < VL) {
-    for (long long l = l0; l < l1; ++l) {
-      const int xh = (int)(l % H), xd = (int)(l / H);
-      const int cdh = (axis_cls(xd, D) << 4) | (axis_cls(xh, H) << 2);
-      const bool face = (cdh != ((1 << 4) | (1 << 2)));
-      const bf16* line = dz + ((size_t)n * vox + (size_t)l * W) * C + c0 + cg * 8;
-      // the two end voxels of the line (their w-class differs): lanes vl == 0 / 1
-      if (vl < 2 && vl < W) {
-        const int xw = vl == 0 ? 0 : W - 1;
-        if (!(vl == 1 && W == 1)) {
-          float f[8];
-          unpack8(*reinterpret_cast<const bf16x8*>(line + (size_t)xw * C), f);
-          const int cls = cdh | axis_cls(xw, W);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) atomicAdd(&bins[cls][cg * 8 + i], f[i]);
-        }
+  const int interior_dh = (1 << 4) | (1 << 2);
+  // ---- phase A
+  if (W > 2) {
+    const int VL = EW_THREADS / CG;
+    const int cg = threadIdx.x % CG, vl = threadIdx.x / CG;
+    const int nd_face = D < 2 ? D : 2, nh_face = H < 2 ? H : 2;
+    const int linesA = nd_face * H, nface = linesA + (D - nd_face) * nh_face;
+    for (int f = p; f < nface; f += P) {
+      int xd, xh;
+      if (f < linesA) {
+        xd = (f < H) ? 0 : D - 1;
+        xh = f - (f < H ? 0 : H);
+      } else {
+        const int g = f - linesA;
+        xd = 1 + g / nh_face;
+        xh = (g % nh_face == 0) ? 0 : H - 1;
       }
-      // the middle of a line that lies on a d/h face: one class for all of it -> registers, one reduction per warp
-      if (face && W > 2) {
-        float acc[8] = {0};
+      const int cls = (axis_cls(xd, D) << 4) | (axis_cls(xh, H) << 2) | 1;
+      const bf16* line = base + ((size_t)xd * H + xh) * W * C + cg * 8;
+      float acc[8] = {0};
+      if (vl < VL)
         for (int xw = 1 + vl; xw < W - 1; xw += VL) {
-          float f[8];
-          unpack8(*reinterpret_cast<const bf16x8*>(line + (size_t)xw * C), f);
+          float v[8];
+          unpack8(*reinterpret_cast<const bf16x8*>(line + (size_t)xw * C), v);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) acc[i] += f[i];
+          for (int i = 0; i < 8; ++i) acc[i] += v[i];
         }
-        // lanes of a warp that share cg differ by multiples of CG (CG <= 8 here, a power of two or 1..8)
-        if ((32 % CG) == 0) {
+      if ((32 % CG) == 0) {  // lanes of a warp that share cg differ by multiples of CG
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            for (int o = CG; o < 32; o <<= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
-          if (lane < CG) {
+        for (int i = 0; i < 8; ++i)
+          for (int o = CG; o < 32; o <<= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+        if (lane < CG) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) atomicAdd(&bins[cdh | 1][cg * 8 + i], acc[i]);
-          }
+          for (int i = 0; i < 8; ++i) atomicAdd(&bins[cls][cg * 8 + i], acc[i]);
+        }
+      } else if (vl < VL) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) atomicAdd(&bins[cls][cg * 8 + i], acc[i]);
+      }
+    }
+  }
+  // ---- phase B
+  {
+    const int ends = W >= 2 ? 2 : 1;
+    const int per_line = ends * CG;
+    const int LPP = EW_THREADS / per_line;  // lines per pass
+    const int cg = threadIdx.x % CG, e = (threadIdx.x / CG) % ends, ls = threadIdx.x / per_line;
+    const int xw = e == 0 ? 0 : W - 1;
+    const int wcls = axis_cls(xw, W);
+    int l0, l1;
+    ew_range_i(D * H, p, P, l0, l1);
+    float acc[8] = {0};
+    if (ls < LPP) {
+      for (int l = l0 + ls; l < l1; l += LPP) {
+        const int xh = l % H, xd = l / H;
+        const int cdh = (axis_cls(xd, D) << 4) | (axis_cls(xh, H) << 2);
+        float v[8];
+        unpack8(*reinterpret_cast<const bf16x8*>(base + ((size_t)l * W + xw) * C + cg * 8), v);
+        if (cdh == interior_dh) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] += v[i];
         } else {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) atomicAdd(&bins[cdh | 1][cg * 8 + i], acc[i]);
+          for (int i = 0; i < 8; ++i) atomicAdd(&bins[cdh | wcls][cg * 8 + i], v[i]);
         }
       }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) atomicAdd(&bins[interior_dh | wcls][cg * 8 + i], acc[i]);
     }
   }
   __syncthreads();
@@ -1112,7 +1160,7 @@ int b200_maxpool_bwd(const void* dpooled, const void* x_full, int N, int D, int 
                      const void* gadd, void* dz_full, b200_stream_t s) {
   B200_CHECK_ARG(C % 8 == 0 && C <= 2048, "maxpool_bwd: C=%d must be a multiple of 8", C);
   long long cells = (long long)((D + 1) / 2) * ((H + 1) / 2) * ((W + 1) / 2);
-  int P = ew_blocks(cells, C);
+  int P = ew_blocks_dense(cells, C);
   dim3 grid(P, N);
   maxpool_bwd_kernel<<<grid, EW_THREADS, 0, ST(s)>>>((const bf16*)dpooled, (const bf16*)x_full, D, H, W, C, P, act, slope,
                                                      (const bf16*)gadd, (bf16*)dz_full);
@@ -1137,7 +1185,7 @@ int b200_upcat_fwd(const void* enc, int C0, const void* x, int C1, int N, int D,
 int b200_upcat_bwd(const void* dcat, int C0, int C1, const void* x_small, int N, int D, int H, int W, int d, int h, int w, int act,
                    float slope, void* dx_small, b200_stream_t s) {
   B200_CHECK_ARG(C0 % 8 == 0 && C1 % 8 == 0, "upcat_bwd: channel counts %d,%d must be multiples of 8", C0, C1);
-  int P = ew_blocks((long long)d * h * w, C1);
+  int P = ew_blocks_dense((long long)d * h * w, C1);
   dim3 grid(P, N);
   upcat_bwd_kernel<<<grid, EW_THREADS, 0, ST(s)>>>((const bf16*)dcat, C0, C1, (const bf16*)x_small, D, H, W, d, h, w, P, act, slope,
                                                    (bf16*)dx_small);
@@ -1147,8 +1195,8 @@ int b200_upcat_bwd(const void* dcat, int C0, int C1, const void* x_small, int N,
 
 static int border_blocks(int D, int H) {
   long long lines = (long long)D * H;
-  long long p = (lines + 15) / 16;
-  return (int)(p > 512 ? 512 : (p < 1 ? 1 : p));
+  long long p = (lines + 63) / 64;
+  return (int)(p > 148 ? 148 : (p < 1 ? 1 : p));
 }
 int b200_border_tap_sums_workspace(int N, int D, int H, int W, int C) {
   // floats: border class partials [N][P][64][C] | totals partials [N][P2][C][2] | (doubles) R [N][64][C] | tot [N][C][2]

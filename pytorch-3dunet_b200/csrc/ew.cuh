@@ -41,6 +41,40 @@ __device__ __forceinline__ void ew_range(long long voxels, int p, int P, long lo
   if (v1 > voxels) v1 = voxels;
   if (v0 > voxels) v0 = voxels;
 }
+// line-structured iteration for kernels that need (d,h,w): the voxel lanes of a block are split into LPB groups of `lpl` lanes;
+// a group walks one (d,h) line at a time (32-bit index math, no per-voxel division), lane lw covering w = lw, lw+lpl, ...
+struct LineMap {
+  int lpl, LPB, ls, lw;
+  bool active;
+};
+__device__ __forceinline__ LineMap line_map(const EwMap& m, int W) {
+  LineMap lm;
+  lm.lpl = m.VL < W ? m.VL : W;
+  if (lm.lpl < 1) lm.lpl = 1;
+  lm.LPB = m.VL / lm.lpl;
+  if (lm.LPB < 1) lm.LPB = 1;
+  lm.ls = m.vl / lm.lpl;
+  lm.lw = m.vl - lm.ls * lm.lpl;
+  lm.active = m.active && lm.ls < lm.LPB;
+  return lm;
+}
+__device__ __forceinline__ void ew_range_i(int items, int p, int P, int& i0, int& i1) {
+  int per = (items + P - 1) / P;
+  i0 = p * per;
+  i1 = i0 + per;
+  if (i1 > items) i1 = items;
+  if (i0 > items) i0 = items;
+}
+// blocks per sample for a pass WITHOUT partial sums (no reason to keep >= 16 voxels per lane): ~4 items per lane
+static inline int ew_blocks_dense(long long items, int C) {
+  int CG = C / 8;
+  int VL = EW_THREADS / CG;
+  if (VL < 1) VL = 1;
+  long long p = (items + (long long)VL * 4 - 1) / ((long long)VL * 4);
+  if (p > 16384) p = 16384;
+  if (p < 1) p = 1;
+  return (int)p;
+}
 // reduce per-thread (s[8], q[8]) over the voxel lanes of the block and write [C][2] partials
 __device__ __forceinline__ void ew_write_partials(const float s[8], const float q[8], const EwMap& m, float* out /*[C][2]*/,
                                                   float* red /* smem EW_THREADS*16 */) {

@@ -287,7 +287,29 @@ __global__ void deconv_weight_permute_kernel(const float* __restrict__ src, int 
 using namespace b200;
 #define ST(s) ((cudaStream_t)(s))
 
+namespace b200 {
+// bf16 weights of the 1x1x1 conv for the tensor-core path: wq[co][ci] (fprop) or wq[ci][co] (dgrad: roles of the channels swap)
+__global__ void pointwise_prep_weights_kernel(const float* __restrict__ W, int Cin, int Cout, int transposed, bf16* __restrict__ wq) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Cin * Cout) return;
+  if (!transposed) {
+    wq[i] = __float2bfloat16(W[i]);
+  } else {
+    int ci = i / Cout, co = i % Cout;
+    wq[i] = __float2bfloat16(W[(size_t)co * Cin + ci]);
+  }
+}
+}  // namespace b200
+
 extern "C" {
+
+int b200_pointwise_prep_weights(const float* W, int Cin, int Cout, int transposed, void* wq, b200_stream_t s) {
+  int total = Cin * Cout;
+  b200::pointwise_prep_weights_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)s>>>(W, Cin, Cout, transposed, (bf16*)wq);
+  B200_CHECK_LAUNCH("pointwise_prep_weights");
+  return 0;
+}
+
 
 int b200_pointwise_partials_count(int N, long long voxels, int Cout) {
   (void)N;
@@ -392,30 +414,30 @@ int b200_deconv_weight_permute(const float* src, int Cin, int Cout, int to_conv,
 // =================================================================================================================
 namespace b200 {
 
-// grid N, block 256.  sums: double [N][C][2]; h,g: float [N][C]
-__global__ void se_gates_fwd_kernel(const double* __restrict__ sums, double count, const float* __restrict__ W1, const float* __restrict__ b1,
-                                    const float* __restrict__ W2, const float* __restrict__ b2, int C, float* __restrict__ sm_out,
-                                    float* __restrict__ h, float* __restrict__ g) {
-  extern __shared__ float sh[];  // s[C] | h[C]
-  const int n = blockIdx.x;
+// cSE gates (ChannelSELayer3D, se.py:12-52): s = mean_v y ; h = relu(W1 s + b1) ; g = sigmoid(W2 h + b2).
+// One fully-connected layer per launch, grid (ceil(C/8), N), block 256: warp w of block b owns output row 8b+w, its lanes
+// stride over the input vector (coalesced reads of the weight row) and reduce with shuffles.
+// mode 0: in = sums (double [N][C][2]) / count, writes the mean to `aux` and relu(.) to out; mode 1: in = vec, sigmoid(.) to out
+__global__ void se_fc_kernel(const double* __restrict__ sums, double count, const float* __restrict__ vec, const float* __restrict__ W,
+                             const float* __restrict__ b, int C, int mode, float* __restrict__ aux, float* __restrict__ out) {
+  extern __shared__ float sh[];  // in[C]
+  const int n = blockIdx.y;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float m = (float)(sums[((size_t)n * C + c) * 2] / count);
+    float m = mode == 0 ? (float)(sums[((size_t)n * C + c) * 2] / count) : vec[(size_t)n * C + c];
     sh[c] = m;
-    sm_out[(size_t)n * C + c] = m;
+    if (mode == 0 && blockIdx.x == 0) aux[(size_t)n * C + c] = m;
   }
   __syncthreads();
-  for (int j = threadIdx.x; j < C; j += blockDim.x) {
-    float acc = b1[j];
-    for (int c = 0; c < C; ++c) acc = fmaf(W1[(size_t)j * C + c], sh[c], acc);
-    acc = acc > 0.f ? acc : 0.f;
-    sh[C + j] = acc;
-    h[(size_t)n * C + j] = acc;
-  }
-  __syncthreads();
-  for (int j = threadIdx.x; j < C; j += blockDim.x) {
-    float acc = b2[j];
-    for (int c = 0; c < C; ++c) acc = fmaf(W2[(size_t)j * C + c], sh[C + c], acc);
-    g[(size_t)n * C + j] = 1.f / (1.f + expf(-acc));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = blockIdx.x * 8 + warp;
+  if (j >= C) return;
+  const float* wr = W + (size_t)j * C;
+  float acc = 0.f;
+  for (int c = lane; c < C; c += 32) acc = fmaf(wr[c], sh[c], acc);
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) {
+    acc += b[j];
+    out[(size_t)n * C + j] = mode == 0 ? fmaxf(acc, 0.f) : 1.f / (1.f + expf(-acc));
   }
 }
 
@@ -441,11 +463,13 @@ __device__ __forceinline__ float se_group_sum(float v, int GL) {
 constexpr int SE_MAX_CPL = 4;  // C <= 1024
 
 // grid (P, N), block 256 (8 warps).  q: float [N][V]
-__global__ void scse_apply_fwd_kernel(const bf16* __restrict__ y, const float* __restrict__ g, const float* __restrict__ ws, float bs, int C,
+__global__ void scse_apply_fwd_kernel(const bf16* __restrict__ y, const float* __restrict__ g, const float* __restrict__ ws,
+                                      const float* __restrict__ bs_ptr, int C,
                                       long long vox, int P, bf16* __restrict__ out, float* __restrict__ q) {
   const int p = blockIdx.x, n = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const SeMap m = se_map(C, lane);
+  const float bs = bs_ptr[0];
   long long v0, v1;
   ew_range(vox, p, P, v0, v1);
   float gg[SE_MAX_CPL][8], ww[SE_MAX_CPL][8];
@@ -593,54 +617,70 @@ __global__ void scse_bwd1_kernel(const bf16* __restrict__ dout, const bf16* __re
   }
 }
 
-// gates backward, grid 1 block 256: sums2 double [N][C][2] = (dg, dws_n).  Outputs: coef[N][C][3] = (1, 0, ds/V) for
-// b200_gn_bwd_apply, dW1,db1,dW2,db2, dws[C] (summed over n)
-__global__ void se_gates_bwd_kernel(const double* __restrict__ sums2, const float* __restrict__ sm, const float* __restrict__ h,
-                                    const float* __restrict__ g, const float* __restrict__ W1, const float* __restrict__ W2, int N, int C,
-                                    double count, float* __restrict__ coef, float* __restrict__ dW1, float* __restrict__ db1,
-                                    float* __restrict__ dW2, float* __restrict__ db2, float* __restrict__ dws, float* __restrict__ scratch /*[N][2][C]*/) {
-  // dl2[n][j] = dg*g*(1-g); dh[n][c] = sum_j W2[j][c] dl2[n][j]; dl1[n][c] = dh * (h>0)
-  for (int i = threadIdx.x; i < N * C; i += blockDim.x) {
-    const int n = i / C, j = i % C;
-    const float gv = g[i];
-    scratch[((size_t)n * 2) * C + j] = (float)sums2[(size_t)i * 2] * gv * (1.f - gv);
-  }
+// ---- gates backward (several small launches).  sums2 double [N][C][2] = (dg, dws_n).
+// dl2[n][j] = dg*g*(1-g)
+__global__ void se_dl2_kernel(const double* __restrict__ sums2, const float* __restrict__ g, int NC, float* __restrict__ dl2) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= NC) return;
+  const float gv = g[i];
+  dl2[i] = (float)sums2[(size_t)i * 2] * gv * (1.f - gv);
+}
+// transposed mat-vec out[n][c] = sum_j W[j][c] * vec[n][j]; grid (ceil(C/64), N), block 256 = 64 columns x 4 slices of j.
+// mode 0: out = (h[n][c] > 0) ? acc : 0  (dl1);  mode 1: coef[n][c] = (1, 0, acc / count)
+__global__ void se_matvec_t_kernel(const float* __restrict__ W, const float* __restrict__ vec, const float* __restrict__ h, int C, int mode,
+                                   double count, float* __restrict__ out) {
+  extern __shared__ float sh[];  // vec[C] | red[4][64]
+  float* red = sh + C;
+  const int n = blockIdx.y;
+  for (int j = threadIdx.x; j < C; j += blockDim.x) sh[j] = vec[(size_t)n * C + j];
   __syncthreads();
-  for (int i = threadIdx.x; i < N * C; i += blockDim.x) {
-    const int n = i / C, c = i % C;
-    float acc = 0.f;
-    for (int j = 0; j < C; ++j) acc = fmaf(W2[(size_t)j * C + c], scratch[((size_t)n * 2) * C + j], acc);
-    scratch[((size_t)n * 2 + 1) * C + c] = h[i] > 0.f ? acc : 0.f;
+  const int cl = threadIdx.x & 63, sl = threadIdx.x >> 6;
+  const int c = blockIdx.x * 64 + cl;
+  float acc = 0.f;
+  if (c < C) {
+    const int per = (C + 3) / 4;
+    const int j0 = sl * per, j1 = min(C, j0 + per);
+#pragma unroll 4
+    for (int j = j0; j < j1; ++j) acc = fmaf(W[(size_t)j * C + c], sh[j], acc);
   }
+  red[sl * 64 + cl] = acc;
   __syncthreads();
-  for (int i = threadIdx.x; i < C * C; i += blockDim.x) {
-    const int j = i / C, c = i % C;
-    float a2 = 0.f, a1 = 0.f;
-    for (int n = 0; n < N; ++n) {
-      a2 = fmaf(scratch[((size_t)n * 2) * C + j], h[(size_t)n * C + c], a2);        // dW2[j][c] = sum_n dl2[n][j] h[n][c]
-      a1 = fmaf(scratch[((size_t)n * 2 + 1) * C + j], sm[(size_t)n * C + c], a1);  // dW1[j][c] = sum_n dl1[n][j] s[n][c]
+  if (sl == 0 && c < C) {
+    acc = red[cl] + red[64 + cl] + red[128 + cl] + red[192 + cl];
+    const size_t i = (size_t)n * C + c;
+    if (mode == 0) {
+      out[i] = h[i] > 0.f ? acc : 0.f;
+    } else {
+      out[i * 3] = 1.f;
+      out[i * 3 + 1] = 0.f;
+      out[i * 3 + 2] = (float)(acc / count);
     }
-    dW2[i] = a2;
-    dW1[i] = a1;
   }
-  for (int j = threadIdx.x; j < C; j += blockDim.x) {
-    float a2 = 0.f, a1 = 0.f, aw = 0.f;
+}
+// dW2[j][c] = sum_n dl2[n][j] h[n][c];  dW1[j][c] = sum_n dl1[n][j] s[n][c];  block (j = 0, first C threads) also db2, db1, dws
+__global__ void se_outer_kernel(const float* __restrict__ dl2, const float* __restrict__ dl1, const float* __restrict__ h,
+                                const float* __restrict__ sm, const double* __restrict__ sums2, int N, int C, float* __restrict__ dW1,
+                                float* __restrict__ db1, float* __restrict__ dW2, float* __restrict__ db2, float* __restrict__ dws) {
+  const int j = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float a2 = 0.f, a1 = 0.f;
+  for (int n = 0; n < N; ++n) {
+    a2 = fmaf(dl2[(size_t)n * C + j], h[(size_t)n * C + c], a2);
+    a1 = fmaf(dl1[(size_t)n * C + j], sm[(size_t)n * C + c], a1);
+  }
+  dW2[(size_t)j * C + c] = a2;
+  dW1[(size_t)j * C + c] = a1;
+  if (j == 0) {
+    float b2 = 0.f, b1 = 0.f, aw = 0.f;
     for (int n = 0; n < N; ++n) {
-      a2 += scratch[((size_t)n * 2) * C + j];
-      a1 += scratch[((size_t)n * 2 + 1) * C + j];
-      aw += (float)sums2[((size_t)n * C + j) * 2 + 1];
+      b2 += dl2[(size_t)n * C + c];
+      b1 += dl1[(size_t)n * C + c];
+      aw += (float)sums2[((size_t)n * C + c) * 2 + 1];
     }
-    db2[j] = a2;
-    db1[j] = a1;
-    dws[j] = aw;
-  }
-  for (int i = threadIdx.x; i < N * C; i += blockDim.x) {
-    const int n = i / C, k = i % C;
-    float acc = 0.f;
-    for (int c = 0; c < C; ++c) acc = fmaf(W1[(size_t)c * C + k], scratch[((size_t)n * 2 + 1) * C + c], acc);  // ds[n][k]
-    coef[(size_t)i * 3] = 1.f;
-    coef[(size_t)i * 3 + 1] = 0.f;
-    coef[(size_t)i * 3 + 2] = (float)(acc / count);
+    db2[c] = b2;
+    db1[c] = b1;
+    dws[c] = aw;
   }
 }
 
@@ -650,17 +690,23 @@ extern "C" {
 
 int b200_se_gates_fwd(const double* sums, double count, const float* W1, const float* b1, const float* W2, const float* b2, int N, int C,
                       float* smean, float* h, float* g, b200_stream_t s) {
-  b200::se_gates_fwd_kernel<<<N, 256, 2 * C * sizeof(float), ST(s)>>>(sums, count, W1, b1, W2, b2, C, smean, h, g);
-  B200_CHECK_LAUNCH("se_gates_fwd");
+  dim3 grid((C + 7) / 8, N);
+  b200::se_fc_kernel<<<grid, 256, C * sizeof(float), ST(s)>>>(sums, count, nullptr, W1, b1, C, 0, smean, h);
+  B200_CHECK_LAUNCH("se_fc1");
+  b200::se_fc_kernel<<<grid, 256, C * sizeof(float), ST(s)>>>(nullptr, 1.0, h, W2, b2, C, 1, nullptr, g);
+  B200_CHECK_LAUNCH("se_fc2");
   return 0;
 }
 int b200_scse_partials_count(int N, long long voxels, int C) {
   (void)N;
-  (void)C;
-  long long p = (voxels + 2047) / 2048;
+  // a block of 8 warps handles 8 * VPW voxels per pass (VPW = voxels per warp, see se_map); >= 4 passes per block
+  int CG = C / 8;
+  int GL = CG < 32 ? CG : 32;
+  long long per_block = (long long)8 * (32 / (GL < 1 ? 1 : GL)) * 4;
+  long long p = (voxels + per_block - 1) / per_block;
   return (int)(p > 1024 ? 1024 : (p < 1 ? 1 : p));
 }
-int b200_scse_apply_fwd(const void* y, const float* g, const float* ws, float bs, int N, long long voxels, int C, void* out, float* q,
+int b200_scse_apply_fwd(const void* y, const float* g, const float* ws, const float* bs, int N, long long voxels, int C, void* out, float* q,
                         b200_stream_t s) {
   int CG = C / 8;
   B200_CHECK_ARG(C % 8 == 0 && C <= 1024 && (CG & (CG - 1)) == 0, "scse_apply_fwd: C=%d must be 8 * a power of two, <= 1024", C);
@@ -684,8 +730,19 @@ int b200_scse_bwd1(const void* dout, const void* y, const float* g, const float*
 }
 int b200_se_gates_bwd(const double* sums2, const float* smean, const float* h, const float* g, const float* W1, const float* W2, int N, int C,
                       double count, float* coef, float* dW1, float* db1, float* dW2, float* db2, float* dws, float* scratch, b200_stream_t s) {
-  b200::se_gates_bwd_kernel<<<1, 256, 0, ST(s)>>>(sums2, smean, h, g, W1, W2, N, C, count, coef, dW1, db1, dW2, db2, dws, scratch);
-  B200_CHECK_LAUNCH("se_gates_bwd");
+  float* dl2 = scratch;                  // [N][C]
+  float* dl1 = scratch + (size_t)N * C;  // [N][C]
+  b200::se_dl2_kernel<<<(N * C + 255) / 256, 256, 0, ST(s)>>>(sums2, g, N * C, dl2);
+  B200_CHECK_LAUNCH("se_dl2");
+  dim3 gt((C + 63) / 64, N);
+  size_t smem = ((size_t)C + 256) * sizeof(float);
+  b200::se_matvec_t_kernel<<<gt, 256, smem, ST(s)>>>(W2, dl2, h, C, 0, count, dl1);
+  B200_CHECK_LAUNCH("se_dh");
+  dim3 go((C + 255) / 256, C);
+  b200::se_outer_kernel<<<go, 256, 0, ST(s)>>>(dl2, dl1, h, smean, sums2, N, C, dW1, db1, dW2, db2, dws);
+  B200_CHECK_LAUNCH("se_outer");
+  b200::se_matvec_t_kernel<<<gt, 256, smem, ST(s)>>>(W1, dl1, h, C, 1, count, coef);
+  B200_CHECK_LAUNCH("se_ds");
   return 0;
 }
 

@@ -236,3 +236,62 @@ extern "C" int b200_probe_tmem_ld_contention(int N, int mma_iters, int ld_iters,
   B200_CHECK_LAUNCH("tmem_ld_contention");
   return 0;
 }
+
+// ---- probe 4: is the per-MMA dispatch floor per issuing warp / per CTA, or per SM? --------------------------------
+// `n_issuers` warps of one CTA each issue iters*4 MMAs (M=128, N, K=16) into their own accumulator; `grid` CTAs run at once
+// (grid = 2 x #SMs with 256 TMEM columns each puts two CTAs on every SM).  out[cta*4 + w] = cycles until warp w's MMAs completed.
+namespace b200 {
+__global__ void __launch_bounds__(128) umma_multi_issue_probe_kernel(int N, int n_issuers, int iters, int tmem_cols, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t done_bar[4];
+  __shared__ uint32_t tmem_slot;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;          // 128 rows x 128 B
+  uint8_t* sB = smem + 16384;  // N x 128 B
+  for (int i = threadIdx.x; i < (16384 + N * 128) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4; ++i) mbar_init(&done_bar[i], 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, (uint32_t)tmem_cols);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  if (warp < n_issuers && lane == 0) {
+    const uint32_t idesc = umma_idesc_bf16(128, N, 0, 0);
+    uint64_t ad[4], bd[4];
+    for (int k = 0; k < 4; ++k) {
+      ad[k] = umma_smem_desc(smem_u32(sA) + k * 32, 16u, 1024u, UMMA_LAYOUT_SW128);
+      bd[k] = umma_smem_desc(smem_u32(sB) + k * 32, 16u, 1024u, UMMA_LAYOUT_SW128);
+    }
+    long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + (uint32_t)(warp * N), ad[k], bd[k], idesc, 1u);
+    }
+    umma_commit(&done_bar[warp]);
+    mbar_wait(&done_bar[warp], 0);
+    out[blockIdx.x * 4 + warp] = clock64() - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
+  }
+}
+}  // namespace b200
+
+extern "C" int b200_probe_umma_multi_issue(int N, int n_issuers, int iters, int grid, long long* out, b200_stream_t s) {
+  B200_CHECK_ARG(N % 16 == 0 && N >= 16 && N <= 256 && n_issuers >= 1 && n_issuers <= 4 && n_issuers * N <= 256 && grid >= 1,
+                 "probe: bad N=%d n_issuers=%d", N, n_issuers);
+  size_t smem = 16384 + (size_t)N * 128 + 2048;
+  cudaFuncSetAttribute(b200::umma_multi_issue_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  b200::umma_multi_issue_probe_kernel<<<grid, 128, smem, (cudaStream_t)s>>>(N, n_issuers, iters, 256, out);
+  B200_CHECK_LAUNCH("umma_multi_issue_probe");
+  return 0;
+}

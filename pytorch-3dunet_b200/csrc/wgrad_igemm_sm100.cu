@@ -36,6 +36,7 @@ struct WgradParams {
   int AWa, AWb;  // channels per smem atom tile (64/32/16) on the x side and the dz side
   int a_stages, a_stage_bytes, b_stage_bytes;
   int tmem_cols;
+  int NTAPS;           // 27, or 1 for the 1x1x1 conv (no shift; G is [n][S][1][Cin][Cout])
   int co0, CoutTotal;  // this launch covers output channels [co0, co0 + Cout) of CoutTotal (C_out > 256 is processed in slices)
   float* G;
 };
@@ -58,7 +59,7 @@ conv3_wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid
   const int grp = blockIdx.y;
   const int m0 = blockIdx.z * 128;
   const int tap0 = grp * p.TG;
-  const int ntaps = min(p.TG, 27 - tap0);
+  const int ntaps = min(p.TG, p.NTAPS - tap0);
   const int t0 = split * p.tiles_per_split;
   const int t1 = min(p.tiles, t0 + p.tiles_per_split);
   const int m_real = min(128, p.Cin - m0);
@@ -106,7 +107,7 @@ conv3_wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid
         }
         for (int tp = 0; tp < ntaps; ++tp, ++ai) {
           const int tap = tap0 + tp;
-          const int td = tap / 9, th = (tap / 3) % 3, tw = tap % 3;
+          const int td = p.NTAPS == 1 ? 1 : tap / 9, th = p.NTAPS == 1 ? 1 : (tap / 3) % 3, tw = p.NTAPS == 1 ? 1 : tap % 3;
           const int as = ai % p.a_stages;
           mbar_wait(&a_empty[as], ((uint32_t)(ai / p.a_stages) & 1u) ^ 1u);
           mbar_arrive_expect_tx(&a_full[as], (uint32_t)(natoms_a * a_atom_bytes));
@@ -154,7 +155,7 @@ conv3_wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
     const bool have_work = t1 > t0;
     for (int tp = 0; tp < ntaps; ++tp) {
-      float* grow = p.G + ((((size_t)n * p.S + split) * 27 + (tap0 + tp)) * p.Cin + (valid ? ci : 0)) * p.CoutTotal + p.co0;
+      float* grow = p.G + ((((size_t)n * p.S + split) * p.NTAPS + (tap0 + tp)) * p.Cin + (valid ? ci : 0)) * p.CoutTotal + p.co0;
       for (int c0 = 0; c0 < p.Cout; c0 += 16) {
         uint32_t raw[16];
         tmem_ld_32x32b_x16(taddr + (uint32_t)(tp * p.Cout + c0), raw);
@@ -197,19 +198,20 @@ static bool wgrad_supported(int N, int D, int H, int W, int Cin, int Cout) {
   return true;
 }
 
-static void wgrad_plan(int N, int D, int H, int W, int Cin, int Cout, WgradParams& p) {
+static void wgrad_plan(int N, int D, int H, int W, int Cin, int Cout, WgradParams& p, int NT = 27) {
   memset(&p, 0, sizeof(p));
   p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
+  p.NTAPS = NT;
   choose_box(D, H, W, &p.BD, &p.BH, &p.BW);
   p.tilesD = (D + p.BD - 1) / p.BD;
   p.tilesH = (H + p.BH - 1) / p.BH;
   p.tilesW = (W + p.BW - 1) / p.BW;
   p.tiles = p.tilesD * p.tilesH * p.tilesW;
   int tgmax = 512 / Cout;
-  if (tgmax > 27) tgmax = 27;
-  p.ngroups = (27 + tgmax - 1) / tgmax;
-  p.TG = (27 + p.ngroups - 1) / p.ngroups;
-  p.ngroups = (27 + p.TG - 1) / p.TG;
+  if (tgmax > NT) tgmax = NT;
+  p.ngroups = (NT + tgmax - 1) / tgmax;
+  p.TG = (NT + p.ngroups - 1) / p.ngroups;
+  p.ngroups = (NT + p.TG - 1) / p.TG;
   p.mchunks = (Cin + 127) / 128;
   // one CTA per SM (TMEM: TG*Cout columns, smem: deep A pipeline) -> size the split count for a single wave
   int ctas_per_split = N * p.ngroups * p.mchunks;
@@ -232,6 +234,29 @@ static void wgrad_plan(int N, int D, int H, int W, int Cin, int Cout, WgradParam
   p.tmem_cols = cols;
 }
 
+static int wgrad_plain_launch(const void* x, const void* dz, int N, int D, int H, int W, int Cin, int Cout, float* G, int NT,
+                              cudaStream_t s) {
+  const int cs = cout_slice(Cout);
+  WgradParams p;
+  wgrad_plan(N, D, H, W, Cin, cs, p, NT);
+  p.G = G;
+  p.CoutTotal = Cout;
+  CUtensorMap tmX, tmZ;
+  int rc = make_act_tmap(&tmX, x, N, D, H, W, Cin, p.AWa, p.BD, p.BH, p.BW);
+  if (rc) return rc;
+  rc = make_act_tmap(&tmZ, dz, N, D, H, W, Cout, p.AWb, p.BD, p.BH, p.BW);
+  if (rc) return rc;
+  size_t smem = (size_t)WG_B_STAGES * p.b_stage_bytes + (size_t)p.a_stages * p.a_stage_bytes + WG_A_FULL_BYTES + 1024;
+  cudaError_t e = cudaFuncSetAttribute(conv3_wgrad_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  B200_CHECK_ARG(e == cudaSuccess, "conv3_wgrad_igemm: cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e));
+  dim3 grid((unsigned)(N * p.S), (unsigned)p.ngroups, (unsigned)p.mchunks);
+  for (int co0 = 0; co0 < Cout; co0 += cs) {
+    p.co0 = co0;
+    conv3_wgrad_igemm_kernel<<<grid, WG_THREADS, smem, s>>>(tmX, tmZ, p);
+    B200_CHECK_LAUNCH("conv3_wgrad_igemm");
+  }
+  return 0;
+}
 }  // namespace b200
 
 using namespace b200;
@@ -263,25 +288,20 @@ int b200_conv3_wgrad_igemm(const void* x, const void* dz, int N, int D, int H, i
     }
     return 0;
   }
+  return wgrad_plain_launch(x, dz, N, D, H, W, Cin, Cout, G, 27, (cudaStream_t)s);
+}
+
+// ---- weight gradient of the 1x1x1 conv: G[n][split][ci][co] = sum_v x[n,v,ci] * dy[n,v,co] (flat voxel list, no shift)
+int b200_pointwise_tc_wgrad_splits(int N, long long vox, int Cin, int Cout) {
+  if (Cin % 16 != 0 || Cout % 16 != 0 || vox < 1 || vox >= (1ll << 31)) return 0;
   WgradParams p;
-  wgrad_plan(N, D, H, W, Cin, cs, p);
-  p.G = G;
-  p.CoutTotal = Cout;
-  CUtensorMap tmX, tmZ;
-  int rc = make_act_tmap(&tmX, x, N, D, H, W, Cin, p.AWa, p.BD, p.BH, p.BW);
-  if (rc) return rc;
-  rc = make_act_tmap(&tmZ, dz, N, D, H, W, Cout, p.AWb, p.BD, p.BH, p.BW);
-  if (rc) return rc;
-  size_t smem = (size_t)WG_B_STAGES * p.b_stage_bytes + (size_t)p.a_stages * p.a_stage_bytes + WG_A_FULL_BYTES + 1024;
-  cudaError_t e = cudaFuncSetAttribute(conv3_wgrad_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  B200_CHECK_ARG(e == cudaSuccess, "conv3_wgrad_igemm: cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e));
-  dim3 grid((unsigned)(N * p.S), (unsigned)p.ngroups, (unsigned)p.mchunks);
-  for (int co0 = 0; co0 < Cout; co0 += cs) {
-    p.co0 = co0;
-    conv3_wgrad_igemm_kernel<<<grid, WG_THREADS, smem, (cudaStream_t)s>>>(tmX, tmZ, p);
-    B200_CHECK_LAUNCH("conv3_wgrad_igemm");
-  }
-  return 0;
+  wgrad_plan(N, 1, 1, (int)vox, Cin, cout_slice(Cout), p, 1);
+  return p.S;
+}
+int b200_pointwise_tc_wgrad(const void* x, const void* dy, int N, long long vox, int Cin, int Cout, float* G, b200_stream_t s) {
+  B200_CHECK_ARG(b200_pointwise_tc_wgrad_splits(N, vox, Cin, Cout) > 0, "pointwise_tc_wgrad: unsupported N=%d vox=%lld Cin=%d Cout=%d", N,
+                 vox, Cin, Cout);
+  return wgrad_plain_launch(x, dy, N, 1, 1, (int)vox, Cin, Cout, G, 1, (cudaStream_t)s);
 }
 
 }  // extern "C"

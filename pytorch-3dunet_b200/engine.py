@@ -13,6 +13,7 @@ Reference semantics implemented (file:line relative to the reference checkout):
 from __future__ import annotations
 
 import os
+import time
 
 import torch
 
@@ -28,6 +29,7 @@ _ACT_OF = {"r": (ACT_RELU, 0.0), "l": (ACT_LEAKY, 0.01), "e": (ACT_ELU, 1.0)}
 # (name, flops, start_event, end_event) appended when enabled
 DEBUG = None   # dict: when set, backward closures stash clones of their intermediates (tools/debug_block.py)
 TIMING = None
+HOST_PROF = None  # dict name -> [calls, seconds] when host profiling is on
 TIMED = {"b200_conv3_fwd", "b200_conv3_wgrad"}
 
 
@@ -106,6 +108,14 @@ class Engine:
         return torch.empty(shape, dtype=dtype, device=self.device)
 
     def call(self, name, *args, launches=1, flops=0.0, tag=None):
+        if HOST_PROF is not None:  # tools/host_profile.py: host seconds spent inside each C-ABI entry point
+            t0 = time.perf_counter()
+            self.L.call(name, *args, self.stream)
+            d = HOST_PROF.setdefault(name, [0, 0.0])
+            d[0] += 1
+            d[1] += time.perf_counter() - t0
+            self.launches += launches
+            return
         if TIMING is not None and name in TIMED:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -452,30 +462,58 @@ class Engine:
         is_f32 = isinstance(x, InputF32)
         W2 = W.reshape(cout, cin).contiguous()
         y = self.empty((n, d, h, w, cout), torch.bfloat16)
-        P = self.L.query("b200_pointwise_partials_count", n, vox, cout)
-        partials = self.empty((n, P, cout, 2), torch.float32) if want_stats else None
-        self.call("b200_pointwise_fwd", _p(x.t), int(is_f32), _p(W2), 0, _p(bias), n, vox, cin, cout, _p(y), _p(partials))
+        # tensor-core path: the tcgen05 conv / wgrad kernels over the flat voxel list (C_in, C_out multiples of 16, bf16 input)
+        tc = (not is_f32) and self.impl != IMPL_DIRECT and bool(self.L.query("b200_pointwise_tc_supported", n, vox, cin, cout))
+        if tc:
+            wq = self.empty((cout, cin), torch.bfloat16)
+            self.call("b200_pointwise_prep_weights", _p(W2), cin, cout, 0, _p(wq))
+            P = self.L.query("b200_pointwise_tc_partials_count", n, vox)
+            partials = self.empty((n, P, cout, 2), torch.float32) if want_stats else None
+            self.call("b200_pointwise_tc_fwd", _p(x.t), _p(wq), _p(bias), n, vox, cin, cout, _p(y), _p(partials),
+                      flops=2.0 * n * vox * cin * cout, tag="fprop_tc")
+        else:
+            P = self.L.query("b200_pointwise_partials_count", n, vox, cout)
+            partials = self.empty((n, P, cout, 2), torch.float32) if want_stats else None
+            self.call("b200_pointwise_fwd", _p(x.t), int(is_f32), _p(W2), 0, _p(bias), n, vox, cin, cout, _p(y), _p(partials))
         out = Act(y, ACT_NONE, 0.0, partials, P)
         if self.record:
             def backward():
                 dy = out.grad
                 if dy is None:
                     return
-                Pw = self.L.query("b200_pointwise_wgrad_partials_count", n, vox)
-                K = cout * cin + cout
-                part = self.empty((n * Pw, K), torch.float32)
-                self.call("b200_pointwise_wgrad", _p(x.t), int(is_f32), _p(dy), n, vox, cin, cout, _p(part))
-                red = self.empty((K,), torch.float32)
-                self.call("b200_reduce_rows", _p(part), n * Pw, K, _p(red))
-                self._add_param_grad(wname, red[: cout * cin].reshape(W.shape))
-                if bias is not None:
-                    self._add_param_grad(bname, red[cout * cin:].clone())
+                if tc:
+                    S = self.L.query("b200_pointwise_tc_wgrad_splits", n, vox, cin, cout)
+                    G = self.empty((n * S, cin * cout), torch.float32)
+                    self.call("b200_pointwise_tc_wgrad", _p(x.t), _p(dy), n, vox, cin, cout, _p(G),
+                              flops=2.0 * n * vox * cin * cout, tag="wgrad_tc")
+                    red = self.empty((cin * cout,), torch.float32)
+                    self.call("b200_reduce_rows", _p(G), n * S, cin * cout, _p(red))
+                    self._add_param_grad(wname, red.view(cin, cout).t().reshape(W.shape))
+                    if bias is not None:
+                        self._add_param_grad(bname, self.sums_of(Act(dy, requires_grad=False))[:, :, 0].sum(0).float())
+                else:
+                    Pw = self.L.query("b200_pointwise_wgrad_partials_count", n, vox)
+                    K = cout * cin + cout
+                    part = self.empty((n * Pw, K), torch.float32)
+                    self.call("b200_pointwise_wgrad", _p(x.t), int(is_f32), _p(dy), n, vox, cin, cout, _p(part))
+                    red = self.empty((K,), torch.float32)
+                    self.call("b200_reduce_rows", _p(part), n * Pw, K, _p(red))
+                    self._add_param_grad(wname, red[: cout * cin].reshape(W.shape))
+                    if bias is not None:
+                        self._add_param_grad(bname, red[cout * cin:].clone())
                 if x.requires_grad:
                     if is_f32:
                         raise NotImplementedError("gradient w.r.t. the fp32 network input is not provided by the engine")
                     g = self.empty(x.t.shape, torch.bfloat16)
-                    self.call("b200_pointwise_fwd", _p(dy), 0, _p(W2), 1, None, n, vox, cout, cin, _p(g), None)
-                    self.call("b200_act_bwd", _p(g), cin, 0, _p(x.t), n, cin, vox, x.act, x.slope, _p(x.grad), _p(g))
+                    if tc:
+                        wqt = self.empty((cin, cout), torch.bfloat16)
+                        self.call("b200_pointwise_prep_weights", _p(W2), cin, cout, 1, _p(wqt))
+                        self.call("b200_pointwise_tc_fwd", _p(dy), _p(wqt), None, n, vox, cout, cin, _p(g), None,
+                                  flops=2.0 * n * vox * cin * cout, tag="dgrad_tc")
+                    else:
+                        self.call("b200_pointwise_fwd", _p(dy), 0, _p(W2), 1, None, n, vox, cout, cin, _p(g), None)
+                    if x.act != ACT_NONE or x.grad is not None:
+                        self.call("b200_act_bwd", _p(g), cin, 0, _p(x.t), n, cin, vox, x.act, x.slope, _p(x.grad), _p(g))
                     x.grad = g
                 out.grad = None
             self.tape.append(backward)
@@ -552,8 +590,8 @@ class Engine:
         self.call("b200_se_gates_fwd", _p(sums), float(vox), _p(W1), _p(b1), _p(W2), _p(b2), n, c, _p(smean), _p(hh), _p(g))
         out_t = self.empty(y.t.shape, torch.bfloat16)
         q = self.empty((n, vox), torch.float32)
-        bs = float(bs_t.item())  # 1-element parameter passed by value (one small D2H per SE block per forward)
-        self.call("b200_scse_apply_fwd", _p(y.t), _p(g), _p(ws), bs, n, vox, c, _p(out_t), _p(q))
+        bs = bs_t.reshape(-1).contiguous()  # 1-element parameter, read on the device (no host sync)
+        self.call("b200_scse_apply_fwd", _p(y.t), _p(g), _p(ws), _p(bs), n, vox, c, _p(out_t), _p(q))
         out = Act(out_t, ACT_NONE, 0.0)
         if DEBUG is not None:
             DEBUG.setdefault("se", {})[prefix] = (y.t, g, q)

@@ -54,6 +54,42 @@ def test_pointwise_fwd_dgrad_wgrad(cin, cout, f32):
         assert U.rel_l2(dx, dy.float() @ Wt) < 5e-3
 
 
+@pytest.mark.parametrize("cin,cout,vox", [(32, 64, 1000), (64, 128, 216), (256, 512, 130), (512, 1024, 27), (16, 16, 4096), (96, 48, 333)])
+def test_pointwise_tc_fwd_dgrad_wgrad(cin, cout, vox):
+    """1x1x1 conv on the tcgen05 conv / wgrad kernels (flat voxel list) against fp32 matmuls on the same bf16 operands."""
+    U, E, L = _ctx()
+    N = 2
+    assert L.query("b200_pointwise_tc_supported", N, vox, cin, cout)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = _rand((N, vox, cin), 2)
+    Wt = torch.randn((cout, cin), device="cuda", generator=g) / cin ** 0.5
+    b = torch.randn(cout, device="cuda", generator=g) * 0.1
+    wq = torch.empty((cout, cin), dtype=torch.bfloat16, device="cuda")
+    L.call("b200_pointwise_prep_weights", U.p(Wt), cin, cout, 0, U.p(wq), U.stream())
+    assert torch.equal(wq, Wt.bfloat16())
+    y = torch.empty((N, vox, cout), dtype=torch.bfloat16, device="cuda")
+    P = L.query("b200_pointwise_tc_partials_count", N, vox)
+    part = torch.full((N, P, cout, 2), float("nan"), device="cuda")
+    L.call("b200_pointwise_tc_fwd", U.p(x), U.p(wq), U.p(b), N, vox, cin, cout, U.p(y), U.p(part), U.stream())
+    ref = x.float() @ wq.float().t() + b
+    assert U.rel_l2(y, ref) < 4e-3
+    yd = y.double()
+    assert U.rel_l2(part.double().sum(1)[..., 0], yd.sum(1)) < 1e-4
+    assert U.rel_l2(part.double().sum(1)[..., 1], (yd * yd).sum(1)) < 1e-4
+    dy = _rand((N, vox, cout), 3)
+    wqt = torch.empty((cin, cout), dtype=torch.bfloat16, device="cuda")
+    L.call("b200_pointwise_prep_weights", U.p(Wt), cin, cout, 1, U.p(wqt), U.stream())
+    assert torch.equal(wqt, Wt.t().bfloat16())
+    dx = torch.full((N, vox, cin), float("nan"), dtype=torch.bfloat16, device="cuda")
+    L.call("b200_pointwise_tc_fwd", U.p(dy), U.p(wqt), None, N, vox, cout, cin, U.p(dx), None, U.stream())
+    assert U.rel_l2(dx, dy.float() @ wq.float()) < 4e-3
+    S = L.query("b200_pointwise_tc_wgrad_splits", N, vox, cin, cout)
+    G = torch.full((N, S, cin, cout), float("nan"), device="cuda")
+    L.call("b200_pointwise_tc_wgrad", U.p(x), U.p(dy), N, vox, cin, cout, U.p(G), U.stream())
+    dW = torch.einsum("nvi,nvo->io", x.double(), dy.double())
+    assert U.rel_l2(G.double().sum((0, 1)), dW) < 1e-4
+
+
 @pytest.mark.parametrize("small,big,cin,cout", [((4, 4, 4), (8, 8, 8), 32, 16), ((3, 5, 4), (5, 9, 7), 16, 8), ((2, 2, 2), (4, 4, 4), 64, 32)])
 def test_deconv_pieces(small, big, cin, cout):
     """zero-insert / weight permute / resize+add / gather / subsample: each against its torch restatement (bit-exact data movement)."""
@@ -161,7 +197,8 @@ def test_scse_fwd_bwd(C):
     L.call("b200_se_gates_fwd", U.p(sums), float(vox), U.p(W1), U.p(b1), U.p(W2), U.p(b2), N, C, U.p(sm), U.p(hh), U.p(gg), U.stream())
     out = torch.empty_like(y)
     q = torch.empty((N, vox), device="cuda")
-    L.call("b200_scse_apply_fwd", U.p(y), U.p(gg), U.p(ws), bs, N, vox, C, U.p(out), U.p(q), U.stream())
+    bs_t = torch.tensor([bs], device="cuda")
+    L.call("b200_scse_apply_fwd", U.p(y), U.p(gg), U.p(ws), U.p(bs_t), N, vox, C, U.p(out), U.p(q), U.stream())
     # torch reference (fp64) with autograd
     yr = y.double().permute(0, 4, 1, 2, 3).requires_grad_(True)
     P_ = [t.double().requires_grad_(True) for t in (W1, b1, W2, b2, ws)]

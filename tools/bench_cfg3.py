@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import pytorch3dunet_b200 as P
 from pytorch3dunet_b200 import engine as E
-for name, fm, B, S in [("ResidualUNet3D", 32, 4, 96), ("ResidualUNetSE3D", 64, 1, 96), ("UNet3D", 32, 2, 128)]:
+for name, fm, B, S in [("ResidualUNet3D", 32, 4, 96), ("ResidualUNetSE3D", 64, 1, 96), ("UNet3D", 32, 2, 128), ("ResidualUNet3D", 32, 4, 96)]:
     torch.manual_seed(0)
     levels = 4 if name == "UNet3D" else 5
     m = P.get_model(dict(name=name, in_channels=1, out_channels=1, f_maps=fm, num_levels=levels)).cuda()
@@ -20,11 +20,15 @@ for name, fm, B, S in [("ResidualUNet3D", 32, 4, 96), ("ResidualUNetSE3D", 64, 1
     torch.cuda.synchronize()
     E.TIMING = []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0 = torch.cuda.memory_stats().get("num_device_alloc", 0)
+    h0 = time.perf_counter()
     e0.record()
     for _ in range(5):
         step()
     e1.record()
+    h1 = time.perf_counter()
     torch.cuda.synchronize()
+    print(f"host enqueue {1e3 * (h1 - h0) / 5:.2f} ms/step, cudaMallocs in timed region {torch.cuda.memory_stats().get('num_device_alloc', 0) - a0}")
     tm, E.TIMING = E.TIMING, None
     by = {}
     for tag, fl, a, b in tm:

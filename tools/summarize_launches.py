@@ -7,12 +7,12 @@ import re
 import sys
 
 
-def main(path):
+def main(path, title="UNet3D f32 d4, batch 2x1x128^3, fwd+BCEDice+bwd"):
     with open(path) as f:
         lines = [l for l in f if not l.startswith("==")]
     rows = list(csv.DictReader(lines))
     starts = [i for i, r in enumerate(rows) if "stats_ncdhw" in r["Kernel Name"]]
-    s = starts[-1]
+    s = starts[-1] if starts else len(rows) // 2  # tools/one_step_model.py runs exactly two identical steps
     e = len(rows)
     step = rows[s:e]
     agg = collections.OrderedDict()
@@ -23,7 +23,7 @@ def main(path):
         d[0] += 1
         d[1] += v
     tot = sum(v[1] for v in agg.values())
-    print(f"# ncu launch list, one training step (UNet3D f32 d4, batch 2x1x128^3, fwd+BCEDice+bwd), {len(step)} launches, "
+    print(f"# ncu launch list, one training step ({title}), {len(step)} launches, "
           f"sum of device times {tot / 1e6:.2f} ms (cold-cache, serialised: read the SHARES)\n")
     print("| kernel | launches | ms | share |\n|---|---:|---:|---:|")
     for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
@@ -38,4 +38,4 @@ def main(path):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1])
+    main(*sys.argv[1:3])
