@@ -28,6 +28,8 @@ extern "C" {
 typedef void* b200_stream_t; /* cudaStream_t */
 
 /* activation kinds (create_conv buildingblocks.py:45-51; ResNetBlock non_linearity :270-275) */
+/* OR into b200_conv3_fwd's pmode: the bias table uses the phase-aware border classes of the virtual-concat convolution */
+#define B200_PMODE_PHASE_BIAS 0x100
 enum { B200_ACT_NONE = 0, B200_ACT_RELU = 1, B200_ACT_LEAKY = 2, B200_ACT_ELU = 3 };
 /* conv implementation selector */
 enum { B200_IMPL_AUTO = 0, B200_IMPL_DIRECT = 1, B200_IMPL_TCGEN05 = 2 };
@@ -173,6 +175,24 @@ int b200_pointwise_partials_count(int N, long long voxels, int Cout);
 int b200_pointwise_fwd(const void* x, int x_is_f32, const float* W, int transposed, const float* bias, int N, long long voxels,
                        int Cin, int Cout, void* y, float* partials, b200_stream_t s);
 /* partial rows [N*P][Cout*Cin + Cout] of dW, db; reduce with b200_reduce_rows */
+/* ---- "virtual concat" decoder convolution: conv3(GN(cat(enc, nearest_up2x(b)))) without the upsampled / concatenated tensor
+ * (replaces F.interpolate + torch.cat + SingleConv of Decoder.forward, buildingblocks.py:466-497, when the encoder feature is
+ * exactly 2x the low-res one).  y = conv3_enc(enc) [+bias, +R, act, stats: b200_conv3_fwd with pmode | B200_PMODE_PHASE_BIAS,
+ * residual = R] where R = b200_conv3_up_phase_fwd(b).  Layouts: wf_enc bf16 [n_w][27][Cout][C0]; wp bf16 [n_w][8 phases][8][Cout][C1];
+ * biascls [n_w][64][Cout] with per-axis classes {0 low face, 1 interior even, 2 high face, 3 interior odd};
+ * wd_enc bf16 [27][C0][Cout]; wd_up bf16 [64][C1][Cout]; Q fp32 [N][S][64][Cout][C1]; G fp32 [N][27][C0+C1][Cout]. */
+int b200_gn_fold_upcat(const double* sums, const float* gamma, const float* beta, int G, double count, const float* W,
+                       const float* conv_bias, int N, int C0, int C1, int Cout, void* wf_enc, void* wp, float* biascls, float* mean_rstd,
+                       float* ab, b200_stream_t s);
+int b200_conv3_up_supported(int N, int d, int h, int w, int C1, int Cout);
+int b200_conv3_up_phase_fwd(const void* b, const void* wp, int n_w, int N, int d, int h, int w, int C1, int Cout, void* R, b200_stream_t s);
+int b200_upcat_prep_dgrad_weights(const float* W, int C0, int C1, int Cout, void* wd_enc, void* wd_up, b200_stream_t s);
+int b200_conv3_up_dgrad(const void* dz, const void* wd, int N, int d, int h, int w, int Cout, int C1, void* dxb, b200_stream_t s);
+int b200_conv3_up_wgrad_splits(int N, int d, int h, int w, int Cout, int C1);
+int b200_conv3_up_wgrad(const void* dz, const void* b, int N, int d, int h, int w, int Cout, int C1, float* Q, b200_stream_t s);
+int b200_upcat_assemble_wgrad(const float* G_enc, int S1, const float* Q, int S2, int N, int C0, int C1, int Cout, float* G,
+                              b200_stream_t s);
+
 /* 1x1x1 conv on the tensor cores (C_in, C_out multiples of 16; bf16 input): the tcgen05 conv / wgrad kernels over a flat voxel list.
  * wq: bf16 [Cout][Cin] from b200_pointwise_prep_weights (transposed=1 gives the dgrad operand [Cin][Cout]); bias fp32 [Cout] or NULL;
  * partials [N][P][Cout][2] (P = b200_pointwise_tc_partials_count) or NULL; G [N][S][Cin][Cout] fp32 (S = ..._wgrad_splits). */

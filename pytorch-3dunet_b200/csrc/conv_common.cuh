@@ -16,7 +16,14 @@ struct ConvParams {
   int BD, BH, BW;
   int tilesD, tilesH, tilesW;
   int n_w, n_b;
-  int ntaps;    // 27 (3x3x3) or 1 (1x1x1 conv: centre tap only, bias row 0 for every voxel) -- plain igemm kernel only
+  // ---- plain igemm kernel only: generic tap table.  Tap i reads the input at  in_mul * (tile origin) + toff[i]  (per axis, TMA
+  // coordinates of the input tensor map; in_mul = 2 with an element-stride-2 map subsamples the input) with weight row
+  // wsample * w_rows + w_row0 + i.  Outputs go to voxel  out_mul * x + out_off  of a volume (OD, OH, OW).
+  int ntaps;             // 27 (3x3x3), 1 (1x1x1), 8 (one phase of conv3 o nearest-upsample), 64 (its transpose, 4x4x4 stride 2)
+  signed char toff[64 * 3];
+  int in_mul, out_mul, out_off[3], OD, OH, OW;
+  int w_rows, w_row0;
+  int cls_mode;  // bias row: 0 = border class of the voxel, 1 = phase-aware border class (interior split by parity), 2 = row 0
   int NT;       // output channels per CTA
   int KC;       // channels per k-block (16/32/64)
   int kchunks;  // Cin / KC
@@ -39,6 +46,18 @@ struct ConvParams {
   long long* dbg;      // optional per-CTA wait-cycle counters (b200_set_debug_buffer), NULL in production
   int dbg_flags;       // experiments only (env B200UNET_DBG_FLAGS): 1 = skip the global stores, 2 = skip the bias add
 };
+
+// row of the [64][Cout] bias table for output voxel (xd,xh,xw) of a (D,H,W) volume
+__device__ __forceinline__ int conv_bias_cls(int cls_mode, int xd, int xh, int xw, int D, int H, int W) {
+  if (cls_mode == 2) return 0;
+  int cd = axis_cls(xd, D), ch = axis_cls(xh, H), cw = axis_cls(xw, W);
+  if (cls_mode == 1) {  // even dims >= 2: class 3 ("both") cannot occur and is reused for "interior, odd coordinate"
+    if (cd == 1 && (xd & 1)) cd = 3;
+    if (ch == 1 && (xh & 1)) ch = 3;
+    if (cw == 1 && (xw & 1)) cw = 3;
+  }
+  return (cd << 4) | (ch << 2) | cw;
+}
 
 // one 32-/16-column slab of the accumulator tile for one thread (= one output voxel row)
 template <int CW>

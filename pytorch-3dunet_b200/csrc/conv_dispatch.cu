@@ -28,6 +28,7 @@ int b200_conv3_fwd(int impl, const void* x, int x_is_f32, const void* wf, int n_
   }
   if (r == B200_IMPL_TCGEN05)
     return b200_conv3_igemm_fwd(x, wf, n_w, biascls, n_b, residual, act, slope, N, D, H, W, Cin, Cout, y, pmode, aux, partials, s);
+  B200_CHECK_ARG((pmode & 0x100) == 0, "conv3_fwd: phase-aware bias classes need the tcgen05 implementation");
   return b200_conv3_direct_fwd(x, x_is_f32, wf, n_w, biascls, n_b, residual, act, slope, N, D, H, W, Cin, Cout, y, pmode, aux, partials,
                                s);
 }

@@ -63,7 +63,7 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
   const int b_region = (p.b_total_bytes + 1023) & ~1023;
   uint8_t* smemA = smem + b_region;
   float* scratch_base = reinterpret_cast<float*>(smemA + (size_t)p.a_stages * p.a_bytes);  // [2 groups][2 alternating][4 warps][NT][2]
-  float* bias_interior = scratch_base + 4 * 4 * p.NT * 2;                                    // [NT]
+  float* bias_interior = scratch_base + 4 * 4 * p.NT * 2;                                    // [8 parity variants][NT]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = blockIdx.y, cta = blockIdx.x, cps = gridDim.x;
   const int tiles = p.tilesD * p.tilesH * p.tilesW;
@@ -88,10 +88,13 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     tma_prefetch_desc(&tmapB);
   }
   if (warp == HALO_WARP_MMA) tmem_alloc(&tmem_slot, (uint32_t)p.tmem_cols);
-  constexpr int kInteriorCls = (1 << 4) | (1 << 2) | 1;
+  // interior bias rows cached in shared memory: variant v = (d odd, h odd, w odd) bits, only v = 0 unless cls_mode == 1
   if (p.n_b)
-    for (int i = threadIdx.x; i < p.NT; i += HALO_THREADS)
-      bias_interior[i] = p.biascls[((size_t)(p.n_b > 1 ? n : 0) * 64 + kInteriorCls) * p.Cout + i];
+    for (int i = threadIdx.x; i < 8 * p.NT; i += HALO_THREADS) {
+      const int v = i / p.NT, c = i - v * p.NT;
+      const int cls = ((v & 4 ? 3 : 1) << 4) | ((v & 2 ? 3 : 1) << 2) | (v & 1 ? 3 : 1);
+      bias_interior[i] = p.biascls[((size_t)(p.n_b > 1 ? n : 0) * 64 + cls) * p.Cout + c];
+    }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -192,8 +195,10 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       const size_t vox_off = (size_t)n * p.D * p.H * p.W + ((size_t)xd * p.H + xh) * p.W + xw;
       const float* bias_row = nullptr;
       if (p.n_b && valid) {
-        const int cls = (axis_cls(xd, p.D) << 4) | (axis_cls(xh, p.H) << 2) | axis_cls(xw, p.W);
-        bias_row = cls == kInteriorCls ? bias_interior : p.biascls + ((size_t)(p.n_b > 1 ? n : 0) * 64 + cls) * p.Cout;
+        const int cls = conv_bias_cls(p.cls_mode, xd, xh, xw, p.D, p.H, p.W);
+        const bool interior = (cls & 0x15) == 0x15;  // every axis class is 1 or 3
+        bias_row = interior ? bias_interior + (((cls >> 3) & 4) | ((cls >> 2) & 2) | ((cls >> 1) & 1)) * p.NT
+                            : p.biascls + ((size_t)(p.n_b > 1 ? n : 0) * 64 + cls) * p.Cout;
       }
       long long cw = clock64();
       mbar_wait(&tmem_full[buf], (uint32_t)(lt >> 1) & 1u);
@@ -253,7 +258,7 @@ bool conv_halo_plan(int N, int D, int H, int W, int Cin, int Cout, ConvParams* p
   if (dis && dis[0] == '1') return false;
   const int budget = 222 * 1024;
   const int b_total = 27 * Cout * Cin * 2;
-  const int scratch = (4 * 4 * Cout * 2 + Cout) * (int)sizeof(float);
+  const int scratch = (4 * 4 * Cout * 2 + 8 * Cout) * (int)sizeof(float);
   int kca = 0, stages = 0, a_bytes = 0;
   for (int kc = 64; kc >= 16; kc >>= 1) {
     if (Cin % kc != 0) continue;
@@ -303,7 +308,7 @@ int conv_halo_launch(const void* x, const void* wf, ConvParams& p, cudaStream_t 
   if (rc) return rc;
   rc = make_w_tmap(&tmB, wf, 27 * p.n_w, p.Cout, p.Cin, p.KCb, p.NT, 27);
   if (rc) return rc;
-  size_t smem = (size_t)((p.b_total_bytes + 1023) & ~1023) + (size_t)p.a_stages * p.a_bytes + (size_t)(4 * 4 * p.NT * 2 + p.NT) * sizeof(float) + 1024;
+  size_t smem = (size_t)((p.b_total_bytes + 1023) & ~1023) + (size_t)p.a_stages * p.a_bytes + (size_t)(4 * 4 * p.NT * 2 + 8 * p.NT) * sizeof(float) + 1024;
   auto kern = p.KC == 64 ? conv3_halo_kernel<64> : (p.KC == 32 ? conv3_halo_kernel<32> : conv3_halo_kernel<16>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   B200_CHECK_ARG(e == cudaSuccess, "conv3_halo: cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e));

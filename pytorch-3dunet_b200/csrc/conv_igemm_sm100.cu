@@ -68,12 +68,12 @@ conv3_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_const
         const uint32_t phase = (uint32_t)(kb / p.stages) & 1u;
         mbar_wait(&empty_bar[stage], phase ^ 1u);
         const int tap = kb / p.kchunks, kc = kb - tap * p.kchunks;
-        const int td = p.ntaps == 1 ? 1 : tap / 9, th = p.ntaps == 1 ? 1 : (tap / 3) % 3, tw = p.ntaps == 1 ? 1 : tap % 3;
+        const int od = p.toff[3 * tap], oh = p.toff[3 * tap + 1], ow = p.toff[3 * tap + 2];
         uint8_t* sa = smem + (size_t)stage * stage_bytes;
         uint8_t* sb = sa + p.a_bytes;
         mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(128 * p.KC * 2 + p.NT * p.KC * 2));
-        tma_load_5d(sa, &tmapA, &full_bar[stage], kc * p.KC, w0 + tw - 1, h0 + th - 1, d0 + td - 1, n);
-        tma_load_3d(sb, &tmapB, &full_bar[stage], kc * p.KC, n0, wsample * p.ntaps + tap);
+        tma_load_5d(sa, &tmapA, &full_bar[stage], kc * p.KC, p.in_mul * w0 + ow, p.in_mul * h0 + oh, p.in_mul * d0 + od, n);
+        tma_load_3d(sb, &tmapB, &full_bar[stage], kc * p.KC, n0, wsample * p.w_rows + p.w_row0 + tap);
       }
     }
   } else if (warp == 1) {
@@ -107,10 +107,12 @@ conv3_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_const
     const int bx = row % p.BW, by = (row / p.BW) % p.BH, bz = row / (p.BW * p.BH);
     const int xd = d0 + bz, xh = h0 + by, xw = w0 + bx;
     const bool valid = xd < p.D && xh < p.H && xw < p.W;
-    const size_t vox_off = (size_t)n * p.D * p.H * p.W + ((size_t)xd * p.H + xh) * p.W + xw;
+    const size_t vox_off = (size_t)n * p.OD * p.OH * p.OW +
+                           ((size_t)(p.out_mul * xd + p.out_off[0]) * p.OH + (p.out_mul * xh + p.out_off[1])) * p.OW +
+                           (p.out_mul * xw + p.out_off[2]);
     const float* bias_row = nullptr;
     if (p.n_b && valid) {
-      const int cls = p.ntaps == 1 ? 0 : ((axis_cls(xd, p.D) << 4) | (axis_cls(xh, p.H) << 2) | axis_cls(xw, p.W));
+      const int cls = conv_bias_cls(p.cls_mode, xd, xh, xw, p.D, p.H, p.W);
       bias_row = p.biascls + ((size_t)(p.n_b > 1 ? n : 0) * 64 + cls) * p.Cout;
     }
     mbar_wait(&tmem_full_bar, 0);
@@ -237,14 +239,55 @@ static int pick_nt(int Cout) {
 }  // namespace b200
 
 namespace b200 {
-// plain (tap-loop) kernel launch; ntaps = 27: 3x3x3 conv over (D,H,W); ntaps = 1: 1x1x1 conv (wf [n_w][1][Cout][Cin], biascls [n_b][Cout])
+// Geometry of a plain (tap-loop) launch.  The defaults describe the 3x3x3 / pad 1 convolution.
+struct PlainGeom {
+  int ntaps = 27;
+  signed char toff[64 * 3];
+  int in_mul = 1;                   // 2: the input map subsamples a (2D,2H,2W) tensor with element stride 2
+  int out_mul = 1, out_off[3] = {0, 0, 0};  // 2: outputs are written to one parity phase of a (2D,2H,2W) volume
+  int w_rows = 27, w_row0 = 0;      // weight rows per sample in wf, first row of this launch
+  int cls_mode = 0;
+  PlainGeom() {
+    for (int t = 0; t < 27; ++t) {
+      toff[3 * t] = (signed char)(t / 9 - 1);
+      toff[3 * t + 1] = (signed char)((t / 3) % 3 - 1);
+      toff[3 * t + 2] = (signed char)(t % 3 - 1);
+    }
+  }
+};
+
+// activation map whose boxes subsample with element stride 2 (box of bd x bh x bw ELEMENTS LOADED)
+int make_act_tmap_stride2(CUtensorMap* tm, const void* ptr, int N, int D, int H, int W, int C, int kc, int bd, int bh, int bw) {
+  EncodeTiledFn enc = get_encode_tiled();
+  B200_CHECK_ARG(enc, "cuTensorMapEncodeTiled entry point not available");
+  B200_CHECK_ARG(2 * bd <= 256 && 2 * bh <= 256 && 2 * bw <= 256, "stride-2 box %dx%dx%d too large", bd, bh, bw);
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+  cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2, (cuuint64_t)D * H * W * C * 2};
+  cuuint32_t box[5] = {(cuuint32_t)kc, (cuuint32_t)(2 * bw), (cuuint32_t)(2 * bh), (cuuint32_t)(2 * bd), 1};
+  cuuint32_t estr[5] = {1, 2, 2, 2, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_row_bytes(kc * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B200_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(stride-2 activation %dx%dx%dx%dx%d) failed: %d", N, D, H, W, C, (int)r);
+  return 0;
+}
+
+// plain (tap-loop) kernel launch over the tile domain (D,H,W) = the OUTPUT lattice the CTAs enumerate
 static int conv_igemm_plain_launch(const void* x, const void* wf, int n_w, const float* biascls, int n_b, const void* residual, int act,
                                    float slope, int N, int D, int H, int W, int Cin, int Cout, void* y, int pmode, const void* aux,
-                                   float* partials, int ntaps, cudaStream_t s) {
+                                   float* partials, const PlainGeom& g, cudaStream_t s) {
   ConvParams p;
   memset(&p, 0, sizeof(p));
   p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
-  p.ntaps = ntaps;
+  p.ntaps = g.ntaps;
+  memcpy(p.toff, g.toff, sizeof(p.toff));
+  p.in_mul = g.in_mul;
+  p.out_mul = g.out_mul;
+  for (int i = 0; i < 3; ++i) p.out_off[i] = g.out_off[i];
+  p.OD = g.out_mul * D; p.OH = g.out_mul * H; p.OW = g.out_mul * W;
+  p.w_rows = g.w_rows;
+  p.w_row0 = g.w_row0;
+  p.cls_mode = g.cls_mode;
   choose_box(D, H, W, &p.BD, &p.BH, &p.BW);
   p.tilesD = (D + p.BD - 1) / p.BD;
   p.tilesH = (H + p.BH - 1) / p.BH;
@@ -257,9 +300,11 @@ static int conv_igemm_plain_launch(const void* x, const void* wf, int n_w, const
   p.a_bytes = (128 * p.KC * 2 + 1023) & ~1023;
   p.b_bytes = (p.NT * p.KC * 2 + 1023) & ~1023;
   const int stage_bytes = p.a_bytes + p.b_bytes;
+  const int numK = g.ntaps * p.kchunks;
   int stages = (96 * 1024) / stage_bytes;
-  if (ntaps == 1 && stages > p.kchunks) stages = p.kchunks;  // short K loop: keep the CTA small so several fit on an SM
-  if (stages < 3) stages = ntaps == 1 ? (stages < 1 ? 1 : stages) : 3;
+  if (stages > numK) stages = numK;  // short K loops: keep the CTA small so several fit on an SM
+  if (stages < 3 && numK >= 3) stages = 3;
+  if (stages < 1) stages = 1;
   if (stages > CONV_MAX_STAGES) stages = CONV_MAX_STAGES;
   p.stages = stages;
   int cols = 32;
@@ -275,9 +320,10 @@ static int conv_igemm_plain_launch(const void* x, const void* wf, int n_w, const
   p.partials = partials;
 
   CUtensorMap tmA, tmB;
-  int rc = make_act_tmap(&tmA, x, N, D, H, W, Cin, p.KC, p.BD, p.BH, p.BW);
+  int rc = g.in_mul == 2 ? make_act_tmap_stride2(&tmA, x, N, 2 * D, 2 * H, 2 * W, Cin, p.KC, p.BD, p.BH, p.BW)
+                         : make_act_tmap(&tmA, x, N, D, H, W, Cin, p.KC, p.BD, p.BH, p.BW);
   if (rc) return rc;
-  rc = make_w_tmap(&tmB, wf, ntaps * n_w, Cout, Cin, p.KC, p.NT, 1);
+  rc = make_w_tmap(&tmB, wf, g.w_rows * n_w, Cout, Cin, p.KC, p.NT, 1);
   if (rc) return rc;
 
   size_t smem = (size_t)stages * stage_bytes + 1024;
@@ -316,6 +362,8 @@ int b200_conv3_igemm_fwd(const void* x, const void* wf, int n_w, const float* bi
                          float* partials, b200_stream_t s) {
   B200_CHECK_ARG(conv_igemm_supported(N, D, H, W, Cin, Cout), "conv3_igemm: unsupported shape N=%d D=%d H=%d W=%d Cin=%d Cout=%d", N, D,
                  H, W, Cin, Cout);
+  const int cls_mode = (pmode >> 8) & 1;  // B200_PMODE_PHASE_BIAS
+  pmode &= 0xff;
   ConvParams p;
   memset(&p, 0, sizeof(p));
   B200_CHECK_ARG(pmode == 0 || partials, "conv3_igemm: pmode=%d needs a partials buffer", pmode);
@@ -327,6 +375,7 @@ int b200_conv3_igemm_fwd(const void* x, const void* wf, int n_w, const float* bi
     p.act = act;
     p.slope = slope;
     p.pmode = pmode;
+    p.cls_mode = cls_mode;
     p.biascls = biascls;
     p.residual = (const bf16*)residual;
     p.aux = (const bf16*)aux;
@@ -334,7 +383,61 @@ int b200_conv3_igemm_fwd(const void* x, const void* wf, int n_w, const float* bi
     p.partials = partials;
     return conv_halo_launch(x, wf, p, (cudaStream_t)s);
   }
-  return conv_igemm_plain_launch(x, wf, n_w, biascls, n_b, residual, act, slope, N, D, H, W, Cin, Cout, y, pmode, aux, partials, 27,
+  PlainGeom g;
+  g.cls_mode = cls_mode;
+  return conv_igemm_plain_launch(x, wf, n_w, biascls, n_b, residual, act, slope, N, D, H, W, Cin, Cout, y, pmode, aux, partials, g,
+                                 (cudaStream_t)s);
+}
+
+// ---- conv3x3x3 over a nearest-2x-upsampled tensor WITHOUT materialising it (decoder concat path, buildingblocks.py:493 + :575).
+// Output parity phase p (per axis) of conv3(up(b)) is a 2x2x2 convolution of the low-res b with phase-specific summed weights:
+//   p = 0: low-res offsets {-1, 0} carry taps {-1}, {0,+1};   p = 1: offsets {0, +1} carry taps {-1,0}, {+1}
+// (8/27 of the MACs).  One launch per phase writes R[2u+p] (bf16, no bias/activation); the caller adds R as the `residual`
+// of the encoder-channel convolution.  Zero padding of the upsampled volume == TMA zero fill of the low-res volume.
+int b200_conv3_up_supported(int N, int d, int h, int w, int C1, int Cout) {
+  (void)N;
+  int bd, bh, bw;
+  if (C1 % 16 != 0 || Cout % 16 != 0 || d < 1 || h < 1 || w < 1) return 0;
+  return choose_box(d, h, w, &bd, &bh, &bw) ? 0 : 1;
+}
+int b200_conv3_up_phase_fwd(const void* b, const void* wp, int n_w, int N, int d, int h, int w, int C1, int Cout, void* R, b200_stream_t s) {
+  B200_CHECK_ARG(b200_conv3_up_supported(N, d, h, w, C1, Cout), "conv3_up_phase_fwd: unsupported N=%d %dx%dx%d C1=%d Cout=%d", N, d, h, w,
+                 C1, Cout);
+  for (int phase = 0; phase < 8; ++phase) {
+    const int pp[3] = {(phase >> 2) & 1, (phase >> 1) & 1, phase & 1};
+    PlainGeom g;
+    g.ntaps = 8;
+    for (int j = 0; j < 8; ++j) {
+      const int jj[3] = {(j >> 2) & 1, (j >> 1) & 1, j & 1};
+      for (int a = 0; a < 3; ++a) g.toff[3 * j + a] = (signed char)(pp[a] == 0 ? (jj[a] == 0 ? -1 : 0) : (jj[a] == 0 ? 0 : 1));
+    }
+    g.out_mul = 2;
+    for (int a = 0; a < 3; ++a) g.out_off[a] = pp[a];
+    g.w_rows = 64;
+    g.w_row0 = phase * 8;
+    g.cls_mode = 2;
+    int rc = conv_igemm_plain_launch(b, wp, n_w, nullptr, 0, nullptr, B200_ACT_NONE, 0.f, N, d, h, w, C1, Cout, R, 0, nullptr, nullptr, g,
+                                     (cudaStream_t)s);
+    if (rc) return rc;
+  }
+  return 0;
+}
+// transpose of the above: d b[u] = sum over the 4x4x4 offsets e in {-1..2}^3 of Wd[e] dz[2u+e]  (stride-2 reads of dz through an
+// element-stride-2 tensor map).  wd: bf16 [64][C1][Cout].
+int b200_conv3_up_dgrad(const void* dz, const void* wd, int N, int d, int h, int w, int Cout, int C1, void* dxb, b200_stream_t s) {
+  B200_CHECK_ARG(b200_conv3_up_supported(N, d, h, w, C1, Cout), "conv3_up_dgrad: unsupported N=%d %dx%dx%d C1=%d Cout=%d", N, d, h, w, C1,
+                 Cout);
+  PlainGeom g;
+  g.ntaps = 64;
+  for (int e = 0; e < 64; ++e) {
+    g.toff[3 * e] = (signed char)((e >> 4) - 1);
+    g.toff[3 * e + 1] = (signed char)(((e >> 2) & 3) - 1);
+    g.toff[3 * e + 2] = (signed char)((e & 3) - 1);
+  }
+  g.in_mul = 2;
+  g.w_rows = 64;
+  g.cls_mode = 2;
+  return conv_igemm_plain_launch(dz, wd, 1, nullptr, 0, nullptr, B200_ACT_NONE, 0.f, N, d, h, w, Cout, C1, dxb, 0, nullptr, nullptr, g,
                                  (cudaStream_t)s);
 }
 
@@ -351,8 +454,13 @@ int b200_pointwise_tc_fwd(const void* x, const void* wq, const float* bias, int 
                           float* partials, b200_stream_t s) {
   B200_CHECK_ARG(b200_pointwise_tc_supported(N, vox, Cin, Cout), "pointwise_tc: unsupported N=%d vox=%lld Cin=%d Cout=%d", N, vox, Cin,
                  Cout);
+  PlainGeom g;
+  g.ntaps = 1;
+  g.toff[0] = g.toff[1] = g.toff[2] = 0;
+  g.w_rows = 1;
+  g.cls_mode = 2;
   return conv_igemm_plain_launch(x, wq, 1, bias, bias ? 1 : 0, nullptr, B200_ACT_NONE, 0.f, N, 1, 1, (int)vox, Cin, Cout, y, partials ? 1 : 0,
-                                 nullptr, partials, 1, (cudaStream_t)s);
+                                 nullptr, partials, g, (cudaStream_t)s);
 }
 
 }  // extern "C"

@@ -19,6 +19,7 @@
 namespace b200 {
 
 int make_act_tmap(CUtensorMap* tm, const void* ptr, int N, int D, int H, int W, int C, int kc, int bd, int bh, int bw);
+int make_act_tmap_stride2(CUtensorMap* tm, const void* ptr, int N, int D, int H, int W, int C, int kc, int bd, int bh, int bw);
 int choose_box(int D, int H, int W, int* bd, int* bh, int* bw);
 int wgrad_halo_splits(int N, int D, int H, int W, int Cin, int Cout);
 int wgrad_halo_run(const void* x, const void* dz, int N, int D, int H, int W, int Cin, int Cout, int co0, int CoutTotal, float* G, cudaStream_t s);
@@ -36,7 +37,9 @@ struct WgradParams {
   int AWa, AWb;  // channels per smem atom tile (64/32/16) on the x side and the dz side
   int a_stages, a_stage_bytes, b_stage_bytes;
   int tmem_cols;
-  int NTAPS;           // 27, or 1 for the 1x1x1 conv (no shift; G is [n][S][1][Cin][Cout])
+  int NTAPS;           // 27; 1 for the 1x1x1 conv; 64 for conv3 o nearest-upsample (G is [n][S][NTAPS][Cin][Cout])
+  signed char toff[64 * 3];  // tap t reads the x-operand at a_mul * (tile origin) + toff[t]
+  int a_mul;
   int co0, CoutTotal;  // this launch covers output channels [co0, co0 + Cout) of CoutTotal (C_out > 256 is processed in slices)
   float* G;
 };
@@ -107,13 +110,13 @@ conv3_wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid
         }
         for (int tp = 0; tp < ntaps; ++tp, ++ai) {
           const int tap = tap0 + tp;
-          const int td = p.NTAPS == 1 ? 1 : tap / 9, th = p.NTAPS == 1 ? 1 : (tap / 3) % 3, tw = p.NTAPS == 1 ? 1 : tap % 3;
+          const int od = p.toff[3 * tap], oh = p.toff[3 * tap + 1], ow = p.toff[3 * tap + 2];
           const int as = ai % p.a_stages;
           mbar_wait(&a_empty[as], ((uint32_t)(ai / p.a_stages) & 1u) ^ 1u);
           mbar_arrive_expect_tx(&a_full[as], (uint32_t)(natoms_a * a_atom_bytes));
           for (int j = 0; j < natoms_a; ++j)
             tma_load_5d(smemA + (size_t)as * p.a_stage_bytes + (size_t)j * a_atom_bytes, &tmapX, &a_full[as], m0 + j * p.AWa,
-                        w0 + tw - 1, h0 + th - 1, d0 + td - 1, n);
+                        p.a_mul * w0 + ow, p.a_mul * h0 + oh, p.a_mul * d0 + od, n);
         }
       }
     }
@@ -202,6 +205,20 @@ static void wgrad_plan(int N, int D, int H, int W, int Cin, int Cout, WgradParam
   memset(&p, 0, sizeof(p));
   p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
   p.NTAPS = NT;
+  p.a_mul = NT == 64 ? 2 : 1;
+  for (int t = 0; t < NT; ++t) {
+    if (NT == 27) {
+      p.toff[3 * t] = (signed char)(t / 9 - 1);
+      p.toff[3 * t + 1] = (signed char)((t / 3) % 3 - 1);
+      p.toff[3 * t + 2] = (signed char)(t % 3 - 1);
+    } else if (NT == 64) {
+      p.toff[3 * t] = (signed char)((t >> 4) - 1);
+      p.toff[3 * t + 1] = (signed char)(((t >> 2) & 3) - 1);
+      p.toff[3 * t + 2] = (signed char)((t & 3) - 1);
+    } else {
+      p.toff[3 * t] = p.toff[3 * t + 1] = p.toff[3 * t + 2] = 0;
+    }
+  }
   choose_box(D, H, W, &p.BD, &p.BH, &p.BW);
   p.tilesD = (D + p.BD - 1) / p.BD;
   p.tilesH = (H + p.BH - 1) / p.BH;
@@ -242,7 +259,8 @@ static int wgrad_plain_launch(const void* x, const void* dz, int N, int D, int H
   p.G = G;
   p.CoutTotal = Cout;
   CUtensorMap tmX, tmZ;
-  int rc = make_act_tmap(&tmX, x, N, D, H, W, Cin, p.AWa, p.BD, p.BH, p.BW);
+  int rc = p.a_mul == 2 ? make_act_tmap_stride2(&tmX, x, N, 2 * D, 2 * H, 2 * W, Cin, p.AWa, p.BD, p.BH, p.BW)
+                        : make_act_tmap(&tmX, x, N, D, H, W, Cin, p.AWa, p.BD, p.BH, p.BW);
   if (rc) return rc;
   rc = make_act_tmap(&tmZ, dz, N, D, H, W, Cout, p.AWb, p.BD, p.BH, p.BW);
   if (rc) return rc;
@@ -302,6 +320,21 @@ int b200_pointwise_tc_wgrad(const void* x, const void* dy, int N, long long vox,
   B200_CHECK_ARG(b200_pointwise_tc_wgrad_splits(N, vox, Cin, Cout) > 0, "pointwise_tc_wgrad: unsupported N=%d vox=%lld Cin=%d Cout=%d", N,
                  vox, Cin, Cout);
   return wgrad_plain_launch(x, dy, N, 1, 1, (int)vox, Cin, Cout, G, 1, (cudaStream_t)s);
+}
+
+// ---- weight gradient of conv3 o nearest-upsample w.r.t. the 64 (offset e) x channel blocks:
+//   Q[n][split][e][co][c1] = sum_u dz[n, 2u+e, co] * b[n, u, c1],  e in {-1..2}^3
+// (dW[t] = sum over the parities r of Q[r - t], assembled by b200_upcat_assemble_wgrad).  The strided, shifted operand is dz.
+int b200_conv3_up_wgrad_splits(int N, int d, int h, int w, int Cout, int C1) {
+  if (!wgrad_supported(N, d, h, w, Cout, C1)) return 0;
+  WgradParams p;
+  wgrad_plan(N, d, h, w, Cout, cout_slice(C1), p, 64);
+  return p.S;
+}
+int b200_conv3_up_wgrad(const void* dz, const void* b, int N, int d, int h, int w, int Cout, int C1, float* Q, b200_stream_t s) {
+  B200_CHECK_ARG(b200_conv3_up_wgrad_splits(N, d, h, w, Cout, C1) > 0, "conv3_up_wgrad: unsupported N=%d %dx%dx%d Cout=%d C1=%d", N, d, h, w,
+                 Cout, C1);
+  return wgrad_plain_launch(dz, b, N, d, h, w, Cout, C1, Q, 64, (cudaStream_t)s);
 }
 
 }  // extern "C"

@@ -29,6 +29,8 @@ _ACT_OF = {"r": (ACT_RELU, 0.0), "l": (ACT_LEAKY, 0.01), "e": (ACT_ELU, 1.0)}
 # (name, flops, start_event, end_event) appended when enabled
 DEBUG = None   # dict: when set, backward closures stash clones of their intermediates (tools/debug_block.py)
 TIMING = None
+VIRTUAL_CAT = os.environ.get("B200UNET_NO_VIRTUAL_CAT", "0") != "1"  # decoder concat without the concatenated tensor
+PMODE_PHASE_BIAS = 0x100  # B200_PMODE_PHASE_BIAS (include/b200unet.h)
 HOST_PROF = None  # dict name -> [calls, seconds] when host profiling is on
 TIMED = {"b200_conv3_fwd", "b200_conv3_wgrad"}
 
@@ -90,6 +92,36 @@ class InputF32:
         return self.t.shape[1] * self.t.shape[2] * self.t.shape[3]
 
 
+_K188 = {}
+
+
+def _const_188(device):
+    """(1, 8, 8) on the device: scales the GroupNorm-backward coefficients of a tensor that appears 8x in a virtual upsample."""
+    key = str(device)
+    if key not in _K188:
+        _K188[key] = torch.tensor([1.0, 8.0, 8.0], device=device)
+    return _K188[key]
+
+
+class VirtualCat:
+    """cat(enc, nearest_up2x(low)) along channels that is never written to memory: its only consumer, the decoder's first
+    convolution, runs as conv3_enc(enc) + conv3_up(low) (Engine._conv3_vcat)."""
+
+    __slots__ = ("enc", "low")
+
+    def __init__(self, enc, low):
+        self.enc, self.low = enc, low
+
+    @property
+    def dims(self):
+        n, d, h, w, c0 = self.enc.dims
+        return n, d, h, w, c0 + self.low.dims[4]
+
+    @property
+    def requires_grad(self):
+        return self.enc.requires_grad or self.low.requires_grad
+
+
 class Engine:
     """One forward (+ optional backward) pass.  Not reusable across passes."""
 
@@ -102,6 +134,7 @@ class Engine:
         self.param_grads = {}
         self.launches = 0
         self.stream = torch.cuda.current_stream(device).cuda_stream
+        self._k188 = _const_188(device)
 
     # ---------------------------------------------------------------- helpers
     def empty(self, shape, dtype):
@@ -210,6 +243,10 @@ class Engine:
         assert W.shape == (cout, cin, 3, 3, 3), (tuple(W.shape), cin)
         if cout % 8 != 0:
             raise NotImplementedError(f"conv with C_out={cout}: the engine needs C_out % 8 == 0")
+        if isinstance(x, VirtualCat):
+            if residual is None and grad_sink is None and self._vcat_conv_ok(x, cout):
+                return self._conv3_vcat(x, W, bias, gn, name, act, want_stats)
+            x = self._upcat_materialize(x.enc, x.low, want_stats=gn is not None)
         vox = d * h * w
         is_f32 = isinstance(x, InputF32)
         L = self.L
@@ -424,10 +461,142 @@ class Engine:
             self.tape.append(backward)
         return out
 
-    def upcat(self, enc, x, want_stats=True):
+    def upcat(self, enc, x, want_stats=True, allow_virtual=False):
+        """Decoder joining for nearest upsampling + concat (buildingblocks.py:482-497).  When the encoder feature is exactly 2x the
+        low-res one the concatenated tensor stays virtual (VirtualCat); otherwise it is materialised."""
         n, D, H, W, c0 = enc.dims
         n2, d, h, w, c1 = x.dims
         assert n == n2
+        if (allow_virtual and VIRTUAL_CAT and self.impl != IMPL_DIRECT and (D, H, W) == (2 * d, 2 * h, 2 * w) and c0 % 16 == 0 and c1 % 16 == 0
+                and isinstance(enc, Act) and isinstance(x, Act)):
+            return VirtualCat(enc, x)
+        return self._upcat_materialize(enc, x, want_stats)
+
+    def _vcat_conv_ok(self, vc, cout):
+        n, D, H, W, c0 = vc.enc.dims
+        _, d, h, w, c1 = vc.low.dims
+        L = self.L
+        return (cout % 16 == 0 and L.query("b200_conv3_up_supported", n, d, h, w, c1, cout)
+                and L.query("b200_conv3_resolve_impl", self.impl, n, D, H, W, c0, cout, 0) == IMPL_TCGEN05
+                and L.query("b200_conv3_wgrad_resolve_impl", self.impl, n, D, H, W, c0, cout, 0) == IMPL_TCGEN05
+                and L.query("b200_conv3_up_wgrad_splits", n, d, h, w, cout, c1) > 0)
+
+    def _conv3_vcat(self, vc, W, bias, gn, name, act, want_stats):
+        """[GroupNorm ->] Conv3d(3x3x3) [-> act] of cat(enc, up2x(low)) as conv3_enc(enc) + conv3_up(low): the upsampled part is a
+        2x2x2 convolution of the low-res tensor per output parity phase (8/27 of its MACs), see csrc/upcat_conv.cu."""
+        enc, low = vc.enc, vc.low
+        n, D, H, Wd, c0 = enc.dims
+        _, d, h, w, c1 = low.dims
+        C, cout = c0 + c1, W.shape[0]
+        vox, lvox = D * H * Wd, d * h * w
+        L = self.L
+        W = W.contiguous()
+        ab = mean_rstd = sums = None
+        gamma = beta = None
+        groups = 1
+        n_w = 1
+        if gn is not None:
+            gamma, beta, groups = gn[0].contiguous(), gn[1].contiguous(), gn[2]
+            # statistics of the virtual tensor: every low-res voxel appears 8 times
+            sums = torch.cat([self.sums_of(enc), self.sums_of(low) * 8.0], dim=1).contiguous()
+            n_w = n
+            ab = self.empty((n, C, 2), torch.float32)
+            mean_rstd = self.empty((n, groups, 2), torch.float32)
+        wf_enc = self.empty((n_w, 27, cout, c0), torch.bfloat16)
+        wp = self.empty((n_w, 64, cout, c1), torch.bfloat16)
+        n_b = n_w if (gn is not None or bias is not None) else 0
+        biascls = self.empty((n_b, 64, cout), torch.float32) if n_b else None
+        self.call("b200_gn_fold_upcat", _p(sums), _p(gamma), _p(beta), groups, float(vox), _p(W), _p(bias), n, c0, c1, cout,
+                  _p(wf_enc), _p(wp), _p(biascls), _p(mean_rstd), _p(ab), launches=4 if gn is not None else 3)
+        R = self.empty((n, D, H, Wd, cout), torch.bfloat16)
+        self.call("b200_conv3_up_phase_fwd", _p(low.t), _p(wp), n_w, n, d, h, w, c1, cout, _p(R), launches=8,
+                  flops=2.0 * n * vox * 8 * c1 * cout, tag="fprop_tc")
+        y = self.empty((n, D, H, Wd, cout), torch.bfloat16)
+        partials, P = None, 0
+        if want_stats:
+            P = L.query("b200_conv3_partials_count", IMPL_TCGEN05, n, D, H, Wd, c0, cout)
+            partials = self.empty((n, P, cout, 2), torch.float32)
+        self.call("b200_conv3_fwd", IMPL_TCGEN05, _p(enc.t), 0, _p(wf_enc), n_w, _p(biascls), n_b, _p(R), act[0], float(act[1]),
+                  n, D, H, Wd, c0, cout, _p(y), (1 if want_stats else 0) | PMODE_PHASE_BIAS, None, _p(partials),
+                  flops=2.0 * n * vox * 27 * c0 * cout, tag="fprop_tc")
+        out = Act(y, act[0], act[1], partials, P)
+        if DEBUG is not None:
+            DEBUG.setdefault("fwd", {})[name] = y
+
+        if self.record:
+            def backward():
+                dz = out.grad
+                if dz is None:
+                    return
+                T = None
+                if gn is not None or bias is not None:
+                    T = self.empty((n, 27, cout), torch.float32)
+                    scratch = self.empty((L.query("b200_border_tap_sums_workspace", n, D, H, Wd, cout),), torch.float32)
+                    self.call("b200_border_tap_sums", _p(dz), n, D, H, Wd, cout, _p(T), _p(scratch), launches=5)
+                S1 = L.query("b200_conv3_wgrad_splits", IMPL_TCGEN05, n, D, H, Wd, c0, cout, 0)
+                G_enc = self.empty((n, S1, 27, c0, cout), torch.float32)
+                self.call("b200_conv3_wgrad", IMPL_TCGEN05, _p(enc.t), 0, _p(dz), n, D, H, Wd, c0, cout, _p(G_enc),
+                          flops=2.0 * n * vox * 27 * c0 * cout, tag="wgrad_tc")
+                S2 = L.query("b200_conv3_up_wgrad_splits", n, d, h, w, cout, c1)
+                Q = self.empty((n, S2, 64, cout, c1), torch.float32)
+                self.call("b200_conv3_up_wgrad", _p(dz), _p(low.t), n, d, h, w, cout, c1, _p(Q),
+                          flops=2.0 * n * lvox * 64 * c1 * cout, tag="wgrad_tc")
+                G = self.empty((n, 1, 27, C, cout), torch.float32)
+                self.call("b200_upcat_assemble_wgrad", _p(G_enc), S1, _p(Q), S2, n, c0, c1, cout, _p(G))
+                dW = torch.empty_like(W)
+                Gsum = self.empty((n, 1, 27, C, cout), torch.float32) if gn is not None else None
+                self.call("b200_wgrad_finalize", _p(G), n, 1, C, cout, _p(ab), _p(T) if ab is not None else None, _p(dW), _p(Gsum))
+                self._add_param_grad(name + "conv.weight", dW)
+                if bias is not None:
+                    db = torch.empty_like(bias)
+                    self.call("b200_bias_grad_from_T", _p(T), n, cout, _p(db))
+                    self._add_param_grad(name + "conv.bias", db)
+                coef = None
+                if gn is not None:
+                    sums2 = self.empty((n, C, 2), torch.float64)
+                    self.call("b200_gn_bwd_sums_from_wgrad", _p(Gsum), 1, _p(T), _p(W), n, C, cout, _p(sums2))
+                    coef = self.empty((n, C, 3), torch.float32)
+                    dgamma, dbeta = torch.empty_like(gamma), torch.empty_like(beta)
+                    self.call("b200_gn_bwd_coeffs", _p(sums2), _p(gamma), _p(mean_rstd), groups, float(vox), n, C,
+                              _p(coef), _p(dgamma), _p(dbeta))
+                    self._add_param_grad(gn[3], dgamma)
+                    self._add_param_grad(gn[4], dbeta)
+                if enc.requires_grad or low.requires_grad:
+                    wd_enc = self.empty((27, c0, cout), torch.bfloat16)
+                    wd_up = self.empty((64, c1, cout), torch.bfloat16)
+                    self.call("b200_upcat_prep_dgrad_weights", _p(W), c0, c1, cout, _p(wd_enc), _p(wd_up))
+                if enc.requires_grad:
+                    dimpl = L.query("b200_conv3_resolve_impl", self.impl, n, D, H, Wd, cout, c0, 0)
+                    if dimpl < 0:
+                        raise B200Error("tcgen05 dgrad requested but unsupported for this shape")
+                    ge = self.empty(enc.t.shape, torch.bfloat16)
+                    self.call("b200_conv3_fwd", dimpl, _p(dz), 0, _p(wd_enc), 1, None, 0, None, ACT_NONE, 0.0,
+                              n, D, H, Wd, cout, c0, _p(ge), 0, None, None, flops=2.0 * n * vox * 27 * c0 * cout,
+                              tag=("dgrad_tc" if dimpl == IMPL_TCGEN05 else "dgrad_direct"))
+                    if coef is not None:
+                        ce = coef[:, :c0].contiguous()
+                        self.call("b200_gn_bwd_apply", _p(ge), _p(enc.t), _p(ce), n, c0, vox, enc.act, enc.slope, _p(enc.grad), _p(ge))
+                    elif enc.act != ACT_NONE or enc.grad is not None:
+                        self.call("b200_act_bwd", _p(ge), c0, 0, _p(enc.t), n, c0, vox, enc.act, enc.slope, _p(enc.grad), _p(ge))
+                    enc.grad = ge
+                if low.requires_grad:
+                    gl = self.empty(low.t.shape, torch.bfloat16)
+                    self.call("b200_conv3_up_dgrad", _p(dz), _p(wd_up), n, d, h, w, cout, c1, _p(gl),
+                              flops=2.0 * n * lvox * 64 * c1 * cout, tag="dgrad_tc")
+                    if coef is not None:
+                        # d b[u] = sum over its 8 copies of (A dxhat + B x + C) = A sum(dxhat) + 8B b + 8C
+                        cl = (coef[:, c0:] * self._k188).contiguous()
+                        self.call("b200_gn_bwd_apply", _p(gl), _p(low.t), _p(cl), n, c1, lvox, low.act, low.slope, _p(low.grad), _p(gl))
+                    elif low.act != ACT_NONE or low.grad is not None:
+                        self.call("b200_act_bwd", _p(gl), c1, 0, _p(low.t), n, c1, lvox, low.act, low.slope, _p(low.grad), _p(gl))
+                    low.grad = gl
+                out.grad = None
+            self.tape.append(backward)
+        return out
+
+    def _upcat_materialize(self, enc, x, want_stats=True):
+        n, D, H, W, c0 = enc.dims
+        n2, d, h, w, c1 = x.dims
         cat = self.empty((n, D, H, W, c0 + c1), torch.bfloat16)
         P = self.L.query("b200_upcat_partials_count", n, D, H, W, c0 + c1)
         partials = self.empty((n, P, c0 + c1, 2), torch.float32) if want_stats else None

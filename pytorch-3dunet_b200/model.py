@@ -139,7 +139,8 @@ def run_basic(eng, x, sd, prefix, spec, out_stats=False):
 def run_join(eng, enc, x, sd, prefix, spec, want_stats):
     """Decoder.forward up to the basic module, reference buildingblocks.py:482-493"""
     if spec["upsample"] == "nearest" and spec["concat"]:
-        return eng.upcat(enc, x, want_stats=want_stats)
+        # only DoubleConv consumes the joined tensor through a single 3x3x3 conv, which lets it stay virtual
+        return eng.upcat(enc, x, want_stats=want_stats, allow_virtual=spec["basic"] == "double")
     if spec["upsample"] == "deconv" and not spec["concat"]:
         return eng.deconv_up_add(enc, x, sd[prefix + "upsampling.upsample.conv_transposed.weight"],
                                  prefix + "upsampling.upsample.conv_transposed.weight", want_stats=want_stats)
