@@ -131,6 +131,9 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+ALLOC_SETTLE_STEPS = 8
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -189,6 +192,10 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
+    # setup, not warm-up: let torch's caching allocator reach its steady state (it keeps cudaMalloc-ing new segments -- a device
+    # synchronisation each -- for the first ~8 identical steps while its best-fit split pattern converges; tools/alloc_probe.py)
+    for _ in range(ALLOC_SETTLE_STEPS):
+        step(x_dev, t_dev)
     for _ in range(max(args.warmup, 3)):
         step(x_dev, t_dev)
     barrier()
@@ -254,7 +261,8 @@ def main():
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD if (S == SIZE and B == BATCH) else f"UNet3D f32 d4 batch {B}x1x{S}^3", "per_gpu_batch": B,
-                       "parallelism": f"dp{world}", "l2": "per-step working set (~1 GB of bf16 activations per patch) >> 126 MB L2; no explicit flush"},
+                       "parallelism": f"dp{world}", "l2": "per-step working set (~1 GB of bf16 activations per patch) >> 126 MB L2; no explicit flush",
+                       "setup_steps_before_warmup": ALLOC_SETTLE_STEPS},
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": "patches/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": x_host.numel() * 4 + t_host.numel() * 4, "d2h_bytes_per_step": 4},

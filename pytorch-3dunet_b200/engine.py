@@ -32,7 +32,8 @@ TIMING = None
 VIRTUAL_CAT = os.environ.get("B200UNET_NO_VIRTUAL_CAT", "0") != "1"  # decoder concat without the concatenated tensor
 PMODE_PHASE_BIAS = 0x100  # B200_PMODE_PHASE_BIAS (include/b200unet.h)
 HOST_PROF = None  # dict name -> [calls, seconds] when host profiling is on
-TIMED = {"b200_conv3_fwd", "b200_conv3_wgrad"}
+TIMED = {"b200_conv3_fwd", "b200_conv3_wgrad", "b200_conv3_up_phase_fwd", "b200_conv3_up_dgrad", "b200_conv3_up_wgrad",
+         "b200_pointwise_tc_fwd", "b200_pointwise_tc_wgrad"}
 
 
 def default_impl() -> int:

@@ -68,7 +68,8 @@ class _EngineFn(torch.autograd.Function):
         for (shape, dtype), name in zip(ctx.param_meta, ctx.names):
             g = pg.get(name)
             grads.append(None if g is None else g.reshape(shape))
-        ctx.eng = None
+        # drop everything the closures keep alive (activations of the last layer, ...) now instead of when the autograd node dies
+        ctx.eng = ctx.seed = ctx.input_grads = None
         return (None, None, None) + tuple(in_grads) + tuple(grads)
 
 
@@ -447,6 +448,9 @@ class AbstractUNet(nn.Module):
             xin = eng.input_f32(ins[0])
             logits, probs, final_bwd = run_unet(eng, xin, sd, spec)
             final = spec["is_segmentation"]
+            # the closure must not hold the tensor OBJECT that forward returns: that object gets grad_fn = this autograd node,
+            # which holds the closure -> a reference cycle that keeps a step's activations alive until Python's cyclic GC runs
+            probs_saved = probs.detach() if probs is not None else None
 
             def seed(eng, grads):
                 g_logits = grads[0]
@@ -454,9 +458,9 @@ class AbstractUNet(nn.Module):
                 if g_probs is not None:
                     # chain rule through the final activation (tiny, C_out channels); only when the loss uses probabilities
                     if spec["final_sigmoid"]:
-                        t = g_probs * probs * (1 - probs)
+                        t = g_probs * probs_saved * (1 - probs_saved)
                     else:
-                        t = probs * (g_probs - (g_probs * probs).sum(dim=1, keepdim=True))
+                        t = probs_saved * (g_probs - (g_probs * probs_saved).sum(dim=1, keepdim=True))
                     g_logits = t if g_logits is None else g_logits + t
                 if g_logits is not None:
                     final_bwd(g_logits)
