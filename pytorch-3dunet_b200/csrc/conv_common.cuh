@@ -23,6 +23,8 @@ struct ConvParams {
   signed char toff[64 * 3];
   int in_mul, out_mul, out_off[3], OD, OH, OW;
   int w_rows, w_row0;
+  int nacc;                 // accumulators per CTA (1; 8 = the eight parity phases): taps [a*ntaps/nacc, (a+1)*ntaps/nacc) feed
+  signed char acc_off[8 * 3];  // accumulator a, whose outputs go to out_mul * x + acc_off[a]  (out_off when nacc == 1)
   int cls_mode;  // bias row: 0 = border class of the voxel, 1 = phase-aware border class (interior split by parity), 2 = row 0
   int NT;       // output channels per CTA
   int KC;       // channels per k-block (16/32/64)

@@ -21,7 +21,7 @@ conv3_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_const
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[CONV_MAX_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[CONV_MAX_STAGES];
-  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ __align__(8) uint64_t tmem_full_bar[8];  // one per accumulator
   __shared__ uint32_t tmem_slot;
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -46,7 +46,7 @@ conv3_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_const
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
-    mbar_init(&tmem_full_bar, 1);
+    for (int i = 0; i < 8; ++i) mbar_init(&tmem_full_bar[i], 1);
     fence_mbar_init();
   }
   if (warp == 0 && lane == 0) {
@@ -83,22 +83,27 @@ conv3_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_const
       const int rb = p.KC * 2;
       const uint64_t hi = umma_smem_desc(0, 16u, 8u * (uint32_t)rb, umma_layout_for_row_bytes(rb)) & 0xFFFFFFFF00000000ull;
       const int ksteps = p.KC / 16;
-      uint32_t accum = 0;
-      for (int kb = 0; kb < numK; ++kb) {
-        const int stage = kb % p.stages;
-        const uint32_t phase = (uint32_t)(kb / p.stages) & 1u;
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-        const uint32_t a_lo = ((sa >> 4) & 0x3FFFu) | (1u << 16);
-        const uint32_t b_lo = (((sa + (uint32_t)p.a_bytes) >> 4) & 0x3FFFu) | (1u << 16);
-        for (int k = 0; k < ksteps; ++k) {
-          umma_bf16_elect(tmem_base, hi | (uint64_t)(a_lo + 2u * k), hi | (uint64_t)(b_lo + 2u * k), idesc, accum);
-          accum = 1u;
+      const int kb_per_acc = numK / p.nacc;
+      int kb = 0;
+      for (int acc = 0; acc < p.nacc; ++acc) {
+        const uint32_t tacc = tmem_base + (uint32_t)(acc * p.NT);
+        uint32_t accum = 0;
+        for (int i = 0; i < kb_per_acc; ++i, ++kb) {
+          const int stage = kb % p.stages;
+          const uint32_t phase = (uint32_t)(kb / p.stages) & 1u;
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint32_t a_lo = ((sa >> 4) & 0x3FFFu) | (1u << 16);
+          const uint32_t b_lo = (((sa + (uint32_t)p.a_bytes) >> 4) & 0x3FFFu) | (1u << 16);
+          for (int k = 0; k < ksteps; ++k) {
+            umma_bf16_elect(tacc, hi | (uint64_t)(a_lo + 2u * k), hi | (uint64_t)(b_lo + 2u * k), idesc, accum);
+            accum = 1u;
+          }
+          umma_commit_elect(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
         }
-        umma_commit_elect(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+        umma_commit_elect(&tmem_full_bar[acc]);  // this accumulator is complete
       }
-      umma_commit_elect(&tmem_full_bar);  // accumulator complete
     }
   } else {
     // ================= epilogue (warps 2..5) =================
@@ -107,23 +112,26 @@ conv3_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_const
     const int bx = row % p.BW, by = (row / p.BW) % p.BH, bz = row / (p.BW * p.BH);
     const int xd = d0 + bz, xh = h0 + by, xw = w0 + bx;
     const bool valid = xd < p.D && xh < p.H && xw < p.W;
-    const size_t vox_off = (size_t)n * p.OD * p.OH * p.OW +
-                           ((size_t)(p.out_mul * xd + p.out_off[0]) * p.OH + (p.out_mul * xh + p.out_off[1])) * p.OW +
-                           (p.out_mul * xw + p.out_off[2]);
     const float* bias_row = nullptr;
     if (p.n_b && valid) {
       const int cls = conv_bias_cls(p.cls_mode, xd, xh, xw, p.D, p.H, p.W);
       bias_row = p.biascls + ((size_t)(p.n_b > 1 ? n : 0) * 64 + cls) * p.Cout;
     }
-    mbar_wait(&tmem_full_bar, 0);
-    __syncwarp();
-    tc_fence_after();
-    // all MMAs have completed -> every smem stage is free; reuse stage 0 as the stats scratch [4][NT][2]
+    // stats scratch [4][NT][2]: stage 0 of the smem ring, free once the (single) accumulator is complete (pmode needs nacc == 1)
     float* scratch = reinterpret_cast<float*>(smem) + (size_t)q * p.NT * 2;
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-    int c0 = 0;
-    for (; c0 + 32 <= p.NT; c0 += 32) conv_epilogue_slab<32>(p, taddr, c0, n0, valid, vox_off, bias_row, lane, scratch);
-    if (c0 < p.NT) conv_epilogue_slab<16>(p, taddr, c0, n0, valid, vox_off, bias_row, lane, scratch);
+    for (int acc = 0; acc < p.nacc; ++acc) {
+      const int o0 = p.nacc > 1 ? p.acc_off[3 * acc] : p.out_off[0], o1 = p.nacc > 1 ? p.acc_off[3 * acc + 1] : p.out_off[1],
+                o2 = p.nacc > 1 ? p.acc_off[3 * acc + 2] : p.out_off[2];
+      const size_t vox_off = (size_t)n * p.OD * p.OH * p.OW + ((size_t)(p.out_mul * xd + o0) * p.OH + (p.out_mul * xh + o1)) * p.OW +
+                             (p.out_mul * xw + o2);
+      mbar_wait(&tmem_full_bar[acc], 0);
+      __syncwarp();
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.NT);
+      int c0 = 0;
+      for (; c0 + 32 <= p.NT; c0 += 32) conv_epilogue_slab<32>(p, taddr, c0, n0, valid, vox_off, bias_row, lane, scratch);
+      if (c0 < p.NT) conv_epilogue_slab<16>(p, taddr, c0, n0, valid, vox_off, bias_row, lane, scratch);
+    }
     if (p.pmode) {
       asm volatile("bar.sync 1, 128;" ::: "memory");  // the 4 epilogue warps only
       const int et = threadIdx.x - 64;
@@ -247,6 +255,8 @@ struct PlainGeom {
   int out_mul = 1, out_off[3] = {0, 0, 0};  // 2: outputs are written to one parity phase of a (2D,2H,2W) volume
   int w_rows = 27, w_row0 = 0;      // weight rows per sample in wf, first row of this launch
   int cls_mode = 0;
+  int nacc = 1;                     // accumulators per CTA (taps split evenly), each with its own output offset acc_off[a]
+  signed char acc_off[8 * 3] = {0};
   PlainGeom() {
     for (int t = 0; t < 27; ++t) {
       toff[3 * t] = (signed char)(t / 9 - 1);
@@ -288,6 +298,9 @@ static int conv_igemm_plain_launch(const void* x, const void* wf, int n_w, const
   p.w_rows = g.w_rows;
   p.w_row0 = g.w_row0;
   p.cls_mode = g.cls_mode;
+  p.nacc = g.nacc;
+  memcpy(p.acc_off, g.acc_off, sizeof(p.acc_off));
+  B200_CHECK_ARG(g.nacc >= 1 && g.nacc <= 8 && g.ntaps % g.nacc == 0 && (g.nacc == 1 || pmode == 0), "conv3_igemm: bad accumulator split");
   choose_box(D, H, W, &p.BD, &p.BH, &p.BW);
   p.tilesD = (D + p.BD - 1) / p.BD;
   p.tilesH = (H + p.BH - 1) / p.BH;
@@ -295,6 +308,8 @@ static int conv_igemm_plain_launch(const void* x, const void* wf, int n_w, const
   p.n_w = n_w;
   p.n_b = biascls ? n_b : 0;
   p.NT = pick_nt(Cout);
+  while (g.nacc * p.NT > 512 && p.NT % 32 == 0) p.NT /= 2;  // all accumulators of a CTA live in its 512 TMEM columns
+  B200_CHECK_ARG(g.nacc * p.NT <= 512 && Cout % p.NT == 0, "conv3_igemm: %d accumulators of %d columns do not fit TMEM", g.nacc, p.NT);
   p.KC = (Cin % 64 == 0) ? 64 : (Cin % 32 == 0 ? 32 : 16);
   p.kchunks = Cin / p.KC;
   p.a_bytes = (128 * p.KC * 2 + 1023) & ~1023;
@@ -308,7 +323,7 @@ static int conv_igemm_plain_launch(const void* x, const void* wf, int n_w, const
   if (stages > CONV_MAX_STAGES) stages = CONV_MAX_STAGES;
   p.stages = stages;
   int cols = 32;
-  while (cols < p.NT) cols <<= 1;
+  while (cols < g.nacc * p.NT) cols <<= 1;
   p.tmem_cols = cols;
   p.act = act;
   p.slope = slope;
@@ -403,24 +418,25 @@ int b200_conv3_up_supported(int N, int d, int h, int w, int C1, int Cout) {
 int b200_conv3_up_phase_fwd(const void* b, const void* wp, int n_w, int N, int d, int h, int w, int C1, int Cout, void* R, b200_stream_t s) {
   B200_CHECK_ARG(b200_conv3_up_supported(N, d, h, w, C1, Cout), "conv3_up_phase_fwd: unsupported N=%d %dx%dx%d C1=%d Cout=%d", N, d, h, w,
                  C1, Cout);
+  // one launch: every CTA owns a tile of 128 low-res voxels and all 8 phases (8 accumulators; the epilogue of phase k overlaps
+  // the MMAs of phase k+1)
+  PlainGeom g;
+  g.ntaps = 64;
+  g.nacc = 8;
   for (int phase = 0; phase < 8; ++phase) {
     const int pp[3] = {(phase >> 2) & 1, (phase >> 1) & 1, phase & 1};
-    PlainGeom g;
-    g.ntaps = 8;
     for (int j = 0; j < 8; ++j) {
       const int jj[3] = {(j >> 2) & 1, (j >> 1) & 1, j & 1};
-      for (int a = 0; a < 3; ++a) g.toff[3 * j + a] = (signed char)(pp[a] == 0 ? (jj[a] == 0 ? -1 : 0) : (jj[a] == 0 ? 0 : 1));
+      for (int a = 0; a < 3; ++a)
+        g.toff[3 * (phase * 8 + j) + a] = (signed char)(pp[a] == 0 ? (jj[a] == 0 ? -1 : 0) : (jj[a] == 0 ? 0 : 1));
     }
-    g.out_mul = 2;
-    for (int a = 0; a < 3; ++a) g.out_off[a] = pp[a];
-    g.w_rows = 64;
-    g.w_row0 = phase * 8;
-    g.cls_mode = 2;
-    int rc = conv_igemm_plain_launch(b, wp, n_w, nullptr, 0, nullptr, B200_ACT_NONE, 0.f, N, d, h, w, C1, Cout, R, 0, nullptr, nullptr, g,
-                                     (cudaStream_t)s);
-    if (rc) return rc;
+    for (int a = 0; a < 3; ++a) g.acc_off[3 * phase + a] = (signed char)pp[a];
   }
-  return 0;
+  g.out_mul = 2;
+  g.w_rows = 64;
+  g.cls_mode = 2;
+  return conv_igemm_plain_launch(b, wp, n_w, nullptr, 0, nullptr, B200_ACT_NONE, 0.f, N, d, h, w, C1, Cout, R, 0, nullptr, nullptr, g,
+                                 (cudaStream_t)s);
 }
 // transpose of the above: d b[u] = sum over the 4x4x4 offsets e in {-1..2}^3 of Wd[e] dz[2u+e]  (stride-2 reads of dz through an
 // element-stride-2 tensor map).  wd: bf16 [64][C1][Cout].

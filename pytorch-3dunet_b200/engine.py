@@ -510,7 +510,7 @@ class Engine:
         self.call("b200_gn_fold_upcat", _p(sums), _p(gamma), _p(beta), groups, float(vox), _p(W), _p(bias), n, c0, c1, cout,
                   _p(wf_enc), _p(wp), _p(biascls), _p(mean_rstd), _p(ab), launches=4 if gn is not None else 3)
         R = self.empty((n, D, H, Wd, cout), torch.bfloat16)
-        self.call("b200_conv3_up_phase_fwd", _p(low.t), _p(wp), n_w, n, d, h, w, c1, cout, _p(R), launches=8,
+        self.call("b200_conv3_up_phase_fwd", _p(low.t), _p(wp), n_w, n, d, h, w, c1, cout, _p(R), launches=1,
                   flops=2.0 * n * vox * 8 * c1 * cout, tag="fprop_tc")
         y = self.empty((n, D, H, Wd, cout), torch.bfloat16)
         partials, P = None, 0
