@@ -40,6 +40,8 @@ struct WgradParams {
   int NTAPS;           // 27; 1 for the 1x1x1 conv; 64 for conv3 o nearest-upsample (G is [n][S][NTAPS][Cin][Cout])
   signed char toff[64 * 3];  // tap t reads the x-operand at a_mul * (tile origin) + toff[t]
   int a_mul;
+  // C_in <= 64: `tps` = 128 / C_in taps are stacked along M of ONE MMA (their x tiles sit side by side as M atoms), NST = stacks
+  int tps, NST;
   int co0, CoutTotal;  // this launch covers output channels [co0, co0 + Cout) of CoutTotal (C_out > 256 is processed in slices)
   float* G;
 };
@@ -61,12 +63,12 @@ conv3_wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid
   const int n = blockIdx.x / p.S;
   const int grp = blockIdx.y;
   const int m0 = blockIdx.z * 128;
-  const int tap0 = grp * p.TG;
-  const int ntaps = min(p.TG, p.NTAPS - tap0);
+  const int st0 = grp * p.TG;                  // first tap stack of this group
+  const int ntaps = min(p.TG, p.NST - st0);    // tap stacks (= accumulators) of this CTA
   const int t0 = split * p.tiles_per_split;
   const int t1 = min(p.tiles, t0 + p.tiles_per_split);
   const int m_real = min(128, p.Cin - m0);
-  const int natoms_a = m_real / p.AWa;
+  const int apt = m_real / p.AWa;  // M atoms per tap
   const int natoms_b = p.Cout / p.AWb;
   const int a_atom_bytes = 128 * p.AWa * 2, b_atom_bytes = 128 * p.AWb * 2;
 
@@ -109,56 +111,68 @@ conv3_wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid
             tma_load_5d(smemB + (size_t)bs * p.b_stage_bytes + (size_t)j * b_atom_bytes, &tmapZ, &b_full[bs], p.co0 + j * p.AWb, w0, h0, d0, n);
         }
         for (int tp = 0; tp < ntaps; ++tp, ++ai) {
-          const int tap = tap0 + tp;
-          const int od = p.toff[3 * tap], oh = p.toff[3 * tap + 1], ow = p.toff[3 * tap + 2];
+          const int tapb = (st0 + tp) * p.tps;
+          const int rt = min(p.tps, p.NTAPS - tapb);  // taps really present in this stack (the last one may be ragged)
           const int as = ai % p.a_stages;
           mbar_wait(&a_empty[as], ((uint32_t)(ai / p.a_stages) & 1u) ^ 1u);
-          mbar_arrive_expect_tx(&a_full[as], (uint32_t)(natoms_a * a_atom_bytes));
-          for (int j = 0; j < natoms_a; ++j)
-            tma_load_5d(smemA + (size_t)as * p.a_stage_bytes + (size_t)j * a_atom_bytes, &tmapX, &a_full[as], m0 + j * p.AWa,
-                        p.a_mul * w0 + ow, p.a_mul * h0 + oh, p.a_mul * d0 + od, n);
+          mbar_arrive_expect_tx(&a_full[as], (uint32_t)(rt * apt * a_atom_bytes));
+          for (int jt = 0; jt < rt; ++jt) {
+            const int tap = tapb + jt;
+            const int od = p.toff[3 * tap], oh = p.toff[3 * tap + 1], ow = p.toff[3 * tap + 2];
+            for (int j = 0; j < apt; ++j)
+              tma_load_5d(smemA + (size_t)as * p.a_stage_bytes + (size_t)(jt * apt + j) * a_atom_bytes, &tmapX, &a_full[as],
+                          m0 + j * p.AWa, p.a_mul * w0 + ow, p.a_mul * h0 + oh, p.a_mul * d0 + od, n);
+          }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // whole warp converged, one elected lane issues; descriptors = constant high word + low word advanced by adds (the loop
+    // must stay under the ~54-cycle dispatch time of a tcgen05.mma)
+    {
       const uint32_t idesc = umma_idesc_bf16(128, p.Cout, 1, 1);
       const int rba = p.AWa * 2, rbb = p.AWb * 2;
-      const uint32_t la = umma_layout_for_row_bytes(rba), lb = umma_layout_for_row_bytes(rbb);
+      const uint64_t hiA = umma_smem_desc(0, 16u, (uint32_t)(8 * rba), umma_layout_for_row_bytes(rba)) & 0xFFFFFFFF00000000ull;
+      const uint64_t hiB = umma_smem_desc(0, 16u, (uint32_t)(8 * rbb), umma_layout_for_row_bytes(rbb)) & 0xFFFFFFFF00000000ull;
+      const uint32_t lboA = (((uint32_t)a_atom_bytes >> 4) & 0x3FFFu) << 16, lboB = (((uint32_t)b_atom_bytes >> 4) & 0x3FFFu) << 16;
+      const uint32_t ka = (uint32_t)rba, kb = (uint32_t)rbb;  // 16 voxel rows of K, in 16-byte units
       int ai = 0;
+      uint32_t accum = 0;
       for (int t = t0, bi = 0; t < t1; ++t, ++bi) {
         const int bs = bi % WG_B_STAGES;
         mbar_wait(&b_full[bs], (uint32_t)(bi / WG_B_STAGES) & 1u);
-        const uint32_t sb = smem_u32(smemB + (size_t)bs * p.b_stage_bytes);
+        const uint32_t b_lo = ((smem_u32(smemB + (size_t)bs * p.b_stage_bytes) >> 4) & 0x3FFFu) | lboB;
         for (int tp = 0; tp < ntaps; ++tp, ++ai) {
           const int as = ai % p.a_stages;
           mbar_wait(&a_full[as], (uint32_t)(ai / p.a_stages) & 1u);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smemA + (size_t)as * p.a_stage_bytes);
+          const uint32_t a_lo = ((smem_u32(smemA + (size_t)as * p.a_stage_bytes) >> 4) & 0x3FFFu) | lboA;
+          const uint32_t tacc = tmem_base + (uint32_t)(tp * p.Cout);
+          umma_bf16_elect(tacc, hiA | (uint64_t)a_lo, hiB | (uint64_t)b_lo, idesc, accum);
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {  // 128 voxels = 8 x K16
-            const uint64_t adesc = umma_smem_desc(sa + (uint32_t)(k * 16 * rba), (uint32_t)a_atom_bytes, (uint32_t)(8 * rba), la);
-            const uint64_t bdesc = umma_smem_desc(sb + (uint32_t)(k * 16 * rbb), (uint32_t)b_atom_bytes, (uint32_t)(8 * rbb), lb);
-            umma_bf16(tmem_base + (uint32_t)(tp * p.Cout), adesc, bdesc, idesc, (t > t0 || k > 0) ? 1u : 0u);
-          }
-          umma_commit(&a_empty[as]);
+          for (uint32_t k = 1; k < 8; ++k)  // 128 voxels = 8 x K16
+            umma_bf16_elect(tacc, hiA | (uint64_t)(a_lo + k * ka), hiB | (uint64_t)(b_lo + k * kb), idesc, 1u);
+          umma_commit_elect(&a_empty[as]);
         }
-        umma_commit(&b_empty[bs]);
+        accum = 1u;
+        umma_commit_elect(&b_empty[bs]);
       }
-      umma_commit(&tmem_full_bar);
+      umma_commit_elect(&tmem_full_bar);
     }
   } else {
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const int ci = m0 + row;
-    const bool valid = row < m_real;
+    const int jt = row / m_real;            // which tap of the stack this accumulator row belongs to
+    const int ci = m0 + row - jt * m_real;
     mbar_wait(&tmem_full_bar, 0);
     __syncwarp();
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
     const bool have_work = t1 > t0;
     for (int tp = 0; tp < ntaps; ++tp) {
-      float* grow = p.G + ((((size_t)n * p.S + split) * p.NTAPS + (tap0 + tp)) * p.Cin + (valid ? ci : 0)) * p.CoutTotal + p.co0;
+      const int tap = (st0 + tp) * p.tps + jt;
+      const bool valid = jt < p.tps && tap < p.NTAPS;
+      float* grow = p.G + ((((size_t)n * p.S + split) * p.NTAPS + (valid ? tap : 0)) * p.Cin + (valid ? ci : 0)) * p.CoutTotal + p.co0;
       for (int c0 = 0; c0 < p.Cout; c0 += 16) {
         uint32_t raw[16];
         tmem_ld_32x32b_x16(taddr + (uint32_t)(tp * p.Cout + c0), raw);
@@ -224,11 +238,14 @@ static void wgrad_plan(int N, int D, int H, int W, int Cin, int Cout, WgradParam
   p.tilesH = (H + p.BH - 1) / p.BH;
   p.tilesW = (W + p.BW - 1) / p.BW;
   p.tiles = p.tilesD * p.tilesH * p.tilesW;
+  p.tps = (Cin <= 64 && NT > 1) ? 128 / Cin : 1;
+  if (p.tps > NT) p.tps = NT;
+  p.NST = (NT + p.tps - 1) / p.tps;
   int tgmax = 512 / Cout;
-  if (tgmax > NT) tgmax = NT;
-  p.ngroups = (NT + tgmax - 1) / tgmax;
-  p.TG = (NT + p.ngroups - 1) / p.ngroups;
-  p.ngroups = (NT + p.TG - 1) / p.TG;
+  if (tgmax > p.NST) tgmax = p.NST;
+  p.ngroups = (p.NST + tgmax - 1) / tgmax;
+  p.TG = (p.NST + p.ngroups - 1) / p.ngroups;
+  p.ngroups = (p.NST + p.TG - 1) / p.TG;
   p.mchunks = (Cin + 127) / 128;
   // one CTA per SM (TMEM: TG*Cout columns, smem: deep A pipeline) -> size the split count for a single wave
   int ctas_per_split = N * p.ngroups * p.mchunks;
@@ -241,7 +258,7 @@ static void wgrad_plan(int N, int D, int H, int W, int Cin, int Cout, WgradParam
   p.AWb = atom_width(Cout);
   p.b_stage_bytes = 128 * Cout * 2;
   // an A stage only holds the channels that exist (garbage M rows of the MMA read past it, into the next stage or the tail pad)
-  p.a_stage_bytes = 128 * (Cin < 128 ? Cin : 128) * 2;
+  p.a_stage_bytes = 128 * (p.tps * Cin < 128 ? p.tps * Cin : 128) * 2;
   int budget = 190 * 1024 - WG_B_STAGES * p.b_stage_bytes - WG_A_FULL_BYTES;
   p.a_stages = budget / p.a_stage_bytes;
   if (p.a_stages > WG_MAX_A_STAGES) p.a_stages = WG_MAX_A_STAGES;
