@@ -769,21 +769,54 @@ __global__ void border_class_sums_kernel(const bf16* __restrict__ dz, int D, int
 // stage 2 (after the border class sums were reduced over P into R[n][cls][c] and the totals into tot[n][c][2], double):
 // T[n][tap][c] = sum_{cls: tap valid} R, with R[interior] = total - sum(border classes); grid (ceil(27*C/256), N), block 256
 __global__ void border_tap_from_class_kernel(const double* __restrict__ R, const double* __restrict__ tot, int C, float* __restrict__ T) {
-  int n = blockIdx.y;
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= 27 * C) return;
-  int tap = idx / C, c = idx % C;
-  int td = tap / 9, th = (tap / 3) % 3, tw = tap % 3;
+  // one thread per (n, c): the 64 class sums are read once (independent, coalesced loads), then contracted axis by axis with the
+  // tap-validity table:  T[td][th][tw] = sum_cd V(cd,td) sum_ch V(ch,th) sum_cw V(cw,tw) R[cd][ch][cw]
+  const int n = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
   const int interior = (1 << 4) | (1 << 2) | 1;
-  double border_all = 0.0, acc = 0.0;
+  double r[64];
+  double border_all = 0.0;
+#pragma unroll
   for (int cls = 0; cls < 64; ++cls) {
-    if (cls == interior) continue;
-    double r = R[((size_t)n * 64 + cls) * C + c];
-    border_all += r;
-    if (tap_valid(cls >> 4, td) && tap_valid((cls >> 2) & 3, th) && tap_valid(cls & 3, tw)) acc += r;
+    r[cls] = cls == interior ? 0.0 : R[((size_t)n * 64 + cls) * C + c];
+    border_all += r[cls];
   }
-  acc += tot[((size_t)n * C + c) * 2] - border_all;  // every tap is valid for interior voxels
-  T[((size_t)n * 27 + tap) * C + c] = (float)acc;
+  r[interior] = tot[((size_t)n * C + c) * 2] - border_all;
+  double s1[16][3];  // [cd][ch][tw]
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+#pragma unroll
+    for (int tw = 0; tw < 3; ++tw) {
+      double acc = 0.0;
+#pragma unroll
+      for (int cw = 0; cw < 4; ++cw)
+        if (tap_valid(cw, tw)) acc += r[i * 4 + cw];
+      s1[i][tw] = acc;
+    }
+  double s2[4][9];  // [cd][th][tw]
+#pragma unroll
+  for (int cd = 0; cd < 4; ++cd)
+#pragma unroll
+    for (int th = 0; th < 3; ++th)
+#pragma unroll
+      for (int tw = 0; tw < 3; ++tw) {
+        double acc = 0.0;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch)
+          if (tap_valid(ch, th)) acc += s1[cd * 4 + ch][tw];
+        s2[cd][th * 3 + tw] = acc;
+      }
+#pragma unroll
+  for (int td = 0; td < 3; ++td)
+#pragma unroll
+    for (int t9 = 0; t9 < 9; ++t9) {
+      double acc = 0.0;
+#pragma unroll
+      for (int cd = 0; cd < 4; ++cd)
+        if (tap_valid(cd, td)) acc += s2[cd][t9];
+      T[((size_t)n * 27 + td * 9 + t9) * C + c] = (float)acc;
+    }
 }
 
 // dW[co][ci][tap] = sum_n ( a[n][ci] * sum_s G[n][s][tap][ci][co] + b[n][ci] * T[n][tap][co] )
@@ -1233,8 +1266,8 @@ int b200_border_tap_sums(const void* dz, int N, int D, int H, int W, int C, floa
     partials_finalize_kernel<<<g2, b2, 0, ST(s)>>>(Rp, P, 32 * C, R);
     B200_CHECK_LAUNCH("border_class_reduce");
   }
-  dim3 g3(ceil_div(27 * C, 256), N);
-  border_tap_from_class_kernel<<<g3, 256, 0, ST(s)>>>(R, tot, C, T);
+  dim3 g3(ceil_div(C, 64), N);
+  border_tap_from_class_kernel<<<g3, 64, 0, ST(s)>>>(R, tot, C, T);
   B200_CHECK_LAUNCH("border_tap_from_class");
   return 0;
 }

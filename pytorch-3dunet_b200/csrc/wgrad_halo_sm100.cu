@@ -23,7 +23,8 @@ namespace b200 {
 
 constexpr int WH_BH = 16, WH_BW = 8, WH_HD = 3, WH_HH = WH_BH + 2, WH_HW = WH_BW + 2;
 constexpr int WH_ROWS = WH_HD * WH_HH * WH_HW;  // 540
-constexpr int WH_THREADS = 192;
+constexpr int WH_THREADS = 224;  // warp 0 TMA producer, warps 1 and 6 MMA issuers, warps 2..5 read-out
+constexpr int WH_ISSUERS = 2;
 constexpr int WH_MAX_A = 6, WH_MAX_B = 4;
 
 struct WgradHaloParams {
@@ -61,13 +62,13 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_consta
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.a_stages; ++i) {
       mbar_init(&a_full[i], 1);
-      mbar_init(&a_empty[i], 1);
+      mbar_init(&a_empty[i], WH_ISSUERS);  // every issuer commits each stage it has read
     }
     for (int i = 0; i < p.b_stages; ++i) {
       mbar_init(&b_full[i], 1);
-      mbar_init(&b_empty[i], 1);
+      mbar_init(&b_empty[i], WH_ISSUERS);
     }
-    mbar_init(&done_bar, 1);
+    mbar_init(&done_bar, WH_ISSUERS);
     fence_mbar_init();
   }
   if (warp == 0 && lane == 0) {
@@ -98,8 +99,14 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_consta
         tma_load_5d(smemA + (size_t)as * p.a_bytes, &tmapX, &a_full[as], slice * CA, w0 - 1, h0 - 1, d0 - 1, n);
       }
     }
-  } else if (warp == 1) {
-    // whole warp converged; one elected lane issues (see sm100_ptx.cuh)
+  } else if (warp == 1 || warp == 6) {
+    // two MMA issuers (warps 1 and 6) share every tile: each owns half of the (dd,dh) accumulators.  One warp can issue an
+    // N <= 64 MMA every ~54 cycles, two warps interleave to ~40 (profiles/probes_r01.md, probe 4).  Both wait on the same
+    // full barriers in lockstep (the producer cannot refill a stage before BOTH have committed it) -> no phase aliasing.
+    // Whole warp converged; one elected lane issues (see sm100_ptx.cuh)
+    const int issuer = warp == 1 ? 0 : 1;
+    const int g_half = (p.PG + 1) / 2;
+    const int g_begin = issuer * g_half, g_end = issuer == 0 ? g_half : p.PG;
     const int rbB = p.AWb * 2;
     const uint32_t idesc = umma_idesc_bf16(128, p.Cout, 1, 1);
     // A: MN-major, atom stride (LBO) = ONE halo row -> atom j = view shifted by j voxels in w; 8-row K group stride (SBO) = one
@@ -119,7 +126,7 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_consta
       const uint32_t b_lo = ((smem_u32(smemB + (size_t)bs * p.b_bytes) >> 4) & 0x3FFFu) | lboB;
       const uint32_t accum = it != 0 ? 1u : 0u;
 #pragma unroll 1
-      for (int g = 0; g < p.PG; ++g) {
+      for (int g = g_begin; g < g_end; ++g) {
         const int pair = pg0 + g;  // dd*3 + dh
         const uint32_t a_g = a_lo + (uint32_t)((pair / 3) * WH_HH + pair % 3) * A_LINE;
         const uint32_t tacc = tmem_base + (uint32_t)(g * p.Cout);
