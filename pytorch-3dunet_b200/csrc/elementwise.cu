@@ -263,27 +263,22 @@ __global__ void fold_weights_kernel(const float* __restrict__ W, const float* __
 __global__ void fold_bias_kernel(const float* __restrict__ W, const float* __restrict__ ab, const float* __restrict__ conv_bias,
                                  const double* __restrict__ sums, double count, int Cin, int Cout, float* __restrict__ biascls) {
   __shared__ float bt[27];
-  __shared__ float red[128];
   int co = blockIdx.x, n = blockIdx.y;
-  for (int tap = 0; tap < 27; ++tap) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int tap = warp; tap < 27; tap += nwarps) {  // one warp per tap, shuffle reduction over the input channels
     float acc = 0.f;
     if (ab)
-      for (int ci = threadIdx.x; ci < Cin; ci += blockDim.x) {
+      for (int ci = lane; ci < Cin; ci += 32) {
         float w = W[((size_t)co * Cin + ci) * 27 + tap];
         float wa = w * ab[((size_t)n * Cin + ci) * 2];
         float resid = wa - __bfloat162float(__float2bfloat16_rn(wa));
         float mean = sums ? (float)(sums[((size_t)n * Cin + ci) * 2] / count) : 0.f;
         acc += w * ab[((size_t)n * Cin + ci) * 2 + 1] + resid * mean;
       }
-    red[threadIdx.x] = acc;
-    __syncthreads();
-    for (int o = 64; o; o >>= 1) {
-      if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
-      __syncthreads();
-    }
-    if (threadIdx.x == 0) bt[tap] = red[0];
-    __syncthreads();
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) bt[tap] = acc;
   }
+  __syncthreads();
   float cb = conv_bias ? conv_bias[co] : 0.f;
   for (int cls = threadIdx.x; cls < 64; cls += blockDim.x) {
     int cd = cls >> 4, ch = (cls >> 2) & 3, cw = cls & 3;
@@ -1119,7 +1114,7 @@ int b200_gn_fold(const double* sums, const float* gamma, const float* beta, int 
   B200_CHECK_LAUNCH("fold_weights");
   if (biascls && (abp || conv_bias)) {
     dim3 grid(Cout, n_w);
-    fold_bias_kernel<<<grid, 128, 0, ST(s)>>>(W, abp, conv_bias, sums, count, Cin, Cout, biascls);
+    fold_bias_kernel<<<grid, 256, 0, ST(s)>>>(W, abp, conv_bias, sums, count, Cin, Cout, biascls);
     B200_CHECK_LAUNCH("fold_bias");
   }
   return 0;

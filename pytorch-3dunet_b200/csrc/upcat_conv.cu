@@ -78,14 +78,14 @@ __global__ void upcat_fold_bias_kernel(const float* __restrict__ W, const float*
                                        float* __restrict__ biascls) {
   __shared__ float bt[27];
   __shared__ float rk[64];
-  __shared__ float red[128];
   const int C = C0 + C1;
   const int co = blockIdx.x, n = blockIdx.y;
-  for (int q = 0; q < 27 + 64; ++q) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int q = warp; q < 27 + 64; q += nwarps) {  // one warp per reduction
     float acc = 0.f;
     if (ab) {
       if (q < 27) {
-        for (int ci = threadIdx.x; ci < C; ci += blockDim.x) {
+        for (int ci = lane; ci < C; ci += 32) {
           const float w = W[((size_t)co * C + ci) * 27 + q];
           const float a = ab[((size_t)n * C + ci) * 2], sh = ab[((size_t)n * C + ci) * 2 + 1];
           acc += w * sh;
@@ -96,7 +96,7 @@ __global__ void upcat_fold_bias_kernel(const float* __restrict__ W, const float*
         }
       } else if (sums) {
         const int pj = q - 27, phase = pj >> 3, j = pj & 7;
-        for (int c1 = threadIdx.x; c1 < C1; c1 += blockDim.x) {
+        for (int c1 = lane; c1 < C1; c1 += 32) {
           const float* w = W + ((size_t)co * C + C0 + c1) * 27;
           float ws = 0.f;
           for (int td = 0; td < 3; ++td)
@@ -110,18 +110,13 @@ __global__ void upcat_fold_bias_kernel(const float* __restrict__ W, const float*
         }
       }
     }
-    red[threadIdx.x] = acc;
-    __syncthreads();
-    for (int o = 64; o; o >>= 1) {
-      if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
-      __syncthreads();
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      if (q < 27) bt[q] = acc;
+      else rk[q - 27] = acc;
     }
-    if (threadIdx.x == 0) {
-      if (q < 27) bt[q] = red[0];
-      else rk[q - 27] = red[0];
-    }
-    __syncthreads();
   }
+  __syncthreads();
   const float cb = conv_bias ? conv_bias[co] : 0.f;
   for (int cls = threadIdx.x; cls < 64; cls += blockDim.x) {
     const int c3[3] = {cls >> 4, (cls >> 2) & 3, cls & 3};
@@ -189,23 +184,31 @@ __global__ void upcat_assemble_wgrad_kernel(const float* __restrict__ Genc, int 
                                             int Cout, float* __restrict__ G) {
   const int C = C0 + C1;
   const int n = blockIdx.y;
-  const size_t total = (size_t)27 * C * Cout;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    int co = (int)(i % Cout);
-    size_t r = i / Cout;
-    int c = (int)(r % C);
-    int t = (int)(r / C);
-    float acc = 0.f;
-    if (c < C0) {
+  const size_t per_n = (size_t)27 * C * Cout;
+  const size_t n_enc = (size_t)27 * C0 * Cout, n_up = (size_t)27 * Cout * C1;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_enc + n_up; i += (size_t)gridDim.x * blockDim.x) {
+    if (i < n_enc) {  // (t, c, co), co fastest: coalesced reads of G_enc and writes of G
+      int co = (int)(i % Cout);
+      size_t r = i / Cout;
+      int c = (int)(r % C0);
+      int t = (int)(r / C0);
+      float acc = 0.f;
       for (int s = 0; s < S1; ++s) acc += Genc[((((size_t)n * S1 + s) * 27 + t) * C0 + c) * Cout + co];
-    } else {
+      G[(size_t)n * per_n + ((size_t)t * C + c) * Cout + co] = acc;
+    } else {  // (t, co, c1), c1 fastest: coalesced reads of the 8 * S2 Q blocks (the single write per element is strided)
+      size_t k = i - n_enc;
+      int c1 = (int)(k % C1);
+      size_t r = k / C1;
+      int co = (int)(r % Cout);
+      int t = (int)(r / Cout);
       const int td = t / 9 - 1, th = (t / 3) % 3 - 1, tw = t % 3 - 1;
+      float acc = 0.f;
       for (int rr = 0; rr < 8; ++rr) {
         const int e = ((((rr >> 2) & 1) - td + 1) << 4) | ((((rr >> 1) & 1) - th + 1) << 2) | ((rr & 1) - tw + 1);
-        for (int s = 0; s < S2; ++s) acc += Q[((((size_t)n * S2 + s) * 64 + e) * Cout + co) * C1 + (c - C0)];
+        for (int s = 0; s < S2; ++s) acc += Q[((((size_t)n * S2 + s) * 64 + e) * Cout + co) * C1 + c1];
       }
+      G[(size_t)n * per_n + ((size_t)t * C + C0 + c1) * Cout + co] = acc;
     }
-    G[(size_t)n * total + i] = acc;
   }
 }
 
@@ -244,7 +247,7 @@ int b200_gn_fold_upcat(const double* sums, const float* gamma, const float* beta
   }
   if (biascls && (abp || conv_bias)) {
     dim3 grid(Cout, n_w);
-    upcat_fold_bias_kernel<<<grid, 128, 0, ST(s)>>>(W, abp, conv_bias, abp ? sums : nullptr, count, C0, C1, Cout, biascls);
+    upcat_fold_bias_kernel<<<grid, 256, 0, ST(s)>>>(W, abp, conv_bias, abp ? sums : nullptr, count, C0, C1, Cout, biascls);
     B200_CHECK_LAUNCH("upcat_fold_bias");
   }
   return 0;
