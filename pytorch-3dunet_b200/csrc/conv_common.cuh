@@ -45,6 +45,7 @@ struct ConvParams {
   int a_stages;        // halo stages of KC channels each
   int b_total_bytes;   // resident weights [Cin/KCb][27][NT][KCb]
   int ctas_per_sample;
+  int tmem_bufs;       // accumulator buffers in TMEM (2 or 4)
   long long* dbg;      // optional per-CTA wait-cycle counters (b200_set_debug_buffer), NULL in production
   int dbg_flags;       // experiments only (env B200UNET_DBG_FLAGS): 1 = skip the global stores, 2 = skip the bias add
 };

@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1)
 conv3_halo_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, const ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[HALO_MAX_STAGES], a_empty[HALO_MAX_STAGES];
-  __shared__ __align__(8) uint64_t b_full, tmem_full[2], tmem_empty[2];
+  __shared__ __align__(8) uint64_t b_full, tmem_full[4], tmem_empty[4];
   __shared__ uint32_t tmem_slot;
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -79,7 +79,7 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       mbar_init(&a_empty[i], 1);
     }
     mbar_init(&b_full, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 4);  // one arrival per epilogue warp
     }
@@ -153,13 +153,17 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       const uint32_t b_tap = (uint32_t)(p.NT * rbB) >> 4;  // one tap of the resident weights, 16-byte units
       mbar_wait(&b_full, 0);
       long long w_afull = 0, w_tempty = 0, t_begin = clock64();
-      const int buf = issuer;
+      // each issuer owns `bpi` accumulator buffers (2 when 4 * C_out columns fit TMEM): while its epilogue group drains one,
+      // it accumulates the next tile in the other -- with a single buffer per issuer MMA and epilogue of a tile pair serialise
+      const int bpi = p.tmem_bufs / HALO_ISSUERS;
       const int G = p.a_stages / HALO_ISSUERS;
-      const uint32_t tacc = tmem_base + (uint32_t)(buf * p.NT);
       int lt = issuer;
       for (int t = cta + issuer * cps; t < tiles; t += HALO_ISSUERS * cps, lt += HALO_ISSUERS) {
+        const int kt = lt >> 1;  // this issuer's tile counter
+        const int buf = issuer * bpi + kt % bpi;
+        const uint32_t tacc = tmem_base + (uint32_t)(buf * p.NT);
         long long c0 = clock64();
-        mbar_wait(&tmem_empty[buf], ((uint32_t)(lt >> 1) & 1u) ^ 1u);
+        mbar_wait(&tmem_empty[buf], ((uint32_t)(kt / bpi) & 1u) ^ 1u);
         w_tempty += clock64() - c0;
         tc_fence_after();
         int cg = (lt >> 1) * nchunksA;  // this issuer's own stage group (see the producer)
@@ -196,7 +200,9 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     long long tim[3] = {0, 0, 0};
     long long* timp = p.dbg ? tim : nullptr;
     for (int t = cta + grp * cps; t < tiles; t += 2 * cps, lt += 2) {
-      const int buf = grp;
+      const int bpi = p.tmem_bufs / HALO_ISSUERS;
+      const int kt = lt >> 1;
+      const int buf = grp * bpi + kt % bpi;
       const int tw_i = t % p.tilesW;
       const int r = t / p.tilesW;
       const int th_i = r % p.tilesH, xd = r / p.tilesH;
@@ -211,7 +217,7 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
                             : p.biascls + ((size_t)(p.n_b > 1 ? n : 0) * 64 + cls) * p.Cout;
       }
       long long cw = clock64();
-      mbar_wait(&tmem_full[buf], (uint32_t)(lt >> 1) & 1u);
+      mbar_wait(&tmem_full[buf], (uint32_t)(kt / bpi) & 1u);
       w_tfull += clock64() - cw;
       __syncwarp();
       tc_fence_after();
@@ -294,8 +300,9 @@ bool conv_halo_plan(int N, int D, int H, int W, int Cin, int Cout, ConvParams* p
   p.a_stages = stages;
   p.a_bytes = a_bytes;
   p.b_total_bytes = b_total;
+  p.tmem_bufs = 4 * Cout <= 512 ? 4 : 2;  // accumulator buffers: two per MMA issuer when they fit
   int cols = 32;
-  while (cols < 2 * Cout) cols <<= 1;
+  while (cols < p.tmem_bufs * Cout) cols <<= 1;
   p.tmem_cols = cols;
   int tiles = p.tilesD * p.tilesH * p.tilesW;
   int sms = 148;
