@@ -121,7 +121,7 @@ def run_reference(args):
     warm = min(args.warmup, 1)
     sec, threads = cpu_reference_steps(args.size, 1, steps, warm)
     val = 1.0 / sec
-    line = {"metric": "UNet3D patches/sec (1x128^3) train step", "value": val, "unit": "patches/s", "n_gpus": args.gpus,
+    line = {"metric": "UNet3D patches/sec (1x128^3 bf16) train step", "value": val, "unit": "patches/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
             "config": {"workload": WORKLOAD, "sample": f"batch 1 of the {args.size}^3 patch per step (the reference's torch-CPU ops via the oracle port)"},

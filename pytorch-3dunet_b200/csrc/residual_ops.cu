@@ -115,29 +115,14 @@ __global__ void pointwise_wgrad_kernel(const InT* __restrict__ x, const bf16* __
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// transposed conv (k3, s2, p1) evaluated at the nearest-resized position + encoder features:
-//   out[o,co] = enc[o,co] + sum_{k valid at s(o)} sum_ci x[i(s,k),ci] * Wt[ci][co][k],   s = nearest_src(o; 2n-1 -> size of enc)
-// per axis: s even -> k=1, i=s/2 ; s odd -> k=0,i=(s+1)/2 and k=2,i=(s-1)/2.  wt: bf16 [27][Cout][Cin].
-// grid (P, N); thread = one output voxel x 8 output channels.
+// helpers of the transposed-conv join (the conv itself runs on the tcgen05 kernels over the zero-inserted input, see
+// Engine.deconv_up_add): nearest resize (2n-1 -> encoder size), its adjoint, zero-insert and its adjoint.
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int nearest_src_i(int dst, int in, int out) {
   float scale = (float)in / (float)out;
   int s = (int)floorf((float)dst * scale);
   return s < in - 1 ? s : in - 1;
 }
-__device__ __forceinline__ int axis_taps(int s, int k[2], int i[2]) {
-  if ((s & 1) == 0) {
-    k[0] = 1;
-    i[0] = s >> 1;
-    return 1;
-  }
-  k[0] = 0;
-  i[0] = (s + 1) >> 1;
-  k[1] = 2;
-  i[1] = (s - 1) >> 1;
-  return 2;
-}
-
 // dT[s,co] = sum over destination voxels o with s(o) == s of dout[o,co]   (adjoint of the nearest resize 2n-1 -> size);
 // grid (P, N) over the (2d-1)(2h-1)(2w-1) deconv grid
 __device__ __forceinline__ void dst_range(int s, int in, int out, int& lo, int& hi) {

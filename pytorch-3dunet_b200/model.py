@@ -158,11 +158,15 @@ def run_unet(eng, x, sd, spec):
     for i in range(nlev):
         if i > 0:
             x = eng.maxpool(x, want_stats=pre_gn)
-        x = run_basic(eng, x, sd, f"encoders.{i}.basic_module.", spec)
+        # with a virtual concat (nearest + concat into a DoubleConv that starts with a GroupNorm) the statistics of the joined tensor
+        # are those of its two parts: have their producers emit them instead of re-reading the tensors
+        join_stats = pre_gn and spec["upsample"] == "nearest" and spec["concat"] and spec["basic"] == "double"
+        x = run_basic(eng, x, sd, f"encoders.{i}.basic_module.", spec, out_stats=join_stats)
         feats.insert(0, x)
+    ndec = len(feats) - 1
     for i, enc in enumerate(feats[1:]):
         x = run_join(eng, enc, x, sd, f"decoders.{i}.", spec, pre_gn)
-        x = run_basic(eng, x, sd, f"decoders.{i}.basic_module.", spec)
+        x = run_basic(eng, x, sd, f"decoders.{i}.basic_module.", spec, out_stats=join_stats and i + 1 < ndec)
     final = E.FINAL_NONE
     if spec["is_segmentation"]:
         final = E.FINAL_SIGMOID if spec["final_sigmoid"] else E.FINAL_SOFTMAX
