@@ -316,7 +316,10 @@ static int conv_igemm_plain_launch(const void* x, const void* wf, int n_w, const
   p.b_bytes = (p.NT * p.KC * 2 + 1023) & ~1023;
   const int stage_bytes = p.a_bytes + p.b_bytes;
   const int numK = g.ntaps * p.kchunks;
-  int stages = (96 * 1024) / stage_bytes;
+  // one tile per CTA: MMA, epilogue and pipeline fill of a CTA are serial, so latency is hidden by CO-RESIDENT CTAs -- size the
+  // ring to ~96 KB (two CTAs per SM); 72 / 48 KB measured no different (env B200UNET_IGEMM_SMEM_KB overrides, for experiments)
+  static const int smem_kb = [] { const char* e = getenv("B200UNET_IGEMM_SMEM_KB"); return e ? atoi(e) : 96; }();
+  int stages = (smem_kb * 1024) / stage_bytes;
   if (stages > numK) stages = numK;  // short K loops: keep the CTA small so several fit on an SM
   if (stages < 3 && numK >= 3) stages = 3;
   if (stages < 1) stages = 1;
