@@ -76,3 +76,40 @@ def test_query_functions_without_gpu():
     assert L.query("b200_conv3_igemm_supported", 2, 128, 128, 128, 1, 16) == 0
     assert L.query("b200_conv3_igemm_partials_count", 2, 128, 128, 128, 96, 32) == 128 ** 3 // 128
     assert L.query("b200_maxpool_partials_count", 1, 64, 64, 64, 32) >= 1
+
+
+def test_planning_entry_points_over_the_model_shapes():
+    """Host-only planning code (tile / split / buffer sizing) for every layer shape of the BASELINE configurations, plus ragged
+    and tiny volumes: supported shapes must yield positive counts, the tensor-core path must be chosen where it exists."""
+    from pytorch3dunet_b200._lib import lib
+    from pytorch3dunet_b200 import engine as E
+    L = lib()
+    layers = []
+    for (N, S, f, levels) in [(2, 128, 32, 4), (4, 96, 32, 5), (1, 96, 64, 5), (1, 17, 16, 3)]:
+        for lv in range(levels):
+            s = max(S >> lv, 1)
+            c = f << lv
+            layers += [(N, s, s, s, c, c), (N, s, s, s, max(c // 2, 16), c), (N, s, s, s, c + 2 * c, c)]
+    layers += [(1, 5, 9, 7, 32, 16), (2, 3, 18, 10, 16, 32), (1, 6, 6, 6, 512, 512), (1, 4, 4, 8, 64, 320)]
+    for (N, D, H, W, Cin, Cout) in layers:
+        if Cin % 16 or Cout % 16:
+            continue
+        assert L.query("b200_conv3_igemm_supported", N, D, H, W, Cin, Cout) == 1, (N, D, H, W, Cin, Cout)
+        assert L.query("b200_conv3_igemm_partials_count", N, D, H, W, Cin, Cout) >= 1
+        assert L.query("b200_conv3_wgrad_igemm_supported", N, D, H, W, Cin, Cout) == 1
+        assert L.query("b200_conv3_wgrad_igemm_splits", N, D, H, W, Cin, Cout) >= 1
+        assert L.query("b200_border_tap_sums_workspace", N, D, H, W, Cout) > 0
+        vox = D * H * W
+        assert L.query("b200_pointwise_tc_supported", N, vox, Cin, Cout) == 1
+        assert L.query("b200_pointwise_tc_partials_count", N, vox) == (vox + 127) // 128
+        assert L.query("b200_pointwise_tc_wgrad_splits", N, vox, Cin, Cout) >= 1
+        if D % 2 == 0 and H % 2 == 0 and W % 2 == 0:  # virtual concat: low-res (D/2,H/2,W/2)
+            assert L.query("b200_conv3_up_supported", N, D // 2, H // 2, W // 2, Cin, Cout) == 1
+            assert L.query("b200_conv3_up_wgrad_splits", N, D // 2, H // 2, W // 2, Cout, Cin) >= 1
+    # shapes the tensor-core kernels do not take: "auto" resolves to the direct CUDA-core kernels, "tcgen05" is refused
+    # (b200_conv3_resolve_impl also requires an sm_100 device, so without a GPU it never answers tcgen05)
+    assert L.query("b200_conv3_igemm_supported", 1, 8, 8, 8, 24, 8) == 0
+    assert L.query("b200_conv3_resolve_impl", E.IMPL_AUTO, 1, 8, 8, 8, 24, 8, 0) == E.IMPL_DIRECT
+    assert L.query("b200_conv3_resolve_impl", E.IMPL_TCGEN05, 1, 8, 8, 8, 24, 8, 0) < 0
+    assert L.query("b200_pointwise_tc_supported", 1, 512, 24, 8) == 0
+    assert L.query("b200_conv3_up_supported", 1, 4, 4, 4, 24, 16) == 0
