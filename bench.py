@@ -35,6 +35,8 @@ def parse():
     ap.add_argument("--size", type=int, default=SIZE)
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fused-loss", type=int, default=int(os.environ.get("B200UNET_FUSED_LOSS", "1")),
+                    help="1: BCEDiceLoss through the engine's two-pass kernels (csrc/loss_ops.cu) instead of eager torch ops")
     return ap.parse_args()
 
 
@@ -169,7 +171,7 @@ def main():
         for p in params:
             p.grad = None
         out, logits = model(x, return_logits=True)
-        loss = P.losses.bce_dice_loss(logits, t)
+        loss = P.losses.bce_dice_loss(logits, t, fused=bool(args.fused_loss))
         loss.backward()
         reducer()  # one gradient allreduce per step over NVLink (replaces DataParallel's reduce-to-GPU-0, trainer.py:203-204)
         return loss
@@ -262,11 +264,12 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD if (S == SIZE and B == BATCH) else f"UNet3D f32 d4 batch {B}x1x{S}^3", "per_gpu_batch": B,
                        "parallelism": f"dp{world}", "l2": "per-step working set (~1 GB of bf16 activations per patch) >> 126 MB L2; no explicit flush",
-                       "setup_steps_before_warmup": ALLOC_SETTLE_STEPS},
+                       "setup_steps_before_warmup": ALLOC_SETTLE_STEPS,
+                       "loss": "fused b200 kernels" if args.fused_loss else "torch ops"},
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": "patches/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": x_host.numel() * 4 + t_host.numel() * 4, "d2h_bytes_per_step": 4},
-            "gpu_launches": (fwd_l + bwd_l) * args.steps, "clocks": clk.summary(),
+            "gpu_launches": (fwd_l + bwd_l + (3 if args.fused_loss else 0)) * args.steps, "clocks": clk.summary(),
             "tflops_effective": value * GFLOP_PER_PATCH_TRAIN / 1e3}
     print(json.dumps(line))
     if world > 1:

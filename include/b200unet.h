@@ -193,6 +193,15 @@ int b200_conv3_up_wgrad(const void* dz, const void* b, int N, int d, int h, int 
 int b200_upcat_assemble_wgrad(const float* G_enc, int S1, const float* Q, int S2, int N, int C0, int C1, int Cout, float* G,
                               b200_stream_t s);
 
+/* ---- fused BCEDiceLoss on fp32 logits [N][C][V] (reference losses.py:187-201).
+ * fwd: partials float [N*C][P][4] (P = b200_bce_dice_partials_count), loss float[1], coef float[1 + 2*C] = (1/count, (k1_c, k2_c)...);
+ * bwd: dlogits = d loss / d logits (for an upstream gradient of 1) from the saved coefficients. */
+int b200_bce_dice_partials_count(int N, int C, long long V);
+int b200_bce_dice_fwd(const float* logits, const float* target, int N, int C, long long V, float alpha, float eps, float* partials,
+                      float* loss, float* coef, b200_stream_t s);
+int b200_bce_dice_bwd(const float* logits, const float* target, const float* coef, int N, int C, long long V, float* dlogits,
+                      b200_stream_t s);
+
 /* 1x1x1 conv on the tensor cores (C_in, C_out multiples of 16; bf16 input): the tcgen05 conv / wgrad kernels over a flat voxel list.
  * wq: bf16 [Cout][Cin] from b200_pointwise_prep_weights (transposed=1 gives the dgrad operand [Cin][Cout]); bias fp32 [Cout] or NULL;
  * partials [N][P][Cout][2] (P = b200_pointwise_tc_partials_count) or NULL; G [N][S][Cin][Cout] fp32 (S = ..._wgrad_splits). */
