@@ -7,7 +7,10 @@ stream; no torch operator runs on the hot path.  Activations live as bf16 NDHWC 
 Reference semantics implemented (file:line relative to the reference checkout):
   SingleConv / create_conv      pytorch3dunet/unet3d/buildingblocks.py:10-135
   Encoder (MaxPool3d(2))        buildingblocks.py:353-384
-  Decoder (nearest + concat)    buildingblocks.py:436-493, 598-614
+  Decoder (nearest + concat)    buildingblocks.py:436-493, 598-614   (virtual concat: Engine._conv3_vcat, csrc/upcat_conv.cu)
+  Decoder (deconv + sum)        buildingblocks.py:617-664, :493        (Engine.deconv_up_add)
+  ResNetBlock                   buildingblocks.py:230-288              (model.run_res_block; 1x1x1 conv = Engine.pointwise)
+  ResNetBlockSE / scSE          buildingblocks.py:291-307, se.py:12-114 (Engine.scse)
   final conv + activation       pytorch3dunet/unet3d/model.py:89-98, 141-147
 """
 from __future__ import annotations
