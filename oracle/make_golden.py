@@ -92,7 +92,20 @@ def run_block_case(name, module, x_shape, seed, extra_inputs=None):
     print(f"{name}: y {tuple(y.shape)}")
 
 
+ONLY = None  # set by `--only name1,name2`: regenerate just these fixtures
+
+
+def _wanted(name):
+    return ONLY is None or name in ONLY
+
+
 def main():
+    global ONLY, run_model_case, run_block_case
+    if "--only" in sys.argv:
+        ONLY = set(sys.argv[sys.argv.index("--only") + 1].split(","))
+        _rm, _rb = run_model_case, run_block_case
+        run_model_case = lambda name, *a, **k: _rm(name, *a, **k) if _wanted(name) else None  # noqa: E731
+        run_block_case = lambda name, *a, **k: _rb(name, *a, **k) if _wanted(name) else None  # noqa: E731
     os.makedirs(OUT, exist_ok=True)
     model_mod, bb, losses_mod = import_reference()
     torch.set_num_threads(1)  # reproducible reductions
@@ -113,6 +126,20 @@ def main():
                    (1, 1, 16, 16, 16), "BCEDiceLoss", 4, model_mod, losses_mod)
     run_model_case("resunetse3d_f16_l3_s16", dict(name="ResidualUNetSE3D", in_channels=1, out_channels=1, f_maps=16, num_levels=3),
                    (1, 1, 16, 16, 16), "BCEDiceLoss", 5, model_mod, losses_mod)
+
+    # more layer orders / activations (oracle pinning only; CPU tests): conv bias + LeakyReLU(0.01), conv-ReLU-GroupNorm,
+    # ResNetBlock's own LeakyReLU(0.1) and ELU (buildingblocks.py:271-275), softmax head with several classes
+    run_model_case("unet3d_f16_l2_cl", dict(name="UNet3D", in_channels=1, out_channels=1, f_maps=16, num_levels=2, layer_order="cl"),
+                   (1, 1, 8, 8, 8), "BCEDiceLoss", 6, model_mod, losses_mod)
+    run_model_case("unet3d_f16_l2_crg", dict(name="UNet3D", in_channels=1, out_channels=2, f_maps=16, num_levels=2, layer_order="crg",
+                                             final_sigmoid=False),
+                   (2, 1, 8, 8, 8), "BCEDiceLoss", 7, model_mod, losses_mod)
+    run_model_case("resunet3d_f16_l2_gcl", dict(name="ResidualUNet3D", in_channels=1, out_channels=1, f_maps=16, num_levels=2,
+                                                layer_order="gcl"),
+                   (1, 1, 8, 8, 8), "BCEDiceLoss", 8, model_mod, losses_mod)
+    run_model_case("resunetse3d_f16_l2_gce", dict(name="ResidualUNetSE3D", in_channels=2, out_channels=1, f_maps=16, num_levels=2,
+                                                  layer_order="gce"),
+                   (1, 2, 8, 8, 8), "DiceLoss", 9, model_mod, losses_mod)
 
     # ---- building blocks -----------------------------------------------------------------
     torch.manual_seed(10)

@@ -24,6 +24,10 @@ def test_library_exports_every_header_symbol():
     ("unet3d_f16_l2_cgr", dict(name="UNet3D", in_channels=1, out_channels=1, f_maps=16, num_levels=2, layer_order="cgr")),
     ("resunet3d_f16_l3_s16", dict(name="ResidualUNet3D", in_channels=1, out_channels=1, f_maps=16, num_levels=3)),
     ("resunetse3d_f16_l3_s16", dict(name="ResidualUNetSE3D", in_channels=1, out_channels=1, f_maps=16, num_levels=3)),
+    ("unet3d_f16_l2_cl", dict(name="UNet3D", in_channels=1, out_channels=1, f_maps=16, num_levels=2, layer_order="cl")),
+    ("unet3d_f16_l2_crg", dict(name="UNet3D", in_channels=1, out_channels=2, f_maps=16, num_levels=2, layer_order="crg", final_sigmoid=False)),
+    ("resunet3d_f16_l2_gcl", dict(name="ResidualUNet3D", in_channels=1, out_channels=1, f_maps=16, num_levels=2, layer_order="gcl")),
+    ("resunetse3d_f16_l2_gce", dict(name="ResidualUNetSE3D", in_channels=2, out_channels=1, f_maps=16, num_levels=2, layer_order="gce")),
 ])
 def test_state_dict_contract_matches_reference(golden, cfg):
     import pytorch3dunet_b200 as P

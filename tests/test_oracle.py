@@ -15,6 +15,14 @@ MODEL_CASES = {
     "unet3d_f16_l2_cgr": (dict(name="UNet3D", in_channels=1, out_channels=1, f_maps=16, num_levels=2, layer_order="cgr"), "bce_dice_loss"),
     "resunet3d_f16_l3_s16": (dict(name="ResidualUNet3D", in_channels=1, out_channels=1, f_maps=16, num_levels=3), "bce_dice_loss"),
     "resunetse3d_f16_l3_s16": (dict(name="ResidualUNetSE3D", in_channels=1, out_channels=1, f_maps=16, num_levels=3), "bce_dice_loss"),
+    # further layer orders / activations / heads (pin the oracle; CPU only)
+    "unet3d_f16_l2_cl": (dict(name="UNet3D", in_channels=1, out_channels=1, f_maps=16, num_levels=2, layer_order="cl"), "bce_dice_loss"),
+    "unet3d_f16_l2_crg": (dict(name="UNet3D", in_channels=1, out_channels=2, f_maps=16, num_levels=2, layer_order="crg",
+                               final_sigmoid=False), "bce_dice_loss"),
+    "resunet3d_f16_l2_gcl": (dict(name="ResidualUNet3D", in_channels=1, out_channels=1, f_maps=16, num_levels=2, layer_order="gcl"),
+                             "bce_dice_loss"),
+    "resunetse3d_f16_l2_gce": (dict(name="ResidualUNetSE3D", in_channels=2, out_channels=1, f_maps=16, num_levels=2, layer_order="gce"),
+                               "dice_loss"),
 }
 
 
