@@ -98,8 +98,8 @@ def single_conv(x, sd, prefix, order, num_groups, padding=1, masks=None):
             x = F.group_norm(x, _groups(w.numel(), num_groups), w, sd[prefix + "groupnorm.bias"], GN_EPS)
         elif ch == "r":
             x = x * masks[prefix].to(x.dtype) if (masks is not None and prefix in masks) else F.relu(x)
-        elif ch == "l":
-            x = F.leaky_relu(x, 0.01)  # nn.LeakyReLU() default slope, buildingblocks.py:49
+        elif ch == "l":  # nn.LeakyReLU() default slope, buildingblocks.py:49 (the kink is pinned like ReLU's when masks are given)
+            x = torch.where(masks[prefix], x, 0.01 * x) if (masks is not None and prefix in masks) else F.leaky_relu(x, 0.01)
         elif ch == "e":
             x = F.elu(x)
         elif ch == "b":
@@ -144,8 +144,9 @@ def res_block(x, sd, prefix, order, num_groups, se=False, masks=None):
     n_order = order.replace("r", "").replace("e", "").replace("l", "")
     out = single_conv(out, sd, prefix + "conv3.", n_order, num_groups, masks=masks)
     out = out + residual
-    if "l" in order:
-        out = F.leaky_relu(out, 0.1)  # buildingblocks.py:271 : slope 0.1 here, not 0.01
+    if "l" in order:  # buildingblocks.py:271 : slope 0.1 here, not 0.01
+        key3 = prefix + "conv3."
+        out = torch.where(masks[key3], out, 0.1 * out) if (masks is not None and key3 in masks) else F.leaky_relu(out, 0.1)
     elif "e" in order:
         out = F.elu(out)
     elif masks is not None and (prefix + "conv3.") in masks:

@@ -378,7 +378,9 @@ class Engine:
             partials = self.empty((n, P, c, 2), torch.float32)
         self.call("b200_gn_apply_act", _p(z.t), _p(ab), n, c, vox, act[0], float(act[1]), _p(y), _p(partials))
         out = Act(y, act[0], act[1], partials, P)
-        if DEBUG is not None:
+        if DEBUG is not None and act[0] != ACT_NONE:
+            # (tests) the tensor whose sign pattern is the layer's activation pattern: for conv -> act -> GroupNorm orders that is the
+            # conv's own (already stashed) output, not this one
             DEBUG.setdefault("fwd", {})[gname[: -len("groupnorm.weight")]] = y
         if self.record:
             def backward():

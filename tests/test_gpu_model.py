@@ -127,6 +127,18 @@ MODEL_CASES = {
 }
 
 
+# further layer orders / activations (LeakyReLU 0.01 with conv bias, conv-ReLU-GroupNorm + softmax head, ResNetBlock's LeakyReLU 0.1, ELU + scSE)
+EXTRA_MODEL_CASES = {
+    "unet3d_f16_l2_cl": (dict(name="UNet3D", in_channels=1, out_channels=1, f_maps=16, num_levels=2, layer_order="cl"), "bce_dice_loss"),
+    "unet3d_f16_l2_crg": (dict(name="UNet3D", in_channels=1, out_channels=2, f_maps=16, num_levels=2, layer_order="crg",
+                               final_sigmoid=False), "bce_dice_loss"),
+    "resunet3d_f16_l2_gcl": (dict(name="ResidualUNet3D", in_channels=1, out_channels=1, f_maps=16, num_levels=2, layer_order="gcl"),
+                             "bce_dice_loss"),
+    "resunetse3d_f16_l2_gce": (dict(name="ResidualUNetSE3D", in_channels=2, out_channels=1, f_maps=16, num_levels=2, layer_order="gce"),
+                               "dice_loss"),
+}
+
+
 def _model_vs_oracle(cfg, loss_name, sd, x, target, monkeypatch, ref=None):
     """engine fwd+bwd vs (a) reference values `ref` (golden) for the forward, (b) the oracle at the engine's ReLU pattern"""
     import pytorch3dunet_b200 as P
@@ -176,6 +188,13 @@ def _model_vs_oracle(cfg, loss_name, sd, x, target, monkeypatch, ref=None):
 def test_model_matches_reference_golden(name, impl, monkeypatch):
     monkeypatch.setenv("B200UNET_CONV_IMPL", impl)
     cfg, loss_name = MODEL_CASES[name]
+    rec, sd, grads = load_golden(name)
+    _model_vs_oracle(cfg, loss_name, sd, rec["x"], rec["target"], monkeypatch, ref=rec)
+
+
+@pytest.mark.parametrize("name", sorted(EXTRA_MODEL_CASES))
+def test_model_matches_reference_golden_more_orders(name, monkeypatch):
+    cfg, loss_name = EXTRA_MODEL_CASES[name]
     rec, sd, grads = load_golden(name)
     _model_vs_oracle(cfg, loss_name, sd, rec["x"], rec["target"], monkeypatch, ref=rec)
 
