@@ -11,6 +11,7 @@ from .model import (AbstractUNet, Decoder, DoubleConv, Encoder, ResidualUNet3D, 
                     get_model, is_model_2d, last_launch_counts, number_of_features_per_level)
 from .install import install  # noqa: F401
 from . import losses  # noqa: F401
+from . import patches  # noqa: F401
 
 __all__ = ["get_model", "UNet3D", "ResidualUNet3D", "ResidualUNetSE3D", "SingleConv", "DoubleConv", "Encoder", "Decoder",
-           "install", "is_model_2d", "losses", "last_launch_counts"]
+           "install", "is_model_2d", "losses", "patches", "last_launch_counts"]
