@@ -72,6 +72,10 @@ int b200_gn_fold(const double* sums, const float* gamma, const float* beta, int 
 /* GroupNorm applied as a standalone op AFTER a conv (orders like 'cgr'): y = act(a*x+b), emits partials of y */
 int b200_gn_apply_act(const void* x, const float* ab, int N, int C, long long voxels, int act, float slope,
                       void* y, float* partials, b200_stream_t s);
+/* same with a residual input: y = act(a*x + b + residual)  (ResNetBlock `out += residual` after a conv3 whose order ends in 'g',
+ * buildingblocks.py:243-288 with the block's default order 'cge'); residual may be NULL */
+int b200_gn_apply_act_res(const void* x, const float* ab, const void* residual, int N, int C, long long voxels, int act, float slope,
+                          void* y, float* partials, b200_stream_t s);
 /* a,b only (no weight folding): ab[N][C][2], mean_rstd[N][G][2] */
 int b200_gn_coeffs(const double* sums, const float* gamma, const float* beta, int G, double count,
                    int N, int C, float* mean_rstd, float* ab, b200_stream_t s);
@@ -134,6 +138,11 @@ int b200_maxpool_partials_count(int N, int D, int H, int W, int C);
 int b200_maxpool_bwd(const void* dpooled, const void* x_full, int N, int D, int H, int W, int C,
                      int act, float slope, const void* gadd, void* dz_full, b200_stream_t s);
 
+/* AvgPool3d(2) (Encoder pool_type='avg', buildingblocks.py:358-363 -> avg_pool3d), floor mode; P = b200_maxpool_partials_count */
+int b200_avgpool_fwd(const void* x, int N, int D, int H, int W, int C, void* y, float* partials, b200_stream_t s);
+int b200_avgpool_bwd(const void* dpooled, const void* x_full, int N, int D, int H, int W, int C,
+                     int act, float slope, const void* gadd, void* dz_full, b200_stream_t s);
+
 /* ---- nearest upsample to the encoder's size + channel concat (buildingblocks.py:614, :491) ------ */
 int b200_upcat_fwd(const void* enc, int C0, const void* x, int C1, int N, int D, int H, int W, int d, int h, int w,
                    void* cat, float* partials, b200_stream_t s);
@@ -141,6 +150,13 @@ int b200_upcat_partials_count(int N, int D, int H, int W, int C);
 /* dx_small = (sum over destination voxels that map to each source voxel of dcat[..., C0:]) * act'(x_small) */
 int b200_upcat_bwd(const void* dcat, int C0, int C1, const void* x_small, int N, int D, int H, int W, int d, int h, int w,
                    int act, float slope, void* dx_small, b200_stream_t s);
+
+/* same join with InterpolateUpsampling(mode='trilinear') (buildingblocks.py:598-614 -> upsample_trilinear3d, align_corners=False):
+ * cat[..., C0:] = trilinear(x -> (D,H,W)); bwd is the adjoint in gather form. P = b200_upcat_partials_count */
+int b200_upcat_trilinear_fwd(const void* enc, int C0, const void* x, int C1, int N, int D, int H, int W, int d, int h, int w,
+                             void* cat, float* partials, b200_stream_t s);
+int b200_upcat_trilinear_bwd(const void* dcat, int C0, int C1, const void* x_small, int N, int D, int H, int W, int d, int h, int w,
+                             int act, float slope, void* dx_small, b200_stream_t s);
 
 /* ---- final 1x1x1 conv + Sigmoid/Softmax (model.py:89,141-147) ------------------------------------ */
 int b200_final_conv_fwd(const void* x, int N, long long voxels, int C, const float* W, const float* bias, int Cout,
@@ -245,18 +261,26 @@ int b200_scse_bwd1(const void* dout, const void* y, const float* g, const float*
 int b200_se_gates_bwd(const double* sums2, const float* smean, const float* h, const float* g, const float* W1, const float* W2, int N, int C,
                       double count, float* coef, float* dW1, float* db1, float* dW2, float* db2, float* dws, float* scratch, b200_stream_t s);
 
-/* hardware probe (test tooling): tcgen05.mma on a row-shifted / odd-strided view of a SWIZZLE_128B tile.
- * A: [rows][64] bf16, B: [16][64] bf16, D: [128][16] f32 with D[r][n] = sum_k A[shift + (r/8)*group_rows + r%8][k] * B[n][k] */
-int b200_probe_umma_rowshift(const void* A, int rows, const void* B, int shift, int group_rows, float* D, b200_stream_t s);
-/* hardware probe: cycles to issue / complete iters*4 tcgen05.mma (M=128,N,K=16) spread over n_acc accumulators;
- * out[0] = issue cycles, out[1] = cycles until all completed */
-/* hardware probe: cycles for ld_iters tcgen05.ld (4 warps, 32 columns each) while mma_iters*4 MMAs (N columns) run; out[0] ld cycles, out[1] mma cycles */
-int b200_probe_tmem_ld_contention(int N, int mma_iters, int ld_iters, long long* out, b200_stream_t s);
-/* out[cta*4 + w] = cycles until issuing warp w's iters*4 MMAs (own accumulator) completed; grid CTAs, 256 TMEM columns each */
-int b200_probe_umma_multi_issue(int N, int n_issuers, int iters, int grid, long long* out, b200_stream_t s);
-/* test tooling: per-CTA wait-cycle counters of the halo kernel (8 x int64 per CTA); NULL disables */
+/* ---- sliding-window inference either side of the model ------------------------------------
+ * gather: out[C][pz][py][px] = reflect-padded vol[C][Z][Y][X] at (z0+z, y0+y, x0+x); (z0,y0,x0) = patch start minus halo, may be
+ * negative / reach past the end by less than one volume size (datasets/utils.py:518-546 mirror_pad + hdf5.py:16-20). */
+int b200_patch_gather_f32(const float* vol, int C, int Z, int Y, int X, int z0, int y0, int x0, int pz, int py, int px, float* out,
+                          b200_stream_t s);
+/* scatter: crop the halo (hz,hy,hx) off pred[C][pz][py][px] and write it at (z0,y0,x0) of out[C][Z][Y][X], but only the voxels
+ * whose LAST covering patch is this one: owner_a[c] (device int[size_a]) == (iz,iy,ix) -- the reference's write order
+ * (predictor.py:148-193, later patches overwrite earlier ones) evaluated analytically, so every voxel is written exactly once. */
+int b200_patch_scatter_f32(const float* pred, int C, int pz, int py, int px, int hz, int hy, int hx, float* out, int Z, int Y, int X,
+                           int z0, int y0, int x0, int iz, int iy, int ix, const int* owner_z, const int* owner_y, const int* owner_x,
+                           b200_stream_t s);
+
+/* ---- fused Adam over a flat fp32 buffer (create_optimizer utils.py:246-316 -> torch.optim.Adam, L2 weight decay in the gradient;
+ * SURVEY section 8(f) row f-4).  bc1 = 1 - beta1^t, bc2 = 1 - beta2^t; g is read as g*grad_scale (1/world after a sum-allreduce). */
+int b200_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps, float wd,
+                   float bc1, float bc2, float grad_scale, b200_stream_t s);
+
+/* debug builds only (make DEBUG=1 -> -DB200_DEBUG): per-CTA wait-cycle counters of the halo kernel (16 x int64 per CTA); NULL
+ * disables.  In a production build the counters are compiled out and this call is a no-op returning 1. */
 int b200_set_debug_buffer(void* buf);
-int b200_probe_umma_issue(int N, int n_acc, int iters, int rb, int group_rows, int shift, long long* out, b200_stream_t s);
 
 #ifdef __cplusplus
 }

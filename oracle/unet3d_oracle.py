@@ -1,7 +1,7 @@
 """CPU oracle for the 3D U-Net hot path  --  TEST INFRASTRUCTURE, NOT PRODUCT CODE.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
-import this module.  The product path (pytorch-3dunet_b200/) never does; it fails loudly when
+import this module.  The product path (pytorch3dunet_b200/) never does; it fails loudly when
 its CUDA library is missing.
 
 This is a *functional restatement* (plain torch CPU ops over a flat state_dict) of the

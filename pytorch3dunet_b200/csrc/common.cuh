@@ -92,4 +92,16 @@ __host__ __device__ __forceinline__ bool tap_valid(int c, int t) {
 
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// number of SMs of the CURRENT device (grids of the persistent kernels are sized from it); cached per device ordinal
+int sm_count();
+
+// cycle counter for the optional per-CTA wait statistics: compiled out (constant 0) unless the library is built with -DB200_DEBUG
+__device__ __forceinline__ long long dbg_clock() {
+#ifdef B200_DEBUG
+  return clock64();
+#else
+  return 0;
+#endif
+}
+
 }  // namespace b200

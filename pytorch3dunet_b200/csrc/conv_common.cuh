@@ -7,6 +7,12 @@
 
 namespace b200 {
 
+#ifdef B200_DEBUG
+#define DBG_FLAG(p, bit) ((p).dbg_flags & (bit))
+#else
+#define DBG_FLAG(p, bit) 0
+#endif
+
 constexpr int CONV_THREADS = 192;
 constexpr int CONV_MAX_STAGES = 8;
 constexpr int HALO_MAX_STAGES = 6;
@@ -68,17 +74,17 @@ __device__ __forceinline__ void conv_epilogue_slab(const ConvParams& p, uint32_t
                                                    size_t vox_off /* (n*vox+v) */, const float* bias_row /* or null */, int lane,
                                                    float* scratch /* [NT][2] for this warp */, long long* tim = nullptr) {
   uint32_t raw[CW];
-  long long t0 = tim ? clock64() : 0;
+  long long t0 = tim ? dbg_clock() : 0;
   if constexpr (CW == 32) tmem_ld_32x32b_x32(taddr + c0, raw);
   else tmem_ld_32x32b_x16(taddr + c0, raw);
   tmem_ld_wait();
-  long long t1 = tim ? clock64() : 0;
+  long long t1 = tim ? dbg_clock() : 0;
   float v[CW];
 #pragma unroll
   for (int i = 0; i < CW; ++i) v[i] = __uint_as_float(raw[i]);
   const size_t goff = vox_off * p.Cout + n0 + c0;
   if (valid) {
-    if (bias_row && !(p.dbg_flags & 2)) {
+    if (bias_row && !DBG_FLAG(p, 2)) {
       const float4* bp = reinterpret_cast<const float4*>(bias_row + n0 + c0);
 #pragma unroll
       for (int i = 0; i < CW / 4; ++i) {
@@ -114,7 +120,7 @@ __device__ __forceinline__ void conv_epilogue_slab(const ConvParams& p, uint32_t
 #pragma unroll
     for (int i = 0; i < CW; ++i) v[i] = bf16_round(v[i]);
     bf16x8* op = reinterpret_cast<bf16x8*>(p.y + goff);
-    if (!(p.dbg_flags & 1)) {
+    if (!DBG_FLAG(p, 1)) {
 #pragma unroll
       for (int i = 0; i < CW / 8; ++i) op[i] = pack8(&v[8 * i]);
     }
@@ -122,7 +128,7 @@ __device__ __forceinline__ void conv_epilogue_slab(const ConvParams& p, uint32_t
 #pragma unroll
     for (int i = 0; i < CW; ++i) v[i] = 0.f;
   }
-  long long t2 = tim ? clock64() : 0;
+  long long t2 = tim ? dbg_clock() : 0;
   if (p.pmode) {
     float w[CW];
     if (p.pmode == 1) {
@@ -151,7 +157,7 @@ __device__ __forceinline__ void conv_epilogue_slab(const ConvParams& p, uint32_t
     }
   }
   if (tim) {
-    long long t3 = clock64();
+    long long t3 = dbg_clock();
     tim[0] += t1 - t0;
     tim[1] += t2 - t1;
     tim[2] += t3 - t2;

@@ -377,7 +377,8 @@ int b200_conv3_direct_wgrad(const void* x, int x_is_f32, const void* dz, int N, 
   int total = 27 * Cin * Cout;
   if (x_is_f32 && Cin <= 4 && (Cout == 8 || Cout == 16 || Cout == 32)) {
     int ntiles = ceil_div(D, SW_TD) * ceil_div(H, SW_TH) * ceil_div(W, SW_TW);
-    int tpb = ceil_div(ntiles, 4 * 148 / (N > 0 ? N : 1) > 0 ? 4 * 148 / N : 1);  // ~4 blocks per SM in total
+    const int sms4 = 4 * sm_count();
+    int tpb = ceil_div(ntiles, sms4 / (N > 0 ? N : 1) > 0 ? sms4 / N : 1);  // ~4 blocks per SM in total
     if (tpb < 1) tpb = 1;
     dim3 g2(ceil_div(ntiles, tpb), N);
     size_t red_floats = (size_t)(256 / (9 * (Cout / 8))) * 9 * (Cout / 8) * 24;

@@ -114,7 +114,7 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       // consumer in strictly consecutive phases (a parity wait can only target the phase in progress, never a later one)
       const int G = p.a_stages / HALO_ISSUERS;
       int lt = 0;
-      long long w_prod = 0, t_begin = clock64();
+      long long w_prod = 0, t_begin = dbg_clock();
       for (int t = cta; t < tiles; t += cps, ++lt) {
         const int tw_i = t % p.tilesW;
         const int r = t / p.tilesW;
@@ -124,18 +124,20 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
         int cg = (lt >> 1) * nchunksA;
         for (int j = 0; j < nchunksA; ++j, ++cg) {
           const int stage = grp * G + cg % G;
-          long long c0 = clock64();
+          long long c0 = dbg_clock();
           mbar_wait(&a_empty[stage], ((uint32_t)(cg / G) & 1u) ^ 1u);
-          w_prod += clock64() - c0;
+          w_prod += dbg_clock() - c0;
           mbar_arrive_expect_tx(&a_full[stage], (uint32_t)(HALO_ROWS * rbA));
           tma_load_5d(smemA + (size_t)stage * p.a_bytes, &tmapA, &a_full[stage], j * KC, w0 - 1, h0 - 1, d0 - 1, n);
         }
       }
+#ifdef B200_DEBUG
       if (p.dbg) {
         long long* o = p.dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16;
         o[0] = w_prod;
-        o[1] = clock64() - t_begin;
+        o[1] = dbg_clock() - t_begin;
       }
+#endif
     }
   } else if (warp >= HALO_WARP_MMA) {
     // ================= MMA issuers (whole warp converged, one elected lane issues); issuer i owns tiles lt = i, i+2, ... =====
@@ -152,7 +154,7 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       const uint32_t sB0 = smem_u32(smemB);
       const uint32_t b_tap = (uint32_t)(p.NT * rbB) >> 4;  // one tap of the resident weights, 16-byte units
       mbar_wait(&b_full, 0);
-      long long w_afull = 0, w_tempty = 0, t_begin = clock64();
+      long long w_afull = 0, w_tempty = 0, t_begin = dbg_clock();
       // each issuer owns `bpi` accumulator buffers (2 when 4 * C_out columns fit TMEM): while its epilogue group drains one,
       // it accumulates the next tile in the other -- with a single buffer per issuer MMA and epilogue of a tile pair serialise
       const int bpi = p.tmem_bufs / HALO_ISSUERS;
@@ -162,16 +164,16 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
         const int kt = lt >> 1;  // this issuer's tile counter
         const int buf = issuer * bpi + kt % bpi;
         const uint32_t tacc = tmem_base + (uint32_t)(buf * p.NT);
-        long long c0 = clock64();
+        long long c0 = dbg_clock();
         mbar_wait(&tmem_empty[buf], ((uint32_t)(kt / bpi) & 1u) ^ 1u);
-        w_tempty += clock64() - c0;
+        w_tempty += dbg_clock() - c0;
         tc_fence_after();
         int cg = (lt >> 1) * nchunksA;  // this issuer's own stage group (see the producer)
         for (int j = 0; j < nchunksA; ++j, ++cg) {
           const int stage = issuer * G + cg % G;
-          long long c1 = clock64();
+          long long c1 = dbg_clock();
           mbar_wait(&a_full[stage], (uint32_t)(cg / G) & 1u);
-          w_afull += clock64() - c1;
+          w_afull += dbg_clock() - c1;
           tc_fence_after();
           const int ch0 = j * KC;
           const uint32_t a_lo0 = ((smem_u32(smemA + (size_t)stage * p.a_bytes) >> 4) & 0x3FFFu) | lo_lbo;
@@ -181,12 +183,14 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
         }
         umma_commit_elect(&tmem_full[buf]);
       }
+#ifdef B200_DEBUG
       if (p.dbg && lane == 0 && issuer == 0) {
         long long* o = p.dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16;
         o[2] = w_afull;
         o[3] = w_tempty;
-        o[4] = clock64() - t_begin;
+        o[4] = dbg_clock() - t_begin;
       }
+#endif
     }
   } else {
     // ================= epilogue: warps 0..3 take even tiles (TMEM buffer 0), warps 4..7 odd tiles (buffer 1) =========
@@ -196,9 +200,13 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     const int bx = row % HALO_BW, by = row / HALO_BW;
     const int n0 = 0;
     int lt = grp;
-    long long w_tfull = 0, t_begin = clock64();
+    long long w_tfull = 0, t_begin = dbg_clock();
     long long tim[3] = {0, 0, 0};
+#ifdef B200_DEBUG
     long long* timp = p.dbg ? tim : nullptr;
+#else
+    long long* timp = nullptr;
+#endif
     for (int t = cta + grp * cps; t < tiles; t += 2 * cps, lt += 2) {
       const int bpi = p.tmem_bufs / HALO_ISSUERS;
       const int kt = lt >> 1;
@@ -216,9 +224,9 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
         bias_row = interior ? bias_interior + (((cls >> 3) & 4) | ((cls >> 2) & 2) | ((cls >> 1) & 1)) * p.NT
                             : p.biascls + ((size_t)(p.n_b > 1 ? n : 0) * 64 + cls) * p.Cout;
       }
-      long long cw = clock64();
+      long long cw = dbg_clock();
       mbar_wait(&tmem_full[buf], (uint32_t)(kt / bpi) & 1u);
-      w_tfull += clock64() - cw;
+      w_tfull += dbg_clock() - cw;
       __syncwarp();
       tc_fence_after();
       float* scratch_tile = scratch_base + (size_t)(grp * 2 + ((lt >> 1) & 1)) * 4 * p.NT * 2;  // alternate: see bar.sync below
@@ -240,15 +248,17 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
           out[i] = scratch_tile[i] + scratch_tile[p.NT * 2 + i] + scratch_tile[p.NT * 4 + i] + scratch_tile[p.NT * 6 + i];
       }
     }
+#ifdef B200_DEBUG
     if (p.dbg && threadIdx.x == 0) {  // group 0 only
       long long* o = p.dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16;
       o[5] = w_tfull;
-      o[6] = clock64() - t_begin;
+      o[6] = dbg_clock() - t_begin;
       o[8] = tim[0];
       o[9] = tim[1];
       o[10] = tim[2];
       o[7] = (tiles - cta + cps - 1) / cps;
     }
+#endif
   }
   __syncthreads();
   if (warp == HALO_WARP_MMA) {
@@ -305,7 +315,7 @@ bool conv_halo_plan(int N, int D, int H, int W, int Cin, int Cout, ConvParams* p
   while (cols < p.tmem_bufs * Cout) cols <<= 1;
   p.tmem_cols = cols;
   int tiles = p.tilesD * p.tilesH * p.tilesW;
-  int sms = 148;
+  int sms = sm_count();
   int cps = sms / N;
   if (cps < 1) cps = 1;
   if (cps > tiles) cps = tiles;
@@ -313,13 +323,17 @@ bool conv_halo_plan(int N, int D, int H, int W, int Cin, int Cout, ConvParams* p
   return true;
 }
 
-static long long* g_dbg = nullptr;
+#ifdef B200_DEBUG
+static thread_local long long* g_dbg = nullptr;  // per host thread (nn.DataParallel drives replicas from Python threads)
 void set_debug_buffer(long long* p) { g_dbg = p; }
+#endif
 
 int conv_halo_launch(const void* x, const void* wf, ConvParams& p, cudaStream_t s) {
+#ifdef B200_DEBUG
   p.dbg = g_dbg;
   const char* fl = getenv("B200UNET_DBG_FLAGS");
   p.dbg_flags = fl ? atoi(fl) : 0;
+#endif
   CUtensorMap tmA, tmB;
   int rc = make_act_tmap(&tmA, x, p.N, p.D, p.H, p.W, p.Cin, p.KC, HALO_HD, HALO_HH, HALO_HW);
   if (rc) return rc;
@@ -338,6 +352,11 @@ int conv_halo_launch(const void* x, const void* wf, ConvParams& p, cudaStream_t 
 }  // namespace b200
 
 extern "C" int b200_set_debug_buffer(void* buf) {
+#ifdef B200_DEBUG
   b200::set_debug_buffer(reinterpret_cast<long long*>(buf));
   return 0;
+#else
+  (void)buf;
+  return 1;  // counters are compiled out of production builds (make DEBUG=1)
+#endif
 }

@@ -19,6 +19,18 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+int sm_count() {
+  static int cached[64] = {0};  // per device ordinal; benign race (every thread writes the same value)
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (!cached[dev]) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
 // ------------------------------------------------------------------------------------------------
 // layout
 // ------------------------------------------------------------------------------------------------
@@ -306,8 +318,9 @@ __global__ void prep_dgrad_weights_kernel(const float* __restrict__ W, int Cin, 
 }
 
 // y = act(a*x + b) with partials of y; grid (P, N)
-__global__ void gn_apply_act_kernel(const bf16* __restrict__ x, const float* __restrict__ ab, int C, long long voxels, int P,
-                                    int act, float slope, bf16* __restrict__ y, float* __restrict__ partials) {
+__global__ void gn_apply_act_kernel(const bf16* __restrict__ x, const float* __restrict__ ab, const bf16* __restrict__ residual, int C,
+                                    long long voxels, int P, int act, float slope, bf16* __restrict__ y,
+                                    float* __restrict__ partials) {
   extern __shared__ float red[];
   int p = blockIdx.x, n = blockIdx.y;
   EwMap m = ew_map(C);
@@ -323,12 +336,14 @@ __global__ void gn_apply_act_kernel(const bf16* __restrict__ x, const float* __r
     }
     const bf16x8* xp = reinterpret_cast<const bf16x8*>(x + (size_t)n * voxels * C);
     bf16x8* yp = reinterpret_cast<bf16x8*>(y + (size_t)n * voxels * C);
+    const bf16x8* rp = residual ? reinterpret_cast<const bf16x8*>(residual + (size_t)n * voxels * C) : nullptr;
     for (long long v = v0 + m.vl; v < v1; v += m.VL) {
-      float f[8];
+      float f[8], r[8] = {0};
       unpack8(xp[v * m.CG + m.cg], f);
+      if (rp) unpack8(rp[v * m.CG + m.cg], r);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        f[i] = bf16_round(act_fwd(a[i] * f[i] + b[i], act, slope));
+        f[i] = bf16_round(act_fwd(a[i] * f[i] + b[i] + r[i], act, slope));
         s[i] += f[i];
         q[i] += f[i] * f[i];
       }
@@ -1129,15 +1144,19 @@ int b200_prep_dgrad_weights(const float* W, int Cin, int Cout, void* wd, b200_st
   return 0;
 }
 
-int b200_gn_apply_act(const void* x, const float* ab, int N, int C, long long voxels, int act, float slope, void* y,
-                      float* partials, b200_stream_t s) {
+int b200_gn_apply_act_res(const void* x, const float* ab, const void* residual, int N, int C, long long voxels, int act, float slope,
+                          void* y, float* partials, b200_stream_t s) {
   B200_CHECK_ARG(C % 8 == 0 && C <= 2048, "gn_apply_act: C=%d must be a multiple of 8", C);
   int P = ew_blocks(voxels, C);
   dim3 grid(P, N);
-  gn_apply_act_kernel<<<grid, EW_THREADS, EW_THREADS * 16 * sizeof(float), ST(s)>>>((const bf16*)x, ab, C, voxels, P, act, slope,
-                                                                                  (bf16*)y, partials);
+  gn_apply_act_kernel<<<grid, EW_THREADS, EW_THREADS * 16 * sizeof(float), ST(s)>>>((const bf16*)x, ab, (const bf16*)residual, C, voxels,
+                                                                                  P, act, slope, (bf16*)y, partials);
   B200_CHECK_LAUNCH("gn_apply_act");
   return 0;
+}
+int b200_gn_apply_act(const void* x, const float* ab, int N, int C, long long voxels, int act, float slope, void* y,
+                      float* partials, b200_stream_t s) {
+  return b200_gn_apply_act_res(x, ab, nullptr, N, C, voxels, act, slope, y, partials, s);
 }
 
 int b200_gn_bwd_coeffs(const double* sums2, const float* gamma, const float* mean_rstd, int G, double count, int N, int C,
@@ -1224,7 +1243,8 @@ int b200_upcat_bwd(const void* dcat, int C0, int C1, const void* x_small, int N,
 static int border_blocks(int D, int H) {
   long long lines = (long long)D * H;
   long long p = (lines + 63) / 64;
-  return (int)(p > 148 ? 148 : (p < 1 ? 1 : p));
+  const int sms = sm_count();
+  return (int)(p > sms ? sms : (p < 1 ? 1 : p));
 }
 int b200_border_tap_sums_workspace(int N, int D, int H, int W, int C) {
   // floats: border class partials [N][P][64][C] | totals partials [N][P2][C][2] | (doubles) R [N][64][C] | tot [N][C][2]

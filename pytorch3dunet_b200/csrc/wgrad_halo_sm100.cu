@@ -207,7 +207,7 @@ bool wgrad_halo_plan(int N, int D, int H, int W, int Cin, int Cout, WgradHaloPar
   while (cols < p.PG * Cout) cols <<= 1;
   p.tmem_cols = cols;
   int ctas_per_split = N * p.nslices * (9 / p.PG);
-  int want = 148 / ctas_per_split;
+  int want = sm_count() / ctas_per_split;
   if (want < 1) want = 1;
   if (want > p.tiles) want = p.tiles;
   p.S = want;

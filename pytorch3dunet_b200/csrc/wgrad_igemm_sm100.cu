@@ -249,7 +249,7 @@ static void wgrad_plan(int N, int D, int H, int W, int Cin, int Cout, WgradParam
   p.mchunks = (Cin + 127) / 128;
   // one CTA per SM (TMEM: TG*Cout columns, smem: deep A pipeline) -> size the split count for a single wave
   int ctas_per_split = N * p.ngroups * p.mchunks;
-  int want = 148 / ctas_per_split;
+  int want = sm_count() / ctas_per_split;
   if (want < 1) want = 1;
   if (want > p.tiles) want = p.tiles;
   p.tiles_per_split = (p.tiles + want - 1) / want;

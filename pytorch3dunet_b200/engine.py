@@ -363,7 +363,9 @@ class Engine:
         return out
 
     # ---------------------------------------------------------------- GroupNorm after the conv ('cg.', 'c.g')
-    def groupnorm_act(self, z, gamma, beta, groups, gname, bname, act=(ACT_NONE, 0.0), want_stats=False):
+    def groupnorm_act(self, z, gamma, beta, groups, gname, bname, act=(ACT_NONE, 0.0), want_stats=False, residual=None):
+        """y = act(GroupNorm(z) [+ residual]); the residual join is ResNetBlock's `out += residual` after a conv3 whose order ends in
+        'g' (the block's own default order 'cge', buildingblocks.py:243-288)."""
         n, d, h, w, c = z.dims
         vox = d * h * w
         gamma, beta = gamma.contiguous(), beta.contiguous()
@@ -376,7 +378,8 @@ class Engine:
         if want_stats:
             P = self.L.query("b200_stats_partials_count", n, c, vox)
             partials = self.empty((n, P, c, 2), torch.float32)
-        self.call("b200_gn_apply_act", _p(z.t), _p(ab), n, c, vox, act[0], float(act[1]), _p(y), _p(partials))
+        self.call("b200_gn_apply_act_res", _p(z.t), _p(ab), _p(residual.t) if residual is not None else None, n, c, vox,
+                  act[0], float(act[1]), _p(y), _p(partials))
         out = Act(y, act[0], act[1], partials, P)
         if DEBUG is not None and act[0] != ACT_NONE:
             # (tests) the tensor whose sign pattern is the layer's activation pattern: for conv -> act -> GroupNorm orders that is the
@@ -398,6 +401,11 @@ class Engine:
                           _p(coef), _p(dgamma), _p(dbeta))
                 self._add_param_grad(gname, dgamma)
                 self._add_param_grad(bname, dbeta)
+                if residual is not None and residual.requires_grad:
+                    gr = self.empty(residual.t.shape, torch.bfloat16)
+                    self.call("b200_act_bwd", _p(du), c, 0, _p(residual.t), n, c, vox, residual.act, residual.slope,
+                              _p(residual.grad), _p(gr))
+                    residual.grad = gr
                 if z.requires_grad:
                     g = self.empty(z.t.shape, torch.bfloat16)
                     self.call("b200_gn_bwd_apply", _p(du), _p(z.t), _p(coef), n, c, vox, z.act, z.slope, _p(z.grad), _p(g))
@@ -435,8 +443,6 @@ class Engine:
             act = final_act
         if "g" not in post:
             return self.conv3(x, W, bias, gn_pre, prefix, act=act, want_stats=want_stats, residual=residual)
-        if residual is not None:
-            raise NotImplementedError("residual join after a post-conv GroupNorm (e.g. order 'cge') is not implemented")
         g = 1 if cout < num_groups else num_groups
         if cout % g != 0:
             raise ValueError(f"GroupNorm: num_channels={cout} not divisible by num_groups={g}")
@@ -444,35 +450,40 @@ class Engine:
         z = self.conv3(x, W, bias, None, prefix, act=act if act_first else (ACT_NONE, 0.0), want_stats=True)
         return self.groupnorm_act(z, sd[prefix + "groupnorm.weight"], sd[prefix + "groupnorm.bias"], g,
                                   prefix + "groupnorm.weight", prefix + "groupnorm.bias",
-                                  act=(ACT_NONE, 0.0) if act_first else act, want_stats=want_stats)
+                                  act=(ACT_NONE, 0.0) if act_first else act, want_stats=want_stats, residual=residual)
 
     # ---------------------------------------------------------------- pooling / upsample+concat
-    def maxpool(self, x, want_stats=True):
+    def maxpool(self, x, want_stats=True, kind="max"):
+        """Encoder pooling, buildingblocks.py:353-363: MaxPool3d(2) or (pool_type='avg') AvgPool3d(2), floor mode."""
         n, d, h, w, c = x.dims
+        fwd, bwd = ("b200_maxpool_fwd", "b200_maxpool_bwd") if kind == "max" else ("b200_avgpool_fwd", "b200_avgpool_bwd")
         y = self.empty((n, d // 2, h // 2, w // 2, c), torch.bfloat16)
         P = self.L.query("b200_maxpool_partials_count", n, d, h, w, c)
         partials = self.empty((n, P, c, 2), torch.float32) if want_stats else None
-        self.call("b200_maxpool_fwd", _p(x.t), n, d, h, w, c, _p(y), _p(partials))
+        self.call(fwd, _p(x.t), n, d, h, w, c, _p(y), _p(partials))
         out = Act(y, ACT_NONE, 0.0, partials, P)
-        if DEBUG is not None:
+        if DEBUG is not None and kind == "max":
             DEBUG.setdefault("pool", []).append(x.t)
         if self.record:
             def backward():
                 if out.grad is None or not x.requires_grad:
                     return
                 g = x.grad if x.grad is not None else self.empty(x.t.shape, torch.bfloat16)
-                self.call("b200_maxpool_bwd", _p(out.grad), _p(x.t), n, d, h, w, c, x.act, x.slope, _p(x.grad), _p(g))
+                self.call(bwd, _p(out.grad), _p(x.t), n, d, h, w, c, x.act, x.slope, _p(x.grad), _p(g))
                 x.grad = g
                 out.grad = None
             self.tape.append(backward)
         return out
 
-    def upcat(self, enc, x, want_stats=True, allow_virtual=False):
-        """Decoder joining for nearest upsampling + concat (buildingblocks.py:482-497).  When the encoder feature is exactly 2x the
-        low-res one the concatenated tensor stays virtual (VirtualCat); otherwise it is materialised."""
+    def upcat(self, enc, x, want_stats=True, allow_virtual=False, mode="nearest"):
+        """Decoder joining for interpolation upsampling + concat (buildingblocks.py:482-497, :598-614).  mode 'nearest': when the
+        encoder feature is exactly 2x the low-res one the concatenated tensor stays virtual (VirtualCat); otherwise, and for
+        mode 'trilinear', it is materialised by one HBM-bound kernel."""
         n, D, H, W, c0 = enc.dims
         n2, d, h, w, c1 = x.dims
         assert n == n2
+        if mode != "nearest":
+            return self._upcat_materialize(enc, x, want_stats, mode=mode)
         if (allow_virtual and VIRTUAL_CAT and self.impl != IMPL_DIRECT and (D, H, W) == (2 * d, 2 * h, 2 * w) and c0 % 16 == 0 and c1 % 16 == 0
                 and isinstance(enc, Act) and isinstance(x, Act)):
             return VirtualCat(enc, x)
@@ -600,13 +611,15 @@ class Engine:
             self.tape.append(backward)
         return out
 
-    def _upcat_materialize(self, enc, x, want_stats=True):
+    def _upcat_materialize(self, enc, x, want_stats=True, mode="nearest"):
         n, D, H, W, c0 = enc.dims
         n2, d, h, w, c1 = x.dims
+        fwd, bwd = {"nearest": ("b200_upcat_fwd", "b200_upcat_bwd"),
+                    "trilinear": ("b200_upcat_trilinear_fwd", "b200_upcat_trilinear_bwd")}[mode]
         cat = self.empty((n, D, H, W, c0 + c1), torch.bfloat16)
         P = self.L.query("b200_upcat_partials_count", n, D, H, W, c0 + c1)
         partials = self.empty((n, P, c0 + c1, 2), torch.float32) if want_stats else None
-        self.call("b200_upcat_fwd", _p(enc.t), c0, _p(x.t), c1, n, D, H, W, d, h, w, _p(cat), _p(partials))
+        self.call(fwd, _p(enc.t), c0, _p(x.t), c1, n, D, H, W, d, h, w, _p(cat), _p(partials))
         out = Act(cat, ACT_NONE, 0.0, partials, P)
         if self.record:
             def backward():
@@ -615,7 +628,7 @@ class Engine:
                     return
                 if x.requires_grad:
                     g = self.empty(x.t.shape, torch.bfloat16)
-                    self.call("b200_upcat_bwd", _p(dcat), c0, c1, _p(x.t), n, D, H, W, d, h, w, x.act, x.slope, _p(g))
+                    self.call(bwd, _p(dcat), c0, c1, _p(x.t), n, D, H, W, d, h, w, x.act, x.slope, _p(g))
                     self.accumulate_grad(x, g)
                 if enc.requires_grad:
                     ge = self.empty(enc.t.shape, torch.bfloat16)
@@ -695,15 +708,14 @@ class Engine:
         return out
 
     # ---------------------------------------------------------------- ConvTranspose3d(k3,s2,p1) + nearest resize + sum-join
-    def deconv_up_add(self, enc, x, Wt, wname, want_stats=True):
-        """TransposeConvUpsampling (buildingblocks.py:617-664) followed by Decoder._joining(concat=False) (:493):
-        out = enc + interpolate(conv_transpose3d(x), size=enc.shape[2:]).
+    def deconv(self, x, Wt, wname):
+        """ConvTranspose3d(k3, s2, p1, bias=False) (TransposeConvUpsampling, buildingblocks.py:617-664) -> Act on the (2d-1)^3 grid.
 
         conv_transpose3d(x, Wt, stride 2, pad 1) == conv3d(zero_insert(x), Wc, pad 1) with Wc[co][ci][k] = Wt[ci][co][26-k], so the
         transposed conv, its input gradient and its weight gradient all run on the tcgen05 3x3x3 kernels (conv3)."""
-        n, D, H, W_, cout = enc.dims
-        n2, d, h, w, cin = x.dims
-        assert n == n2 and tuple(Wt.shape) == (cin, cout, 3, 3, 3), (tuple(Wt.shape), cin, cout)
+        n, d, h, w, cin = x.dims
+        cout = Wt.shape[1]
+        assert tuple(Wt.shape) == (cin, cout, 3, 3, 3), (tuple(Wt.shape), cin, cout)
         Wt = Wt.contiguous()
         sd_, sh_, sw_ = 2 * d - 1, 2 * h - 1, 2 * w - 1
         Wc = self.empty((cout, cin, 3, 3, 3), torch.float32)
@@ -725,7 +737,16 @@ class Engine:
             dWt = torch.empty_like(Wt)
             self.call("b200_deconv_weight_permute", _p(dWc), cin, cout, 0, _p(dWt))
             self._add_param_grad(wname, dWt)
-        T = self.conv3(xz, Wc, None, None, wname + "#conv.", want_stats=False, grad_sink=sink)
+        return self.conv3(xz, Wc, None, None, wname + "#conv.", want_stats=False, grad_sink=sink)
+
+    def deconv_up_add(self, enc, x, Wt, wname, want_stats=True):
+        """TransposeConvUpsampling followed by Decoder._joining(concat=False) (buildingblocks.py:493):
+        out = enc + interpolate(conv_transpose3d(x), size=enc.shape[2:]) (nearest resize of the (2d-1)^3 grid)."""
+        n, D, H, W_, cout = enc.dims
+        n2, d, h, w, cin = x.dims
+        assert n == n2
+        sd_, sh_, sw_ = 2 * d - 1, 2 * h - 1, 2 * w - 1
+        T = self.deconv(x, Wt, wname)
         out_t = self.empty((n, D, H, W_, cout), torch.bfloat16)
         P = self.L.query("b200_resize_add_partials_count", n, D, H, W_, cout)
         partials = self.empty((n, P, cout, 2), torch.float32) if want_stats else None

@@ -13,10 +13,39 @@ get_model :361-363; block wiring buildingblocks.py:138-227 (DoubleConv), :310-38
 """
 from __future__ import annotations
 
+import threading
+
 import torch
 from torch import nn
 
 from . import engine as E
+
+
+class UnsupportedConfig(NotImplementedError):
+    """A configuration that is valid for the reference but that the b200 engine does not build.  Raised at CONSTRUCTION time
+    (never on the first batch); `install()`'s get_model catches it and constructs the reference's own class instead
+    (graph-level fallback, no Python re-implementation of arithmetic)."""
+
+
+INTERP_MODES = ("nearest", "trilinear")   # InterpolateUpsampling modes built as kernels (buildingblocks.py:598-614)
+
+
+def validate_layer_order(order, residual_block=False):
+    """The order strings create_conv accepts (buildingblocks.py:44-94) that the engine fuses: [g]c[r|l|e], c g [r|l|e],
+    c [r|l|e] g.  BatchNorm ('b') needs cross-replica running statistics and Dropout ('d'/'D') a device RNG stream
+    matching torch's: both stay on the reference."""
+    assert "c" in order, "Conv layer MUST be present"
+    assert order[0] not in "rle", "Non-linearity cannot be the first operation in the layer"
+    for ch in order:
+        if ch not in "bgrlecdD":
+            raise ValueError(f"Unsupported layer type '{ch}'. MUST be one of ['b', 'g', 'r', 'l', 'e', 'c', 'd', 'D']")
+    if any(ch in order for ch in "bdD"):
+        raise UnsupportedConfig(f"layer_order {order!r}: BatchNorm/Dropout layers are not built in the b200 engine")
+    ic = order.index("c")
+    pre, post = order[:ic], order[ic + 1:]
+    acts = [ch for ch in post if ch in "rle"]
+    if pre not in ("", "g") or order.count("c") != 1 or len(acts) > 1 or post.count("g") > 1 or (pre == "g" and "g" in post):
+        raise UnsupportedConfig(f"layer_order {order!r} is not built in the b200 engine")
 
 
 def number_of_features_per_level(init_channel_number, num_levels):
@@ -29,7 +58,7 @@ def number_of_features_per_level(init_channel_number, num_levels):
 # ----------------------------------------------------------------------------------------------------
 class _EngineFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, program, n_inputs, names, *tensors):
+    def forward(ctx, program, n_inputs, names, grad_mode, *tensors):
         inputs, params = tensors[:n_inputs], tensors[n_inputs:]
         x0 = inputs[0]
         if not x0.is_cuda:
@@ -37,18 +66,22 @@ class _EngineFn(torch.autograd.Function):
         for t in tensors:
             if t.dtype != torch.float32 or t.device != x0.device:
                 raise RuntimeError("b200 engine: inputs and parameters must be float32 tensors on one CUDA device")
-        needs_grad = any(ctx.needs_input_grad[3:])
+        # needs_input_grad mirrors tensor.requires_grad whatever the grad mode is, and grad mode is always off inside
+        # Function.forward: the caller's mode comes in as an argument.  Under torch.no_grad() (the predictor's path,
+        # reference predictor.py:164) nothing is taped, so no closure pins a layer's activations.
+        needs_grad = bool(grad_mode) and any(ctx.needs_input_grad[4:])
         with torch.cuda.device(x0.device):
             eng = E.Engine(x0.device, record=needs_grad)
             sd = dict(zip(names, params))
-            in_req = [bool(g) for g in ctx.needs_input_grad[3:3 + n_inputs]]
+            in_req = [needs_grad and bool(g) for g in ctx.needs_input_grad[4:4 + n_inputs]]
             outs, seed, input_grads = program(eng, [t.detach() for t in inputs], sd, in_req)
         ctx.eng, ctx.seed, ctx.input_grads = eng, seed, input_grads
         ctx.names, ctx.n_inputs = names, n_inputs
         ctx.param_meta = [(p.shape, p.dtype) for p in params]
         ctx.set_materialize_grads(False)
         ctx.device = x0.device
-        _EngineFn.last_launches = eng.launches
+        _STATS.launches_fwd = eng.launches
+        _STATS.tape_len = len(eng.tape)
         return tuple(outs)
 
     @staticmethod
@@ -62,7 +95,7 @@ class _EngineFn(torch.autograd.Function):
             ctx.seed(eng, grad_outs)
             eng.run_backward()
             in_grads = ctx.input_grads(eng)
-            _EngineFn.last_launches_bwd = eng.launches - l0
+            _STATS.launches_bwd = eng.launches - l0
         pg = eng.param_grads
         grads = []
         for (shape, dtype), name in zip(ctx.param_meta, ctx.names):
@@ -70,24 +103,50 @@ class _EngineFn(torch.autograd.Function):
             grads.append(None if g is None else g.reshape(shape))
         # drop everything the closures keep alive (activations of the last layer, ...) now instead of when the autograd node dies
         ctx.eng = ctx.seed = ctx.input_grads = None
-        return (None, None, None) + tuple(in_grads) + tuple(grads)
+        return (None, None, None, None) + tuple(in_grads) + tuple(grads)
 
 
-_EngineFn.last_launches = 0
-_EngineFn.last_launches_bwd = 0
+class _Stats(threading.local):
+    """launch counters of the most recent call ON THIS HOST THREAD (nn.DataParallel runs replicas on Python threads)"""
+    launches_fwd = 0
+    launches_bwd = 0
+    tape_len = 0
+
+
+_STATS = _Stats()
+
+
+def _named_params(module):
+    """[(qualified name, tensor)] in named_parameters() order, also for nn.DataParallel replicas: `replicate` empties each
+    replica's `_parameters` and re-attaches the broadcast copies as plain attributes listed in `_former_parameters`
+    (torch/nn/parallel/replicate.py), so `named_parameters()` of a replica is empty.  The reference wraps the model in
+    DataParallel whenever more than one GPU is visible (trainer.py:203-204, predict.py:63-65)."""
+    out = []
+    for mname, m in module.named_modules():
+        former = getattr(m, "_former_parameters", None)
+        items = list(m._parameters.items())
+        if former:
+            items += [(k, v) for k, v in former.items() if k not in m._parameters or m._parameters[k] is None]
+        for k, p in items:
+            if p is not None:
+                out.append((f"{mname}.{k}" if mname else k, p))
+    return out
 
 
 def _run(module, program, inputs):
-    names, params = [], []
-    for k, p in module.named_parameters():
-        names.append(k)
-        params.append(p)
-    return _EngineFn.apply(program, len(inputs), tuple(names), *inputs, *params)
+    np_ = _named_params(module)
+    names = tuple(k for k, _ in np_)
+    return _EngineFn.apply(program, len(inputs), names, torch.is_grad_enabled(), *inputs, *(p for _, p in np_))
 
 
 def last_launch_counts():
-    """(forward, backward) number of engine kernels launched by the most recent call."""
-    return _EngineFn.last_launches, _EngineFn.last_launches_bwd
+    """(forward, backward) number of engine kernels launched by the most recent call (of this host thread)."""
+    return _STATS.launches_fwd, _STATS.launches_bwd
+
+
+def last_tape_length():
+    """number of backward closures the most recent forward recorded (0 under torch.no_grad())"""
+    return _STATS.tape_len
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -139,14 +198,16 @@ def run_basic(eng, x, sd, prefix, spec, out_stats=False):
 
 def run_join(eng, enc, x, sd, prefix, spec, want_stats):
     """Decoder.forward up to the basic module, reference buildingblocks.py:482-493"""
-    if spec["upsample"] == "nearest" and spec["concat"]:
+    wkey = prefix + "upsampling.upsample.conv_transposed.weight"
+    if spec["upsample"] in INTERP_MODES and spec["concat"]:
         # only DoubleConv consumes the joined tensor through a single 3x3x3 conv, which lets it stay virtual
-        return eng.upcat(enc, x, want_stats=want_stats, allow_virtual=spec["basic"] == "double")
+        return eng.upcat(enc, x, want_stats=want_stats, allow_virtual=spec["basic"] == "double", mode=spec["upsample"])
     if spec["upsample"] == "deconv" and not spec["concat"]:
-        return eng.deconv_up_add(enc, x, sd[prefix + "upsampling.upsample.conv_transposed.weight"],
-                                 prefix + "upsampling.upsample.conv_transposed.weight", want_stats=want_stats)
-    raise NotImplementedError(f"decoder upsample={spec['upsample']!r} concat={spec['concat']} is not built in the b200 engine "
-                              "(built: nearest+concat, deconv+sum)")
+        return eng.deconv_up_add(enc, x, sd[wkey], wkey, want_stats=want_stats)
+    if spec["upsample"] == "deconv":
+        # explicit upsample='deconv': the transposed conv's (2d-1)^3 output is nearest-resized to the encoder size and concatenated
+        return eng.upcat(enc, eng.deconv(x, sd[wkey], wkey), want_stats=want_stats)
+    raise UnsupportedConfig(f"decoder upsample={spec['upsample']!r} concat={spec['concat']} is not built in the b200 engine")
 
 
 def run_unet(eng, x, sd, spec):
@@ -239,7 +300,8 @@ class SingleConv(_EngineModule):
     def __init__(self, in_channels, out_channels, kernel_size=3, order="gcr", num_groups=8, padding=1, dropout_prob=0.1, is3d=True):
         super().__init__()
         if not is3d or kernel_size != 3 or padding != 1:
-            raise NotImplementedError("the b200 engine implements 3-D 3x3x3 convolutions with padding 1")
+            raise UnsupportedConfig("the b200 engine implements 3-D 3x3x3 convolutions with padding 1")
+        validate_layer_order(order)
         self.order, self.num_groups = order, num_groups
         for name, m in _conv_layers(in_channels, out_channels, order, num_groups):
             self.add_module(name, m)
@@ -278,9 +340,11 @@ class _Marker(nn.Module):
 
 class Encoder(_EngineModule):
     def __init__(self, in_channels, out_channels, apply_pooling=True, basic="double", conv_layer_order="gcr", num_groups=8,
-                 upscale=2):
+                 upscale=2, pool_type="max"):
         super().__init__()
-        self.pooling = _Marker("MaxPool3d(kernel_size=2) [fused b200 kernel]") if apply_pooling else None
+        assert pool_type in ("max", "avg")   # buildingblocks.py:352
+        self.pool_type = pool_type
+        self.pooling = _Marker(f"{'Max' if pool_type == 'max' else 'Avg'}Pool3d(kernel_size=2) [b200 kernel]") if apply_pooling else None
         self.spec = dict(basic=basic, layer_order=conv_layer_order, num_groups=num_groups)
         self.basic_module = _make_basic(basic, in_channels, out_channels, True, conv_layer_order, num_groups, upscale)
 
@@ -288,7 +352,7 @@ class Encoder(_EngineModule):
         def prog(eng, acts, sd):
             x = acts[0]
             if self.pooling is not None:
-                x = eng.maxpool(x, want_stats=_has_pre_gn(self.spec["layer_order"]))
+                x = eng.maxpool(x, want_stats=_has_pre_gn(self.spec["layer_order"]), kind=self.pool_type)
             return run_basic(eng, x, sd, "basic_module.", self.spec)
         return prog
 
@@ -403,9 +467,10 @@ class AbstractUNet(nn.Module):
                  dropout_prob=0.1, is3d=True):
         super().__init__()
         if not is3d:
-            raise NotImplementedError("2-D models are out of scope of the b200 engine (SURVEY.md section 2, row 1)")
+            raise UnsupportedConfig("2-D models are out of scope of the b200 engine (SURVEY.md section 2, row 1)")
         if conv_kernel_size != 3 or pool_kernel_size != 2 or conv_padding != 1:
-            raise NotImplementedError("the b200 engine implements conv 3x3x3 / padding 1 / pool 2 (what UNet3D & co. always use)")
+            raise UnsupportedConfig("the b200 engine implements conv 3x3x3 / padding 1 / pool 2 (what UNet3D & co. always use)")
+        validate_layer_order(layer_order)
         if isinstance(f_maps, int):
             f_maps = number_of_features_per_level(f_maps, num_levels=num_levels)
         assert isinstance(f_maps, (list, tuple))
@@ -413,12 +478,17 @@ class AbstractUNet(nn.Module):
         if "g" in layer_order:
             assert num_groups is not None, "num_groups must be specified if GroupNorm is used"
         f_maps = list(f_maps)
-        concat = True
+        concat = True   # Decoder.__init__, buildingblocks.py:431-468: only 'default' on a residual block switches to the sum join
         if upsample == "default":
             if basic == "double":
                 upsample, concat = "nearest", True
             else:
                 upsample, concat = "deconv", False
+        elif upsample not in INTERP_MODES + ("deconv",):
+            # None / 'none' (no upsampling), 'area' (adaptive average pooling), 'linear' / 'bilinear' (not 5-D modes)
+            raise UnsupportedConfig(f"upsample={upsample!r} is not built in the b200 engine (built: 'default', 'nearest', 'trilinear', 'deconv')")
+        if any(f % 8 for f in f_maps):
+            raise UnsupportedConfig(f"f_maps={f_maps}: the engine's activations need channel counts that are multiples of 8")
         self.spec = dict(basic=basic, f_maps=f_maps, layer_order=layer_order, num_groups=num_groups, upsample=upsample,
                          concat=concat, is_segmentation=is_segmentation, final_sigmoid=final_sigmoid,
                          in_channels=in_channels, out_channels=out_channels)

@@ -122,9 +122,12 @@ def test_tcgen05_wgrad_matches_torch(shape):
 
 @pytest.mark.parametrize("shift,group_rows", [(0, 8), (1, 8), (3, 8), (8, 8), (0, 10), (1, 10), (2, 10), (11, 10)])
 def test_probe_umma_row_shifted_swizzled_view(shift, group_rows):
-    """hardware fact the halo-reuse conv design depends on (see csrc/umma_probe.cu)"""
+    """hardware fact the halo-reuse conv design depends on (probe kernels: tools/probes/umma_probe.cu, their own small library)"""
     from tests import gpu_util as U
-    from pytorch3dunet_b200._lib import lib
+    from tools.probes import probe_lib
+    if not probe_lib.available():
+        pytest.skip("tools/probes/libb200probe.so not built")
+    lib = probe_lib.ProbeLib
     rows = 200
     g = torch.Generator(device="cuda").manual_seed(7)
     A = torch.randn((rows, 64), device="cuda", generator=g).bfloat16()

@@ -1,9 +1,9 @@
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import pytorch3dunet_b200
-from pytorch3dunet_b200._lib import lib
-L = lib()
+from tools.probes.probe_lib import ProbeLib
+L = ProbeLib()
 s = torch.cuda.current_stream().cuda_stream
 iters = 512
 print("N issuers grid | cycles per MMA per issuer (max over CTAs)  -> aggregate cycles per MMA per SM")

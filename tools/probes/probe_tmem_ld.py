@@ -1,9 +1,9 @@
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import pytorch3dunet_b200
-from pytorch3dunet_b200._lib import lib
-L = lib()
+from tools.probes.probe_lib import ProbeLib
+L = ProbeLib()
 out = torch.zeros(4, dtype=torch.int64, device="cuda")
 s = torch.cuda.current_stream().cuda_stream
 for N in (32, 96, 256):

@@ -7,6 +7,7 @@
 
 #include "common.cuh"
 #include "sm100_ptx.cuh"
+#include "b200probe.h"
 
 namespace b200 {
 
