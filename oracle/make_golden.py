@@ -141,6 +141,22 @@ def main():
                                                   layer_order="gce"),
                    (1, 2, 8, 8, 8), "DiceLoss", 9, model_mod, losses_mod)
 
+    # upsampling modes reachable through the model config (buildingblocks.py:431-468): trilinear interpolation + concat (odd sizes:
+    # a non-2x scale), explicit 'deconv' with the concat join for DoubleConv and for ResNetBlock, and the residual block's own
+    # default order 'cge' (GroupNorm between conv3 and the residual add)
+    run_model_case("unet3d_f16_l2_trilinear", dict(name="UNet3D", in_channels=1, out_channels=1, f_maps=16, num_levels=2,
+                                                   upsample="trilinear"),
+                   (1, 1, 9, 12, 10), "BCEDiceLoss", 20, model_mod, losses_mod)
+    run_model_case("unet3d_f16_l2_deconv", dict(name="UNet3D", in_channels=1, out_channels=1, f_maps=16, num_levels=2,
+                                                upsample="deconv"),
+                   (1, 1, 8, 8, 8), "BCEDiceLoss", 21, model_mod, losses_mod)
+    run_model_case("resunet3d_f16_l2_cge", dict(name="ResidualUNet3D", in_channels=1, out_channels=1, f_maps=16, num_levels=2,
+                                                layer_order="cge"),
+                   (1, 1, 8, 8, 8), "BCEDiceLoss", 22, model_mod, losses_mod)
+    run_model_case("resunet3d_f16_l2_deconvcat", dict(name="ResidualUNet3D", in_channels=1, out_channels=1, f_maps=16, num_levels=2,
+                                                      upsample="deconv"),
+                   (1, 1, 8, 8, 8), "BCEDiceLoss", 23, model_mod, losses_mod)
+
     # ---- building blocks -----------------------------------------------------------------
     torch.manual_seed(10)
     run_block_case("block_singleconv_gcr_16_32", bb.SingleConv(16, 32, order="gcr", num_groups=8), (2, 16, 8, 8, 8), 10)

@@ -97,6 +97,8 @@ def single_conv(x, sd, prefix, order, num_groups, padding=1, masks=None):
             w = sd[prefix + "groupnorm.weight"]
             x = F.group_norm(x, _groups(w.numel(), num_groups), w, sd[prefix + "groupnorm.bias"], GN_EPS)
         elif ch == "r":
+            if masks is not None and "__record__" in masks:  # tests: capture this run's own activation pattern (flip-rate checks)
+                masks["__record__"][prefix] = x > 0
             x = x * masks[prefix].to(x.dtype) if (masks is not None and prefix in masks) else F.relu(x)
         elif ch == "l":  # nn.LeakyReLU() default slope, buildingblocks.py:49 (the kink is pinned like ReLU's when masks are given)
             x = torch.where(masks[prefix], x, 0.01 * x) if (masks is not None and prefix in masks) else F.leaky_relu(x, 0.01)
@@ -152,6 +154,8 @@ def res_block(x, sd, prefix, order, num_groups, se=False, masks=None):
     elif masks is not None and (prefix + "conv3.") in masks:
         out = out * masks[prefix + "conv3."].to(out.dtype)
     else:
+        if masks is not None and "__record__" in masks:
+            masks["__record__"][prefix + "conv3."] = out > 0
         out = F.relu(out)
     if se:
         cse = channel_se(out, sd, prefix + "se_module.cSE.")

@@ -12,6 +12,8 @@ from .model import (AbstractUNet, Decoder, DoubleConv, Encoder, ResidualUNet3D, 
 from .install import install, uninstall  # noqa: F401
 from . import losses  # noqa: F401
 from . import patches  # noqa: F401
+from . import optim  # noqa: F401
+from . import pipeline  # noqa: F401
 
 __all__ = ["get_model", "UNet3D", "ResidualUNet3D", "ResidualUNetSE3D", "SingleConv", "DoubleConv", "Encoder", "Decoder",
-           "install", "is_model_2d", "losses", "patches", "last_launch_counts"]
+           "install", "uninstall", "is_model_2d", "losses", "patches", "optim", "pipeline", "last_launch_counts", "UnsupportedConfig"]

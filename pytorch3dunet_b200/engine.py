@@ -129,8 +129,10 @@ class VirtualCat:
 class Engine:
     """One forward (+ optional backward) pass.  Not reusable across passes."""
 
-    def __init__(self, device, impl=None, record=True):
+    def __init__(self, device, impl=None, record=True, sink=None):
         self.L = lib()
+        self.sink = sink      # optim.FlatParameters: parameter gradients are written straight into its flat buffer
+        self.sunk = set()
         self.device = device
         self.impl = default_impl() if impl is None else impl
         self.record = record
@@ -163,7 +165,25 @@ class Engine:
             self.L.call(name, *args, self.stream)
         self.launches += launches
 
+    def grad_like(self, name, like):
+        """output buffer for the gradient of parameter `name`: its slot in the flat gradient buffer when there is one"""
+        if self.sink is not None and name not in self.sunk:
+            v = self.sink.view(name)
+            if v is not None and v.shape == like.shape:
+                return v
+        return torch.empty_like(like)
+
     def _add_param_grad(self, name, g):
+        if self.sink is not None:
+            v = self.sink.view(name)
+            if v is not None:
+                if name in self.sunk:
+                    v.add_(g.reshape(v.shape))          # a parameter used twice in one pass (not in the reference's models)
+                elif g.data_ptr() != v.data_ptr():
+                    v.copy_(g.reshape(v.shape))
+                self.sunk.add(name)
+                self.sink.written(name)
+                return
         if name in self.param_grads:
             self.param_grads[name] = self.param_grads[name] + g
         else:
@@ -307,7 +327,7 @@ class Engine:
                 self.call("b200_conv3_wgrad", wimpl, _p(x.t), int(is_f32), _p(dz), n, d, h, w, cin, cout, _p(G),
                           launches=1 if wimpl == IMPL_TCGEN05 else 2, flops=2.0 * n * vox * 27 * cin * cout,
                           tag=("wgrad_tc" if wimpl == IMPL_TCGEN05 else "wgrad_direct"))
-                dW = torch.empty_like(W)
+                dW = torch.empty_like(W) if grad_sink is not None else self.grad_like(name + "conv.weight", W)
                 Gsum = self.empty((n, 1, 27, cin, cout), torch.float32) if gn is not None else None
                 self.call("b200_wgrad_finalize", _p(G), n, S, cin, cout, _p(ab), _p(T) if ab is not None else None, _p(dW), _p(Gsum))
                 if grad_sink is not None:
@@ -560,7 +580,7 @@ class Engine:
                           flops=2.0 * n * lvox * 64 * c1 * cout, tag="wgrad_tc")
                 G = self.empty((n, 1, 27, C, cout), torch.float32)
                 self.call("b200_upcat_assemble_wgrad", _p(G_enc), S1, _p(Q), S2, n, c0, c1, cout, _p(G))
-                dW = torch.empty_like(W)
+                dW = self.grad_like(name + "conv.weight", W)
                 Gsum = self.empty((n, 1, 27, C, cout), torch.float32) if gn is not None else None
                 self.call("b200_wgrad_finalize", _p(G), n, 1, C, cout, _p(ab), _p(T) if ab is not None else None, _p(dW), _p(Gsum))
                 self._add_param_grad(name + "conv.weight", dW)
@@ -734,7 +754,7 @@ class Engine:
             self.tape.append(backward_zero_insert)
 
         def sink(dWc):
-            dWt = torch.empty_like(Wt)
+            dWt = self.grad_like(wname, Wt)
             self.call("b200_deconv_weight_permute", _p(dWc), cin, cout, 0, _p(dWt))
             self._add_param_grad(wname, dWt)
         return self.conv3(xz, Wc, None, None, wname + "#conv.", want_stats=False, grad_sink=sink)

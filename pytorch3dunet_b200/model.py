@@ -58,7 +58,7 @@ def number_of_features_per_level(init_channel_number, num_levels):
 # ----------------------------------------------------------------------------------------------------
 class _EngineFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, program, n_inputs, names, grad_mode, *tensors):
+    def forward(ctx, program, n_inputs, names, grad_mode, sink, *tensors):
         inputs, params = tensors[:n_inputs], tensors[n_inputs:]
         x0 = inputs[0]
         if not x0.is_cuda:
@@ -69,11 +69,11 @@ class _EngineFn(torch.autograd.Function):
         # needs_input_grad mirrors tensor.requires_grad whatever the grad mode is, and grad mode is always off inside
         # Function.forward: the caller's mode comes in as an argument.  Under torch.no_grad() (the predictor's path,
         # reference predictor.py:164) nothing is taped, so no closure pins a layer's activations.
-        needs_grad = bool(grad_mode) and any(ctx.needs_input_grad[4:])
+        needs_grad = bool(grad_mode) and any(ctx.needs_input_grad[5:])
         with torch.cuda.device(x0.device):
-            eng = E.Engine(x0.device, record=needs_grad)
+            eng = E.Engine(x0.device, record=needs_grad, sink=sink)
             sd = dict(zip(names, params))
-            in_req = [needs_grad and bool(g) for g in ctx.needs_input_grad[4:4 + n_inputs]]
+            in_req = [needs_grad and bool(g) for g in ctx.needs_input_grad[5:5 + n_inputs]]
             outs, seed, input_grads = program(eng, [t.detach() for t in inputs], sd, in_req)
         ctx.eng, ctx.seed, ctx.input_grads = eng, seed, input_grads
         ctx.names, ctx.n_inputs = names, n_inputs
@@ -99,11 +99,13 @@ class _EngineFn(torch.autograd.Function):
         pg = eng.param_grads
         grads = []
         for (shape, dtype), name in zip(ctx.param_meta, ctx.names):
-            g = pg.get(name)
+            g = pg.get(name)   # names written straight into the flat gradient buffer (eng.sunk) are not in pg: autograd gets None
             grads.append(None if g is None else g.reshape(shape))
+        if eng.sink is not None:
+            eng.sink.restore_grad_views()
         # drop everything the closures keep alive (activations of the last layer, ...) now instead of when the autograd node dies
         ctx.eng = ctx.seed = ctx.input_grads = None
-        return (None, None, None, None) + tuple(in_grads) + tuple(grads)
+        return (None, None, None, None, None) + tuple(in_grads) + tuple(grads)
 
 
 class _Stats(threading.local):
@@ -122,21 +124,26 @@ def _named_params(module):
     (torch/nn/parallel/replicate.py), so `named_parameters()` of a replica is empty.  The reference wraps the model in
     DataParallel whenever more than one GPU is visible (trainer.py:203-204, predict.py:63-65)."""
     out = []
+    replica = False
     for mname, m in module.named_modules():
         former = getattr(m, "_former_parameters", None)
+        replica = replica or bool(former)
         items = list(m._parameters.items())
         if former:
             items += [(k, v) for k, v in former.items() if k not in m._parameters or m._parameters[k] is None]
         for k, p in items:
             if p is not None:
                 out.append((f"{mname}.{k}" if mname else k, p))
-    return out
+    return out, replica
 
 
 def _run(module, program, inputs):
-    np_ = _named_params(module)
+    np_, replica = _named_params(module)
     names = tuple(k for k, _ in np_)
-    return _EngineFn.apply(program, len(inputs), names, torch.is_grad_enabled(), *inputs, *(p for _, p in np_))
+    # optim.FlatParameters registers itself on the model it was built from; DataParallel replicas share that attribute but must
+    # not share the buffer (their gradients flow back through the broadcast instead)
+    sink = None if replica else getattr(module, "_b200_grad_sink", None)
+    return _EngineFn.apply(program, len(inputs), names, torch.is_grad_enabled(), sink, *inputs, *(p for _, p in np_))
 
 
 def last_launch_counts():

@@ -1,9 +1,17 @@
-"""Data-parallel replicas: one process per GPU, ONE gradient allreduce per step.
+"""Data-parallel replicas: one process per GPU, the gradients are the only thing exchanged.
 
 Replaces the reference's single-process `nn.DataParallel` (trainer.py:203-204: per-step parameter broadcast,
-scatter/gather through GPU 0, gradient reduce-to-GPU-0) with identical replicas that only exchange gradients:
-`allreduce_gradients` flattens every `.grad` into one buffer, issues a single `all_reduce` (NCCL over NVLink on the
-GPU box, gloo in the CPU tests), averages, and scatters the result back.  16.3 MB for UNet3D f_maps=32.
+scatter/gather through GPU 0, gradient reduce-to-GPU-0) with identical replicas.  Two reducers:
+
+* `optim.BucketedAllReduce` over `optim.FlatParameters` (what bench.py uses): the engine writes gradients straight into one flat
+  buffer and each bucket's NCCL allreduce starts while backward is still running;
+* `GradAllReducer` below: the plain fallback for arbitrary parameter lists (flatten, one all_reduce, average, scatter back) --
+  gloo in the CPU tests.
+
+Semantics note (differs from the reference and is deliberate): every replica computes the loss of ITS OWN per-GPU batch and the
+gradients are averaged.  nn.DataParallel gathers the outputs and evaluates the loss once on the global batch; for the mean-reduced
+BCE term the two agree, for the Dice term (a ratio of batch sums, losses.py:11-37) they do not -- averaging per-replica Dice
+gradients is what torch DistributedDataParallel would do as well.
 """
 from __future__ import annotations
 
@@ -25,20 +33,26 @@ class GradAllReducer:
         self.flat = None
 
     def __call__(self):
-        if self.world == 1:
+        if self.world == 1 or not self.params:
             return
-        p0 = self.params[0]
-        if self.flat is None or self.flat.device != p0.grad.device:
-            self.flat = torch.empty(self.numel, dtype=torch.float32, device=p0.grad.device)
+        dev = next((p.grad.device for p in self.params if p.grad is not None), self.params[0].device)
+        if self.flat is None or self.flat.device != dev:
+            self.flat = torch.empty(self.numel, dtype=torch.float32, device=dev)
         off = 0
         for p in self.params:
             n = p.numel()
-            self.flat[off:off + n].copy_(p.grad.reshape(-1))
+            if p.grad is None:  # unused / frozen on this rank this step: contributes zeros (all ranks reduce the same layout)
+                self.flat[off:off + n].zero_()
+            else:
+                self.flat[off:off + n].copy_(p.grad.reshape(-1))
             off += n
         dist.all_reduce(self.flat)
         self.flat.div_(self.world)
         off = 0
         for p in self.params:
             n = p.numel()
-            p.grad.copy_(self.flat[off:off + n].view_as(p.grad))
+            if p.grad is None:
+                p.grad = self.flat[off:off + n].view_as(p).clone()
+            else:
+                p.grad.copy_(self.flat[off:off + n].view_as(p.grad))
             off += n

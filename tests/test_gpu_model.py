@@ -136,6 +136,15 @@ EXTRA_MODEL_CASES = {
                              "bce_dice_loss"),
     "resunetse3d_f16_l2_gce": (dict(name="ResidualUNetSE3D", in_channels=2, out_channels=1, f_maps=16, num_levels=2, layer_order="gce"),
                                "dice_loss"),
+    # upsampling modes reachable through the model config (trilinear at a non-2x scale, explicit deconv + concat for both block
+    # families) and the residual block's own default order 'cge' (GroupNorm between conv3 and the residual add)
+    "unet3d_f16_l2_trilinear": (dict(name="UNet3D", in_channels=1, out_channels=1, f_maps=16, num_levels=2, upsample="trilinear"),
+                                "bce_dice_loss"),
+    "unet3d_f16_l2_deconv": (dict(name="UNet3D", in_channels=1, out_channels=1, f_maps=16, num_levels=2, upsample="deconv"), "bce_dice_loss"),
+    "resunet3d_f16_l2_cge": (dict(name="ResidualUNet3D", in_channels=1, out_channels=1, f_maps=16, num_levels=2, layer_order="cge"),
+                             "bce_dice_loss"),
+    "resunet3d_f16_l2_deconvcat": (dict(name="ResidualUNet3D", in_channels=1, out_channels=1, f_maps=16, num_levels=2, upsample="deconv"),
+                                   "bce_dice_loss"),
 }
 
 
@@ -222,6 +231,25 @@ def test_eval_no_grad_and_determinism():
     assert torch.equal(y1, y2)
     assert torch.all(y1 >= 0) and torch.all(y1 <= 1)
     assert torch.allclose(y1.sum(dim=1), torch.ones_like(y1[:, 0]), atol=1e-5)
+    # under no_grad nothing is taped (the predictor's path): no backward closure pins a layer's activations
+    assert P.last_tape_length() == 0
+    y3 = model(x)
+    assert P.last_tape_length() > 0 and y3.requires_grad
+    # inference peak memory stays well below the training peak of the same call
+    torch.cuda.synchronize()
+    torch.cuda.reset_peak_memory_stats()
+    base = torch.cuda.memory_allocated()
+    with torch.no_grad():
+        model(x)
+    torch.cuda.synchronize()
+    peak_inf = torch.cuda.max_memory_allocated() - base
+    torch.cuda.reset_peak_memory_stats()
+    y4 = model(x)
+    torch.cuda.synchronize()
+    peak_train = torch.cuda.max_memory_allocated() - base
+    del y3, y4
+    print("peak bytes: inference", peak_inf, "training forward", peak_train)
+    assert peak_inf < 0.7 * peak_train
 
 
 def test_missing_library_fails_loudly(monkeypatch):

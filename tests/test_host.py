@@ -28,6 +28,10 @@ def test_library_exports_every_header_symbol():
     ("unet3d_f16_l2_crg", dict(name="UNet3D", in_channels=1, out_channels=2, f_maps=16, num_levels=2, layer_order="crg", final_sigmoid=False)),
     ("resunet3d_f16_l2_gcl", dict(name="ResidualUNet3D", in_channels=1, out_channels=1, f_maps=16, num_levels=2, layer_order="gcl")),
     ("resunetse3d_f16_l2_gce", dict(name="ResidualUNetSE3D", in_channels=2, out_channels=1, f_maps=16, num_levels=2, layer_order="gce")),
+    ("unet3d_f16_l2_trilinear", dict(name="UNet3D", in_channels=1, out_channels=1, f_maps=16, num_levels=2, upsample="trilinear")),
+    ("unet3d_f16_l2_deconv", dict(name="UNet3D", in_channels=1, out_channels=1, f_maps=16, num_levels=2, upsample="deconv")),
+    ("resunet3d_f16_l2_cge", dict(name="ResidualUNet3D", in_channels=1, out_channels=1, f_maps=16, num_levels=2, layer_order="cge")),
+    ("resunet3d_f16_l2_deconvcat", dict(name="ResidualUNet3D", in_channels=1, out_channels=1, f_maps=16, num_levels=2, upsample="deconv")),
 ])
 def test_state_dict_contract_matches_reference(golden, cfg):
     import pytorch3dunet_b200 as P
@@ -67,7 +71,7 @@ def test_cpu_tensor_is_rejected_not_silently_computed():
 
 def test_unsupported_orders_fail_loudly():
     import pytorch3dunet_b200 as P
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(NotImplementedError):   # UnsupportedConfig is a NotImplementedError
         P.get_model(dict(name="UNet3D", in_channels=1, out_channels=1, f_maps=8, num_levels=2, layer_order="bcr"))
     with pytest.raises(NotImplementedError):
         P.get_model(dict(name="UNet2D", in_channels=1, out_channels=1))

@@ -23,6 +23,14 @@ MODEL_CASES = {
                              "bce_dice_loss"),
     "resunetse3d_f16_l2_gce": (dict(name="ResidualUNetSE3D", in_channels=2, out_channels=1, f_maps=16, num_levels=2, layer_order="gce"),
                                "dice_loss"),
+    # upsampling modes reachable through the model config + the residual block's default order
+    "unet3d_f16_l2_trilinear": (dict(name="UNet3D", in_channels=1, out_channels=1, f_maps=16, num_levels=2, upsample="trilinear"),
+                                "bce_dice_loss"),
+    "unet3d_f16_l2_deconv": (dict(name="UNet3D", in_channels=1, out_channels=1, f_maps=16, num_levels=2, upsample="deconv"), "bce_dice_loss"),
+    "resunet3d_f16_l2_cge": (dict(name="ResidualUNet3D", in_channels=1, out_channels=1, f_maps=16, num_levels=2, layer_order="cge"),
+                             "bce_dice_loss"),
+    "resunet3d_f16_l2_deconvcat": (dict(name="ResidualUNet3D", in_channels=1, out_channels=1, f_maps=16, num_levels=2, upsample="deconv"),
+                                   "bce_dice_loss"),
 }
 
 
