@@ -2,7 +2,7 @@
 # round 2, GPU call A: full GPU test suite, smoke, and the four benchmark workloads at N=1
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader > gpurun_out/a_gpu.txt 2>&1
-( time timeout 1500 python -m pytest tests -m gpu -q --maxfail=25 -x --deselect tests/test_gpu_parity_configs.py -p no:cacheprovider ) > gpurun_out/a_tests.log 2>&1
+( time timeout 1500 python -m pytest tests -m gpu -q --maxfail=25 --deselect tests/test_gpu_parity_configs.py -p no:cacheprovider ) > gpurun_out/a_tests.log 2>&1
 echo "rc=$?" >> gpurun_out/a_tests.log
 ( time timeout 900 python -m pytest tests/test_gpu_parity_configs.py -q -s -p no:cacheprovider ) > gpurun_out/a_parity.log 2>&1
 echo "rc=$?" >> gpurun_out/a_parity.log
