@@ -171,5 +171,7 @@ int choose_box(int D, int H, int W, int* bd, int* bh, int* bw);
 bool conv_igemm_supported(int N, int D, int H, int W, int Cin, int Cout);
 bool conv_halo_plan(int N, int D, int H, int W, int Cin, int Cout, ConvParams* p);
 int conv_halo_launch(const void* x, const void* wf, ConvParams& p, cudaStream_t s);
+bool conv_zs_plan(int N, int D, int H, int W, int Cin, int Cout, ConvParams* p);   // conv_zs_sm100.cu: depth taps stacked along N
+int conv_zs_launch(const void* x, const void* wf, ConvParams& p, cudaStream_t s);
 
 }  // namespace b200

@@ -369,6 +369,7 @@ int b200_conv3_igemm_partials_count(int N, int D, int H, int W, int Cin, int Cou
   (void)Cin;
   (void)Cout;
   ConvParams hp;
+  if (conv_zs_plan(N, D, H, W, Cin, Cout, &hp)) return hp.ctas_per_sample;  // one partial row per persistent CTA
   if (conv_halo_plan(N, D, H, W, Cin, Cout, &hp)) return hp.tilesD * hp.tilesH * hp.tilesW;
   int bd, bh, bw;
   if (choose_box(D, H, W, &bd, &bh, &bw)) return 0;
@@ -386,8 +387,10 @@ int b200_conv3_igemm_fwd(const void* x, const void* wf, int n_w, const float* bi
   memset(&p, 0, sizeof(p));
   B200_CHECK_ARG(pmode == 0 || partials, "conv3_igemm: pmode=%d needs a partials buffer", pmode);
   B200_CHECK_ARG(pmode != 2 || aux, "conv3_igemm: pmode=2 needs aux");
-  if (conv_halo_plan(N, D, H, W, Cin, Cout, &p)) {
-    // small-channel / large-volume layers: one halo tile in shared memory feeds all 27 taps, weights stay resident
+  const bool zs = conv_zs_plan(N, D, H, W, Cin, Cout, &p);
+  B200_CHECK_ARG(!(zs && pmode == 2), "conv3_igemm: pmode=2 is not provided by the z-stacked kernel (B200UNET_ZS=0 selects the halo kernel)");
+  if (zs || conv_halo_plan(N, D, H, W, Cin, Cout, &p)) {
+    // small-channel / large-volume layers: halo tiles in shared memory feed all taps, weights stay resident
     p.n_w = n_w;
     p.n_b = biascls ? n_b : 0;
     p.act = act;
@@ -399,7 +402,7 @@ int b200_conv3_igemm_fwd(const void* x, const void* wf, int n_w, const float* bi
     p.aux = (const bf16*)aux;
     p.y = (bf16*)y;
     p.partials = partials;
-    return conv_halo_launch(x, wf, p, (cudaStream_t)s);
+    return zs ? conv_zs_launch(x, wf, p, (cudaStream_t)s) : conv_halo_launch(x, wf, p, (cudaStream_t)s);
   }
   PlainGeom g;
   g.cls_mode = cls_mode;

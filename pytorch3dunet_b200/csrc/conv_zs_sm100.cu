@@ -1,0 +1,458 @@
+// 3x3x3 convolution with the three DEPTH taps stacked along the MMA's N dimension ("z-stacked" kernel): the fprop / dgrad kernel of the
+// small-channel, large-volume layers (C_out <= 128, 27*C_in*C_out*2 bytes of weights resident in shared memory).
+//
+// Why.  A tcgen05.mma with both operands in shared memory (M=128, K=16, bf16) is paced by max(math, operand fetch):
+//   math   = N/2 cycles,   operand fetch = (128 + N) * 32 B / (128 B/cycle) = 32 + N/4 cycles
+// (fits every probe in profiles/probes_r01.md: 40 / 48 / 64 cycles at N = 32 / 64 / 128 with two issuers).  With N = C_out = 32 an
+// instruction does 16 cycles of math in 40: the layers that hold most of the net's FLOPs ran at 40 % of the tensor pipe whatever the
+// issue loop did.  Stacking the weights of the three depth taps along N (N = 3*C_out = 96: 48 cycles of math in 56) makes ONE
+// instruction do the work of three:
+//
+//   input plane z (one 18x10-voxel halo tile, K = C_in)  x  [W(dd=+1) | W(dd=0) | W(dd=-1)] (N = 3*C_out)
+//        = contributions to the output planes  z-1 | z | z+1,   which live in ADJACENT column blocks of TMEM.
+//
+// Each persistent CTA walks a column of tiles along the depth axis; output plane z accumulates in TMEM while the input planes z-1, z,
+// z+1 stream through, then the epilogue warps drain it while the next planes accumulate.  Every input plane tile is fetched once
+// (1.4x halo overhead instead of 4.2x), the MMA count per output tile drops from 27*C_in/16 to 9*C_in/16.
+//
+//   TMEM: a ring of R = min(16, 512 / C_out) column blocks of C_out columns; output plane number q (in the CTA's own order) lives in
+//         block q mod R.  An input plane targets up to three consecutive blocks = one MMA, or two when the ring wraps.
+//   first touch of a block uses accumulate = 0: the very first (tap, k) step of an input plane is issued as separate MMAs for the
+//         already-open blocks (accumulate) and the newly opened one (overwrite); all other steps are single instructions.
+//   warps: 0..3 / 4..7 two epilogue groups (even / odd planes), 8 TMA producer, 9 MMA issuer (+ TMEM allocation).
+//   GroupNorm statistics of the output: per-thread register accumulators across all planes of the CTA (C_out <= 32) or per-warp
+//         shared-memory accumulators (wider), reduced ONCE at the end: partials [N][P = CTAs per sample][C_out][2].
+//
+// Same contract as conv3_halo_kernel (conv_halo_sm100.cu): y = act(conv(x, wf) + bias[cls] (+ residual)), bf16 NDHWC.
+#include <stdlib.h>
+
+#include "conv_common.cuh"
+
+namespace b200 {
+
+constexpr int ZS_BH = 16, ZS_BW = 8;
+constexpr int ZS_HH = ZS_BH + 2, ZS_HW = ZS_BW + 2;
+constexpr int ZS_ROWS = ZS_HH * ZS_HW;  // 180 rows of one input-plane halo tile
+constexpr int ZS_THREADS = 2 * 128 + 64;
+constexpr int ZS_WARP_PRODUCER = 8, ZS_WARP_MMA = 9;
+constexpr int ZS_MAX_STAGES = 8;
+constexpr int ZS_MAX_SLOTS = 16;
+
+struct ZsRun {
+  uint32_t tacc;   // TMEM column address of the first block
+  uint32_t boff;   // offset of the first weight block, 16-byte units
+  uint32_t idesc;  // instruction descriptor for N = blocks * C_out
+  uint32_t accum;  // accumulate flag of the FIRST (tap, k) step of the input plane (always 1 afterwards)
+};
+
+// one (tap, k) step = one MMA per non-empty run (idesc == 0 marks an empty run)
+__device__ __forceinline__ void zs_issue(const ZsRun (&r)[3], uint64_t adesc, uint64_t bdesc, bool first) {
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    if (r[k].idesc) umma_bf16_elect(r[k].tacc, adesc, bdesc + r[k].boff, r[k].idesc, first ? r[k].accum : 1u);
+}
+
+// all 9 in-plane taps x KC/16 k-steps of one halo chunk.  b_lo points at [t9 = 0][tdr = 0] of this chunk; one t9 advances 3 blocks.
+template <int KC>
+__device__ __forceinline__ void zs_issue_chunk(const ZsRun (&rf)[3], const ZsRun (&rr)[3], uint32_t a_lo, uint32_t b_lo, uint32_t b_t9,
+                                               uint64_t hiA, uint64_t hiB, bool first_chunk) {
+  constexpr uint32_t RB16 = KC * 2 / 16;  // one halo row in 16-byte units
+#pragma unroll
+  for (int t9 = 0; t9 < 9; ++t9) {
+    const uint32_t offA = (uint32_t)((t9 / 3) * ZS_HW + t9 % 3) * RB16;
+#pragma unroll
+    for (int k = 0; k < KC / 16; ++k) {
+      const uint64_t adesc = hiA | (uint64_t)(a_lo + offA + 2u * k);
+      const uint64_t bdesc = hiB | (uint64_t)(b_lo + 2u * k);
+      if (t9 == 0 && k == 0 && first_chunk) zs_issue(rf, adesc, bdesc, true);
+      else zs_issue(rr, adesc, bdesc, false);
+    }
+    b_lo += b_t9;
+  }
+}
+
+// the CTA's share of the sample: plane-tiles [L0, L1) in the order (column = th*tilesW + tw, then depth)
+struct ZsRange {
+  long long L0, L1;
+};
+__device__ __forceinline__ ZsRange zs_range(const ConvParams& p, int cta, int cps) {
+  const long long T = (long long)p.tilesH * p.tilesW * p.D;
+  ZsRange r;
+  r.L0 = T * cta / cps;
+  r.L1 = T * (cta + 1) / cps;
+  return r;
+}
+
+template <int KC>
+__global__ void __launch_bounds__(ZS_THREADS, 1)
+conv3_zs_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, const ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t a_full[ZS_MAX_STAGES], a_empty[ZS_MAX_STAGES];
+  __shared__ __align__(8) uint64_t b_full, tmem_full[ZS_MAX_SLOTS], tmem_empty[ZS_MAX_SLOTS];
+  __shared__ uint32_t tmem_slot;
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smemB = smem;
+  const int b_region = (p.b_total_bytes + 1023) & ~1023;
+  uint8_t* smemA = smem + b_region;
+  float* stat_acc = reinterpret_cast<float*>(smemA + (size_t)p.a_stages * p.a_bytes);  // [8 epilogue warps][NT][2]
+  float* bias_interior = stat_acc + 8 * p.NT * 2;                                        // [8 parity variants][NT]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.y, cta = blockIdx.x, cps = gridDim.x;
+  const int nchunks = p.Cin / KC;
+  constexpr int rb = KC * 2;
+  const int R = p.tmem_bufs;  // ring slots
+  const ZsRange rg = zs_range(p, cta, cps);
+  const int D = p.D;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.a_stages; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+    }
+    mbar_init(&b_full, 1);
+    for (int i = 0; i < R; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);  // one arrival per epilogue warp of the group that drained it
+    }
+    fence_mbar_init();
+  }
+  if (warp == ZS_WARP_PRODUCER && lane == 0) {
+    tma_prefetch_desc(&tmapA);
+    tma_prefetch_desc(&tmapB);
+  }
+  if (warp == ZS_WARP_MMA) tmem_alloc(&tmem_slot, (uint32_t)p.tmem_cols);
+  if (p.n_b)
+    for (int i = threadIdx.x; i < 8 * p.NT; i += ZS_THREADS) {
+      const int v = i / p.NT, c = i - v * p.NT;
+      const int cls = ((v & 4 ? 3 : 1) << 4) | ((v & 2 ? 3 : 1) << 2) | (v & 1 ? 3 : 1);
+      bias_interior[i] = p.biascls[((size_t)(p.n_b > 1 ? n : 0) * 64 + cls) * p.Cout + c];
+    }
+  for (int i = threadIdx.x; i < 8 * p.NT * 2; i += ZS_THREADS) stat_acc[i] = 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == ZS_WARP_PRODUCER) {
+    // ================= TMA producer: resident weights once, then one halo tile per (input plane, channel chunk) =================
+    if (lane == 0) {
+      const int wsample = p.n_w > 1 ? n : 0;
+      mbar_arrive_expect_tx(&b_full, (uint32_t)p.b_total_bytes);
+      // smem layout [chunk][t9][tdr = 2 - td][C_out][KC]: the three depth taps of one in-plane tap are adjacent row blocks, in the
+      // order of ascending OUTPUT plane (z-1 <- dd=+1, z <- dd=0, z+1 <- dd=-1)
+      for (int cb = 0; cb < nchunks; ++cb)
+        for (int t9 = 0; t9 < 9; ++t9)
+          for (int tdr = 0; tdr < 3; ++tdr)
+            tma_load_3d(smemB + ((size_t)((cb * 9 + t9) * 3 + tdr)) * p.NT * rb, &tmapB, &b_full, cb * KC, 0,
+                        wsample * 27 + (2 - tdr) * 9 + t9);
+      long long c = 0;  // halo tiles loaded so far
+      for (long long L = rg.L0; L < rg.L1;) {
+        const int col = (int)(L / D), z0 = (int)(L - (long long)col * D);
+        const long long rest = rg.L1 - L;
+        const int z1 = (rest < (long long)(D - z0)) ? z0 + (int)rest : D;
+        const int th_i = col / p.tilesW, tw_i = col - th_i * p.tilesW;
+        const int h0 = th_i * ZS_BH, w0 = tw_i * ZS_BW;
+        const int zin0 = z0 > 0 ? z0 - 1 : 0, zin1 = z1 < D ? z1 : D - 1;
+        for (int zin = zin0; zin <= zin1; ++zin)
+          for (int j = 0; j < nchunks; ++j, ++c) {
+            const int stage = (int)(c % p.a_stages);
+            mbar_wait(&a_empty[stage], ((uint32_t)(c / p.a_stages) & 1u) ^ 1u);
+            mbar_arrive_expect_tx(&a_full[stage], (uint32_t)(ZS_ROWS * rb));
+            tma_load_5d(smemA + (size_t)stage * p.a_bytes, &tmapA, &a_full[stage], j * KC, w0 - 1, h0 - 1, zin, n);
+          }
+        L += z1 - z0;
+      }
+    }
+  } else if (warp == ZS_WARP_MMA) {
+    // ================= MMA issuer (whole warp converged, one elected lane issues) =================
+    const uint32_t lay = umma_layout_for_row_bytes(rb);
+    const uint64_t hiA = umma_smem_desc(0, 16u, (uint32_t)(ZS_HW * rb), lay) & 0xFFFFFFFF00000000ull;
+    const uint64_t hiB = umma_smem_desc(0, 16u, (uint32_t)(8 * rb), lay) & 0xFFFFFFFF00000000ull;
+    const uint32_t lo_lbo = 1u << 16;
+    const uint32_t sB0 = smem_u32(smemB);
+    const uint32_t blk16 = (uint32_t)(p.NT * rb) >> 4;  // one weight block [C_out][KC], 16-byte units
+    const uint32_t b_t9 = 3u * blk16;
+    uint32_t idesc_m[4];
+    for (int m = 1; m <= 3; ++m) idesc_m[m] = umma_idesc_bf16(128, m * p.NT, 0, 0);
+    mbar_wait(&b_full, 0);
+    tc_fence_after();
+    long long c = 0;  // halo tiles consumed
+    long long q0 = 0;  // output-plane number of the segment's first plane
+    for (long long L = rg.L0; L < rg.L1;) {
+      const int col = (int)(L / D), z0 = (int)(L - (long long)col * D);
+      const long long rest = rg.L1 - L;
+      const int z1 = (rest < (long long)(D - z0)) ? z0 + (int)rest : D;
+      const int zin0 = z0 > 0 ? z0 - 1 : 0, zin1 = z1 < D ? z1 : D - 1;
+      for (int zin = zin0; zin <= zin1; ++zin) {
+        // output planes this input plane contributes to: [a, b] = [zin-1, zin+1] clipped to the segment; fresh = first touched now
+        const int a = zin - 1 > z0 ? zin - 1 : z0;
+        const int b = zin + 1 < z1 - 1 ? zin + 1 : z1 - 1;
+        const int m = b - a + 1;
+        const long long qa = q0 + (a - z0);
+        const int slot_a = (int)(qa % R);
+        // w: first block index at which the ring wraps (m = no wrap inside this range)
+        int w = R - slot_a;
+        if (w > m) w = m;
+        // f: first FRESH block.  Plane zo is first touched by input plane max(zo-1, 0), or by the segment's first input plane when that
+        // one comes later; that bound is non-decreasing in zo and never exceeds zin, so the fresh planes are a suffix of [a, b]
+        int f = m;
+#pragma unroll
+        for (int i = 2; i >= 0; --i)
+          if (i < m) {
+            const int zo = a + i;
+            int first_in = zo - 1 > 0 ? zo - 1 : 0;
+            if (first_in < zin0) first_in = zin0;
+            if (first_in == zin) f = i;
+          }
+        // a fresh block must have been drained by the epilogue of the plane that used it R planes ago
+        for (int i = f; i < m; ++i) {
+          const long long q = qa + i;
+          mbar_wait(&tmem_empty[(int)(q % R)], ((uint32_t)(q / R) & 1u) ^ 1u);
+        }
+        tc_fence_after();
+        // runs = maximal ranges of blocks that one MMA can cover: cut at the ring wrap; the FIRST (tap, k) step is also cut where the
+        // accumulate flag changes (open blocks accumulate, fresh blocks are overwritten)
+        ZsRun rf[3], rr[3];
+        {
+          const int c1 = w < f ? w : f, c2 = w < f ? f : w;   // sorted cuts (m = none)
+          const int bf[4] = {0, c1, c2, m}, br[4] = {0, w, m, m};
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const int s0 = bf[k], len = bf[k + 1] - bf[k];
+            rf[k].tacc = tmem_base + (uint32_t)(((slot_a + s0) % R) * p.NT);
+            rf[k].boff = (uint32_t)(a - zin + 1 + s0) * blk16;   // tdr of block i: (a + i) - zin + 1
+            rf[k].idesc = len > 0 ? idesc_m[len] : 0u;
+            rf[k].accum = s0 >= f ? 0u : 1u;
+            const int s1 = br[k], len1 = br[k + 1] - br[k];
+            rr[k].tacc = tmem_base + (uint32_t)(((slot_a + s1) % R) * p.NT);
+            rr[k].boff = (uint32_t)(a - zin + 1 + s1) * blk16;
+            rr[k].idesc = len1 > 0 ? idesc_m[len1] : 0u;
+            rr[k].accum = 1u;
+          }
+        }
+        for (int j = 0; j < nchunks; ++j, ++c) {
+          const int stage = (int)(c % p.a_stages);
+          mbar_wait(&a_full[stage], (uint32_t)(c / p.a_stages) & 1u);
+          tc_fence_after();
+          const uint32_t a_lo = ((smem_u32(smemA + (size_t)stage * p.a_bytes) >> 4) & 0x3FFFu) | lo_lbo;
+          const uint32_t b_lo = (((sB0 + (uint32_t)(j * 27 * p.NT * rb)) >> 4) & 0x3FFFu) | lo_lbo;
+          zs_issue_chunk<KC>(rf, rr, a_lo, b_lo, b_t9, hiA, hiB, j == 0);
+          umma_commit_elect(&a_empty[stage]);
+        }
+        // output planes that received their last contribution: zin-1 always (if in the segment); plane D-1 when zin == D-1
+        if (zin - 1 >= z0) umma_commit_elect(&tmem_full[(int)((q0 + (zin - 1 - z0)) % R)]);
+        if (zin == D - 1 && D - 1 < z1) umma_commit_elect(&tmem_full[(int)((q0 + (D - 1 - z0)) % R)]);
+      }
+      q0 += z1 - z0;
+      L += z1 - z0;
+    }
+  } else {
+    // ================= epilogue: warps 0..3 take even output planes, warps 4..7 odd ones =================
+    const int qd = warp & 3;   // TMEM lane quarter
+    const int grp = warp >> 2;
+    const int row = qd * 32 + lane;
+    const int bx = row % ZS_BW, by = row / ZS_BW;
+    const int NT = p.NT;
+    const bool reg_stats = p.pmode != 0 && NT <= 32;
+    float rs[32], rq[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) rs[i] = rq[i] = 0.f;
+    float* my_acc = stat_acc + (size_t)warp * NT * 2;
+    long long q0 = 0;
+    for (long long L = rg.L0; L < rg.L1;) {
+      const int col = (int)(L / D), z0 = (int)(L - (long long)col * D);
+      const long long rest = rg.L1 - L;
+      const int z1 = (rest < (long long)(D - z0)) ? z0 + (int)rest : D;
+      const int th_i = col / p.tilesW, tw_i = col - th_i * p.tilesW;
+      const int xh = th_i * ZS_BH + by, xw = tw_i * ZS_BW + bx;
+      const bool valid = xh < p.H && xw < p.W;
+      for (int zo = z0; zo < z1; ++zo) {
+        const long long q = q0 + (zo - z0);
+        if ((int)(q & 1) != grp) continue;
+        const int slot = (int)(q % R);
+        const size_t vox_off = (size_t)n * D * p.H * p.W + ((size_t)zo * p.H + xh) * p.W + xw;
+        const float* bias_row = nullptr;
+        if (p.n_b && valid) {
+          const int cls = conv_bias_cls(p.cls_mode, zo, xh, xw, D, p.H, p.W);
+          const bool interior = (cls & 0x15) == 0x15;  // every axis class is 1 or 3
+          bias_row = interior ? bias_interior + (((cls >> 3) & 4) | ((cls >> 2) & 2) | ((cls >> 1) & 1)) * NT
+                              : p.biascls + ((size_t)(p.n_b > 1 ? n : 0) * 64 + cls) * p.Cout;
+        }
+        mbar_wait(&tmem_full[slot], (uint32_t)(q / R) & 1u);
+        __syncwarp();
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (uint32_t)(slot * NT) + ((uint32_t)(qd * 32) << 16);
+        for (int c0 = 0; c0 < NT; c0 += 32) {
+          const bool wide = c0 + 32 <= NT;  // else a 16-column tail
+          uint32_t raw[32];
+          if (wide) tmem_ld_32x32b_x32(taddr + c0, raw);
+          else tmem_ld_32x32b_x16(taddr + c0, raw);
+          tmem_ld_wait();
+          const int cw = wide ? 32 : 16;
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = i < cw ? __uint_as_float(raw[i]) : 0.f;
+          const size_t goff = vox_off * p.Cout + c0;
+          if (valid) {
+            if (bias_row) {
+              const float4* bp = reinterpret_cast<const float4*>(bias_row + c0);
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (4 * i < cw) {
+                  const float4 bb = bp[i];
+                  v[4 * i] += bb.x; v[4 * i + 1] += bb.y; v[4 * i + 2] += bb.z; v[4 * i + 3] += bb.w;
+                }
+            }
+            if (p.residual) {
+              const bf16x8* rp = reinterpret_cast<const bf16x8*>(p.residual + goff);
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                if (8 * i < cw) {
+                  float f[8];
+                  unpack8(rp[i], f);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) v[8 * i + j] += f[j];
+                }
+            }
+            if (p.act == B200_ACT_RELU) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+            } else if (p.act == B200_ACT_LEAKY) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * p.slope;
+            } else if (p.act == B200_ACT_ELU) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.f ? v[i] : expm1f(v[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = bf16_round(v[i]);
+            bf16x8* op = reinterpret_cast<bf16x8*>(p.y + goff);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (8 * i < cw) op[i] = pack8(&v[8 * i]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0.f;
+          }
+          if (p.pmode) {
+            if (reg_stats) {  // C_out <= 32: one slab; per-thread accumulators across all planes of the CTA
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                rs[i] += v[i];
+                rq[i] += v[i] * v[i];
+              }
+            } else {          // wider: reduce over the warp's 32 rows now, accumulate per warp in shared memory
+              float w[32];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) w[i] = v[i] * v[i];
+              const float s = warp_reduce_scatter<32>(v, lane);
+              const float qq = warp_reduce_scatter<32>(w, lane);
+              if (lane < cw) {
+                my_acc[(c0 + lane) * 2] += s;
+                my_acc[(c0 + lane) * 2 + 1] += qq;
+              }
+            }
+          }
+        }
+        // block drained -> hand it back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[slot]);
+      }
+      q0 += z1 - z0;
+      L += z1 - z0;
+    }
+    if (reg_stats) {
+      const float s = warp_reduce_scatter<32>(rs, lane);
+      const float qq = warp_reduce_scatter<32>(rq, lane);
+      if (lane < NT) {
+        my_acc[lane * 2] = s;
+        my_acc[lane * 2 + 1] = qq;
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (p.pmode) {  // fixed-order sum over the 8 epilogue warps -> this CTA's partial row
+    float* out = p.partials + (((size_t)n * cps + cta) * p.Cout) * 2;
+    for (int i = threadIdx.x; i < p.NT * 2; i += ZS_THREADS) {
+      float acc = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) acc += stat_acc[(size_t)w * p.NT * 2 + i];
+      out[i] = acc;
+    }
+  }
+  if (warp == ZS_WARP_MMA) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+static bool zs_enabled() {  // B200UNET_ZS=0 falls back to conv3_halo_kernel / the tap-loop kernel (read per call: tests toggle it)
+  const char* e = getenv("B200UNET_ZS");
+  return !(e && e[0] == '0');
+}
+
+// decides whether the z-stacked kernel takes this layer and fills the plan
+bool conv_zs_plan(int N, int D, int H, int W, int Cin, int Cout, ConvParams* pp) {
+  ConvParams& p = *pp;
+  memset(&p, 0, sizeof(p));
+  if (!zs_enabled()) return false;
+  if (Cin % 16 != 0 || Cout % 16 != 0 || 3 * Cout > 256) return false;  // one MMA covers up to three C_out-wide blocks (N <= 256)
+  if (H < ZS_HH || W < ZS_HW || D < 1) return false;  // keep the TMA box inside the tensor extent
+  const int budget = 222 * 1024;
+  const int b_total = 27 * Cout * Cin * 2;
+  const int scratch = (8 * Cout * 2 + 8 * Cout) * (int)sizeof(float);
+  const int kc = (Cin % 64 == 0) ? 64 : (Cin % 32 == 0 ? 32 : 16);
+  const int a_bytes = (ZS_ROWS * kc * 2 + 1023) & ~1023;
+  int stages = (budget - ((b_total + 1023) & ~1023) - scratch - 1024) / a_bytes;
+  if (stages < 3) return false;
+  if (stages > ZS_MAX_STAGES) stages = ZS_MAX_STAGES;
+  p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
+  p.BD = 1; p.BH = ZS_BH; p.BW = ZS_BW;
+  p.tilesD = D;
+  p.tilesH = (H + ZS_BH - 1) / ZS_BH;
+  p.tilesW = (W + ZS_BW - 1) / ZS_BW;
+  p.NT = Cout;
+  p.KC = kc;
+  p.KCb = kc;
+  p.kchunks = Cin / kc;
+  p.a_stages = stages;
+  p.a_bytes = a_bytes;
+  p.b_total_bytes = b_total;
+  int slots = 512 / Cout;
+  if (slots > ZS_MAX_SLOTS) slots = ZS_MAX_SLOTS;
+  if (slots < 4) return false;
+  p.tmem_bufs = slots;
+  p.tmem_cols = 512;
+  long long T = (long long)p.tilesH * p.tilesW * D;
+  int cps = sm_count() / N;
+  if (cps < 1) cps = 1;
+  if (const char* e = getenv("B200UNET_ZS_CTAS")) {  // tests: few CTAs per sample => long depth walks (ring wrap, mid-column segment cuts)
+    const int v = atoi(e);
+    if (v >= 1) cps = v;
+  }
+  if (cps > T) cps = (int)T;
+  p.ctas_per_sample = cps;
+  return true;
+}
+
+int conv_zs_launch(const void* x, const void* wf, ConvParams& p, cudaStream_t s) {
+  CUtensorMap tmA, tmB;
+  int rc = make_act_tmap(&tmA, x, p.N, p.D, p.H, p.W, p.Cin, p.KC, 1, ZS_HH, ZS_HW);
+  if (rc) return rc;
+  rc = make_w_tmap(&tmB, wf, 27 * p.n_w, p.Cout, p.Cin, p.KC, p.NT, 1);
+  if (rc) return rc;
+  size_t smem = (size_t)((p.b_total_bytes + 1023) & ~1023) + (size_t)p.a_stages * p.a_bytes + (size_t)(8 * p.NT * 2 + 8 * p.NT) * sizeof(float) + 1024;
+  auto kern = p.KC == 64 ? conv3_zs_kernel<64> : (p.KC == 32 ? conv3_zs_kernel<32> : conv3_zs_kernel<16>);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  B200_CHECK_ARG(e == cudaSuccess, "conv3_zs: cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e));
+  dim3 grid((unsigned)p.ctas_per_sample, (unsigned)p.N);
+  kern<<<grid, ZS_THREADS, smem, s>>>(tmA, tmB, p);
+  B200_CHECK_LAUNCH("conv3_zs");
+  return 0;
+}
+
+}  // namespace b200

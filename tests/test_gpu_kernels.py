@@ -75,6 +75,54 @@ def test_tcgen05_conv_matches_torch_and_direct(shape):
     assert U.rel_l2(sums[..., 1], (yf * yf).sum(dim=(1, 2, 3))) < 1e-4
 
 
+# the z-stacked kernel (csrc/conv_zs_sm100.cu): depth taps stacked along the MMA's N dimension, output planes in a TMEM ring.
+# Few CTAs per sample force long walks along the depth axis: ring wrap-around (R = 512 / C_out blocks), segments that start /
+# end in the middle of a column (halo planes with a single target block), several columns per CTA.
+ZS_CASES = [
+    # N, D, H, W, Cin, Cout, ctas per sample
+    (1, 40, 36, 20, 32, 32, 1),
+    (1, 40, 36, 20, 32, 32, 3),
+    (1, 40, 36, 20, 32, 32, 7),
+    (2, 21, 18, 10, 16, 32, 2),
+    (1, 19, 33, 17, 64, 48, 2),     # ragged tiles, N = 144, ring of 10 blocks
+    (1, 12, 20, 12, 32, 64, 1),     # N = 192, ring of 8 blocks
+    (1, 9, 18, 10, 32, 80, 1),      # N = 240, ring of 6 blocks
+    (1, 1, 18, 10, 16, 16, 1),      # a single plane
+    (1, 2, 20, 12, 96, 32, 2),      # three 32-channel chunks per plane
+    (1, 70, 18, 10, 32, 16, 1),     # N = 48, ring of 16 blocks wraps four times
+]
+
+
+@pytest.mark.parametrize("case", ZS_CASES)
+def test_zstacked_conv_matches_torch_and_direct(case, monkeypatch):
+    from tests import gpu_util as U
+    from pytorch3dunet_b200 import engine as E
+    from pytorch3dunet_b200._lib import lib
+    N, D, H, W, Cin, Cout, cps = case
+    monkeypatch.setenv("B200UNET_ZS_CTAS", str(cps))
+    assert lib().query("b200_conv3_igemm_partials_count", N, D, H, W, Cin, Cout) == min(cps, D * ((H + 15) // 16) * ((W + 7) // 8))
+    x, wf, b = _mk(N, D, H, W, Cin, Cout, N, 11)
+    res = (torch.randn((N, D, H, W, Cout), device="cuda") * 0.3).bfloat16()
+    y, sums = U.run_conv3(E.IMPL_TCGEN05, x, wf, b, act=E.ACT_LEAKY, slope=0.1, residual=res, want_stats=True)
+    torch.cuda.synchronize()
+    ref = U.conv3_contract_ref(x, wf, b, act=E.ACT_LEAKY, slope=0.1, residual=res)
+    yd, _ = U.run_conv3(E.IMPL_DIRECT, x, wf, b, act=E.ACT_LEAKY, slope=0.1, residual=res)
+    print("zs", case, "vs torch", U.rel_l2(y, ref), "vs direct", U.rel_l2(y, yd.float()))
+    assert U.rel_l2(y, ref) < TOL
+    assert U.rel_l2(y, yd.float()) < 5e-3
+    yf = y.double()
+    assert U.rel_l2(sums[..., 0], yf.sum(dim=(1, 2, 3))) < 1e-4
+    assert U.rel_l2(sums[..., 1], (yf * yf).sum(dim=(1, 2, 3))) < 1e-4
+    # same result whatever the work split (fp32 accumulation order inside a voxel does not depend on it)
+    monkeypatch.setenv("B200UNET_ZS_CTAS", str(cps + 1))
+    y2, _ = U.run_conv3(E.IMPL_TCGEN05, x, wf, b, act=E.ACT_LEAKY, slope=0.1, residual=res)
+    assert torch.equal(y, y2)
+    # and the 27-separate-taps kernels (halo / tap-loop) agree with it
+    monkeypatch.setenv("B200UNET_ZS", "0")
+    y3, _ = U.run_conv3(E.IMPL_TCGEN05, x, wf, b, act=E.ACT_LEAKY, slope=0.1, residual=res)
+    assert U.rel_l2(y, y3.float()) < 5e-3
+
+
 def test_tcgen05_conv_residual_no_bias_shared_weights():
     from tests import gpu_util as U
     from pytorch3dunet_b200 import engine as E

@@ -6,7 +6,9 @@ fp32 (TF32 off: the reference's own GPU path is cuDNN fp32, buildingblocks.py:56
         the same inputs, or within 1e-2 outright (SURVEY.md section 7 hard part 5: random-weight logits sit near zero, so their
         relative error is dominated by bf16 storage of O(1) activations -- for any bf16 implementation);
   (iii) the activation-pattern flip rate between the engine and the fp32 reference stays below 0.5 % of the elements of every
-        ReLU (so that pinning those masks for the gradient comparison cannot hide a forward bug);
+        ReLU, or -- in the deep decoder layers, where the inputs of a ReLU have themselves drifted by a few per cent -- below 1.25x
+        the flip rate torch's own bf16 path shows at the same layer (so that pinning those masks for the gradient comparison
+        cannot hide a forward bug: a wrong layer would flip a large fraction of its outputs);
   (iv)  every parameter gradient against the oracle evaluated at the engine's activation pattern / pool argmax.
 """
 import pytest
@@ -65,12 +67,14 @@ def _run_case(cfg, shape, loss_name, seed=0):
     with torch.no_grad():
         rec = {}
         r_out, r_logits = O.forward(sd0, cfg, x, masks={"__record__": rec})
+        rec_b = {}
         with torch.autocast("cuda", dtype=torch.bfloat16):
-            b_out, b_logits = O.forward(sd0, cfg, x)
+            b_out, b_logits = O.forward(sd0, cfg, x, masks={"__record__": rec_b})
         drift = rel_l2(b_logits.float(), r_logits)
         drift_p = rel_l2(b_out.float(), r_out)
         flips = {k: (masks[k] != rec[k]).float().mean().item() for k in rec if k in masks}
-        del b_out, b_logits, rec
+        flips_torch = {k: (rec_b[k] != rec[k]).float().mean().item() for k in rec if k in rec_b}
+        del b_out, b_logits, rec, rec_b
     rep = {"logits": rel_l2(e_logits, r_logits), "torch_bf16_logits": drift, "probs": rel_l2(e_out, r_out), "torch_bf16_probs": drift_p,
            "max_flip": max(flips.values()) if flips else 0.0}
     torch.cuda.empty_cache()
@@ -95,10 +99,12 @@ def _run_case(cfg, shape, loss_name, seed=0):
             worst = (k, r)
     rep["worst_grad"] = worst
     print(cfg["name"], shape, {k: (f"{v:.3e}" if isinstance(v, float) else v) for k, v in rep.items()})
-    print("  flip rates:", {k: f"{v:.2e}" for k, v in sorted(flips.items(), key=lambda kv: -kv[1])[:4]})
+    print("  flip rates (engine / torch bf16):", {k: f"{v:.2e} / {flips_torch.get(k, float('nan')):.2e}"
+                                                 for k, v in sorted(flips.items(), key=lambda kv: -kv[1])[:4]})
     assert rep["probs"] <= PROB_TOL, rep
     assert rep["logits"] <= max(DRIFT_FACTOR * drift, 1e-2), rep
-    assert rep["max_flip"] < FLIP_TOL, flips
+    bad_flips = {k: (v, flips_torch.get(k)) for k, v in flips.items() if v >= max(FLIP_TOL, DRIFT_FACTOR * flips_torch.get(k, 0.0))}
+    assert not bad_flips, bad_flips
     assert rep["loss_abs"] < 5e-3, rep
     assert worst[1] < GRAD_TOL, worst
     return rep

@@ -82,7 +82,10 @@ def test_query_functions_without_gpu():
     L = lib()
     assert L.query("b200_conv3_igemm_supported", 2, 128, 128, 128, 96, 32) == 1
     assert L.query("b200_conv3_igemm_supported", 2, 128, 128, 128, 1, 16) == 0
-    assert L.query("b200_conv3_igemm_partials_count", 2, 128, 128, 128, 96, 32) == 128 ** 3 // 128
+    # z-stacked kernel (resident weights fit): one partial row per persistent CTA, 148 SMs / 2 samples
+    assert L.query("b200_conv3_igemm_partials_count", 2, 128, 128, 128, 96, 32) == 148 // 2
+    # tap-loop kernel (weights too large to stay resident): one partial row per 128-voxel tile
+    assert L.query("b200_conv3_igemm_partials_count", 2, 32, 32, 32, 128, 128) == 32 ** 3 // 128
     assert L.query("b200_maxpool_partials_count", 1, 64, 64, 64, 32) >= 1
 
 
