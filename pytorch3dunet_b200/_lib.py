@@ -12,7 +12,7 @@ import re
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 HEADER = os.path.join(_ROOT, "include", "b200unet.h")
-LIB_PATH = os.path.join(_HERE, "libb200unet.so")
+LIB_PATH = os.environ.get("B200UNET_LIB") or os.path.join(_HERE, "libb200unet.so")   # B200UNET_LIB: e.g. the debug build with wait counters
 
 _CTYPES = {
     "int": ctypes.c_int,

