@@ -352,11 +352,18 @@ def run_train(args, wl):
 
     pk, pk_src = peaks()
     by = {}
-    for tag, fl, a, b in timing:
+    blocks = {}
+    for tag, fl, a, b, layer in timing:
         d = by.setdefault(tag, [0.0, 0.0, 0])
+        t_ms = a.elapsed_time(b)
         d[0] += fl
-        d[1] += a.elapsed_time(b)
+        d[1] += t_ms
         d[2] += 1
+        if layer:
+            bl = blocks.setdefault(layer.rstrip("."), {})
+            e = bl.setdefault(tag.split("_")[0], [0.0, 0.0])
+            e[0] += fl
+            e[1] += t_ms
     tc = {k: v for k, v in by.items() if k.endswith("_tc")}
     tc_flops = sum(v[0] for v in tc.values())
     tc_ms = sum(v[1] for v in tc.values())
@@ -378,7 +385,12 @@ def run_train(args, wl):
                 "share_of_step": (tc_ms / 3) / (ms_instr / 3) if ms_instr else None,
                 "measured_in": "a separate instrumented pass of 3 steps (per-launch CUDA events), not the pass that produced `value`",
                 "per_kernel": {k: {"tflops": v[0] / (v[1] / 1e3) / 1e12 if v[1] else None, "ms_per_step": v[1] / 3, "launches_per_step": v[2] / 3}
-                               for k, v in by.items()}}
+                               for k, v in by.items()},
+                # every fused block (SingleConv = GroupNorm + conv + activation): achieved TFLOP/s of its fprop / dgrad / wgrad launches
+                # (algorithmic FLOPs as executed; a virtual-concat conv counts its encoder conv and its phase conv together) and the
+                # fraction of the measured sustained bf16 peak
+                "per_block": {name: {kind: {"ms": round(v[1] / 3, 4), "tflops": round(v[0] / (v[1] / 1e3) / 1e12, 1), "frac": round(v[0] / (v[1] / 1e3) / 1e12 / peak, 3)}
+                                     for kind, v in kinds.items() if v[1] > 0} for name, kinds in blocks.items()}}
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:

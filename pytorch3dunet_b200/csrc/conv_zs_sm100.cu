@@ -45,7 +45,7 @@ struct ZsRun {
   uint32_t accum;  // accumulate flag of the FIRST (tap, k) step of the input plane (always 1 afterwards)
 };
 
-// one (tap, k) step = one MMA per non-empty run (idesc == 0 marks an empty run)
+// one (tap, k) step = one MMA per non-empty run (idesc == 0 marks an empty run) -- general path (ring wrap, first step of a plane)
 __device__ __forceinline__ void zs_issue(const ZsRun (&r)[3], uint64_t adesc, uint64_t bdesc, bool first) {
 #pragma unroll
   for (int k = 0; k < 3; ++k)
@@ -53,10 +53,14 @@ __device__ __forceinline__ void zs_issue(const ZsRun (&r)[3], uint64_t adesc, ui
 }
 
 // all 9 in-plane taps x KC/16 k-steps of one halo chunk.  b_lo points at [t9 = 0][tdr = 0] of this chunk; one t9 advances 3 blocks.
-template <int KC>
-__device__ __forceinline__ void zs_issue_chunk(const ZsRun (&rf)[3], const ZsRun (&rr)[3], uint32_t a_lo, uint32_t b_lo, uint32_t b_t9,
-                                               uint64_t hiA, uint64_t hiB, bool first_chunk) {
+// `skip_first`: the (t9 = 0, k = 0) step of the plane's first chunk has been issued separately (its accumulate flags differ per block).
+// ONE_RUN: the plane's blocks are contiguous in TMEM (no ring wrap): one instruction per step, descriptors advance by immediates --
+// the issuing warp must sustain one MMA per ~56 cycles, so no run loop / predicates in here.
+template <int KC, bool ONE_RUN>
+__device__ __forceinline__ void zs_issue_chunk(const ZsRun (&rr)[3], uint32_t a_lo, uint32_t b_lo, uint32_t b_t9, uint64_t hiA, uint64_t hiB,
+                                               bool skip_first) {
   constexpr uint32_t RB16 = KC * 2 / 16;  // one halo row in 16-byte units
+  if (ONE_RUN) b_lo += rr[0].boff;
 #pragma unroll
   for (int t9 = 0; t9 < 9; ++t9) {
     const uint32_t offA = (uint32_t)((t9 / 3) * ZS_HW + t9 % 3) * RB16;
@@ -64,24 +68,57 @@ __device__ __forceinline__ void zs_issue_chunk(const ZsRun (&rf)[3], const ZsRun
     for (int k = 0; k < KC / 16; ++k) {
       const uint64_t adesc = hiA | (uint64_t)(a_lo + offA + 2u * k);
       const uint64_t bdesc = hiB | (uint64_t)(b_lo + 2u * k);
-      if (t9 == 0 && k == 0 && first_chunk) zs_issue(rf, adesc, bdesc, true);
-      else zs_issue(rr, adesc, bdesc, false);
+      if (t9 == 0 && k == 0) {
+        if (!skip_first) {
+          if (ONE_RUN) umma_bf16_elect(rr[0].tacc, adesc, bdesc, rr[0].idesc, 1u);
+          else zs_issue(rr, adesc, bdesc, false);
+        }
+      } else {
+        if (ONE_RUN) umma_bf16_elect(rr[0].tacc, adesc, bdesc, rr[0].idesc, 1u);
+        else zs_issue(rr, adesc, bdesc, false);
+      }
     }
     b_lo += b_t9;
   }
 }
 
-// the CTA's share of the sample: plane-tiles [L0, L1) in the order (column = th*tilesW + tw, then depth)
-struct ZsRange {
-  long long L0, L1;
+// The CTA's share of the sample: plane-tiles [L0, L1) in the order (column = th*tilesW + tw, then depth), cut into segments that stay
+// inside one column.  All per-plane bookkeeping below is 32-bit and incremental (ring indices and mbarrier phase bits are carried,
+// never recomputed with divisions: a 64-bit division costs hundreds of cycles and the issuing warp has ~56 per instruction).
+struct ZsSeg {
+  int col, z0, z1;
 };
-__device__ __forceinline__ ZsRange zs_range(const ConvParams& p, int cta, int cps) {
-  const long long T = (long long)p.tilesH * p.tilesW * p.D;
-  ZsRange r;
-  r.L0 = T * cta / cps;
-  r.L1 = T * (cta + 1) / cps;
-  return r;
+struct ZsWalk {
+  int L, L1, D;
+  __device__ __forceinline__ bool next(ZsSeg& s) {
+    if (L >= L1) return false;
+    s.col = L / D;
+    s.z0 = L - s.col * D;
+    const int rest = L1 - L;
+    s.z1 = rest < D - s.z0 ? s.z0 + rest : D;
+    L += s.z1 - s.z0;
+    return true;
+  }
+};
+__device__ __forceinline__ ZsWalk zs_walk(const ConvParams& p, int cta, int cps) {
+  const long long T = (long long)p.tilesH * p.tilesW * p.D;  // < 2^31 (checked by the plan)
+  ZsWalk w;
+  w.L = (int)(T * cta / cps);
+  w.L1 = (int)(T * (cta + 1) / cps);
+  w.D = p.D;
+  return w;
 }
+// ring position: index + phase bit of its current use, advanced one step at a time
+struct ZsRing {
+  int idx;
+  uint32_t ph;
+  __device__ __forceinline__ void step(int n) {
+    if (++idx == n) {
+      idx = 0;
+      ph ^= 1u;
+    }
+  }
+};
 
 template <int KC>
 __global__ void __launch_bounds__(ZS_THREADS, 1)
@@ -102,11 +139,15 @@ conv3_zs_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
   const int nchunks = p.Cin / KC;
   constexpr int rb = KC * 2;
   const int R = p.tmem_bufs;  // ring slots
-  const ZsRange rg = zs_range(p, cta, cps);
+  const int S = p.a_stages;
   const int D = p.D;
+  ZsWalk walk = zs_walk(p, cta, cps);
+#ifdef B200_DEBUG
+  const int planes_mine = walk.L1 - walk.L;
+#endif
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < p.a_stages; ++i) {
+    for (int i = 0; i < S; ++i) {
       mbar_init(&a_full[i], 1);
       mbar_init(&a_empty[i], 1);
     }
@@ -146,25 +187,22 @@ conv3_zs_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
           for (int tdr = 0; tdr < 3; ++tdr)
             tma_load_3d(smemB + ((size_t)((cb * 9 + t9) * 3 + tdr)) * p.NT * rb, &tmapB, &b_full, cb * KC, 0,
                         wsample * 27 + (2 - tdr) * 9 + t9);
-      long long c = 0;  // halo tiles loaded so far
+      ZsRing st = {0, 0u};
       long long w_prod = 0, t_begin = dbg_clock();
-      for (long long L = rg.L0; L < rg.L1;) {
-        const int col = (int)(L / D), z0 = (int)(L - (long long)col * D);
-        const long long rest = rg.L1 - L;
-        const int z1 = (rest < (long long)(D - z0)) ? z0 + (int)rest : D;
-        const int th_i = col / p.tilesW, tw_i = col - th_i * p.tilesW;
+      ZsSeg sg;
+      while (walk.next(sg)) {
+        const int th_i = sg.col / p.tilesW, tw_i = sg.col - th_i * p.tilesW;
         const int h0 = th_i * ZS_BH, w0 = tw_i * ZS_BW;
-        const int zin0 = z0 > 0 ? z0 - 1 : 0, zin1 = z1 < D ? z1 : D - 1;
+        const int zin0 = sg.z0 > 0 ? sg.z0 - 1 : 0, zin1 = sg.z1 < D ? sg.z1 : D - 1;
         for (int zin = zin0; zin <= zin1; ++zin)
-          for (int j = 0; j < nchunks; ++j, ++c) {
-            const int stage = (int)(c % p.a_stages);
+          for (int j = 0; j < nchunks; ++j) {
             const long long c0 = dbg_clock();
-            mbar_wait(&a_empty[stage], ((uint32_t)(c / p.a_stages) & 1u) ^ 1u);
+            mbar_wait(&a_empty[st.idx], st.ph ^ 1u);
             w_prod += dbg_clock() - c0;
-            mbar_arrive_expect_tx(&a_full[stage], (uint32_t)(ZS_ROWS * rb));
-            tma_load_5d(smemA + (size_t)stage * p.a_bytes, &tmapA, &a_full[stage], j * KC, w0 - 1, h0 - 1, zin, n);
+            mbar_arrive_expect_tx(&a_full[st.idx], (uint32_t)(ZS_ROWS * rb));
+            tma_load_5d(smemA + (size_t)st.idx * p.a_bytes, &tmapA, &a_full[st.idx], j * KC, w0 - 1, h0 - 1, zin, n);
+            st.step(S);
           }
-        L += z1 - z0;
       }
 #ifdef B200_DEBUG
       if (p.dbg) {
@@ -185,49 +223,47 @@ conv3_zs_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
     const uint32_t sB0 = smem_u32(smemB);
     const uint32_t blk16 = (uint32_t)(p.NT * rb) >> 4;  // one weight block [C_out][KC], 16-byte units
     const uint32_t b_t9 = 3u * blk16;
-    uint32_t idesc_m[4];
-    for (int m = 1; m <= 3; ++m) idesc_m[m] = umma_idesc_bf16(128, m * p.NT, 0, 0);
+    const uint32_t chunkB16 = 27u * blk16;
+    const uint32_t idesc1 = umma_idesc_bf16(128, p.NT, 0, 0), idesc2 = umma_idesc_bf16(128, 2 * p.NT, 0, 0),
+                   idesc3 = umma_idesc_bf16(128, 3 * p.NT, 0, 0);
     mbar_wait(&b_full, 0);
     tc_fence_after();
-    long long c = 0;  // halo tiles consumed
-    long long q0 = 0;  // output-plane number of the segment's first plane
+    ZsRing st = {0, 0u};      // halo stage being consumed
+    ZsRing open = {0, 0u};    // TMEM block of the NEXT output plane to be opened (planes are opened and completed in order)
+    ZsRing done = {0, 0u};    // TMEM block of the next output plane to complete
+    int slot_a = 0;           // TMEM block of plane `a` (the oldest plane the current input plane touches)
     long long w_afull = 0, w_tempty = 0, t_begin = dbg_clock();
-    for (long long L = rg.L0; L < rg.L1;) {
-      const int col = (int)(L / D), z0 = (int)(L - (long long)col * D);
-      const long long rest = rg.L1 - L;
-      const int z1 = (rest < (long long)(D - z0)) ? z0 + (int)rest : D;
+    ZsSeg sg;
+    while (walk.next(sg)) {
+      const int z0 = sg.z0, z1 = sg.z1;
       const int zin0 = z0 > 0 ? z0 - 1 : 0, zin1 = z1 < D ? z1 : D - 1;
+      slot_a = open.idx;  // the segment's first output plane is the next one to be opened
+      int a_prev = z0;
+      int opened = z0;     // output planes [z0, opened) have been opened
       for (int zin = zin0; zin <= zin1; ++zin) {
-        // output planes this input plane contributes to: [a, b] = [zin-1, zin+1] clipped to the segment; fresh = first touched now
+        // output planes this input plane contributes to: [a, b] = [zin-1, zin+1] clipped to the segment
         const int a = zin - 1 > z0 ? zin - 1 : z0;
         const int b = zin + 1 < z1 - 1 ? zin + 1 : z1 - 1;
         const int m = b - a + 1;
-        const long long qa = q0 + (a - z0);
-        const int slot_a = (int)(qa % R);
-        // w: first block index at which the ring wraps (m = no wrap inside this range)
-        int w = R - slot_a;
-        if (w > m) w = m;
-        // f: first FRESH block.  Plane zo is first touched by input plane max(zo-1, 0), or by the segment's first input plane when that
-        // one comes later; that bound is non-decreasing in zo and never exceeds zin, so the fresh planes are a suffix of [a, b]
-        int f = m;
-#pragma unroll
-        for (int i = 2; i >= 0; --i)
-          if (i < m) {
-            const int zo = a + i;
-            int first_in = zo - 1 > 0 ? zo - 1 : 0;
-            if (first_in < zin0) first_in = zin0;
-            if (first_in == zin) f = i;
-          }
-        // a fresh block must have been drained by the epilogue of the plane that used it R planes ago
+        if (a != a_prev) {  // a advances by at most one plane per input plane
+          if (++slot_a == R) slot_a = 0;
+          a_prev = a;
+        }
+        // fresh blocks = planes not opened yet: [opened, b]; f = index of the first one inside [a, b] (m = none)
+        const int f = opened - a;  // opened >= a always (plane a was opened by an earlier input plane or is opened now)
         {
           const long long c0 = dbg_clock();
-          for (int i = f; i < m; ++i) {
-            const long long q = qa + i;
-            mbar_wait(&tmem_empty[(int)(q % R)], ((uint32_t)(q / R) & 1u) ^ 1u);
+          for (int zo = opened; zo <= b; ++zo) {  // the block must have been drained by the epilogue of the plane that used it R planes ago
+            mbar_wait(&tmem_empty[open.idx], open.ph ^ 1u);
+            open.step(R);
           }
+          opened = b + 1;
           w_tempty += dbg_clock() - c0;
         }
         tc_fence_after();
+        // w: first block index at which the ring wraps (m = no wrap inside this range)
+        int w = R - slot_a;
+        if (w > m) w = m;
         // runs = maximal ranges of blocks that one MMA can cover: cut at the ring wrap; the FIRST (tap, k) step is also cut where the
         // accumulate flag changes (open blocks accumulate, fresh blocks are overwritten)
         ZsRun rf[3], rr[3];
@@ -237,34 +273,49 @@ conv3_zs_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
 #pragma unroll
           for (int k = 0; k < 3; ++k) {
             const int s0 = bf[k], len = bf[k + 1] - bf[k];
-            rf[k].tacc = tmem_base + (uint32_t)(((slot_a + s0) % R) * p.NT);
+            int sl = slot_a + s0;
+            if (sl >= R) sl -= R;
+            rf[k].tacc = tmem_base + (uint32_t)(sl * p.NT);
             rf[k].boff = (uint32_t)(a - zin + 1 + s0) * blk16;   // tdr of block i: (a + i) - zin + 1
-            rf[k].idesc = len > 0 ? idesc_m[len] : 0u;
+            rf[k].idesc = len <= 0 ? 0u : (len == 1 ? idesc1 : (len == 2 ? idesc2 : idesc3));
             rf[k].accum = s0 >= f ? 0u : 1u;
             const int s1 = br[k], len1 = br[k + 1] - br[k];
-            rr[k].tacc = tmem_base + (uint32_t)(((slot_a + s1) % R) * p.NT);
+            int sl1 = slot_a + s1;
+            if (sl1 >= R) sl1 -= R;
+            rr[k].tacc = tmem_base + (uint32_t)(sl1 * p.NT);
             rr[k].boff = (uint32_t)(a - zin + 1 + s1) * blk16;
-            rr[k].idesc = len1 > 0 ? idesc_m[len1] : 0u;
+            rr[k].idesc = len1 <= 0 ? 0u : (len1 == 1 ? idesc1 : (len1 == 2 ? idesc2 : idesc3));
             rr[k].accum = 1u;
           }
         }
-        for (int j = 0; j < nchunks; ++j, ++c) {
-          const int stage = (int)(c % p.a_stages);
+        const bool one_run = w >= m;
+        uint32_t b_lo = ((sB0 >> 4) & 0x3FFFu) | lo_lbo;
+        for (int j = 0; j < nchunks; ++j) {
           const long long c1 = dbg_clock();
-          mbar_wait(&a_full[stage], (uint32_t)(c / p.a_stages) & 1u);
+          mbar_wait(&a_full[st.idx], st.ph);
           w_afull += dbg_clock() - c1;
           tc_fence_after();
-          const uint32_t a_lo = ((smem_u32(smemA + (size_t)stage * p.a_bytes) >> 4) & 0x3FFFu) | lo_lbo;
-          const uint32_t b_lo = (((sB0 + (uint32_t)(j * 27 * p.NT * rb)) >> 4) & 0x3FFFu) | lo_lbo;
-          if (!DBG_FLAG(p, 8)) zs_issue_chunk<KC>(rf, rr, a_lo, b_lo, b_t9, hiA, hiB, j == 0);
-          umma_commit_elect(&a_empty[stage]);
+          const uint32_t a_lo = ((smem_u32(smemA + (size_t)st.idx * p.a_bytes) >> 4) & 0x3FFFu) | lo_lbo;
+          if (!DBG_FLAG(p, 8)) {
+            if (j == 0)  // first (tap, k) step of the plane: per-block accumulate flags
+              zs_issue(rf, hiA | (uint64_t)a_lo, hiB | (uint64_t)b_lo, true);
+            if (one_run) zs_issue_chunk<KC, true>(rr, a_lo, b_lo, b_t9, hiA, hiB, j == 0);
+            else zs_issue_chunk<KC, false>(rr, a_lo, b_lo, b_t9, hiA, hiB, j == 0);
+          }
+          umma_commit_elect(&a_empty[st.idx]);
+          st.step(S);
+          b_lo += chunkB16;
         }
         // output planes that received their last contribution: zin-1 always (if in the segment); plane D-1 when zin == D-1
-        if (zin - 1 >= z0) umma_commit_elect(&tmem_full[(int)((q0 + (zin - 1 - z0)) % R)]);
-        if (zin == D - 1 && D - 1 < z1) umma_commit_elect(&tmem_full[(int)((q0 + (D - 1 - z0)) % R)]);
+        if (zin - 1 >= z0) {
+          umma_commit_elect(&tmem_full[done.idx]);
+          done.step(R);
+        }
+        if (zin == D - 1 && D - 1 < z1) {
+          umma_commit_elect(&tmem_full[done.idx]);
+          done.step(R);
+        }
       }
-      q0 += z1 - z0;
-      L += z1 - z0;
     }
 #ifdef B200_DEBUG
     if (p.dbg && lane == 0) {
@@ -272,7 +323,7 @@ conv3_zs_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
       o[2] = w_afull;
       o[3] = w_tempty;
       o[4] = dbg_clock() - t_begin;
-      o[7] = rg.L1 - rg.L0;
+      o[7] = planes_mine;
     }
 #else
     (void)w_afull; (void)w_tempty; (void)t_begin;
@@ -289,20 +340,20 @@ conv3_zs_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
 #pragma unroll
     for (int i = 0; i < 32; ++i) rs[i] = rq[i] = 0.f;
     float* my_acc = stat_acc + (size_t)warp * NT * 2;
-    long long q0 = 0;
+    ZsRing cur = {0, 0u};   // TMEM block of the plane being visited (every plane, either group's)
+    int parity = 0;          // plane number & 1
     long long w_tfull = 0, t_ld = 0, t_begin = dbg_clock();
-    for (long long L = rg.L0; L < rg.L1;) {
-      const int col = (int)(L / D), z0 = (int)(L - (long long)col * D);
-      const long long rest = rg.L1 - L;
-      const int z1 = (rest < (long long)(D - z0)) ? z0 + (int)rest : D;
-      const int th_i = col / p.tilesW, tw_i = col - th_i * p.tilesW;
+    const size_t HW = (size_t)p.H * p.W;
+    ZsSeg sg;
+    while (walk.next(sg)) {
+      const int th_i = sg.col / p.tilesW, tw_i = sg.col - th_i * p.tilesW;
       const int xh = th_i * ZS_BH + by, xw = tw_i * ZS_BW + bx;
       const bool valid = xh < p.H && xw < p.W;
-      for (int zo = z0; zo < z1; ++zo) {
-        const long long q = q0 + (zo - z0);
-        if ((int)(q & 1) != grp) continue;
-        const int slot = (int)(q % R);
-        const size_t vox_off = (size_t)n * D * p.H * p.W + ((size_t)zo * p.H + xh) * p.W + xw;
+      const size_t vox_hw = (size_t)n * D * HW + (size_t)xh * p.W + xw;
+      for (int zo = sg.z0; zo < sg.z1; ++zo, cur.step(R), parity ^= 1) {
+        if (parity != grp) continue;
+        const int slot = cur.idx;
+        const size_t vox_off = vox_hw + (size_t)zo * HW;
         const float* bias_row = nullptr;
         if (p.n_b && valid) {
           const int cls = conv_bias_cls(p.cls_mode, zo, xh, xw, D, p.H, p.W);
@@ -311,7 +362,7 @@ conv3_zs_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
                               : p.biascls + ((size_t)(p.n_b > 1 ? n : 0) * 64 + cls) * p.Cout;
         }
         const long long cw0 = dbg_clock();
-        mbar_wait(&tmem_full[slot], (uint32_t)(q / R) & 1u);
+        mbar_wait(&tmem_full[slot], cur.ph);
         w_tfull += dbg_clock() - cw0;
         __syncwarp();
         tc_fence_after();
@@ -398,8 +449,6 @@ conv3_zs_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty[slot]);
       }
-      q0 += z1 - z0;
-      L += z1 - z0;
     }
 #ifdef B200_DEBUG
     if (p.dbg && threadIdx.x == 0) {
@@ -476,6 +525,7 @@ bool conv_zs_plan(int N, int D, int H, int W, int Cin, int Cout, ConvParams* pp)
   p.tmem_bufs = slots;
   p.tmem_cols = 512;
   long long T = (long long)p.tilesH * p.tilesW * D;
+  if (T >= (1ll << 30)) return false;  // the kernel's plane-tile counters are 32-bit
   int cps = sm_count() / N;
   if (cps < 1) cps = 1;
   if (const char* e = getenv("B200UNET_ZS_CTAS")) {  // tests: few CTAs per sample => long depth walks (ring wrap, mid-column segment cuts)

@@ -146,7 +146,7 @@ class Engine:
     def empty(self, shape, dtype):
         return torch.empty(shape, dtype=dtype, device=self.device)
 
-    def call(self, name, *args, launches=1, flops=0.0, tag=None):
+    def call(self, name, *args, launches=1, flops=0.0, tag=None, layer=""):
         if HOST_PROF is not None:  # tools/host_profile.py: host seconds spent inside each C-ABI entry point
             t0 = time.perf_counter()
             self.L.call(name, *args, self.stream)
@@ -160,7 +160,7 @@ class Engine:
             e0.record()
             self.L.call(name, *args, self.stream)
             e1.record()
-            TIMING.append((tag or name, flops, e0, e1))
+            TIMING.append((tag or name, flops, e0, e1, layer))
         else:
             self.L.call(name, *args, self.stream)
         self.launches += launches
@@ -303,7 +303,7 @@ class Engine:
         self.call("b200_conv3_fwd", impl, _p(x.t), int(is_f32), _p(wf), n_w, _p(biascls), n_b,
                   _p(residual.t) if residual is not None else None, act[0], float(act[1]),
                   n, d, h, w, cin, cout, _p(y), 1 if want_stats else 0, None, _p(partials),
-                  flops=2.0 * n * vox * 27 * cin * cout, tag=("fprop_tc" if impl == IMPL_TCGEN05 else "fprop_direct"))
+                  flops=2.0 * n * vox * 27 * cin * cout, tag=("fprop_tc" if impl == IMPL_TCGEN05 else "fprop_direct"), layer=name)
         out = Act(y, act[0], act[1], partials, P)
         if DEBUG is not None:
             DEBUG.setdefault("fwd", {})[name] = y
@@ -326,7 +326,7 @@ class Engine:
                 G = self.empty((n, S, 27, cin, cout), torch.float32)
                 self.call("b200_conv3_wgrad", wimpl, _p(x.t), int(is_f32), _p(dz), n, d, h, w, cin, cout, _p(G),
                           launches=1 if wimpl == IMPL_TCGEN05 else 2, flops=2.0 * n * vox * 27 * cin * cout,
-                          tag=("wgrad_tc" if wimpl == IMPL_TCGEN05 else "wgrad_direct"))
+                          tag=("wgrad_tc" if wimpl == IMPL_TCGEN05 else "wgrad_direct"), layer=name)
                 dW = torch.empty_like(W) if grad_sink is not None else self.grad_like(name + "conv.weight", W)
                 Gsum = self.empty((n, 1, 27, cin, cout), torch.float32) if gn is not None else None
                 self.call("b200_wgrad_finalize", _p(G), n, S, cin, cout, _p(ab), _p(T) if ab is not None else None, _p(dW), _p(Gsum))
@@ -369,7 +369,7 @@ class Engine:
                     dxhat = self.empty((n, d, h, w, cin), torch.bfloat16)
                     self.call("b200_conv3_fwd", dimpl, _p(dz), 0, _p(wd), 1, None, 0, None, ACT_NONE, 0.0,
                               n, d, h, w, cout, cin, _p(dxhat), 0, None, None, flops=2.0 * n * vox * 27 * cin * cout,
-                              tag=("dgrad_tc" if dimpl == IMPL_TCGEN05 else "dgrad_direct"))
+                              tag=("dgrad_tc" if dimpl == IMPL_TCGEN05 else "dgrad_direct"), layer=name)
                     if coef is not None:
                         self.call("b200_gn_bwd_apply", _p(dxhat), _p(x.t), _p(coef), n, cin, vox, x.act, x.slope,
                                   _p(x.grad), _p(dxhat))
@@ -547,7 +547,7 @@ class Engine:
                   _p(wf_enc), _p(wp), _p(biascls), _p(mean_rstd), _p(ab), launches=4 if gn is not None else 3)
         R = self.empty((n, D, H, Wd, cout), torch.bfloat16)
         self.call("b200_conv3_up_phase_fwd", _p(low.t), _p(wp), n_w, n, d, h, w, c1, cout, _p(R), launches=1,
-                  flops=2.0 * n * vox * 8 * c1 * cout, tag="fprop_tc")
+                  flops=2.0 * n * vox * 8 * c1 * cout, tag="fprop_tc", layer=name)
         y = self.empty((n, D, H, Wd, cout), torch.bfloat16)
         partials, P = None, 0
         if want_stats:
@@ -555,7 +555,7 @@ class Engine:
             partials = self.empty((n, P, cout, 2), torch.float32)
         self.call("b200_conv3_fwd", IMPL_TCGEN05, _p(enc.t), 0, _p(wf_enc), n_w, _p(biascls), n_b, _p(R), act[0], float(act[1]),
                   n, D, H, Wd, c0, cout, _p(y), (1 if want_stats else 0) | PMODE_PHASE_BIAS, None, _p(partials),
-                  flops=2.0 * n * vox * 27 * c0 * cout, tag="fprop_tc")
+                  flops=2.0 * n * vox * 27 * c0 * cout, tag="fprop_tc", layer=name)
         out = Act(y, act[0], act[1], partials, P)
         if DEBUG is not None:
             DEBUG.setdefault("fwd", {})[name] = y
@@ -573,11 +573,11 @@ class Engine:
                 S1 = L.query("b200_conv3_wgrad_splits", IMPL_TCGEN05, n, D, H, Wd, c0, cout, 0)
                 G_enc = self.empty((n, S1, 27, c0, cout), torch.float32)
                 self.call("b200_conv3_wgrad", IMPL_TCGEN05, _p(enc.t), 0, _p(dz), n, D, H, Wd, c0, cout, _p(G_enc),
-                          flops=2.0 * n * vox * 27 * c0 * cout, tag="wgrad_tc")
+                          flops=2.0 * n * vox * 27 * c0 * cout, tag="wgrad_tc", layer=name)
                 S2 = L.query("b200_conv3_up_wgrad_splits", n, d, h, w, cout, c1)
                 Q = self.empty((n, S2, 64, cout, c1), torch.float32)
                 self.call("b200_conv3_up_wgrad", _p(dz), _p(low.t), n, d, h, w, cout, c1, _p(Q),
-                          flops=2.0 * n * lvox * 64 * c1 * cout, tag="wgrad_tc")
+                          flops=2.0 * n * lvox * 64 * c1 * cout, tag="wgrad_tc", layer=name)
                 G = self.empty((n, 1, 27, C, cout), torch.float32)
                 self.call("b200_upcat_assemble_wgrad", _p(G_enc), S1, _p(Q), S2, n, c0, c1, cout, _p(G))
                 dW = self.grad_like(name + "conv.weight", W)
@@ -609,7 +609,7 @@ class Engine:
                     ge = self.empty(enc.t.shape, torch.bfloat16)
                     self.call("b200_conv3_fwd", dimpl, _p(dz), 0, _p(wd_enc), 1, None, 0, None, ACT_NONE, 0.0,
                               n, D, H, Wd, cout, c0, _p(ge), 0, None, None, flops=2.0 * n * vox * 27 * c0 * cout,
-                              tag=("dgrad_tc" if dimpl == IMPL_TCGEN05 else "dgrad_direct"))
+                              tag=("dgrad_tc" if dimpl == IMPL_TCGEN05 else "dgrad_direct"), layer=name)
                     if coef is not None:
                         ce = coef[:, :c0].contiguous()
                         self.call("b200_gn_bwd_apply", _p(ge), _p(enc.t), _p(ce), n, c0, vox, enc.act, enc.slope, _p(enc.grad), _p(ge))
@@ -619,7 +619,7 @@ class Engine:
                 if low.requires_grad:
                     gl = self.empty(low.t.shape, torch.bfloat16)
                     self.call("b200_conv3_up_dgrad", _p(dz), _p(wd_up), n, d, h, w, cout, c1, _p(gl),
-                              flops=2.0 * n * lvox * 64 * c1 * cout, tag="dgrad_tc")
+                              flops=2.0 * n * lvox * 64 * c1 * cout, tag="dgrad_tc", layer=name)
                     if coef is not None:
                         # d b[u] = sum over its 8 copies of (A dxhat + B x + C) = A sum(dxhat) + 8B b + 8C
                         cl = (coef[:, c0:] * self._k188).contiguous()
