@@ -33,8 +33,8 @@ namespace b200 {
 constexpr int ZS_BH = 16, ZS_BW = 8;
 constexpr int ZS_HH = ZS_BH + 2, ZS_HW = ZS_BW + 2;
 constexpr int ZS_ROWS = ZS_HH * ZS_HW;  // 180 rows of one input-plane halo tile
-constexpr int ZS_THREADS = 2 * 128 + 64;
-constexpr int ZS_WARP_PRODUCER = 8, ZS_WARP_MMA = 9;
+constexpr int ZS_THREADS = 2 * 128 + 96;
+constexpr int ZS_WARP_PRODUCER = 8, ZS_WARP_MMA = 9, ZS_ISSUERS = 2;  // warps 9 and 10 issue MMAs
 constexpr int ZS_MAX_STAGES = 8;
 constexpr int ZS_MAX_SLOTS = 16;
 
@@ -52,11 +52,12 @@ __device__ __forceinline__ void zs_issue(const ZsRun (&r)[3], uint64_t adesc, ui
     if (r[k].idesc) umma_bf16_elect(r[k].tacc, adesc, bdesc + r[k].boff, r[k].idesc, first ? r[k].accum : 1u);
 }
 
-// all 9 in-plane taps x KC/16 k-steps of one halo chunk.  b_lo points at [t9 = 0][tdr = 0] of this chunk; one t9 advances 3 blocks.
-// `skip_first`: the (t9 = 0, k = 0) step of the plane's first chunk has been issued separately (its accumulate flags differ per block).
-// ONE_RUN: the plane's blocks are contiguous in TMEM (no ring wrap): one instruction per step, descriptors advance by immediates --
-// the issuing warp must sustain one MMA per ~56 cycles, so no run loop / predicates in here.
-template <int KC, bool ONE_RUN>
+// all 9 in-plane taps x KC/16 k-steps of one halo chunk, the steps of ONE issuer: the two issuer warps take alternate (tap, k) steps
+// (a single warp sustains one tcgen05.mma per ~54-80 cycles, the tensor pipe wants one N = 3*C_out instruction per 56).  PAR = parity
+// of the in-chunk step index this issuer takes.  b_lo points at [t9 = 0][tdr = 0] of this chunk; one t9 advances 3 blocks.
+// `skip_first`: the (t9 = 0, k = 0) step of the plane's first chunk is issued separately (its accumulate flags differ per block).
+// ONE_RUN: the plane's blocks are contiguous in TMEM (no ring wrap): one instruction per step, descriptors advance by immediates.
+template <int KC, bool ONE_RUN, int PAR>
 __device__ __forceinline__ void zs_issue_chunk(const ZsRun (&rr)[3], uint32_t a_lo, uint32_t b_lo, uint32_t b_t9, uint64_t hiA, uint64_t hiB,
                                                bool skip_first) {
   constexpr uint32_t RB16 = KC * 2 / 16;  // one halo row in 16-byte units
@@ -66,6 +67,7 @@ __device__ __forceinline__ void zs_issue_chunk(const ZsRun (&rr)[3], uint32_t a_
     const uint32_t offA = (uint32_t)((t9 / 3) * ZS_HW + t9 % 3) * RB16;
 #pragma unroll
     for (int k = 0; k < KC / 16; ++k) {
+      if (((t9 * (KC / 16) + k) & 1) != PAR) continue;
       const uint64_t adesc = hiA | (uint64_t)(a_lo + offA + 2u * k);
       const uint64_t bdesc = hiB | (uint64_t)(b_lo + 2u * k);
       if (t9 == 0 && k == 0) {
@@ -125,7 +127,7 @@ __global__ void __launch_bounds__(ZS_THREADS, 1)
 conv3_zs_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, const ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[ZS_MAX_STAGES], a_empty[ZS_MAX_STAGES];
-  __shared__ __align__(8) uint64_t b_full, tmem_full[ZS_MAX_SLOTS], tmem_empty[ZS_MAX_SLOTS];
+  __shared__ __align__(8) uint64_t b_full, tmem_full[ZS_MAX_SLOTS], tmem_empty[ZS_MAX_SLOTS], first_done[ZS_MAX_STAGES];
   __shared__ uint32_t tmem_slot;
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -149,13 +151,14 @@ conv3_zs_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
   if (threadIdx.x == 0) {
     for (int i = 0; i < S; ++i) {
       mbar_init(&a_full[i], 1);
-      mbar_init(&a_empty[i], 1);
+      mbar_init(&a_empty[i], ZS_ISSUERS);   // every issuer commits each stage it has read
     }
     mbar_init(&b_full, 1);
     for (int i = 0; i < R; ++i) {
-      mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);  // one arrival per epilogue warp of the group that drained it
+      mbar_init(&tmem_full[i], ZS_ISSUERS);  // complete when both issuers' MMAs on it have executed
+      mbar_init(&tmem_empty[i], 4);          // one arrival per epilogue warp of the group that drained it
     }
+    for (int i = 0; i < ZS_MAX_STAGES; ++i) mbar_init(&first_done[i], 1);
     fence_mbar_init();
   }
   if (warp == ZS_WARP_PRODUCER && lane == 0) {
@@ -214,8 +217,9 @@ conv3_zs_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
       (void)w_prod; (void)t_begin;
 #endif
     }
-  } else if (warp == ZS_WARP_MMA) {
-    // ================= MMA issuer (whole warp converged, one elected lane issues) =================
+  } else if (warp >= ZS_WARP_MMA) {
+    // ================= MMA issuers (whole warp converged, one elected lane issues); both walk every input plane =================
+    const int issuer = warp - ZS_WARP_MMA;
     const uint32_t lay = umma_layout_for_row_bytes(rb);
     const uint64_t hiA = umma_smem_desc(0, 16u, (uint32_t)(ZS_HW * rb), lay) & 0xFFFFFFFF00000000ull;
     const uint64_t hiB = umma_smem_desc(0, 16u, (uint32_t)(8 * rb), lay) & 0xFFFFFFFF00000000ull;
@@ -231,7 +235,9 @@ conv3_zs_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
     ZsRing st = {0, 0u};      // halo stage being consumed
     ZsRing open = {0, 0u};    // TMEM block of the NEXT output plane to be opened (planes are opened and completed in order)
     ZsRing done = {0, 0u};    // TMEM block of the next output plane to complete
+    ZsRing fd = {0, 0u};      // first_done barrier of the current input plane
     int slot_a = 0;           // TMEM block of plane `a` (the oldest plane the current input plane touches)
+    constexpr int SPC = 9 * (KC / 16);  // (tap, k) steps per chunk
     long long w_afull = 0, w_tempty = 0, t_begin = dbg_clock();
     ZsSeg sg;
     while (walk.next(sg)) {
@@ -254,20 +260,31 @@ conv3_zs_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
         {
           const long long c0 = dbg_clock();
           for (int zo = opened; zo <= b; ++zo) {  // the block must have been drained by the epilogue of the plane that used it R planes ago
-            mbar_wait(&tmem_empty[open.idx], open.ph ^ 1u);
+            if (issuer == 0) mbar_wait(&tmem_empty[open.idx], open.ph ^ 1u);  // issuer 1 is ordered behind issuer 0's first step
             open.step(R);
           }
           opened = b + 1;
           w_tempty += dbg_clock() - c0;
         }
         tc_fence_after();
-        // w: first block index at which the ring wraps (m = no wrap inside this range)
-        int w = R - slot_a;
-        if (w > m) w = m;
-        // runs = maximal ranges of blocks that one MMA can cover: cut at the ring wrap; the FIRST (tap, k) step is also cut where the
-        // accumulate flag changes (open blocks accumulate, fresh blocks are overwritten)
         ZsRun rf[3], rr[3];
-        {
+        bool one_run;
+        if (m == 3 && f == 2 && slot_a + 3 <= R) {
+          // steady state: blocks z-1, z (open) and z+1 (fresh) are contiguous: ONE instruction of N = 3*C_out per step; the first
+          // step is an N = 2*C_out accumulate plus an N = C_out overwrite
+          const uint32_t t0 = tmem_base + (uint32_t)(slot_a * p.NT);
+          rr[0].tacc = t0; rr[0].boff = 0u; rr[0].idesc = idesc3; rr[0].accum = 1u;
+          rr[1].idesc = 0u; rr[2].idesc = 0u; rr[1].tacc = rr[2].tacc = t0; rr[1].boff = rr[2].boff = 0u; rr[1].accum = rr[2].accum = 1u;
+          rf[0].tacc = t0; rf[0].boff = 0u; rf[0].idesc = idesc2; rf[0].accum = 1u;
+          rf[1].tacc = t0 + (uint32_t)(2 * p.NT); rf[1].boff = 2u * blk16; rf[1].idesc = idesc1; rf[1].accum = 0u;
+          rf[2].idesc = 0u; rf[2].tacc = t0; rf[2].boff = 0u; rf[2].accum = 1u;
+          one_run = true;
+        } else {
+          // w: first block index at which the ring wraps (m = no wrap inside this range).  Runs = maximal ranges of blocks that one
+          // MMA can cover: cut at the ring wrap; the FIRST (tap, k) step is also cut where the accumulate flag changes (open blocks
+          // accumulate, fresh blocks are overwritten)
+          int w = R - slot_a;
+          if (w > m) w = m;
           const int c1 = w < f ? w : f, c2 = w < f ? f : w;   // sorted cuts (m = none)
           const int bf[4] = {0, c1, c2, m}, br[4] = {0, w, m, m};
 #pragma unroll
@@ -287,8 +304,8 @@ conv3_zs_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
             rr[k].idesc = len1 <= 0 ? 0u : (len1 == 1 ? idesc1 : (len1 == 2 ? idesc2 : idesc3));
             rr[k].accum = 1u;
           }
+          one_run = w >= m;
         }
-        const bool one_run = w >= m;
         uint32_t b_lo = ((sB0 >> 4) & 0x3FFFu) | lo_lbo;
         for (int j = 0; j < nchunks; ++j) {
           const long long c1 = dbg_clock();
@@ -297,15 +314,30 @@ conv3_zs_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
           tc_fence_after();
           const uint32_t a_lo = ((smem_u32(smemA + (size_t)st.idx * p.a_bytes) >> 4) & 0x3FFFu) | lo_lbo;
           if (!DBG_FLAG(p, 8)) {
-            if (j == 0)  // first (tap, k) step of the plane: per-block accumulate flags
-              zs_issue(rf, hiA | (uint64_t)a_lo, hiB | (uint64_t)b_lo, true);
-            if (one_run) zs_issue_chunk<KC, true>(rr, a_lo, b_lo, b_t9, hiA, hiB, j == 0);
-            else zs_issue_chunk<KC, false>(rr, a_lo, b_lo, b_t9, hiA, hiB, j == 0);
+            if (j == 0) {
+              if (issuer == 0) {  // first (tap, k) step of the plane: per-block accumulate flags; tell issuer 1 when it has EXECUTED
+                zs_issue(rf, hiA | (uint64_t)a_lo, hiB | (uint64_t)b_lo, true);
+                umma_commit_elect(&first_done[fd.idx]);
+              } else {            // nothing of this plane may accumulate into a fresh block before it has been overwritten
+                mbar_wait(&first_done[fd.idx], fd.ph);
+                tc_fence_after();
+              }
+            }
+            // this issuer's steps: in-chunk step parity (issuer + j * SPC) & 1
+            const int par = (issuer + j * SPC) & 1;
+            if (one_run) {
+              if (par) zs_issue_chunk<KC, true, 1>(rr, a_lo, b_lo, b_t9, hiA, hiB, j == 0);
+              else zs_issue_chunk<KC, true, 0>(rr, a_lo, b_lo, b_t9, hiA, hiB, j == 0);
+            } else {
+              if (par) zs_issue_chunk<KC, false, 1>(rr, a_lo, b_lo, b_t9, hiA, hiB, j == 0);
+              else zs_issue_chunk<KC, false, 0>(rr, a_lo, b_lo, b_t9, hiA, hiB, j == 0);
+            }
           }
           umma_commit_elect(&a_empty[st.idx]);
           st.step(S);
           b_lo += chunkB16;
         }
+        fd.step(ZS_MAX_STAGES);
         // output planes that received their last contribution: zin-1 always (if in the segment); plane D-1 when zin == D-1
         if (zin - 1 >= z0) {
           umma_commit_elect(&tmem_full[done.idx]);
@@ -318,7 +350,7 @@ conv3_zs_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
       }
     }
 #ifdef B200_DEBUG
-    if (p.dbg && lane == 0) {
+    if (p.dbg && lane == 0 && issuer == 0) {
       long long* o = p.dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16;
       o[2] = w_afull;
       o[3] = w_tempty;

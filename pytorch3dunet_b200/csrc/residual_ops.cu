@@ -114,6 +114,58 @@ __global__ void pointwise_wgrad_kernel(const InT* __restrict__ x, const bf16* __
   if (ci0 == 0 && tci == 0 && co0 + tco < Cout) row[(size_t)Cout * Cin + co0 + tco] = accb;
 }
 
+// the same for the fp32 network input with C_in <= 4 (ResNetBlock.conv1 of the first encoder, buildingblocks.py:251): one streaming pass,
+// a thread keeps 8 output channels x C_in products + the bias sums in registers; grid (P, N); HBM-bound (reads dy once)
+template <int CIN>
+__global__ void pointwise_wgrad_small_kernel(const float* __restrict__ x, const bf16* __restrict__ dy, long long vox, int Cout, int P,
+                                             float* __restrict__ partials) {
+  extern __shared__ float red[];  // [EW_THREADS][8]
+  const int p = blockIdx.x, n = blockIdx.y;
+  const EwMap m = ew_map(Cout);
+  long long v0, v1;
+  ew_range(vox, p, P, v0, v1);
+  float aw[CIN][8], ab[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    ab[i] = 0.f;
+#pragma unroll
+    for (int c = 0; c < CIN; ++c) aw[c][i] = 0.f;
+  }
+  if (m.active) {
+    const bf16x8* dp = reinterpret_cast<const bf16x8*>(dy + (size_t)n * vox * Cout) + m.cg;
+    const float* xp = x + (size_t)n * vox * CIN;
+    for (long long v = v0 + m.vl; v < v1; v += m.VL) {
+      float f[8], xv[CIN];
+      unpack8(dp[v * m.CG], f);
+#pragma unroll
+      for (int c = 0; c < CIN; ++c) xv[c] = xp[v * CIN + c];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        ab[i] += f[i];
+#pragma unroll
+        for (int c = 0; c < CIN; ++c) aw[c][i] = fmaf(f[i], xv[c], aw[c][i]);
+      }
+    }
+  }
+  float* row = partials + ((size_t)n * P + p) * ((size_t)Cout * CIN + Cout);
+#pragma unroll
+  for (int pass = 0; pass <= CIN; ++pass) {
+    __syncthreads();
+    if (m.active) {
+      float* r = red + (size_t)(m.vl * m.CG + m.cg) * 8;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) r[i] = pass < CIN ? aw[pass < CIN ? pass : 0][i] : ab[i];
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < m.CG * 8; idx += EW_THREADS) {  // idx = output channel
+      float acc = 0.f;
+      for (int vl = 0; vl < m.VL; ++vl) acc += red[(size_t)(vl * m.CG) * 8 + idx];
+      if (pass < CIN) row[(size_t)idx * CIN + pass] = acc;
+      else row[(size_t)Cout * CIN + idx] = acc;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // helpers of the transposed-conv join (the conv itself runs on the tcgen05 kernels over the zero-inserted input, see
 // Engine.deconv_up_add): nearest resize (2n-1 -> encoder size), its adjoint, zero-insert and its adjoint.
@@ -324,12 +376,24 @@ int b200_pointwise_fwd(const void* x, int x_is_f32, const float* W, int transpos
 
 int b200_pointwise_wgrad_partials_count(int N, long long voxels) {
   (void)N;
-  long long p = (voxels + 4095) / 4096;
-  return (int)(p > 64 ? 64 : (p < 1 ? 1 : p));
+  long long p = (voxels + 2047) / 2048;
+  return (int)(p > 256 ? 256 : (p < 1 ? 1 : p));
 }
 int b200_pointwise_wgrad(const void* x, int x_is_f32, const void* dy, int N, long long voxels, int Cin, int Cout, float* partials,
                          b200_stream_t s) {
   int P = b200_pointwise_wgrad_partials_count(N, voxels);
+  if (x_is_f32 && Cin <= 4 && Cout % 8 == 0 && Cout <= 2048) {
+    dim3 g2(P, N);
+    const size_t sm = EW_THREADS * 8 * sizeof(float);
+    switch (Cin) {
+      case 1: pointwise_wgrad_small_kernel<1><<<g2, EW_THREADS, sm, ST(s)>>>((const float*)x, (const bf16*)dy, voxels, Cout, P, partials); break;
+      case 2: pointwise_wgrad_small_kernel<2><<<g2, EW_THREADS, sm, ST(s)>>>((const float*)x, (const bf16*)dy, voxels, Cout, P, partials); break;
+      case 3: pointwise_wgrad_small_kernel<3><<<g2, EW_THREADS, sm, ST(s)>>>((const float*)x, (const bf16*)dy, voxels, Cout, P, partials); break;
+      default: pointwise_wgrad_small_kernel<4><<<g2, EW_THREADS, sm, ST(s)>>>((const float*)x, (const bf16*)dy, voxels, Cout, P, partials); break;
+    }
+    B200_CHECK_LAUNCH("pointwise_wgrad_small");
+    return 0;
+  }
   dim3 grid(P, N, ceil_div(Cout, 16) * ceil_div(Cin, 16));
   if (x_is_f32) pointwise_wgrad_kernel<float><<<grid, 256, 0, ST(s)>>>((const float*)x, (const bf16*)dy, voxels, Cin, Cout, P, partials);
   else pointwise_wgrad_kernel<bf16><<<grid, 256, 0, ST(s)>>>((const bf16*)x, (const bf16*)dy, voxels, Cin, Cout, P, partials);

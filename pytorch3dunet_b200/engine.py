@@ -33,6 +33,8 @@ _ACT_OF = {"r": (ACT_RELU, 0.0), "l": (ACT_LEAKY, 0.01), "e": (ACT_ELU, 1.0)}
 DEBUG = None   # dict: when set, backward closures stash clones of their intermediates (tools/debug_block.py)
 TIMING = None
 VIRTUAL_CAT = os.environ.get("B200UNET_NO_VIRTUAL_CAT", "0") != "1"  # decoder concat without the concatenated tensor
+EXPLICIT_GN = os.environ.get("B200UNET_EXPLICIT_GN", "1") != "0"      # deep levels: GroupNorm as its own pass instead of per-sample weights
+EXPLICIT_GN_VOX_PER_COUT = 40
 PMODE_PHASE_BIAS = 0x100  # B200_PMODE_PHASE_BIAS (include/b200unet.h)
 HOST_PROF = None  # dict name -> [calls, seconds] when host profiling is on
 TIMED = {"b200_conv3_fwd", "b200_conv3_wgrad", "b200_conv3_up_phase_fwd", "b200_conv3_up_dgrad", "b200_conv3_up_wgrad",
@@ -462,6 +464,12 @@ class Engine:
             assert not acts
             act = final_act
         if "g" not in post:
+            if gn_pre is not None and isinstance(x, Act) and EXPLICIT_GN and x.voxels < EXPLICIT_GN_VOX_PER_COUT * cout:
+                # deep levels (few voxels, wide channels): folding the GroupNorm scale into PER-SAMPLE weight copies moves
+                # ~12 * N * 27*C_in*C_out bytes (folded copies, their fp32 gradient sums) while normalising the small activation
+                # explicitly moves ~8 * N * voxels * C_in: apply the GroupNorm as its own pass and convolve with the shared weights
+                xh = self.groupnorm_act(x, gn_pre[0], gn_pre[1], gn_pre[2], gn_pre[3], gn_pre[4])
+                return self.conv3(xh, W, bias, None, prefix, act=act, want_stats=want_stats, residual=residual)
             return self.conv3(x, W, bias, gn_pre, prefix, act=act, want_stats=want_stats, residual=residual)
         g = 1 if cout < num_groups else num_groups
         if cout % g != 0:
