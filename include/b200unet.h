@@ -246,6 +246,21 @@ int b200_deconv_gather(const void* dout, int N, int d, int h, int w, int D, int 
 /* to_conv=1: Wc[co][ci][k] = Wt[ci][co][26-k]; to_conv=0: dWt[ci][co][k] = dWc[co][ci][26-k] */
 int b200_deconv_weight_permute(const float* src, int Cin, int Cout, int to_conv, float* dst, b200_stream_t s);
 
+/* ---- the same transposed conv + join by OUTPUT PARITY PHASES (8x fewer MACs; used when the encoder feature is exactly twice the low-res
+ * size): P[j] = T[j-1] on the (2d)^3 grid computed on the low-res lattice (27 (phase, tap) products, 8 accumulators per CTA), then
+ * out[j] = enc[j] + P[max(j,1)] (= the nearest resize of the (2d-1)^3 grid).  Backward: gp = fold(g) (adjoint of j -> max(j,1)),
+ * dx = 3x3x3 stride-2 convolution of gp, dWt[e] = sum_u gp[2u+e] (x) x[u].
+ * wq bf16 [27][Cout][Cin] ((phase, tap) order), wd bf16 [27][Cin][Cout], Q fp32 [N][S][27][Cout][Cin] (S = ..._wgrad_splits). */
+int b200_deconv_phase_supported(int N, int d, int h, int w, int Cin, int Cout);
+int b200_deconv_phase_weights(const float* Wt, int Cin, int Cout, void* wq, void* wd, b200_stream_t s);
+int b200_deconv_phase_fwd(const void* x, const void* wq, int N, int d, int h, int w, int Cin, int Cout, void* P, b200_stream_t s);
+int b200_shift_add_fwd(const void* P, const void* enc, int N, int D, int H, int W, int C, void* out, float* partials, b200_stream_t s);
+int b200_shift_fold_bwd(const void* g, int N, int D, int H, int W, int C, void* gp, b200_stream_t s);
+int b200_deconv_phase_dgrad(const void* gp, const void* wd, int N, int d, int h, int w, int Cout, int Cin, void* dx, b200_stream_t s);
+int b200_deconv_phase_wgrad_splits(int N, int d, int h, int w, int Cout, int Cin);
+int b200_deconv_phase_wgrad(const void* gp, const void* x, int N, int d, int h, int w, int Cout, int Cin, float* Q, b200_stream_t s);
+int b200_deconv_phase_wgrad_finalize(const float* Q, int rows, int Cin, int Cout, float* dWt, b200_stream_t s);
+
 /* ---- scSE, reduction_ratio 1 (ChannelSpatialSELayer3D se.py:96-114; cSE :18-51, sSE :54-93) ----------------------------
  * gates: smean[N][C] = channel means (from the producer's partial sums), h = relu(W1 s + b1), g = sigmoid(W2 h + b2) */
 int b200_se_gates_fwd(const double* sums, double count, const float* W1, const float* b1, const float* W2, const float* b2, int N, int C,

@@ -29,6 +29,7 @@ struct ConvParams {
   signed char toff[64 * 3];
   int in_mul, out_mul, out_off[3], OD, OH, OW;
   int w_rows, w_row0;
+  signed char acc_ntaps[8];  // taps of accumulator a (0 = the even split ntaps / nacc): the transposed conv's phases have 1..8 taps
   int nacc;                 // accumulators per CTA (1; 8 = the eight parity phases): taps [a*ntaps/nacc, (a+1)*ntaps/nacc) feed
   signed char acc_off[8 * 3];  // accumulator a, whose outputs go to out_mul * x + acc_off[a]  (out_off when nacc == 1)
   int cls_mode;  // bias row: 0 = border class of the voxel, 1 = phase-aware border class (interior split by parity), 2 = row 0
@@ -171,6 +172,9 @@ int choose_box(int D, int H, int W, int* bd, int* bh, int* bw);
 bool conv_igemm_supported(int N, int D, int H, int W, int Cin, int Cout);
 bool conv_halo_plan(int N, int D, int H, int W, int Cin, int Cout, ConvParams* p);
 int conv_halo_launch(const void* x, const void* wf, ConvParams& p, cudaStream_t s);
+// (phase, tap) enumeration of the transposed conv by output parity phases (conv_igemm_sm100.cu): k3[27*3] kernel index per axis,
+// off[27*3] low-res input offset per axis, ntaps[8] taps per phase
+void deconv_phase_table(signed char* k3, signed char* off, signed char* ntaps);
 bool conv_zs_plan(int N, int D, int H, int W, int Cin, int Cout, ConvParams* p);   // conv_zs_sm100.cu: depth taps stacked along N
 int conv_zs_launch(const void* x, const void* wf, ConvParams& p, cudaStream_t s);
 

@@ -83,10 +83,10 @@ conv3_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_const
       const int rb = p.KC * 2;
       const uint64_t hi = umma_smem_desc(0, 16u, 8u * (uint32_t)rb, umma_layout_for_row_bytes(rb)) & 0xFFFFFFFF00000000ull;
       const int ksteps = p.KC / 16;
-      const int kb_per_acc = numK / p.nacc;
       int kb = 0;
       for (int acc = 0; acc < p.nacc; ++acc) {
         const uint32_t tacc = tmem_base + (uint32_t)(acc * p.NT);
+        const int kb_per_acc = (p.acc_ntaps[acc] ? p.acc_ntaps[acc] : p.ntaps / p.nacc) * p.kchunks;
         uint32_t accum = 0;
         for (int i = 0; i < kb_per_acc; ++i, ++kb) {
           const int stage = kb % p.stages;
@@ -257,6 +257,7 @@ struct PlainGeom {
   int cls_mode = 0;
   int nacc = 1;                     // accumulators per CTA (taps split evenly), each with its own output offset acc_off[a]
   signed char acc_off[8 * 3] = {0};
+  signed char acc_ntaps[8] = {0};   // uneven split: taps per accumulator (all 0 = even)
   PlainGeom() {
     for (int t = 0; t < 27; ++t) {
       toff[3 * t] = (signed char)(t / 9 - 1);
@@ -300,7 +301,9 @@ static int conv_igemm_plain_launch(const void* x, const void* wf, int n_w, const
   p.cls_mode = g.cls_mode;
   p.nacc = g.nacc;
   memcpy(p.acc_off, g.acc_off, sizeof(p.acc_off));
-  B200_CHECK_ARG(g.nacc >= 1 && g.nacc <= 8 && g.ntaps % g.nacc == 0 && (g.nacc == 1 || pmode == 0), "conv3_igemm: bad accumulator split");
+  memcpy(p.acc_ntaps, g.acc_ntaps, sizeof(p.acc_ntaps));
+  B200_CHECK_ARG(g.nacc >= 1 && g.nacc <= 8 && (g.acc_ntaps[0] || g.ntaps % g.nacc == 0) && (g.nacc == 1 || pmode == 0),
+                 "conv3_igemm: bad accumulator split");
   choose_box(D, H, W, &p.BD, &p.BH, &p.BW);
   p.tilesD = (D + p.BD - 1) / p.BD;
   p.tilesH = (H + p.BH - 1) / p.BH;
@@ -353,6 +356,29 @@ static int conv_igemm_plain_launch(const void* x, const void* wf, int n_w, const
   conv3_igemm_kernel<<<grid, CONV_THREADS, smem, s>>>(tmA, tmB, p);
   B200_CHECK_LAUNCH("conv3_igemm");
   return 0;
+}
+}  // namespace b200
+
+namespace b200 {
+void deconv_phase_table(signed char* k3 /*[27*3]: kernel index per axis*/, signed char* off /*[27*3]: low-res input offset*/,
+                        signed char* ntaps /*[8]*/) {
+  int r = 0;
+  for (int phase = 0; phase < 8; ++phase) {
+    const int pp[3] = {(phase >> 2) & 1, (phase >> 1) & 1, phase & 1};
+    const int cnt[3] = {pp[0] ? 1 : 2, pp[1] ? 1 : 2, pp[2] ? 1 : 2};
+    int n = 0;
+    for (int a = 0; a < cnt[0]; ++a)
+      for (int b = 0; b < cnt[1]; ++b)
+        for (int c = 0; c < cnt[2]; ++c, ++r, ++n) {
+          const int sel[3] = {a, b, c};
+          for (int ax = 0; ax < 3; ++ax) {
+            // p = 1: (k 1, offset 0);  p = 0: selection 0 -> (k 2, offset -1), selection 1 -> (k 0, offset 0)
+            k3[3 * r + ax] = (signed char)(pp[ax] ? 1 : (sel[ax] == 0 ? 2 : 0));
+            off[3 * r + ax] = (signed char)(pp[ax] ? 0 : (sel[ax] == 0 ? -1 : 0));
+          }
+        }
+    ntaps[phase] = (signed char)n;
+  }
 }
 }  // namespace b200
 
@@ -460,6 +486,58 @@ int b200_conv3_up_dgrad(const void* dz, const void* wd, int N, int d, int h, int
   g.w_rows = 64;
   g.cls_mode = 2;
   return conv_igemm_plain_launch(dz, wd, 1, nullptr, 0, nullptr, B200_ACT_NONE, 0.f, N, d, h, w, Cout, C1, dxb, 0, nullptr, nullptr, g,
+                                 (cudaStream_t)s);
+}
+
+// ---- ConvTranspose3d(k3, s2, p1) by output parity phases (TransposeConvUpsampling, buildingblocks.py:617-664), on the LOW-RES lattice:
+//   T[o] = sum_{i, k : 2i - 1 + k = o} Wt[k] x[i]  on the (2d-1)^3 grid;  written here as  P[j] = T[j - 1]  on a (2d)^3 grid (P[0] along
+//   an axis is a don't-care: the nearest resize to the encoder size reads T[max(j-1, 0)] = P[max(j, 1)], see b200_shift_add_fwd).
+//   Per axis, j = 2u + p:  p = 1 (T index 2u, even):   one tap  Wt[1] x[u]
+//                          p = 0 (T index 2u-1, odd):  two taps Wt[2] x[u-1] + Wt[0] x[u]
+// => 27 (phase, tap) products in total (1,2,2,4,2,4,4,8 per phase) instead of the 27 taps PER OUTPUT VOXEL of a convolution over the
+// zero-inserted input: 8x fewer MACs.  One launch, 8 accumulators per CTA (one per phase, unequal tap counts).
+// wq: bf16 [27][Cout][Cin] in the (phase, tap) order of deconv_phase_table(); b200_deconv_phase_weights writes it.
+int b200_deconv_phase_supported(int N, int d, int h, int w, int Cin, int Cout) {
+  (void)N;
+  int bd, bh, bw;
+  if (Cin % 16 != 0 || Cout % 16 != 0 || d < 1 || h < 1 || w < 1) return 0;
+  return choose_box(d, h, w, &bd, &bh, &bw) ? 0 : 1;
+}
+int b200_deconv_phase_fwd(const void* x, const void* wq, int N, int d, int h, int w, int Cin, int Cout, void* P, b200_stream_t s) {
+  B200_CHECK_ARG(b200_deconv_phase_supported(N, d, h, w, Cin, Cout), "deconv_phase_fwd: unsupported N=%d %dx%dx%d Cin=%d Cout=%d", N, d, h, w,
+                 Cin, Cout);
+  PlainGeom g;
+  g.ntaps = 27;
+  g.nacc = 8;
+  signed char k3[27 * 3];
+  deconv_phase_table(k3, g.toff, g.acc_ntaps);
+  for (int phase = 0; phase < 8; ++phase) {
+    g.acc_off[3 * phase] = (signed char)((phase >> 2) & 1);
+    g.acc_off[3 * phase + 1] = (signed char)((phase >> 1) & 1);
+    g.acc_off[3 * phase + 2] = (signed char)(phase & 1);
+  }
+  g.out_mul = 2;
+  g.w_rows = 27;
+  g.cls_mode = 2;
+  return conv_igemm_plain_launch(x, wq, 1, nullptr, 0, nullptr, B200_ACT_NONE, 0.f, N, d, h, w, Cin, Cout, P, 0, nullptr, nullptr, g,
+                                 (cudaStream_t)s);
+}
+// adjoint: dx[u] = sum_{e in {0,1,2}^3} Wt[e]^T gp[2u + e]  -- a 3x3x3 STRIDE-2 convolution of the (folded) output gradient, read through an
+// element-stride-2 tensor map; indices past the (2d)^3 grid are zero-filled.  wd: bf16 [27][Cin][Cout] (b200_deconv_phase_weights).
+int b200_deconv_phase_dgrad(const void* gp, const void* wd, int N, int d, int h, int w, int Cout, int Cin, void* dx, b200_stream_t s) {
+  B200_CHECK_ARG(b200_deconv_phase_supported(N, d, h, w, Cin, Cout), "deconv_phase_dgrad: unsupported N=%d %dx%dx%d Cin=%d Cout=%d", N, d, h, w,
+                 Cin, Cout);
+  PlainGeom g;
+  g.ntaps = 27;
+  for (int e = 0; e < 27; ++e) {
+    g.toff[3 * e] = (signed char)(e / 9);
+    g.toff[3 * e + 1] = (signed char)((e / 3) % 3);
+    g.toff[3 * e + 2] = (signed char)(e % 3);
+  }
+  g.in_mul = 2;
+  g.w_rows = 27;
+  g.cls_mode = 2;
+  return conv_igemm_plain_launch(gp, wd, 1, nullptr, 0, nullptr, B200_ACT_NONE, 0.f, N, d, h, w, Cout, Cin, dx, 0, nullptr, nullptr, g,
                                  (cudaStream_t)s);
 }
 

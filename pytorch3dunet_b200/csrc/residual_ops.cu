@@ -9,6 +9,10 @@
 #include "ew.cuh"
 
 namespace b200 {
+void deconv_phase_table(signed char* k3, signed char* off, signed char* ntaps);  // conv_igemm_sm100.cu
+}
+
+namespace b200 {
 
 template <typename T>
 __device__ __forceinline__ float ldv(const T* p);
@@ -162,6 +166,109 @@ __global__ void pointwise_wgrad_small_kernel(const float* __restrict__ x, const 
       for (int vl = 0; vl < m.VL; ++vl) acc += red[(size_t)(vl * m.CG) * 8 + idx];
       if (pass < CIN) row[(size_t)idx * CIN + pass] = acc;
       else row[(size_t)Cout * CIN + idx] = acc;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// transposed conv by output parity phases (conv_igemm_sm100.cu: b200_deconv_phase_*): operand packing, weight-gradient assembly, and
+// the join  out[j] = enc[j] + P[max(j, 1)]  (= enc + nearest-resize(T) for an encoder feature of exactly twice the low-res size)
+// ---------------------------------------------------------------------------------------------------------------
+struct DeconvK {
+  signed char k3[27 * 3];
+};
+// wq[r][co][ci] = bf16(Wt[ci][co][k(r)])  (forward, (phase, tap) order);  wd[e][ci][co] = bf16(Wt[ci][co][e])  (adjoint)
+__global__ void deconv_phase_weights_kernel(const float* __restrict__ Wt, int Cin, int Cout, DeconvK tab, bf16* __restrict__ wq,
+                                            bf16* __restrict__ wd) {
+  const size_t per = (size_t)Cin * Cout, total = 27 * per;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * total; i += (size_t)gridDim.x * blockDim.x) {
+    if (i < total) {
+      const int ci = (int)(i % Cin);
+      const size_t r2 = i / Cin;
+      const int co = (int)(r2 % Cout), r = (int)(r2 / Cout);
+      const int k = (tab.k3[3 * r] * 3 + tab.k3[3 * r + 1]) * 3 + tab.k3[3 * r + 2];
+      wq[i] = __float2bfloat16_rn(Wt[((size_t)ci * Cout + co) * 27 + k]);
+    } else {
+      const size_t t = i - total;
+      const int co = (int)(t % Cout);
+      const size_t r2 = t / Cout;
+      const int ci = (int)(r2 % Cin), e = (int)(r2 / Cin);
+      wd[t] = __float2bfloat16_rn(Wt[((size_t)ci * Cout + co) * 27 + e]);
+    }
+  }
+}
+// dWt[ci][co][e] = sum_rows Q[row][e][co][ci]   (rows = N * splits)
+__global__ void deconv_phase_wgrad_finalize_kernel(const float* __restrict__ Q, int rows, int Cin, int Cout, float* __restrict__ dWt) {
+  const size_t per = (size_t)27 * Cout * Cin;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < per; i += (size_t)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % Cin);   // ci fastest: coalesced reads of Q
+    const size_t r2 = i / Cin;
+    const int co = (int)(r2 % Cout), e = (int)(r2 / Cout);
+    float acc = 0.f;
+    for (int r = 0; r < rows; ++r) acc += Q[(size_t)r * per + i];
+    dWt[((size_t)ci * Cout + co) * 27 + e] = acc;
+  }
+}
+// out[j] = enc[j] + P[max(jd,1), max(jh,1), max(jw,1)]; partials of out.  grid (P, N)
+__global__ void shift_add_fwd_kernel(const bf16* __restrict__ Pt, const bf16* __restrict__ enc, int D, int H, int W, int C, int P,
+                                     bf16* __restrict__ out, float* __restrict__ partials) {
+  extern __shared__ float red[];
+  const int p = blockIdx.x, n = blockIdx.y;
+  const EwMap m = ew_map(C);
+  const LineMap lm = line_map(m, W);
+  int l0, l1;
+  ew_range_i(D * H, p, P, l0, l1);
+  float s[8] = {0}, q[8] = {0};
+  if (lm.active) {
+    const size_t base = (size_t)n * D * H * W;
+    const bf16x8* ep = reinterpret_cast<const bf16x8*>(enc + base * C) + m.cg;
+    const bf16x8* pp = reinterpret_cast<const bf16x8*>(Pt + base * C) + m.cg;
+    bf16x8* op = reinterpret_cast<bf16x8*>(out + base * C) + m.cg;
+    for (int l = l0 + lm.ls; l < l1; l += lm.LPB) {
+      const int xh = l % H, xd = l / H;
+      const size_t srow = ((size_t)(xd > 1 ? xd : 1) * H + (xh > 1 ? xh : 1)) * W;
+      for (int xw = lm.lw; xw < W; xw += lm.lpl) {
+        float a[8], b[8];
+        unpack8(ep[((size_t)l * W + xw) * m.CG], a);
+        unpack8(pp[(srow + (xw > 1 ? xw : 1)) * m.CG], b);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          a[i] = bf16_round(a[i] + b[i]);
+          s[i] += a[i];
+          q[i] += a[i] * a[i];
+        }
+        op[((size_t)l * W + xw) * m.CG] = pack8(a);
+      }
+    }
+  }
+  if (partials) ew_write_partials(s, q, m, partials + ((size_t)n * P + p) * C * 2, red);
+}
+// adjoint of j -> max(j, 1) per axis: gp[j] = 0 where any coordinate is 0, else the sum of g over {0,1} along every axis where j == 1
+__global__ void shift_fold_bwd_kernel(const bf16* __restrict__ g, int D, int H, int W, int C, int P, bf16* __restrict__ gp) {
+  const int p = blockIdx.x, n = blockIdx.y;
+  const EwMap m = ew_map(C);
+  const LineMap lm = line_map(m, W);
+  int l0, l1;
+  ew_range_i(D * H, p, P, l0, l1);
+  if (!lm.active) return;
+  const size_t base = (size_t)n * D * H * W;
+  const bf16x8* ip = reinterpret_cast<const bf16x8*>(g + base * C) + m.cg;
+  bf16x8* op = reinterpret_cast<bf16x8*>(gp + base * C) + m.cg;
+  for (int l = l0 + lm.ls; l < l1; l += lm.LPB) {
+    const int xh = l % H, xd = l / H;
+    for (int xw = lm.lw; xw < W; xw += lm.lpl) {
+      float acc[8] = {0};
+      if (xd > 0 && xh > 0 && xw > 0) {
+        for (int zd = (xd == 1 ? 0 : xd); zd <= xd; ++zd)
+          for (int zh = (xh == 1 ? 0 : xh); zh <= xh; ++zh)
+            for (int zw = (xw == 1 ? 0 : xw); zw <= xw; ++zw) {
+              float f[8];
+              unpack8(ip[(((size_t)zd * H + zh) * W + zw) * m.CG], f);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) acc[i] += f[i];
+            }
+      }
+      op[((size_t)l * W + xw) * m.CG] = pack8(acc);
     }
   }
 }
@@ -398,6 +505,43 @@ int b200_pointwise_wgrad(const void* x, int x_is_f32, const void* dy, int N, lon
   if (x_is_f32) pointwise_wgrad_kernel<float><<<grid, 256, 0, ST(s)>>>((const float*)x, (const bf16*)dy, voxels, Cin, Cout, P, partials);
   else pointwise_wgrad_kernel<bf16><<<grid, 256, 0, ST(s)>>>((const bf16*)x, (const bf16*)dy, voxels, Cin, Cout, P, partials);
   B200_CHECK_LAUNCH("pointwise_wgrad");
+  return 0;
+}
+
+int b200_deconv_phase_weights(const float* Wt, int Cin, int Cout, void* wq, void* wd, b200_stream_t s) {
+  DeconvK tab;
+  signed char off[27 * 3], nt[8];
+  deconv_phase_table(tab.k3, off, nt);
+  const size_t total = (size_t)2 * 27 * Cin * Cout;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 4096) blocks = 4096;
+  deconv_phase_weights_kernel<<<blocks, 256, 0, ST(s)>>>(Wt, Cin, Cout, tab, (bf16*)wq, (bf16*)wd);
+  B200_CHECK_LAUNCH("deconv_phase_weights");
+  return 0;
+}
+int b200_deconv_phase_wgrad_finalize(const float* Q, int rows, int Cin, int Cout, float* dWt, b200_stream_t s) {
+  const size_t per = (size_t)27 * Cin * Cout;
+  int blocks = (int)((per + 255) / 256);
+  if (blocks > 4096) blocks = 4096;
+  deconv_phase_wgrad_finalize_kernel<<<blocks, 256, 0, ST(s)>>>(Q, rows, Cin, Cout, dWt);
+  B200_CHECK_LAUNCH("deconv_phase_wgrad_finalize");
+  return 0;
+}
+int b200_shift_add_fwd(const void* P, const void* enc, int N, int D, int H, int W, int C, void* out, float* partials, b200_stream_t s) {
+  B200_CHECK_ARG(C % 8 == 0 && C <= 2048 && D >= 2 && H >= 2 && W >= 2, "shift_add_fwd: bad shape C=%d %dx%dx%d", C, D, H, W);
+  int Pn = b200_upcat_partials_count(N, D, H, W, C);
+  dim3 grid(Pn, N);
+  shift_add_fwd_kernel<<<grid, EW_THREADS, EW_THREADS * 16 * sizeof(float), ST(s)>>>((const bf16*)P, (const bf16*)enc, D, H, W, C, Pn, (bf16*)out,
+                                                                                 partials);
+  B200_CHECK_LAUNCH("shift_add_fwd");
+  return 0;
+}
+int b200_shift_fold_bwd(const void* g, int N, int D, int H, int W, int C, void* gp, b200_stream_t s) {
+  B200_CHECK_ARG(C % 8 == 0 && C <= 2048, "shift_fold_bwd: C=%d must be a multiple of 8", C);
+  int Pn = ew_blocks_dense((long long)D * H * W, C);
+  dim3 grid(Pn, N);
+  shift_fold_bwd_kernel<<<grid, EW_THREADS, 0, ST(s)>>>((const bf16*)g, D, H, W, C, Pn, (bf16*)gp);
+  B200_CHECK_LAUNCH("shift_fold_bwd");
   return 0;
 }
 

@@ -215,13 +215,22 @@ static bool wgrad_supported(int N, int D, int H, int W, int Cin, int Cout) {
   return true;
 }
 
+// NT = 27: 3x3x3 taps at offsets -1..1;  64: 4x4x4 at -1..2 over a stride-2 operand;  1: no shift;
+// NT_DECONV: 3x3x3 at offsets 0..2 over a stride-2 operand (transposed-conv weight gradient)
+constexpr int NT_DECONV = -27;
 static void wgrad_plan(int N, int D, int H, int W, int Cin, int Cout, WgradParams& p, int NT = 27) {
   memset(&p, 0, sizeof(p));
   p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
+  const bool deconv = NT == NT_DECONV;
+  if (deconv) NT = 27;
   p.NTAPS = NT;
-  p.a_mul = NT == 64 ? 2 : 1;
+  p.a_mul = (NT == 64 || deconv) ? 2 : 1;
   for (int t = 0; t < NT; ++t) {
-    if (NT == 27) {
+    if (deconv) {
+      p.toff[3 * t] = (signed char)(t / 9);
+      p.toff[3 * t + 1] = (signed char)((t / 3) % 3);
+      p.toff[3 * t + 2] = (signed char)(t % 3);
+    } else if (NT == 27) {
       p.toff[3 * t] = (signed char)(t / 9 - 1);
       p.toff[3 * t + 1] = (signed char)((t / 3) % 3 - 1);
       p.toff[3 * t + 2] = (signed char)(t % 3 - 1);
@@ -347,6 +356,18 @@ int b200_conv3_up_wgrad_splits(int N, int d, int h, int w, int Cout, int C1) {
   WgradParams p;
   wgrad_plan(N, d, h, w, Cout, cout_slice(C1), p, 64);
   return p.S;
+}
+// ---- weight gradient of the transposed conv by phases: Q[n][split][e][co][ci] = sum_u gp[n, 2u+e, co] * x[n, u, ci], e in {0,1,2}^3
+int b200_deconv_phase_wgrad_splits(int N, int d, int h, int w, int Cout, int Cin) {
+  if (!wgrad_supported(N, d, h, w, Cout, Cin)) return 0;
+  WgradParams p;
+  wgrad_plan(N, d, h, w, Cout, cout_slice(Cin), p, NT_DECONV);
+  return p.S;
+}
+int b200_deconv_phase_wgrad(const void* gp, const void* x, int N, int d, int h, int w, int Cout, int Cin, float* Q, b200_stream_t s) {
+  B200_CHECK_ARG(b200_deconv_phase_wgrad_splits(N, d, h, w, Cout, Cin) > 0, "deconv_phase_wgrad: unsupported N=%d %dx%dx%d Cout=%d Cin=%d", N, d, h,
+                 w, Cout, Cin);
+  return wgrad_plain_launch(gp, x, N, d, h, w, Cout, Cin, Q, NT_DECONV, (cudaStream_t)s);
 }
 int b200_conv3_up_wgrad(const void* dz, const void* b, int N, int d, int h, int w, int Cout, int C1, float* Q, b200_stream_t s) {
   B200_CHECK_ARG(b200_conv3_up_wgrad_splits(N, d, h, w, Cout, C1) > 0, "conv3_up_wgrad: unsupported N=%d %dx%dx%d Cout=%d C1=%d", N, d, h, w,

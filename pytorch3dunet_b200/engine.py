@@ -33,12 +33,13 @@ _ACT_OF = {"r": (ACT_RELU, 0.0), "l": (ACT_LEAKY, 0.01), "e": (ACT_ELU, 1.0)}
 DEBUG = None   # dict: when set, backward closures stash clones of their intermediates (tools/debug_block.py)
 TIMING = None
 VIRTUAL_CAT = os.environ.get("B200UNET_NO_VIRTUAL_CAT", "0") != "1"  # decoder concat without the concatenated tensor
+DECONV_PHASES = os.environ.get("B200UNET_DECONV_PHASES", "1") != "0"  # transposed conv by output parity phases (exact 2x joins)
 EXPLICIT_GN = os.environ.get("B200UNET_EXPLICIT_GN", "1") != "0"      # deep levels: GroupNorm as its own pass instead of per-sample weights
 EXPLICIT_GN_VOX_PER_COUT = 40
 PMODE_PHASE_BIAS = 0x100  # B200_PMODE_PHASE_BIAS (include/b200unet.h)
 HOST_PROF = None  # dict name -> [calls, seconds] when host profiling is on
 TIMED = {"b200_conv3_fwd", "b200_conv3_wgrad", "b200_conv3_up_phase_fwd", "b200_conv3_up_dgrad", "b200_conv3_up_wgrad",
-         "b200_pointwise_tc_fwd", "b200_pointwise_tc_wgrad"}
+         "b200_pointwise_tc_fwd", "b200_pointwise_tc_wgrad", "b200_deconv_phase_fwd", "b200_deconv_phase_dgrad", "b200_deconv_phase_wgrad"}
 
 
 def default_impl() -> int:
@@ -773,6 +774,10 @@ class Engine:
         n, D, H, W_, cout = enc.dims
         n2, d, h, w, cin = x.dims
         assert n == n2
+        if (DECONV_PHASES and self.impl != IMPL_DIRECT and (D, H, W_) == (2 * d, 2 * h, 2 * w) and d >= 1
+                and self.L.query("b200_device_is_sm100") and self.L.query("b200_deconv_phase_supported", n, d, h, w, cin, cout)
+                and self.L.query("b200_deconv_phase_wgrad_splits", n, d, h, w, cout, cin) > 0):
+            return self._deconv_up_add_phases(enc, x, Wt, wname, want_stats)
         sd_, sh_, sw_ = 2 * d - 1, 2 * h - 1, 2 * w - 1
         T = self.deconv(x, Wt, wname)
         out_t = self.empty((n, D, H, W_, cout), torch.bfloat16)
@@ -788,6 +793,54 @@ class Engine:
                 dT = self.empty(T.t.shape, torch.bfloat16)
                 self.call("b200_deconv_gather", _p(g), n, d, h, w, D, H, W_, cout, _p(dT))
                 self.accumulate_grad(T, dT)
+                if enc.requires_grad:
+                    ge = self.empty(enc.t.shape, torch.bfloat16)
+                    self.call("b200_act_bwd", _p(g), cout, 0, _p(enc.t), n, cout, D * H * W_, enc.act, enc.slope, _p(enc.grad), _p(ge))
+                    enc.grad = ge
+                out.grad = None
+            self.tape.append(backward)
+        return out
+
+    def _deconv_up_add_phases(self, enc, x, Wt, wname, want_stats):
+        """deconv_up_add for an encoder feature of exactly twice the low-res size, by output parity phases (csrc: b200_deconv_phase_*):
+        27 (phase, tap) products on the low-res lattice instead of 27 taps per voxel of the zero-inserted grid (8x fewer MACs), no
+        zero-inserted tensor, the (2d-1)^3 -> (2d)^3 nearest resize folded into the join's index map."""
+        n, D, H, W_, cout = enc.dims
+        _, d, h, w, cin = x.dims
+        Wt = Wt.contiguous()
+        wq = self.empty((27, cout, cin), torch.bfloat16)
+        wd = self.empty((27, cin, cout), torch.bfloat16)
+        self.call("b200_deconv_phase_weights", _p(Wt), cin, cout, _p(wq), _p(wd))
+        Pt = self.empty((n, D, H, W_, cout), torch.bfloat16)
+        self.call("b200_deconv_phase_fwd", _p(x.t), _p(wq), n, d, h, w, cin, cout, _p(Pt),
+                  flops=2.0 * n * d * h * w * 27 * cin * cout, tag="fprop_tc", layer=wname)
+        out_t = self.empty((n, D, H, W_, cout), torch.bfloat16)
+        Pn = self.L.query("b200_upcat_partials_count", n, D, H, W_, cout)
+        partials = self.empty((n, Pn, cout, 2), torch.float32) if want_stats else None
+        self.call("b200_shift_add_fwd", _p(Pt), _p(enc.t), n, D, H, W_, cout, _p(out_t), _p(partials))
+        del Pt
+        out = Act(out_t, ACT_NONE, 0.0, partials, Pn)
+        if self.record:
+            def backward():
+                g = out.grad
+                if g is None:
+                    return
+                gp = self.empty((n, D, H, W_, cout), torch.bfloat16)
+                self.call("b200_shift_fold_bwd", _p(g), n, D, H, W_, cout, _p(gp))
+                S = self.L.query("b200_deconv_phase_wgrad_splits", n, d, h, w, cout, cin)
+                Q = self.empty((n * S, 27, cout, cin), torch.float32)
+                self.call("b200_deconv_phase_wgrad", _p(gp), _p(x.t), n, d, h, w, cout, cin, _p(Q),
+                          flops=2.0 * n * d * h * w * 27 * cin * cout, tag="wgrad_tc", layer=wname)
+                dWt = self.grad_like(wname, Wt)
+                self.call("b200_deconv_phase_wgrad_finalize", _p(Q), n * S, cin, cout, _p(dWt))
+                self._add_param_grad(wname, dWt)
+                if x.requires_grad:
+                    gx = self.empty(x.t.shape, torch.bfloat16)
+                    self.call("b200_deconv_phase_dgrad", _p(gp), _p(wd), n, d, h, w, cout, cin, _p(gx),
+                              flops=2.0 * n * d * h * w * 27 * cin * cout, tag="dgrad_tc", layer=wname)
+                    if x.act != ACT_NONE or x.grad is not None:
+                        self.call("b200_act_bwd", _p(gx), cin, 0, _p(x.t), n, cin, d * h * w, x.act, x.slope, _p(x.grad), _p(gx))
+                    x.grad = gx
                 if enc.requires_grad:
                     ge = self.empty(enc.t.shape, torch.bfloat16)
                     self.call("b200_act_bwd", _p(g), cout, 0, _p(enc.t), n, cout, D * H * W_, enc.act, enc.slope, _p(enc.grad), _p(ge))

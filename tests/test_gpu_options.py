@@ -155,3 +155,39 @@ def test_data_parallel_two_replicas_forward_backward():
         assert rel_l2(b.grad, a.grad) < 2e-2, (k, rel_l2(b.grad, a.grad))  # replica split changes the bf16 summation order only
     with torch.no_grad():
         assert torch.allclose(dp(x), out_s, atol=1e-5)
+
+
+@pytest.mark.parametrize("phases", [True, False])
+@pytest.mark.parametrize("shape", [((2, 16, 12, 10, 8), (2, 32, 6, 5, 4)), ((1, 32, 16, 16, 16), (1, 64, 8, 8, 8)),
+                                   ((1, 16, 9, 11, 7), (1, 32, 5, 6, 4))])   # the last one: odd encoder size -> zero-insert path either way
+def test_deconv_join_matches_torch(shape, phases, monkeypatch):
+    """ConvTranspose3d(k3,s2,p1) + nearest resize + sum join (buildingblocks.py:617-664, :493), through the engine: the phase-decomposed
+    path (exact 2x sizes) and the zero-insert path against conv_transpose3d + interpolate and their autograd"""
+    from pytorch3dunet_b200 import engine as E
+    monkeypatch.setattr(E, "DECONV_PHASES", phases)
+    (n, c_out, D, H, W), (_, c_in, d, h, w) = shape
+    torch.manual_seed(3)
+    dev = torch.device("cuda")
+    enc = torch.randn(n, c_out, D, H, W)
+    x = torch.randn(n, c_in, d, h, w)
+    Wt = torch.randn(c_in, c_out, 3, 3, 3) * (1.0 / (27 * c_in)) ** 0.5
+    eng = E.Engine(dev, record=True)
+    a_enc = eng.input_bf16(enc.to(dev), True)
+    a_x = eng.input_bf16(x.to(dev), True)
+    out = eng.deconv_up_add(a_enc, a_x, Wt.to(dev), "up.weight", want_stats=True)
+    y = eng.to_ncdhw_f32(out.t)
+    g = torch.randn(y.shape)
+    eng.grad_from_ncdhw(out, g.to(dev))
+    eng.run_backward()
+    g_enc, g_x = eng.to_ncdhw_f32(a_enc.grad).cpu(), eng.to_ncdhw_f32(a_x.grad).cpu()
+    dWt = eng.param_grads["up.weight"].cpu()
+    sums = eng.sums_of(out).cpu()
+    eo, xo = enc.bfloat16().float().requires_grad_(True), x.bfloat16().float().requires_grad_(True)
+    Wo = Wt.bfloat16().float().requires_grad_(True)
+    ref = eo + F.interpolate(F.conv_transpose3d(xo, Wo, None, stride=2, padding=1), size=(D, H, W))
+    (ref * g.bfloat16().float()).sum().backward()
+    rep = {"y": rel_l2(y, ref), "g_enc": rel_l2(g_enc, eo.grad), "g_x": rel_l2(g_x, xo.grad), "dWt": rel_l2(dWt, Wo.grad)}
+    print("deconv join", shape, "phases" if phases else "zero-insert", {k: f"{v:.2e}" for k, v in rep.items()})
+    assert rep["y"] < 6e-3 and rep["g_enc"] < 4e-3 and rep["g_x"] < 1e-2 and rep["dWt"] < 1e-2, rep
+    refb = y.cpu().double()
+    assert torch.allclose(sums[..., 0], refb.sum(dim=(2, 3, 4)), rtol=1e-4, atol=1e-2)
