@@ -15,11 +15,11 @@
 // z+1 stream through, then the epilogue warps drain it while the next planes accumulate.  Every input plane tile is fetched once
 // (1.4x halo overhead instead of 4.2x), the MMA count per output tile drops from 27*C_in/16 to 9*C_in/16.
 //
-//   TMEM: a ring of R = min(16, 512 / C_out) column blocks of C_out columns; output plane number q (in the CTA's own order) lives in
-//         block q mod R.  An input plane targets up to three consecutive blocks = one MMA, or two when the ring wraps.
+//   TMEM: per lane a ring of R = min(16, 512 / C_out) / 2 column blocks of C_out columns; output plane number q (in the lane's own order)
+//         lives in block q mod R.  An input plane targets up to three consecutive blocks = one MMA, or two when the ring wraps.
 //   first touch of a block uses accumulate = 0: the very first (tap, k) step of an input plane is issued as separate MMAs for the
 //         already-open blocks (accumulate) and the newly opened one (overwrite); all other steps are single instructions.
-//   warps: 0..3 / 4..7 two epilogue groups (even / odd planes), 8 TMA producer, 9 MMA issuer (+ TMEM allocation).
+//   warps: two independent lanes per CTA (see ZS_LANES): 0..3 / 4..7 epilogue warpgroups, 8 / 9 TMA producers, 10 / 11 MMA issuers.
 //   GroupNorm statistics of the output: per-thread register accumulators across all planes of the CTA (C_out <= 32) or per-warp
 //         shared-memory accumulators (wider), reduced ONCE at the end: partials [N][P = CTAs per sample][C_out][2].
 //
@@ -33,8 +33,13 @@ namespace b200 {
 constexpr int ZS_BH = 16, ZS_BW = 8;
 constexpr int ZS_HH = ZS_BH + 2, ZS_HW = ZS_BW + 2;
 constexpr int ZS_ROWS = ZS_HH * ZS_HW;  // 180 rows of one input-plane halo tile
-constexpr int ZS_THREADS = 2 * 128 + 96;
-constexpr int ZS_WARP_PRODUCER = 8, ZS_WARP_MMA = 9, ZS_ISSUERS = 2;  // warps 9 and 10 issue MMAs
+// two independent LANES per CTA, each = one epilogue warpgroup + one TMA producer warp + one MMA issuer warp + half of the halo stages + half of
+// the TMEM ring, walking its own half of the CTA's plane-tiles.  (One issuing warp sustains an MMA per ~55-80 cycles; two warps
+// issuing into DIFFERENT accumulators keep the tensor pipe fed -- and, unlike two warps sharing an accumulator, leave the fp32
+// accumulation order, hence the result bits, independent of warp timing.)
+constexpr int ZS_LANES = 2;
+constexpr int ZS_THREADS = 2 * 128 + 4 * 32;
+constexpr int ZS_WARP_PRODUCER = 8, ZS_WARP_MMA = 10;  // warps 8,9 producers; 10,11 issuers (lane = warp & 1)
 constexpr int ZS_MAX_STAGES = 8;
 constexpr int ZS_MAX_SLOTS = 16;
 
@@ -52,12 +57,10 @@ __device__ __forceinline__ void zs_issue(const ZsRun (&r)[3], uint64_t adesc, ui
     if (r[k].idesc) umma_bf16_elect(r[k].tacc, adesc, bdesc + r[k].boff, r[k].idesc, first ? r[k].accum : 1u);
 }
 
-// all 9 in-plane taps x KC/16 k-steps of one halo chunk, the steps of ONE issuer: the two issuer warps take alternate (tap, k) steps
-// (a single warp sustains one tcgen05.mma per ~54-80 cycles, the tensor pipe wants one N = 3*C_out instruction per 56).  PAR = parity
-// of the in-chunk step index this issuer takes.  b_lo points at [t9 = 0][tdr = 0] of this chunk; one t9 advances 3 blocks.
+// all 9 in-plane taps x KC/16 k-steps of one halo chunk.  b_lo points at [t9 = 0][tdr = 0] of this chunk; one t9 advances 3 blocks.
 // `skip_first`: the (t9 = 0, k = 0) step of the plane's first chunk is issued separately (its accumulate flags differ per block).
 // ONE_RUN: the plane's blocks are contiguous in TMEM (no ring wrap): one instruction per step, descriptors advance by immediates.
-template <int KC, bool ONE_RUN, int PAR>
+template <int KC, bool ONE_RUN>
 __device__ __forceinline__ void zs_issue_chunk(const ZsRun (&rr)[3], uint32_t a_lo, uint32_t b_lo, uint32_t b_t9, uint64_t hiA, uint64_t hiB,
                                                bool skip_first) {
   constexpr uint32_t RB16 = KC * 2 / 16;  // one halo row in 16-byte units
@@ -67,7 +70,6 @@ __device__ __forceinline__ void zs_issue_chunk(const ZsRun (&rr)[3], uint32_t a_
     const uint32_t offA = (uint32_t)((t9 / 3) * ZS_HW + t9 % 3) * RB16;
 #pragma unroll
     for (int k = 0; k < KC / 16; ++k) {
-      if (((t9 * (KC / 16) + k) & 1) != PAR) continue;
       const uint64_t adesc = hiA | (uint64_t)(a_lo + offA + 2u * k);
       const uint64_t bdesc = hiB | (uint64_t)(b_lo + 2u * k);
       if (t9 == 0 && k == 0) {
@@ -126,8 +128,8 @@ template <int KC>
 __global__ void __launch_bounds__(ZS_THREADS, 1)
 conv3_zs_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, const ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t a_full[ZS_MAX_STAGES], a_empty[ZS_MAX_STAGES];
-  __shared__ __align__(8) uint64_t b_full, tmem_full[ZS_MAX_SLOTS], tmem_empty[ZS_MAX_SLOTS], first_done[ZS_MAX_STAGES];
+  __shared__ __align__(8) uint64_t a_full_[ZS_MAX_STAGES], a_empty_[ZS_MAX_STAGES];   // lane l owns entries [l*S, (l+1)*S)
+  __shared__ __align__(8) uint64_t b_full, tmem_full_[ZS_MAX_SLOTS], tmem_empty_[ZS_MAX_SLOTS];  // lane l owns [l*R, (l+1)*R)
   __shared__ uint32_t tmem_slot;
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -140,25 +142,30 @@ conv3_zs_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
   const int n = blockIdx.y, cta = blockIdx.x, cps = gridDim.x;
   const int nchunks = p.Cin / KC;
   constexpr int rb = KC * 2;
-  const int R = p.tmem_bufs;  // ring slots
-  const int S = p.a_stages;
+  const int R = p.tmem_bufs / ZS_LANES;  // ring slots per lane
+  const int S = p.a_stages / ZS_LANES;   // halo stages per lane
   const int D = p.D;
-  ZsWalk walk = zs_walk(p, cta, cps);
+  // lane of this warp: epilogue warps 0..3 -> 0, 4..7 -> 1; producer / issuer warps alternate
+  const int lane_id = warp < 8 ? (warp >> 2) : (warp & 1);
+  ZsWalk walk = zs_walk(p, cta * ZS_LANES + lane_id, cps * ZS_LANES);
+  uint64_t* a_full = a_full_ + lane_id * S;
+  uint64_t* a_empty = a_empty_ + lane_id * S;
+  uint64_t* tmem_full = tmem_full_ + lane_id * R;
+  uint64_t* tmem_empty = tmem_empty_ + lane_id * R;
 #ifdef B200_DEBUG
   const int planes_mine = walk.L1 - walk.L;
 #endif
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < S; ++i) {
-      mbar_init(&a_full[i], 1);
-      mbar_init(&a_empty[i], ZS_ISSUERS);   // every issuer commits each stage it has read
+    for (int i = 0; i < ZS_LANES * S; ++i) {
+      mbar_init(&a_full_[i], 1);
+      mbar_init(&a_empty_[i], 1);
     }
     mbar_init(&b_full, 1);
-    for (int i = 0; i < R; ++i) {
-      mbar_init(&tmem_full[i], ZS_ISSUERS);  // complete when both issuers' MMAs on it have executed
-      mbar_init(&tmem_empty[i], 4);          // one arrival per epilogue warp of the group that drained it
+    for (int i = 0; i < ZS_LANES * R; ++i) {
+      mbar_init(&tmem_full_[i], 1);
+      mbar_init(&tmem_empty_[i], 4);  // one arrival per epilogue warp of the lane's warpgroup
     }
-    for (int i = 0; i < ZS_MAX_STAGES; ++i) mbar_init(&first_done[i], 1);
     fence_mbar_init();
   }
   if (warp == ZS_WARP_PRODUCER && lane == 0) {
@@ -176,16 +183,17 @@ conv3_zs_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = tmem_slot;
+  const uint32_t tmem_base = tmem_slot + (uint32_t)(lane_id * R * p.NT);   // this lane's half of the accumulator ring
+  uint8_t* smemA_lane = smemA + (size_t)lane_id * S * p.a_bytes;
 
-  if (warp == ZS_WARP_PRODUCER) {
+  if (warp >= ZS_WARP_PRODUCER && warp < ZS_WARP_MMA) {
     // ================= TMA producer: resident weights once, then one halo tile per (input plane, channel chunk) =================
     if (lane == 0) {
       const int wsample = p.n_w > 1 ? n : 0;
-      mbar_arrive_expect_tx(&b_full, (uint32_t)p.b_total_bytes);
+      if (lane_id == 0) mbar_arrive_expect_tx(&b_full, (uint32_t)p.b_total_bytes);
       // smem layout [chunk][t9][tdr = 2 - td][C_out][KC]: the three depth taps of one in-plane tap are adjacent row blocks, in the
       // order of ascending OUTPUT plane (z-1 <- dd=+1, z <- dd=0, z+1 <- dd=-1)
-      for (int cb = 0; cb < nchunks; ++cb)
+      for (int cb = 0; cb < nchunks && lane_id == 0; ++cb)
         for (int t9 = 0; t9 < 9; ++t9)
           for (int tdr = 0; tdr < 3; ++tdr)
             tma_load_3d(smemB + ((size_t)((cb * 9 + t9) * 3 + tdr)) * p.NT * rb, &tmapB, &b_full, cb * KC, 0,
@@ -203,12 +211,12 @@ conv3_zs_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
             mbar_wait(&a_empty[st.idx], st.ph ^ 1u);
             w_prod += dbg_clock() - c0;
             mbar_arrive_expect_tx(&a_full[st.idx], (uint32_t)(ZS_ROWS * rb));
-            tma_load_5d(smemA + (size_t)st.idx * p.a_bytes, &tmapA, &a_full[st.idx], j * KC, w0 - 1, h0 - 1, zin, n);
+            tma_load_5d(smemA_lane + (size_t)st.idx * p.a_bytes, &tmapA, &a_full[st.idx], j * KC, w0 - 1, h0 - 1, zin, n);
             st.step(S);
           }
       }
 #ifdef B200_DEBUG
-      if (p.dbg) {
+      if (p.dbg && lane_id == 0) {
         long long* o = p.dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16;
         o[0] = w_prod;
         o[1] = dbg_clock() - t_begin;
@@ -218,8 +226,7 @@ conv3_zs_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
 #endif
     }
   } else if (warp >= ZS_WARP_MMA) {
-    // ================= MMA issuers (whole warp converged, one elected lane issues); both walk every input plane =================
-    const int issuer = warp - ZS_WARP_MMA;
+    // ================= MMA issuer of this lane (whole warp converged, one elected lane issues) =================
     const uint32_t lay = umma_layout_for_row_bytes(rb);
     const uint64_t hiA = umma_smem_desc(0, 16u, (uint32_t)(ZS_HW * rb), lay) & 0xFFFFFFFF00000000ull;
     const uint64_t hiB = umma_smem_desc(0, 16u, (uint32_t)(8 * rb), lay) & 0xFFFFFFFF00000000ull;
@@ -235,9 +242,7 @@ conv3_zs_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
     ZsRing st = {0, 0u};      // halo stage being consumed
     ZsRing open = {0, 0u};    // TMEM block of the NEXT output plane to be opened (planes are opened and completed in order)
     ZsRing done = {0, 0u};    // TMEM block of the next output plane to complete
-    ZsRing fd = {0, 0u};      // first_done barrier of the current input plane
     int slot_a = 0;           // TMEM block of plane `a` (the oldest plane the current input plane touches)
-    constexpr int SPC = 9 * (KC / 16);  // (tap, k) steps per chunk
     long long w_afull = 0, w_tempty = 0, t_begin = dbg_clock();
     ZsSeg sg;
     while (walk.next(sg)) {
@@ -260,7 +265,7 @@ conv3_zs_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
         {
           const long long c0 = dbg_clock();
           for (int zo = opened; zo <= b; ++zo) {  // the block must have been drained by the epilogue of the plane that used it R planes ago
-            if (issuer == 0) mbar_wait(&tmem_empty[open.idx], open.ph ^ 1u);  // issuer 1 is ordered behind issuer 0's first step
+            mbar_wait(&tmem_empty[open.idx], open.ph ^ 1u);
             open.step(R);
           }
           opened = b + 1;
@@ -312,32 +317,17 @@ conv3_zs_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
           mbar_wait(&a_full[st.idx], st.ph);
           w_afull += dbg_clock() - c1;
           tc_fence_after();
-          const uint32_t a_lo = ((smem_u32(smemA + (size_t)st.idx * p.a_bytes) >> 4) & 0x3FFFu) | lo_lbo;
+          const uint32_t a_lo = ((smem_u32(smemA_lane + (size_t)st.idx * p.a_bytes) >> 4) & 0x3FFFu) | lo_lbo;
           if (!DBG_FLAG(p, 8)) {
-            if (j == 0) {
-              if (issuer == 0) {  // first (tap, k) step of the plane: per-block accumulate flags; tell issuer 1 when it has EXECUTED
-                zs_issue(rf, hiA | (uint64_t)a_lo, hiB | (uint64_t)b_lo, true);
-                umma_commit_elect(&first_done[fd.idx]);
-              } else {            // nothing of this plane may accumulate into a fresh block before it has been overwritten
-                mbar_wait(&first_done[fd.idx], fd.ph);
-                tc_fence_after();
-              }
-            }
-            // this issuer's steps: in-chunk step parity (issuer + j * SPC) & 1
-            const int par = (issuer + j * SPC) & 1;
-            if (one_run) {
-              if (par) zs_issue_chunk<KC, true, 1>(rr, a_lo, b_lo, b_t9, hiA, hiB, j == 0);
-              else zs_issue_chunk<KC, true, 0>(rr, a_lo, b_lo, b_t9, hiA, hiB, j == 0);
-            } else {
-              if (par) zs_issue_chunk<KC, false, 1>(rr, a_lo, b_lo, b_t9, hiA, hiB, j == 0);
-              else zs_issue_chunk<KC, false, 0>(rr, a_lo, b_lo, b_t9, hiA, hiB, j == 0);
-            }
+            if (j == 0)  // first (tap, k) step of the plane: per-block accumulate flags
+              zs_issue(rf, hiA | (uint64_t)a_lo, hiB | (uint64_t)b_lo, true);
+            if (one_run) zs_issue_chunk<KC, true>(rr, a_lo, b_lo, b_t9, hiA, hiB, j == 0);
+            else zs_issue_chunk<KC, false>(rr, a_lo, b_lo, b_t9, hiA, hiB, j == 0);
           }
           umma_commit_elect(&a_empty[st.idx]);
           st.step(S);
           b_lo += chunkB16;
         }
-        fd.step(ZS_MAX_STAGES);
         // output planes that received their last contribution: zin-1 always (if in the segment); plane D-1 when zin == D-1
         if (zin - 1 >= z0) {
           umma_commit_elect(&tmem_full[done.idx]);
@@ -350,20 +340,19 @@ conv3_zs_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
       }
     }
 #ifdef B200_DEBUG
-    if (p.dbg && lane == 0 && issuer == 0) {
+    if (p.dbg && lane == 0 && lane_id == 0) {
       long long* o = p.dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16;
       o[2] = w_afull;
       o[3] = w_tempty;
       o[4] = dbg_clock() - t_begin;
-      o[7] = planes_mine;
+      o[7] = planes_mine * ZS_LANES;
     }
 #else
     (void)w_afull; (void)w_tempty; (void)t_begin;
 #endif
   } else {
-    // ================= epilogue: warps 0..3 take even output planes, warps 4..7 odd ones =================
+    // ================= epilogue: warps 0..3 drain lane 0's planes, warps 4..7 lane 1's =================
     const int qd = warp & 3;   // TMEM lane quarter
-    const int grp = warp >> 2;
     const int row = qd * 32 + lane;
     const int bx = row % ZS_BW, by = row / ZS_BW;
     const int NT = p.NT;
@@ -372,8 +361,7 @@ conv3_zs_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
 #pragma unroll
     for (int i = 0; i < 32; ++i) rs[i] = rq[i] = 0.f;
     float* my_acc = stat_acc + (size_t)warp * NT * 2;
-    ZsRing cur = {0, 0u};   // TMEM block of the plane being visited (every plane, either group's)
-    int parity = 0;          // plane number & 1
+    ZsRing cur = {0, 0u};   // TMEM block of the plane being drained
     long long w_tfull = 0, t_ld = 0, t_begin = dbg_clock();
     const size_t HW = (size_t)p.H * p.W;
     ZsSeg sg;
@@ -382,8 +370,7 @@ conv3_zs_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
       const int xh = th_i * ZS_BH + by, xw = tw_i * ZS_BW + bx;
       const bool valid = xh < p.H && xw < p.W;
       const size_t vox_hw = (size_t)n * D * HW + (size_t)xh * p.W + xw;
-      for (int zo = sg.z0; zo < sg.z1; ++zo, cur.step(R), parity ^= 1) {
-        if (parity != grp) continue;
+      for (int zo = sg.z0; zo < sg.z1; ++zo, cur.step(R)) {
         const int slot = cur.idx;
         const size_t vox_off = vox_hw + (size_t)zo * HW;
         const float* bias_row = nullptr;
@@ -537,8 +524,9 @@ bool conv_zs_plan(int N, int D, int H, int W, int Cin, int Cout, ConvParams* pp)
   const int kc = (Cin % 64 == 0) ? 64 : (Cin % 32 == 0 ? 32 : 16);
   const int a_bytes = (ZS_ROWS * kc * 2 + 1023) & ~1023;
   int stages = (budget - ((b_total + 1023) & ~1023) - scratch - 1024) / a_bytes;
-  if (stages < 3) return false;
   if (stages > ZS_MAX_STAGES) stages = ZS_MAX_STAGES;
+  stages &= ~1;  // two lanes, half of the stages each
+  if (stages < 4) return false;
   p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
   p.BD = 1; p.BH = ZS_BH; p.BW = ZS_BW;
   p.tilesD = D;
@@ -553,7 +541,8 @@ bool conv_zs_plan(int N, int D, int H, int W, int Cin, int Cout, ConvParams* pp)
   p.b_total_bytes = b_total;
   int slots = 512 / Cout;
   if (slots > ZS_MAX_SLOTS) slots = ZS_MAX_SLOTS;
-  if (slots < 4) return false;
+  slots &= ~1;  // two lanes, half of the ring each: three blocks accumulating + one being drained
+  if (slots < 8) return false;
   p.tmem_bufs = slots;
   p.tmem_cols = 512;
   long long T = (long long)p.tilesH * p.tilesW * D;
@@ -564,7 +553,7 @@ bool conv_zs_plan(int N, int D, int H, int W, int Cin, int Cout, ConvParams* pp)
     const int v = atoi(e);
     if (v >= 1) cps = v;
   }
-  if (cps > T) cps = (int)T;
+  if ((long long)cps * ZS_LANES > T) cps = (int)((T + ZS_LANES - 1) / ZS_LANES);
   p.ctas_per_sample = cps;
   return true;
 }
