@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-baseline", action="store_true")
+    ap.add_argument("--operand-dtype", default=None, choices=["bf16", "fp16"], help="16-bit type of activations / tensor-core operands "
+                    "(default: fp16 for cfg4, as BASELINE names it; bf16 otherwise)")
     ap.add_argument("--buckets", type=int, default=4, help="gradient allreduce buckets (launched as backward finishes them)")
     ap.add_argument("--fused-loss", type=int, default=int(os.environ.get("B200UNET_FUSED_LOSS", "1")),
                     help="1: BCEDiceLoss through the engine's two-pass kernels (csrc/loss_ops.cu) instead of eager torch ops")
@@ -258,7 +260,8 @@ def run_train(args, wl):
         dist.init_process_group("nccl", device_id=dev)
 
     torch.manual_seed(0)  # identical replicas on every rank (the reference's DataParallel broadcasts rank-0 weights)
-    model = P.get_model(wl["cfg"]).to(dev)
+    odt = args.operand_dtype or ("fp16" if args.workload == "cfg4" else "bf16")
+    model = P.get_model({**wl["cfg"], "operand_dtype": odt}).to(dev)
     flat = P.optim.FlatParameters(model)          # parameters / gradients as views of two flat buffers; the engine writes wgrads in place
     reducer = P.optim.BucketedAllReduce(flat, world, n_buckets=args.buckets)
     adam = P.optim.FusedAdam(flat, lr=2e-4, weight_decay=1e-5, grad_scale=1.0 / world)   # the shipped configs' optimizer (utils.py:246-316)
@@ -412,7 +415,7 @@ def run_train(args, wl):
 
     line = {"metric": wl["metric"], "value": value, "unit": "patches/s", "n_gpus": world,
             "steps": args.steps, "warmup": W, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": odt, "data": "synthetic",
             "config": {"workload": wl["text"] if (S == wl["size"] and B == wl["batch"]) else f"{wl['cfg']['name']} batch {B}x1x{S}^3", "per_gpu_batch": B,
                        "parallelism": f"dp{world}", "l2": "per-step working set (~1 GB of bf16 activations per patch) >> 126 MB L2; no explicit flush",
                        "setup_steps_before_warmup": ALLOC_SETTLE_STEPS, "grad_allreduce_buckets": len(reducer.buckets) if world > 1 else 0,

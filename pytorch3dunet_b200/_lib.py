@@ -13,6 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 HEADER = os.path.join(_ROOT, "include", "b200unet.h")
 LIB_PATH = os.environ.get("B200UNET_LIB") or os.path.join(_HERE, "libb200unet.so")   # B200UNET_LIB: e.g. the debug build with wait counters
+LIB_PATH_F16 = os.path.join(_HERE, "libb200unet_f16.so")   # the same sources built with fp16 activations / operands (-DB200_ACT_F16)
 
 _CTYPES = {
     "int": ctypes.c_int,
@@ -55,12 +56,14 @@ class B200Error(RuntimeError):
 
 
 class _Lib:
-    def __init__(self):
-        if not os.path.exists(LIB_PATH):
+    def __init__(self, path=None):
+        path = path or LIB_PATH
+        if not os.path.exists(path):
             raise B200Error(
-                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(there is no CPU/PyTorch fallback for the b200 3D U-Net engine)")
-        self.cdll = ctypes.CDLL(LIB_PATH)
+        self.path = path
+        self.cdll = ctypes.CDLL(path)
         self.protos = parse_header()
         for name, argtypes in self.protos.items():
             fn = getattr(self.cdll, name)  # AttributeError if the header declares something the .so lacks
@@ -84,10 +87,16 @@ class _Lib:
 
 
 _lib = None
+_lib_f16 = None
 
 
-def lib() -> _Lib:
-    global _lib
+def lib(operand_dtype: str = "bf16") -> _Lib:
+    """the library whose 16-bit activation / tensor-core operand type is `operand_dtype` ("bf16" default, "fp16")"""
+    global _lib, _lib_f16
+    if operand_dtype in ("fp16", "f16", "float16"):
+        if _lib_f16 is None:
+            _lib_f16 = _Lib(LIB_PATH_F16)
+        return _lib_f16
     if _lib is None:
         _lib = _Lib()
     return _lib

@@ -28,7 +28,23 @@ void set_error(const char* fmt, ...);
     }                                                                               \
   } while (0)
 
+// The 16-bit ACTIVATION / tensor-core OPERAND type.  Default bf16; building with -DB200_ACT_F16 (libb200unet_f16.so) makes it IEEE fp16
+// (tcgen05 kind::f16 takes either; BASELINE configs[3] names fp16).  The name `bf16` is kept for the type throughout the kernels: read
+// it as "the 16-bit storage type".  fp32 accumulation, fp32 statistics and fp32 parameters are the same in both builds.
+#ifdef B200_ACT_F16
+#include <cuda_fp16.h>
+typedef __half bf16;
+#define B200_TMAP_DTYPE CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+#define B200_UMMA_FMT 0u   /* kind::f16 operand format: 0 = f16, 1 = bf16 */
+__host__ __device__ __forceinline__ bf16 to_act(float x) { return __float2half_rn(x); }
+__host__ __device__ __forceinline__ float from_act(bf16 x) { return __half2float(x); }
+#else
 typedef __nv_bfloat16 bf16;
+#define B200_TMAP_DTYPE CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+#define B200_UMMA_FMT 1u
+__host__ __device__ __forceinline__ bf16 to_act(float x) { return __float2bfloat16_rn(x); }
+__host__ __device__ __forceinline__ float from_act(bf16 x) { return __bfloat162float(x); }
+#endif
 
 // 8 bf16 = one 16-byte vector.  Held as a uint4 so that every copy / dereference is ONE 128-bit load or store
 // (a struct of four __nv_bfloat162 members is copied member-wise: four 32-bit accesses).
@@ -36,6 +52,21 @@ struct alignas(16) bf16x8 {
   uint4 u;
 };
 
+#ifdef B200_ACT_F16
+__device__ __forceinline__ void unpack8(const bf16x8& p, float f[8]) {
+  const uint32_t w[4] = {p.u.x, p.u.y, p.u.z, p.u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  __half2 t = __floats2half2_rn(lo, hi);  // .x (low half) = lo
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+#else
 __device__ __forceinline__ void unpack8(const bf16x8& p, float f[8]) {
   f[0] = __uint_as_float(p.u.x << 16);
   f[1] = __uint_as_float(p.u.x & 0xffff0000u);
@@ -50,6 +81,7 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);  // .x (low half) = lo
   return *reinterpret_cast<uint32_t*>(&t);
 }
+#endif
 __device__ __forceinline__ bf16x8 pack8(const float f[8]) {
   bf16x8 p;
   p.u.x = pack2(f[0], f[1]);
@@ -58,7 +90,7 @@ __device__ __forceinline__ bf16x8 pack8(const float f[8]) {
   p.u.w = pack2(f[6], f[7]);
   return p;
 }
-__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+__device__ __forceinline__ float bf16_round(float x) { return from_act(to_act(x)); }  // round to the 16-bit storage type
 
 // activation and its derivative expressed through the OUTPUT y (valid for relu / leaky / elu(alpha=1))
 __device__ __forceinline__ float act_fwd(float z, int act, float slope) {

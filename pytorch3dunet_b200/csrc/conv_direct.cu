@@ -15,7 +15,7 @@ __device__ __forceinline__ float ldf<float>(const float* p) {
 }
 template <>
 __device__ __forceinline__ float ldf<bf16>(const bf16* p) {
-  return __bfloat162float(*p);
+  return from_act(*p);
 }
 
 // one thread = one output voxel x 8 output channels.  grid (P, N)
@@ -55,7 +55,7 @@ __global__ void conv3_direct_fwd_kernel(const InT* __restrict__ x, const bf16* _
             for (int ci = 0; ci < Cin; ++ci) {
               float xv = ldf<InT>(xp + ci);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) acc[i] += xv * __bfloat162float(wp[(size_t)i * Cin + ci]);
+              for (int i = 0; i < 8; ++i) acc[i] += xv * from_act(wp[(size_t)i * Cin + ci]);
             }
           }
         }
@@ -123,7 +123,7 @@ __global__ void conv3_direct_wgrad_kernel(const InT* __restrict__ x, const bf16*
   for (long long v = v0; v < v1; ++v) {
     int zd = xd + td, zh = xh + th, zw = xw + tw;
     if (zd >= 0 && zd < D && zh >= 0 && zh < H && zw >= 0 && zw < W)
-      acc += __bfloat162float(dn[(size_t)v * Cout + co]) * ldf<InT>(xn + (((size_t)zd * H + zh) * W + zw) * Cin + ci);
+      acc += from_act(dn[(size_t)v * Cout + co]) * ldf<InT>(xn + (((size_t)zd * H + zh) * W + zw) * Cin + ci);
     if (++xw == W) {
       xw = 0;
       if (++xh == H) {
@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(256, 2) stem_conv_fwd_kernel(const float* __re
   const bf16* wn = wf + (size_t)(n_w > 1 ? n : 0) * 27 * COUT * Cin;
   for (int i = threadIdx.x; i < 27 * Cin * COUT; i += 256) {
     int co = i % COUT, r = i / COUT, ci = r % Cin, tap = r / Cin;
-    wsm[i] = __bfloat162float(wn[((size_t)tap * COUT + co) * Cin + ci]);
+    wsm[i] = from_act(wn[((size_t)tap * COUT + co) * Cin + ci]);
   }
   for (int i = threadIdx.x; i < 64 * COUT; i += 256) bsm[i] = n_b ? biascls[(size_t)(n_b > 1 ? n : 0) * 64 * COUT + i] : 0.f;
   __syncthreads();

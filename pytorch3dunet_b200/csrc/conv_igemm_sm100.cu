@@ -180,7 +180,7 @@ int make_act_tmap(CUtensorMap* tm, const void* ptr, int N, int D, int H, int W, 
   cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2, (cuuint64_t)D * H * W * C * 2};
   cuuint32_t box[5] = {(cuuint32_t)kc, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bd, 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = enc(tm, B200_TMAP_DTYPE, 5, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_row_bytes(kc * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   B200_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activation %dx%dx%dx%dx%d, box %d,%d,%d,%d) failed: %d", N, D, H, W, C, kc,
@@ -195,7 +195,7 @@ int make_w_tmap(CUtensorMap* tm, const void* ptr, int rows2, int rows1, int C, i
   cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)rows1 * C * 2};
   cuuint32_t box[3] = {(cuuint32_t)kc, (cuuint32_t)nt, (cuuint32_t)ntaps_box};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = enc(tm, B200_TMAP_DTYPE, 3, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_row_bytes(kc * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   B200_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weights %dx%dx%d, box %d,%d) failed: %d", rows2, rows1, C, kc, nt, (int)r);
@@ -276,7 +276,7 @@ int make_act_tmap_stride2(CUtensorMap* tm, const void* ptr, int N, int D, int H,
   cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2, (cuuint64_t)D * H * W * C * 2};
   cuuint32_t box[5] = {(cuuint32_t)kc, (cuuint32_t)(2 * bw), (cuuint32_t)(2 * bh), (cuuint32_t)(2 * bd), 1};
   cuuint32_t estr[5] = {1, 2, 2, 2, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = enc(tm, B200_TMAP_DTYPE, 5, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_row_bytes(kc * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   B200_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(stride-2 activation %dx%dx%dx%dx%d) failed: %d", N, D, H, W, C, (int)r);

@@ -45,7 +45,7 @@ __global__ void ncdhw_to_ndhwc_kernel(const float* __restrict__ src, OutT* __res
   OutT* d = dst + ((size_t)n * voxels + v) * C;
   for (int c = 0; c < C; ++c) {
     float f = s[(size_t)c * voxels];
-    if constexpr (sizeof(OutT) == 2) d[c] = __float2bfloat16_rn(f);
+    if constexpr (sizeof(OutT) == 2) d[c] = to_act(f);
     else d[c] = f;
   }
 }
@@ -55,7 +55,7 @@ __global__ void ndhwc_to_ncdhw_kernel(const bf16* __restrict__ src, float* __res
   if (v >= voxels) return;
   const bf16* s = src + ((size_t)n * voxels + v) * C;
   float* d = dst + (size_t)n * C * voxels + v;
-  for (int c = 0; c < C; ++c) d[(size_t)c * voxels] = __bfloat162float(s[c]);
+  for (int c = 0; c < C; ++c) d[(size_t)c * voxels] = from_act(s[c]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -263,7 +263,7 @@ __global__ void fold_weights_kernel(const float* __restrict__ W, const float* __
     int tap = (int)(r % 27);
     int n = (int)(r / 27);
     float a = ab ? ab[((size_t)n * Cin + ci) * 2] : 1.f;
-    wf[i] = __float2bfloat16_rn(W[((size_t)co * Cin + ci) * 27 + tap] * a);
+    wf[i] = to_act(W[((size_t)co * Cin + ci) * 27 + tap] * a);
   }
 }
 
@@ -283,7 +283,7 @@ __global__ void fold_bias_kernel(const float* __restrict__ W, const float* __res
       for (int ci = lane; ci < Cin; ci += 32) {
         float w = W[((size_t)co * Cin + ci) * 27 + tap];
         float wa = w * ab[((size_t)n * Cin + ci) * 2];
-        float resid = wa - __bfloat162float(__float2bfloat16_rn(wa));
+        float resid = wa - from_act(to_act(wa));
         float mean = sums ? (float)(sums[((size_t)n * Cin + ci) * 2] / count) : 0.f;
         acc += w * ab[((size_t)n * Cin + ci) * 2 + 1] + resid * mean;
       }
@@ -313,7 +313,7 @@ __global__ void prep_dgrad_weights_kernel(const float* __restrict__ W, int Cin, 
     size_t r = i / Cout;
     int ci = (int)(r % Cin);
     int tap = (int)(r / Cin);
-    wd[i] = __float2bfloat16_rn(W[((size_t)co * Cin + ci) * 27 + (26 - tap)]);
+    wd[i] = to_act(W[((size_t)co * Cin + ci) * 27 + (26 - tap)]);
   }
 }
 

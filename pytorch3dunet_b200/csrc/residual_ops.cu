@@ -22,7 +22,7 @@ __device__ __forceinline__ float ldv<float>(const float* p) {
 }
 template <>
 __device__ __forceinline__ float ldv<bf16>(const bf16* p) {
-  return __bfloat162float(*p);
+  return from_act(*p);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -104,7 +104,7 @@ __global__ void pointwise_wgrad_kernel(const InT* __restrict__ x, const bf16* __
       long long v = vb + vv;
       bool ok = v < v1;
       xs[vv][c] = (ok && ci0 + c < Cin) ? ldv<InT>(x + ((size_t)n * vox + v) * Cin + ci0 + c) : 0.f;
-      ds[vv][c] = (ok && co0 + c < Cout) ? __bfloat162float(dy[((size_t)n * vox + v) * Cout + co0 + c]) : 0.f;
+      ds[vv][c] = (ok && co0 + c < Cout) ? from_act(dy[((size_t)n * vox + v) * Cout + co0 + c]) : 0.f;
     }
     __syncthreads();
 #pragma unroll 16
@@ -187,13 +187,13 @@ __global__ void deconv_phase_weights_kernel(const float* __restrict__ Wt, int Ci
       const size_t r2 = i / Cin;
       const int co = (int)(r2 % Cout), r = (int)(r2 / Cout);
       const int k = (tab.k3[3 * r] * 3 + tab.k3[3 * r + 1]) * 3 + tab.k3[3 * r + 2];
-      wq[i] = __float2bfloat16_rn(Wt[((size_t)ci * Cout + co) * 27 + k]);
+      wq[i] = to_act(Wt[((size_t)ci * Cout + co) * 27 + k]);
     } else {
       const size_t t = i - total;
       const int co = (int)(t % Cout);
       const size_t r2 = t / Cout;
       const int ci = (int)(r2 % Cin), e = (int)(r2 / Cin);
-      wd[t] = __float2bfloat16_rn(Wt[((size_t)ci * Cout + co) * 27 + e]);
+      wd[t] = to_act(Wt[((size_t)ci * Cout + co) * 27 + e]);
     }
   }
 }
@@ -437,10 +437,10 @@ __global__ void pointwise_prep_weights_kernel(const float* __restrict__ W, int C
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Cin * Cout) return;
   if (!transposed) {
-    wq[i] = __float2bfloat16(W[i]);
+    wq[i] = to_act(W[i]);
   } else {
     int ci = i / Cout, co = i % Cout;
-    wq[i] = __float2bfloat16(W[(size_t)co * Cin + ci]);
+    wq[i] = to_act(W[(size_t)co * Cin + ci]);
   }
 }
 }  // namespace b200

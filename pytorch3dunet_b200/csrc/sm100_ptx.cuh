@@ -156,7 +156,7 @@ __host__ __device__ __forceinline__ uint32_t umma_layout_for_row_bytes(int rb) {
 // instruction descriptor, kind::f16 : D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, a_major bit15, b_major bit16,
 // N>>3 [17,23), M>>4 [24,29)
 __host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+  return (1u << 4) | (B200_UMMA_FMT << 7) | (B200_UMMA_FMT << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 

@@ -39,7 +39,7 @@ __global__ void upcat_fold_enc_kernel(const float* __restrict__ W, const float* 
     int tap = (int)(r % 27);
     int n = (int)(r / 27);
     float a = ab ? ab[((size_t)n * C + ci) * 2] : 1.f;
-    wf[i] = __float2bfloat16_rn(W[((size_t)co * C + ci) * 27 + tap] * a);
+    wf[i] = to_act(W[((size_t)co * C + ci) * 27 + tap] * a);
   }
 }
 // wp[n][phase*8 + j][co][c1] = bf16( sum_{t in S(phase,j)} W[co][C0+c1][t] * a[n][C0+c1] )
@@ -64,7 +64,7 @@ __global__ void upcat_fold_phase_kernel(const float* __restrict__ W, const float
             for (int tw = 0; tw < 3; ++tw)
               if (phase_has_tap(phase & 1, j & 1, tw)) acc += w[(td * 3 + th) * 3 + tw];
     float a = ab ? ab[((size_t)n * C + C0 + c1) * 2] : 1.f;
-    wp[i] = __float2bfloat16_rn(acc * a);
+    wp[i] = to_act(acc * a);
   }
 }
 
@@ -91,7 +91,7 @@ __global__ void upcat_fold_bias_kernel(const float* __restrict__ W, const float*
           acc += w * sh;
           if (ci < C0 && sums) {
             const float wa = w * a;
-            acc += (wa - __bfloat162float(__float2bfloat16_rn(wa))) * (float)(sums[((size_t)n * C + ci) * 2] / count);
+            acc += (wa - from_act(to_act(wa))) * (float)(sums[((size_t)n * C + ci) * 2] / count);
           }
         }
       } else if (sums) {
@@ -106,7 +106,7 @@ __global__ void upcat_fold_bias_kernel(const float* __restrict__ W, const float*
                   for (int tw = 0; tw < 3; ++tw)
                     if (phase_has_tap(phase & 1, j & 1, tw)) ws += w[(td * 3 + th) * 3 + tw];
           const float wa = ws * ab[((size_t)n * C + C0 + c1) * 2];
-          acc += (wa - __bfloat162float(__float2bfloat16_rn(wa))) * (float)(sums[((size_t)n * C + C0 + c1) * 2] / count);
+          acc += (wa - from_act(to_act(wa))) * (float)(sums[((size_t)n * C + C0 + c1) * 2] / count);
         }
       }
     }
@@ -158,7 +158,7 @@ __global__ void upcat_prep_dgrad_kernel(const float* __restrict__ W, int C0, int
       size_t r = i / Cout;
       int ci = (int)(r % C0);
       int tap = (int)(r / C0);
-      wd_enc[i] = __float2bfloat16_rn(W[((size_t)co * C + ci) * 27 + (26 - tap)]);
+      wd_enc[i] = to_act(W[((size_t)co * C + ci) * 27 + (26 - tap)]);
     } else {
       size_t k = i - n_enc;
       int co = (int)(k % Cout);
@@ -173,7 +173,7 @@ __global__ void upcat_prep_dgrad_kernel(const float* __restrict__ W, int C0, int
             if (offset_has_tap((e >> 2) & 3, th))
               for (int tw = 0; tw < 3; ++tw)
                 if (offset_has_tap(e & 3, tw)) acc += w[(td * 3 + th) * 3 + tw];
-      wd_up[k] = __float2bfloat16_rn(acc);
+      wd_up[k] = to_act(acc);
     }
   }
 }

@@ -132,8 +132,13 @@ class VirtualCat:
 class Engine:
     """One forward (+ optional backward) pass.  Not reusable across passes."""
 
-    def __init__(self, device, impl=None, record=True, sink=None):
-        self.L = lib()
+    def __init__(self, device, impl=None, record=True, sink=None, operand_dtype="bf16", loss_scale=1.0):
+        # operand_dtype: the 16-bit type of activations and tensor-core operands ("bf16" | "fp16": two builds of the same kernels).
+        # loss_scale (fp16): the seed gradient is multiplied by it and every parameter gradient divided by it, so that the backward
+        # pass's activation gradients (~1e-7 for a mean-reduced loss over millions of voxels) stay inside fp16's range
+        self.L = lib(operand_dtype)
+        self.adt = torch.float16 if operand_dtype in ("fp16", "f16", "float16") else torch.bfloat16
+        self.loss_scale = float(loss_scale)
         self.sink = sink      # optim.FlatParameters: parameter gradients are written straight into its flat buffer
         self.sunk = set()
         self.device = device
@@ -177,6 +182,8 @@ class Engine:
         return torch.empty_like(like)
 
     def _add_param_grad(self, name, g):
+        if self.loss_scale != 1.0:
+            g.mul_(1.0 / self.loss_scale)   # (in place: also when g IS the flat-buffer view the kernel wrote into)
         if self.sink is not None:
             v = self.sink.view(name)
             if v is not None:
@@ -238,7 +245,7 @@ class Engine:
         if c % 8 != 0:
             raise NotImplementedError(f"block-level input with C={c}: internal activations need C % 8 == 0")
         x_ncdhw = x_ncdhw.contiguous()
-        t = self.empty((n, d, h, w, c), torch.bfloat16)
+        t = self.empty((n, d, h, w, c), self.adt)
         self.call("b200_ncdhw_f32_to_ndhwc_bf16", _p(x_ncdhw), _p(t), n, c, d, h, w)
         return Act(t, ACT_NONE, 0.0, requires_grad=requires_grad)
 
@@ -251,10 +258,10 @@ class Engine:
     def grad_from_ncdhw(self, y, g_ncdhw):
         """seed y.grad from an external NCDHW fp32 gradient w.r.t. the (post-activation) output y."""
         n, d, h, w, c = y.dims
-        g = self.empty((n, d, h, w, c), torch.bfloat16)
+        g = self.empty((n, d, h, w, c), self.adt)
         g_src = g_ncdhw.contiguous()  # keep the (possible) copy alive until the kernel is enqueued
         self.call("b200_ncdhw_f32_to_ndhwc_bf16", _p(g_src), _p(g), n, c, d, h, w)
-        gm = self.empty((n, d, h, w, c), torch.bfloat16)
+        gm = self.empty((n, d, h, w, c), self.adt)
         self.call("b200_act_bwd", _p(g), c, 0, _p(y.t), n, c, d * h * w, y.act, y.slope, None, _p(gm))
         self.accumulate_grad(y, gm)
 
@@ -289,7 +296,7 @@ class Engine:
             n_w = n
             ab = self.empty((n, cin, 2), torch.float32)
             mean_rstd = self.empty((n, groups, 2), torch.float32)
-        wf = self.empty((n_w, 27, cout, cin), torch.bfloat16)
+        wf = self.empty((n_w, 27, cout, cin), self.adt)
         n_b = n_w if (gn is not None or bias is not None) else 0
         biascls = self.empty((n_b, 64, cout), torch.float32) if n_b else None
         if gn is not None:
@@ -298,7 +305,7 @@ class Engine:
         else:
             self.call("b200_gn_fold", None, None, None, 1, float(vox), _p(W), _p(bias), n, cin, cout,
                       _p(wf), _p(biascls), None, None, launches=2 if bias is not None else 1)
-        y = self.empty((n, d, h, w, cout), torch.bfloat16)
+        y = self.empty((n, d, h, w, cout), self.adt)
         partials, P = None, 0
         if want_stats:
             P = L.query("b200_conv3_partials_count", impl, n, d, h, w, cin, cout)
@@ -357,19 +364,19 @@ class Engine:
                                        sums2=None if gn is None else sums2.clone(), coef=None if coef is None else coef.clone(),
                                        mean_rstd=None if mean_rstd is None else mean_rstd.clone())
                 if residual is not None and residual.requires_grad:
-                    g = self.empty(residual.t.shape, torch.bfloat16)
+                    g = self.empty(residual.t.shape, self.adt)
                     self.call("b200_act_bwd", _p(dz), cout, 0, _p(residual.t), n, cout, vox, residual.act, residual.slope,
                               _p(residual.grad), _p(g))
                     residual.grad = g
                 if x.requires_grad:
                     if is_f32:
                         raise NotImplementedError("gradient w.r.t. the fp32 network input is not provided by the engine")
-                    wd = self.empty((27, cin, cout), torch.bfloat16)
+                    wd = self.empty((27, cin, cout), self.adt)
                     self.call("b200_prep_dgrad_weights", _p(W), cin, cout, _p(wd))
                     dimpl = L.query("b200_conv3_resolve_impl", self.impl, n, d, h, w, cout, cin, 0)
                     if dimpl < 0:
                         raise B200Error("tcgen05 dgrad requested but unsupported for this shape")
-                    dxhat = self.empty((n, d, h, w, cin), torch.bfloat16)
+                    dxhat = self.empty((n, d, h, w, cin), self.adt)
                     self.call("b200_conv3_fwd", dimpl, _p(dz), 0, _p(wd), 1, None, 0, None, ACT_NONE, 0.0,
                               n, d, h, w, cout, cin, _p(dxhat), 0, None, None, flops=2.0 * n * vox * 27 * cin * cout,
                               tag=("dgrad_tc" if dimpl == IMPL_TCGEN05 else "dgrad_direct"), layer=name)
@@ -396,7 +403,7 @@ class Engine:
         ab = self.empty((n, c, 2), torch.float32)
         mean_rstd = self.empty((n, groups, 2), torch.float32)
         self.call("b200_gn_coeffs", _p(sums), _p(gamma), _p(beta), groups, float(vox), n, c, _p(mean_rstd), _p(ab))
-        y = self.empty(z.t.shape, torch.bfloat16)
+        y = self.empty(z.t.shape, self.adt)
         partials, P = None, 0
         if want_stats:
             P = self.L.query("b200_stats_partials_count", n, c, vox)
@@ -425,12 +432,12 @@ class Engine:
                 self._add_param_grad(gname, dgamma)
                 self._add_param_grad(bname, dbeta)
                 if residual is not None and residual.requires_grad:
-                    gr = self.empty(residual.t.shape, torch.bfloat16)
+                    gr = self.empty(residual.t.shape, self.adt)
                     self.call("b200_act_bwd", _p(du), c, 0, _p(residual.t), n, c, vox, residual.act, residual.slope,
                               _p(residual.grad), _p(gr))
                     residual.grad = gr
                 if z.requires_grad:
-                    g = self.empty(z.t.shape, torch.bfloat16)
+                    g = self.empty(z.t.shape, self.adt)
                     self.call("b200_gn_bwd_apply", _p(du), _p(z.t), _p(coef), n, c, vox, z.act, z.slope, _p(z.grad), _p(g))
                     z.grad = g
                 out.grad = None
@@ -486,7 +493,7 @@ class Engine:
         """Encoder pooling, buildingblocks.py:353-363: MaxPool3d(2) or (pool_type='avg') AvgPool3d(2), floor mode."""
         n, d, h, w, c = x.dims
         fwd, bwd = ("b200_maxpool_fwd", "b200_maxpool_bwd") if kind == "max" else ("b200_avgpool_fwd", "b200_avgpool_bwd")
-        y = self.empty((n, d // 2, h // 2, w // 2, c), torch.bfloat16)
+        y = self.empty((n, d // 2, h // 2, w // 2, c), self.adt)
         P = self.L.query("b200_maxpool_partials_count", n, d, h, w, c)
         partials = self.empty((n, P, c, 2), torch.float32) if want_stats else None
         self.call(fwd, _p(x.t), n, d, h, w, c, _p(y), _p(partials))
@@ -497,7 +504,7 @@ class Engine:
             def backward():
                 if out.grad is None or not x.requires_grad:
                     return
-                g = x.grad if x.grad is not None else self.empty(x.t.shape, torch.bfloat16)
+                g = x.grad if x.grad is not None else self.empty(x.t.shape, self.adt)
                 self.call(bwd, _p(out.grad), _p(x.t), n, d, h, w, c, x.act, x.slope, _p(x.grad), _p(g))
                 x.grad = g
                 out.grad = None
@@ -548,16 +555,16 @@ class Engine:
             n_w = n
             ab = self.empty((n, C, 2), torch.float32)
             mean_rstd = self.empty((n, groups, 2), torch.float32)
-        wf_enc = self.empty((n_w, 27, cout, c0), torch.bfloat16)
-        wp = self.empty((n_w, 64, cout, c1), torch.bfloat16)
+        wf_enc = self.empty((n_w, 27, cout, c0), self.adt)
+        wp = self.empty((n_w, 64, cout, c1), self.adt)
         n_b = n_w if (gn is not None or bias is not None) else 0
         biascls = self.empty((n_b, 64, cout), torch.float32) if n_b else None
         self.call("b200_gn_fold_upcat", _p(sums), _p(gamma), _p(beta), groups, float(vox), _p(W), _p(bias), n, c0, c1, cout,
                   _p(wf_enc), _p(wp), _p(biascls), _p(mean_rstd), _p(ab), launches=4 if gn is not None else 3)
-        R = self.empty((n, D, H, Wd, cout), torch.bfloat16)
+        R = self.empty((n, D, H, Wd, cout), self.adt)
         self.call("b200_conv3_up_phase_fwd", _p(low.t), _p(wp), n_w, n, d, h, w, c1, cout, _p(R), launches=1,
                   flops=2.0 * n * vox * 8 * c1 * cout, tag="fprop_tc", layer=name)
-        y = self.empty((n, D, H, Wd, cout), torch.bfloat16)
+        y = self.empty((n, D, H, Wd, cout), self.adt)
         partials, P = None, 0
         if want_stats:
             P = L.query("b200_conv3_partials_count", IMPL_TCGEN05, n, D, H, Wd, c0, cout)
@@ -608,14 +615,14 @@ class Engine:
                     self._add_param_grad(gn[3], dgamma)
                     self._add_param_grad(gn[4], dbeta)
                 if enc.requires_grad or low.requires_grad:
-                    wd_enc = self.empty((27, c0, cout), torch.bfloat16)
-                    wd_up = self.empty((64, c1, cout), torch.bfloat16)
+                    wd_enc = self.empty((27, c0, cout), self.adt)
+                    wd_up = self.empty((64, c1, cout), self.adt)
                     self.call("b200_upcat_prep_dgrad_weights", _p(W), c0, c1, cout, _p(wd_enc), _p(wd_up))
                 if enc.requires_grad:
                     dimpl = L.query("b200_conv3_resolve_impl", self.impl, n, D, H, Wd, cout, c0, 0)
                     if dimpl < 0:
                         raise B200Error("tcgen05 dgrad requested but unsupported for this shape")
-                    ge = self.empty(enc.t.shape, torch.bfloat16)
+                    ge = self.empty(enc.t.shape, self.adt)
                     self.call("b200_conv3_fwd", dimpl, _p(dz), 0, _p(wd_enc), 1, None, 0, None, ACT_NONE, 0.0,
                               n, D, H, Wd, cout, c0, _p(ge), 0, None, None, flops=2.0 * n * vox * 27 * c0 * cout,
                               tag=("dgrad_tc" if dimpl == IMPL_TCGEN05 else "dgrad_direct"), layer=name)
@@ -626,7 +633,7 @@ class Engine:
                         self.call("b200_act_bwd", _p(ge), c0, 0, _p(enc.t), n, c0, vox, enc.act, enc.slope, _p(enc.grad), _p(ge))
                     enc.grad = ge
                 if low.requires_grad:
-                    gl = self.empty(low.t.shape, torch.bfloat16)
+                    gl = self.empty(low.t.shape, self.adt)
                     self.call("b200_conv3_up_dgrad", _p(dz), _p(wd_up), n, d, h, w, cout, c1, _p(gl),
                               flops=2.0 * n * lvox * 64 * c1 * cout, tag="dgrad_tc", layer=name)
                     if coef is not None:
@@ -645,7 +652,7 @@ class Engine:
         n2, d, h, w, c1 = x.dims
         fwd, bwd = {"nearest": ("b200_upcat_fwd", "b200_upcat_bwd"),
                     "trilinear": ("b200_upcat_trilinear_fwd", "b200_upcat_trilinear_bwd")}[mode]
-        cat = self.empty((n, D, H, W, c0 + c1), torch.bfloat16)
+        cat = self.empty((n, D, H, W, c0 + c1), self.adt)
         P = self.L.query("b200_upcat_partials_count", n, D, H, W, c0 + c1)
         partials = self.empty((n, P, c0 + c1, 2), torch.float32) if want_stats else None
         self.call(fwd, _p(enc.t), c0, _p(x.t), c1, n, D, H, W, d, h, w, _p(cat), _p(partials))
@@ -656,11 +663,11 @@ class Engine:
                 if dcat is None:
                     return
                 if x.requires_grad:
-                    g = self.empty(x.t.shape, torch.bfloat16)
+                    g = self.empty(x.t.shape, self.adt)
                     self.call(bwd, _p(dcat), c0, c1, _p(x.t), n, D, H, W, d, h, w, x.act, x.slope, _p(g))
                     self.accumulate_grad(x, g)
                 if enc.requires_grad:
-                    ge = self.empty(enc.t.shape, torch.bfloat16)
+                    ge = self.empty(enc.t.shape, self.adt)
                     # ge = dcat[..., :c0] * act'(enc) + enc.grad (enc.grad, if any, is already in dz form)
                     self.call("b200_act_bwd", _p(dcat), c0 + c1, 0, _p(enc.t), n, c0, D * H * W, enc.act, enc.slope,
                               _p(enc.grad), _p(ge))
@@ -678,11 +685,11 @@ class Engine:
             raise NotImplementedError(f"1x1x1 conv with C_out={cout}: the engine needs C_out % 8 == 0")
         is_f32 = isinstance(x, InputF32)
         W2 = W.reshape(cout, cin).contiguous()
-        y = self.empty((n, d, h, w, cout), torch.bfloat16)
+        y = self.empty((n, d, h, w, cout), self.adt)
         # tensor-core path: the tcgen05 conv / wgrad kernels over the flat voxel list (C_in, C_out multiples of 16, bf16 input)
         tc = (not is_f32) and self.impl != IMPL_DIRECT and bool(self.L.query("b200_pointwise_tc_supported", n, vox, cin, cout))
         if tc:
-            wq = self.empty((cout, cin), torch.bfloat16)
+            wq = self.empty((cout, cin), self.adt)
             self.call("b200_pointwise_prep_weights", _p(W2), cin, cout, 0, _p(wq))
             P = self.L.query("b200_pointwise_tc_partials_count", n, vox)
             partials = self.empty((n, P, cout, 2), torch.float32) if want_stats else None
@@ -721,9 +728,9 @@ class Engine:
                 if x.requires_grad:
                     if is_f32:
                         raise NotImplementedError("gradient w.r.t. the fp32 network input is not provided by the engine")
-                    g = self.empty(x.t.shape, torch.bfloat16)
+                    g = self.empty(x.t.shape, self.adt)
                     if tc:
-                        wqt = self.empty((cin, cout), torch.bfloat16)
+                        wqt = self.empty((cin, cout), self.adt)
                         self.call("b200_pointwise_prep_weights", _p(W2), cin, cout, 1, _p(wqt))
                         self.call("b200_pointwise_tc_fwd", _p(dy), _p(wqt), None, n, vox, cout, cin, _p(g), None,
                                   flops=2.0 * n * vox * cin * cout, tag="dgrad_tc")
@@ -749,14 +756,14 @@ class Engine:
         sd_, sh_, sw_ = 2 * d - 1, 2 * h - 1, 2 * w - 1
         Wc = self.empty((cout, cin, 3, 3, 3), torch.float32)
         self.call("b200_deconv_weight_permute", _p(Wt), cin, cout, 1, _p(Wc))
-        xz_t = self.empty((n, sd_, sh_, sw_, cin), torch.bfloat16)
+        xz_t = self.empty((n, sd_, sh_, sw_, cin), self.adt)
         self.call("b200_zero_insert", _p(x.t), n, d, h, w, cin, _p(xz_t))
         xz = Act(xz_t, ACT_NONE, 0.0, requires_grad=x.requires_grad)
         if self.record:
             def backward_zero_insert():
                 if xz.grad is None or not x.requires_grad:
                     return
-                gx = self.empty(x.t.shape, torch.bfloat16)
+                gx = self.empty(x.t.shape, self.adt)
                 self.call("b200_subsample2_bwd", _p(xz.grad), _p(x.t), n, d, h, w, cin, x.act, x.slope, _p(x.grad), _p(gx))
                 x.grad = gx
                 xz.grad = None
@@ -780,7 +787,7 @@ class Engine:
             return self._deconv_up_add_phases(enc, x, Wt, wname, want_stats)
         sd_, sh_, sw_ = 2 * d - 1, 2 * h - 1, 2 * w - 1
         T = self.deconv(x, Wt, wname)
-        out_t = self.empty((n, D, H, W_, cout), torch.bfloat16)
+        out_t = self.empty((n, D, H, W_, cout), self.adt)
         P = self.L.query("b200_resize_add_partials_count", n, D, H, W_, cout)
         partials = self.empty((n, P, cout, 2), torch.float32) if want_stats else None
         self.call("b200_resize_add_fwd", _p(T.t), _p(enc.t), n, sd_, sh_, sw_, D, H, W_, cout, _p(out_t), _p(partials))
@@ -790,11 +797,11 @@ class Engine:
                 g = out.grad
                 if g is None:
                     return
-                dT = self.empty(T.t.shape, torch.bfloat16)
+                dT = self.empty(T.t.shape, self.adt)
                 self.call("b200_deconv_gather", _p(g), n, d, h, w, D, H, W_, cout, _p(dT))
                 self.accumulate_grad(T, dT)
                 if enc.requires_grad:
-                    ge = self.empty(enc.t.shape, torch.bfloat16)
+                    ge = self.empty(enc.t.shape, self.adt)
                     self.call("b200_act_bwd", _p(g), cout, 0, _p(enc.t), n, cout, D * H * W_, enc.act, enc.slope, _p(enc.grad), _p(ge))
                     enc.grad = ge
                 out.grad = None
@@ -808,13 +815,13 @@ class Engine:
         n, D, H, W_, cout = enc.dims
         _, d, h, w, cin = x.dims
         Wt = Wt.contiguous()
-        wq = self.empty((27, cout, cin), torch.bfloat16)
-        wd = self.empty((27, cin, cout), torch.bfloat16)
+        wq = self.empty((27, cout, cin), self.adt)
+        wd = self.empty((27, cin, cout), self.adt)
         self.call("b200_deconv_phase_weights", _p(Wt), cin, cout, _p(wq), _p(wd))
-        Pt = self.empty((n, D, H, W_, cout), torch.bfloat16)
+        Pt = self.empty((n, D, H, W_, cout), self.adt)
         self.call("b200_deconv_phase_fwd", _p(x.t), _p(wq), n, d, h, w, cin, cout, _p(Pt),
                   flops=2.0 * n * d * h * w * 27 * cin * cout, tag="fprop_tc", layer=wname)
-        out_t = self.empty((n, D, H, W_, cout), torch.bfloat16)
+        out_t = self.empty((n, D, H, W_, cout), self.adt)
         Pn = self.L.query("b200_upcat_partials_count", n, D, H, W_, cout)
         partials = self.empty((n, Pn, cout, 2), torch.float32) if want_stats else None
         self.call("b200_shift_add_fwd", _p(Pt), _p(enc.t), n, D, H, W_, cout, _p(out_t), _p(partials))
@@ -825,7 +832,7 @@ class Engine:
                 g = out.grad
                 if g is None:
                     return
-                gp = self.empty((n, D, H, W_, cout), torch.bfloat16)
+                gp = self.empty((n, D, H, W_, cout), self.adt)
                 self.call("b200_shift_fold_bwd", _p(g), n, D, H, W_, cout, _p(gp))
                 S = self.L.query("b200_deconv_phase_wgrad_splits", n, d, h, w, cout, cin)
                 Q = self.empty((n * S, 27, cout, cin), torch.float32)
@@ -835,14 +842,14 @@ class Engine:
                 self.call("b200_deconv_phase_wgrad_finalize", _p(Q), n * S, cin, cout, _p(dWt))
                 self._add_param_grad(wname, dWt)
                 if x.requires_grad:
-                    gx = self.empty(x.t.shape, torch.bfloat16)
+                    gx = self.empty(x.t.shape, self.adt)
                     self.call("b200_deconv_phase_dgrad", _p(gp), _p(wd), n, d, h, w, cout, cin, _p(gx),
                               flops=2.0 * n * d * h * w * 27 * cin * cout, tag="dgrad_tc", layer=wname)
                     if x.act != ACT_NONE or x.grad is not None:
                         self.call("b200_act_bwd", _p(gx), cin, 0, _p(x.t), n, cin, d * h * w, x.act, x.slope, _p(x.grad), _p(gx))
                     x.grad = gx
                 if enc.requires_grad:
-                    ge = self.empty(enc.t.shape, torch.bfloat16)
+                    ge = self.empty(enc.t.shape, self.adt)
                     self.call("b200_act_bwd", _p(g), cout, 0, _p(enc.t), n, cout, D * H * W_, enc.act, enc.slope, _p(enc.grad), _p(ge))
                     enc.grad = ge
                 out.grad = None
@@ -865,7 +872,7 @@ class Engine:
         hh = self.empty((n, c), torch.float32)
         g = self.empty((n, c), torch.float32)
         self.call("b200_se_gates_fwd", _p(sums), float(vox), _p(W1), _p(b1), _p(W2), _p(b2), n, c, _p(smean), _p(hh), _p(g))
-        out_t = self.empty(y.t.shape, torch.bfloat16)
+        out_t = self.empty(y.t.shape, self.adt)
         q = self.empty((n, vox), torch.float32)
         bs = bs_t.reshape(-1).contiguous()  # 1-element parameter, read on the device (no host sync)
         self.call("b200_scse_apply_fwd", _p(y.t), _p(g), _p(ws), _p(bs), n, vox, c, _p(out_t), _p(q))
@@ -878,7 +885,7 @@ class Engine:
                 if dout is None:
                     return
                 P = self.L.query("b200_scse_partials_count", n, vox, c)
-                tmp = self.empty(y.t.shape, torch.bfloat16)
+                tmp = self.empty(y.t.shape, self.adt)
                 part = self.empty((n, P, c, 2), torch.float32)
                 dbs_part = self.empty((n * P, 1), torch.float32)
                 self.call("b200_scse_bwd1", _p(dout), _p(y.t), _p(g), _p(q), _p(ws), n, vox, c, _p(tmp), _p(part), _p(dbs_part))
@@ -900,7 +907,7 @@ class Engine:
                 self._add_param_grad(prefix + "sSE.conv.weight", dws.reshape(sd[prefix + "sSE.conv.weight"].shape))
                 self._add_param_grad(prefix + "sSE.conv.bias", dbs)
                 if y.requires_grad:
-                    gy = self.empty(y.t.shape, torch.bfloat16)
+                    gy = self.empty(y.t.shape, self.adt)
                     self.call("b200_gn_bwd_apply", _p(tmp), _p(y.t), _p(coef), n, c, vox, y.act, y.slope, _p(y.grad), _p(gy))
                     y.grad = gy
                 out.grad = None
@@ -922,7 +929,7 @@ class Engine:
             P = self.L.query("b200_final_conv_bwd_partials_count", n, vox, c, cout)
             K = cout * c + cout
             partials = self.empty((n * P, K), torch.float32)
-            dz = self.empty(x.t.shape, torch.bfloat16)
+            dz = self.empty(x.t.shape, self.adt)
             self.call("b200_final_conv_bwd", _p(dlogits), _p(x.t), n, vox, c, _p(W2), cout, x.act, x.slope, _p(dz), _p(partials))
             red = self.empty((K,), torch.float32)
             self.call("b200_reduce_rows", _p(partials), n * P, K, _p(red))

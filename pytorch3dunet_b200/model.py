@@ -13,6 +13,7 @@ get_model :361-363; block wiring buildingblocks.py:138-227 (DoubleConv), :310-38
 """
 from __future__ import annotations
 
+import os
 import threading
 
 import torch
@@ -58,7 +59,7 @@ def number_of_features_per_level(init_channel_number, num_levels):
 # ----------------------------------------------------------------------------------------------------
 class _EngineFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, program, n_inputs, names, grad_mode, sink, *tensors):
+    def forward(ctx, program, n_inputs, names, grad_mode, sink, opts, *tensors):
         inputs, params = tensors[:n_inputs], tensors[n_inputs:]
         x0 = inputs[0]
         if not x0.is_cuda:
@@ -69,11 +70,11 @@ class _EngineFn(torch.autograd.Function):
         # needs_input_grad mirrors tensor.requires_grad whatever the grad mode is, and grad mode is always off inside
         # Function.forward: the caller's mode comes in as an argument.  Under torch.no_grad() (the predictor's path,
         # reference predictor.py:164) nothing is taped, so no closure pins a layer's activations.
-        needs_grad = bool(grad_mode) and any(ctx.needs_input_grad[5:])
+        needs_grad = bool(grad_mode) and any(ctx.needs_input_grad[6:])
         with torch.cuda.device(x0.device):
-            eng = E.Engine(x0.device, record=needs_grad, sink=sink)
+            eng = E.Engine(x0.device, record=needs_grad, sink=sink, operand_dtype=opts[0], loss_scale=opts[1] if needs_grad else 1.0)
             sd = dict(zip(names, params))
-            in_req = [needs_grad and bool(g) for g in ctx.needs_input_grad[5:5 + n_inputs]]
+            in_req = [needs_grad and bool(g) for g in ctx.needs_input_grad[6:6 + n_inputs]]
             outs, seed, input_grads = program(eng, [t.detach() for t in inputs], sd, in_req)
         ctx.eng, ctx.seed, ctx.input_grads = eng, seed, input_grads
         ctx.names, ctx.n_inputs = names, n_inputs
@@ -105,7 +106,7 @@ class _EngineFn(torch.autograd.Function):
             eng.sink.restore_grad_views()
         # drop everything the closures keep alive (activations of the last layer, ...) now instead of when the autograd node dies
         ctx.eng = ctx.seed = ctx.input_grads = None
-        return (None, None, None, None, None) + tuple(in_grads) + tuple(grads)
+        return (None, None, None, None, None, None) + tuple(in_grads) + tuple(grads)
 
 
 class _Stats(threading.local):
@@ -143,7 +144,24 @@ def _run(module, program, inputs):
     # optim.FlatParameters registers itself on the model it was built from; DataParallel replicas share that attribute but must
     # not share the buffer (their gradients flow back through the broadcast instead)
     sink = None if replica else getattr(module, "_b200_grad_sink", None)
-    return _EngineFn.apply(program, len(inputs), names, torch.is_grad_enabled(), sink, *inputs, *(p for _, p in np_))
+    opts = operand_options(module)
+    return _EngineFn.apply(program, len(inputs), names, torch.is_grad_enabled(), sink, opts, *inputs, *(p for _, p in np_))
+
+
+DEFAULT_OPERAND_DTYPE = os.environ.get("B200UNET_OPERAND_DTYPE", "bf16")
+DEFAULT_LOSS_SCALE_FP16 = float(os.environ.get("B200UNET_LOSS_SCALE", "65536"))
+
+
+def operand_options(module):
+    """(operand dtype, loss scale) of a module: `module.operand_dtype` in {"bf16", "fp16"} (attribute, `operand_dtype=` constructor keyword
+    of the models, or B200UNET_OPERAND_DTYPE) and, for fp16, `module.loss_scale` (default 65536: a mean-reduced loss over 4 M voxels
+    seeds gradients of ~2e-7, below fp16's normal range; parameter gradients are returned UNscaled)."""
+    dt = getattr(module, "operand_dtype", None) or DEFAULT_OPERAND_DTYPE
+    if dt in ("fp16", "f16", "float16", "half"):
+        return ("fp16", float(getattr(module, "loss_scale", None) or DEFAULT_LOSS_SCALE_FP16))
+    if dt not in ("bf16", "bfloat16"):
+        raise ValueError(f"operand_dtype {dt!r}: expected 'bf16' or 'fp16'")
+    return ("bf16", 1.0)
 
 
 def last_launch_counts():
@@ -287,13 +305,14 @@ class _EngineModule(nn.Module):
 
             def seed(eng, grads):
                 if grads[0] is not None:
-                    eng.grad_from_ncdhw(y, grads[0])
+                    eng.grad_from_ncdhw(y, grads[0] * eng.loss_scale if eng.loss_scale != 1.0 else grads[0])
 
             def input_grads(eng):
                 res = []
                 for a, r in zip(acts, in_req):
                     if r and a.grad is not None:
-                        res.append(eng.to_ncdhw_f32(a.grad))
+                        gi = eng.to_ncdhw_f32(a.grad)
+                        res.append(gi / eng.loss_scale if eng.loss_scale != 1.0 else gi)
                     elif r:
                         res.append(torch.zeros((a.t.shape[0], a.t.shape[4]) + tuple(a.t.shape[1:4]), device=a.t.device))
                     else:
@@ -471,8 +490,11 @@ class AbstractUNet(nn.Module):
 
     def __init__(self, in_channels, out_channels, final_sigmoid, basic, f_maps=64, layer_order="gcr", num_groups=8, num_levels=4,
                  is_segmentation=True, conv_kernel_size=3, pool_kernel_size=2, conv_padding=1, conv_upscale=2, upsample="default",
-                 dropout_prob=0.1, is3d=True):
+                 dropout_prob=0.1, is3d=True, operand_dtype=None, loss_scale=None):
         super().__init__()
+        # b200 extensions (not reference keywords): 16-bit type of activations / tensor-core operands and the fp16 loss scale
+        self.operand_dtype, self.loss_scale = operand_dtype, loss_scale
+        operand_options(self)  # validate
         if not is3d:
             raise UnsupportedConfig("2-D models are out of scope of the b200 engine (SURVEY.md section 2, row 1)")
         if conv_kernel_size != 3 or pool_kernel_size != 2 or conv_padding != 1:
@@ -544,7 +566,7 @@ class AbstractUNet(nn.Module):
                         t = probs_saved * (g_probs - (g_probs * probs_saved).sum(dim=1, keepdim=True))
                     g_logits = t if g_logits is None else g_logits + t
                 if g_logits is not None:
-                    final_bwd(g_logits)
+                    final_bwd(g_logits * eng.loss_scale if eng.loss_scale != 1.0 else g_logits)
             outs = [logits, probs] if final else [logits]
             return outs, seed, lambda eng: [None]
         res = _run(self, program, [x])
@@ -560,7 +582,8 @@ class UNet3D(AbstractUNet):
                  is_segmentation=True, conv_padding=1, conv_upscale=2, upsample="default", dropout_prob=0.1, **kwargs):
         super().__init__(in_channels, out_channels, final_sigmoid, "double", f_maps=f_maps, layer_order=layer_order,
                          num_groups=num_groups, num_levels=num_levels, is_segmentation=is_segmentation,
-                         conv_padding=conv_padding, conv_upscale=conv_upscale, upsample=upsample, dropout_prob=dropout_prob)
+                         conv_padding=conv_padding, conv_upscale=conv_upscale, upsample=upsample, dropout_prob=dropout_prob,
+                         operand_dtype=kwargs.get("operand_dtype"), loss_scale=kwargs.get("loss_scale"))
 
 
 class ResidualUNet3D(AbstractUNet):
@@ -568,7 +591,8 @@ class ResidualUNet3D(AbstractUNet):
                  is_segmentation=True, conv_padding=1, conv_upscale=2, upsample="default", dropout_prob=0.1, **kwargs):
         super().__init__(in_channels, out_channels, final_sigmoid, "res", f_maps=f_maps, layer_order=layer_order,
                          num_groups=num_groups, num_levels=num_levels, is_segmentation=is_segmentation,
-                         conv_padding=conv_padding, conv_upscale=conv_upscale, upsample=upsample, dropout_prob=dropout_prob)
+                         conv_padding=conv_padding, conv_upscale=conv_upscale, upsample=upsample, dropout_prob=dropout_prob,
+                         operand_dtype=kwargs.get("operand_dtype"), loss_scale=kwargs.get("loss_scale"))
 
 
 class ResidualUNetSE3D(AbstractUNet):
@@ -576,7 +600,8 @@ class ResidualUNetSE3D(AbstractUNet):
                  is_segmentation=True, conv_padding=1, conv_upscale=2, upsample="default", dropout_prob=0.1, **kwargs):
         super().__init__(in_channels, out_channels, final_sigmoid, "res_se", f_maps=f_maps, layer_order=layer_order,
                          num_groups=num_groups, num_levels=num_levels, is_segmentation=is_segmentation,
-                         conv_padding=conv_padding, conv_upscale=conv_upscale, upsample=upsample, dropout_prob=dropout_prob)
+                         conv_padding=conv_padding, conv_upscale=conv_upscale, upsample=upsample, dropout_prob=dropout_prob,
+                         operand_dtype=kwargs.get("operand_dtype"), loss_scale=kwargs.get("loss_scale"))
 
 
 _MODELS = {"UNet3D": UNet3D, "ResidualUNet3D": ResidualUNet3D, "ResidualUNetSE3D": ResidualUNetSE3D}

@@ -208,6 +208,16 @@ def test_model_matches_reference_golden_more_orders(name, monkeypatch):
     _model_vs_oracle(cfg, loss_name, sd, rec["x"], rec["target"], monkeypatch, ref=rec)
 
 
+@pytest.mark.parametrize("name", ["unet3d_f16_l3_s16", "resunet3d_f16_l3_s16", "resunetse3d_f16_l3_s16", "unet3d_f16_l2_trilinear"])
+def test_model_fp16_operands_match_reference_golden(name, monkeypatch):
+    """the fp16 build of the kernels (libb200unet_f16.so: fp16 activations / tensor-core operands, loss-scaled backward; BASELINE configs[3]
+    names fp16) against the same goldens: parameter gradients come back unscaled"""
+    cfg, loss_name = {**MODEL_CASES, **EXTRA_MODEL_CASES}[name]
+    rec, sd, grads = load_golden(name)
+    rep = _model_vs_oracle({**cfg, "operand_dtype": "fp16"}, loss_name, sd, rec["x"], rec["target"], monkeypatch, ref=rec)
+    assert rep["logits"] < 1.5e-2   # 10 mantissa bits instead of 7: tighter than the bf16 build
+
+
 def test_model_vs_oracle_fresh_seed_cfg1_shape(monkeypatch):
     """BASELINE cfg 1: UNet3D f_maps=16 depth=3, 1x1x64^3, DiceLoss -- engine vs the CPU oracle on seeded inputs."""
     import pytorch3dunet_b200 as P

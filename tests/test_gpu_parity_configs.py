@@ -125,3 +125,9 @@ def test_cfg3_residual_unet3d_f32_l5_widths():
 def test_cfg4_residual_unet_se3d_f64_l5_widths():
     """BASELINE configs[3] widths: ResidualUNetSE3D f_maps=64, 5 levels (1024 channels, scSE at every level), 1x1x64^3."""
     _run_case(dict(name="ResidualUNetSE3D", in_channels=1, out_channels=1, f_maps=64, num_levels=5), (1, 1, 64, 64, 64), "bce_dice_loss", seed=2)
+
+
+def test_cfg4_residual_unet_se3d_f64_l5_widths_fp16_operands():
+    """the same with fp16 activations / operands (what BASELINE configs[3] names): the drift gates are still torch's bf16 path's (looser)"""
+    _run_case(dict(name="ResidualUNetSE3D", in_channels=1, out_channels=1, f_maps=64, num_levels=5, operand_dtype="fp16"), (1, 1, 64, 64, 64),
+              "bce_dice_loss", seed=2)
