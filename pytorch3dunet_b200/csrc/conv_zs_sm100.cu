@@ -140,6 +140,7 @@ conv3_zs_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
   float* bias_interior = stat_acc + 8 * p.NT * 2;                                        // [8 parity variants][NT]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = blockIdx.y, cta = blockIdx.x, cps = gridDim.x;
+  const int n0 = blockIdx.z * p.NT;  // output-channel slice of this CTA (C_out > NT: the resident weights of NT channels fit, those of C_out do not)
   const int nchunks = p.Cin / KC;
   constexpr int rb = KC * 2;
   const int R = p.tmem_bufs / ZS_LANES;  // ring slots per lane
@@ -177,7 +178,7 @@ conv3_zs_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
     for (int i = threadIdx.x; i < 8 * p.NT; i += ZS_THREADS) {
       const int v = i / p.NT, c = i - v * p.NT;
       const int cls = ((v & 4 ? 3 : 1) << 4) | ((v & 2 ? 3 : 1) << 2) | (v & 1 ? 3 : 1);
-      bias_interior[i] = p.biascls[((size_t)(p.n_b > 1 ? n : 0) * 64 + cls) * p.Cout + c];
+      bias_interior[i] = p.biascls[((size_t)(p.n_b > 1 ? n : 0) * 64 + cls) * p.Cout + n0 + c];
     }
   for (int i = threadIdx.x; i < 8 * p.NT * 2; i += ZS_THREADS) stat_acc[i] = 0.f;
   tc_fence_before();
@@ -196,7 +197,7 @@ conv3_zs_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
       for (int cb = 0; cb < nchunks && lane_id == 0; ++cb)
         for (int t9 = 0; t9 < 9; ++t9)
           for (int tdr = 0; tdr < 3; ++tdr)
-            tma_load_3d(smemB + ((size_t)((cb * 9 + t9) * 3 + tdr)) * p.NT * rb, &tmapB, &b_full, cb * KC, 0,
+            tma_load_3d(smemB + ((size_t)((cb * 9 + t9) * 3 + tdr)) * p.NT * rb, &tmapB, &b_full, cb * KC, n0,
                         wsample * 27 + (2 - tdr) * 9 + t9);
       ZsRing st = {0, 0u};
       long long w_prod = 0, t_begin = dbg_clock();
@@ -378,7 +379,7 @@ conv3_zs_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
           const int cls = conv_bias_cls(p.cls_mode, zo, xh, xw, D, p.H, p.W);
           const bool interior = (cls & 0x15) == 0x15;  // every axis class is 1 or 3
           bias_row = interior ? bias_interior + (((cls >> 3) & 4) | ((cls >> 2) & 2) | ((cls >> 1) & 1)) * NT
-                              : p.biascls + ((size_t)(p.n_b > 1 ? n : 0) * 64 + cls) * p.Cout;
+                              : p.biascls + ((size_t)(p.n_b > 1 ? n : 0) * 64 + cls) * p.Cout + n0;
         }
         const long long cw0 = dbg_clock();
         mbar_wait(&tmem_full[slot], cur.ph);
@@ -399,7 +400,7 @@ conv3_zs_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = i < cw ? __uint_as_float(raw[i]) : 0.f;
-          const size_t goff = vox_off * p.Cout + c0;
+          const size_t goff = vox_off * p.Cout + n0 + c0;
           if (valid) {
             if (bias_row) {
               const float4* bp = reinterpret_cast<const float4*>(bias_row + c0);
@@ -491,7 +492,7 @@ conv3_zs_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
   }
   __syncthreads();
   if (p.pmode) {  // fixed-order sum over the 8 epilogue warps -> this CTA's partial row
-    float* out = p.partials + (((size_t)n * cps + cta) * p.Cout) * 2;
+    float* out = p.partials + (((size_t)n * cps + cta) * p.Cout + n0) * 2;
     for (int i = threadIdx.x; i < p.NT * 2; i += ZS_THREADS) {
       float acc = 0.f;
 #pragma unroll
@@ -516,30 +517,41 @@ bool conv_zs_plan(int N, int D, int H, int W, int Cin, int Cout, ConvParams* pp)
   ConvParams& p = *pp;
   memset(&p, 0, sizeof(p));
   if (!zs_enabled()) return false;
-  if (Cin % 16 != 0 || Cout % 16 != 0 || 3 * Cout > 256) return false;  // one MMA covers up to three C_out-wide blocks (N <= 256)
+  if (Cin % 16 != 0 || Cout % 16 != 0) return false;
   if (H < ZS_HH || W < ZS_HW || D < 1) return false;  // keep the TMA box inside the tensor extent
   const int budget = 222 * 1024;
-  const int b_total = 27 * Cout * Cin * 2;
-  const int scratch = (8 * Cout * 2 + 8 * Cout) * (int)sizeof(float);
   const int kc = (Cin % 64 == 0) ? 64 : (Cin % 32 == 0 ? 32 : 16);
   const int a_bytes = (ZS_ROWS * kc * 2 + 1023) & ~1023;
-  int stages = (budget - ((b_total + 1023) & ~1023) - scratch - 1024) / a_bytes;
-  if (stages > ZS_MAX_STAGES) stages = ZS_MAX_STAGES;
-  stages &= ~1;  // two lanes, half of the stages each
-  if (stages < 4) return false;
+  // NT = output channels per CTA: all of them when their resident weights fit and one MMA can cover three NT-wide blocks (N <= 256,
+  // TMEM ring of >= 8 blocks); else HALF of them (>= 32) when that fits -- the slices re-read the input from L2, which
+  // still beats the tap-loop kernel by ~2x on these shapes (64->64 at 64^3 / 160^3).  Wider layers stay on the tap-loop kernel
+  // (N = C_out >= 128 is math-bound there).
+  int NT = 0, stages = 0, b_total = 0;
+  for (int nt : {Cout, 64, 48, 32}) {
+    if (nt > Cout || Cout % nt != 0 || nt > 64 || (nt != Cout && (nt < 32 || 2 * nt < Cout))) continue;  // at most two slices
+    const int bt = 27 * nt * Cin * 2;
+    const int scratch = (8 * nt * 2 + 8 * nt) * (int)sizeof(float);
+    int st = (budget - ((bt + 1023) & ~1023) - scratch - 1024) / a_bytes;
+    if (st > ZS_MAX_STAGES) st = ZS_MAX_STAGES;
+    st &= ~1;  // two lanes, half of the stages each
+    if (st < 4) continue;
+    NT = nt; stages = st; b_total = bt;
+    break;
+  }
+  if (!NT) return false;
   p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
   p.BD = 1; p.BH = ZS_BH; p.BW = ZS_BW;
   p.tilesD = D;
   p.tilesH = (H + ZS_BH - 1) / ZS_BH;
   p.tilesW = (W + ZS_BW - 1) / ZS_BW;
-  p.NT = Cout;
+  p.NT = NT;
   p.KC = kc;
   p.KCb = kc;
   p.kchunks = Cin / kc;
   p.a_stages = stages;
   p.a_bytes = a_bytes;
   p.b_total_bytes = b_total;
-  int slots = 512 / Cout;
+  int slots = 512 / NT;
   if (slots > ZS_MAX_SLOTS) slots = ZS_MAX_SLOTS;
   slots &= ~1;  // two lanes, half of the ring each: three blocks accumulating + one being drained
   if (slots < 8) return false;
@@ -547,7 +559,7 @@ bool conv_zs_plan(int N, int D, int H, int W, int Cin, int Cout, ConvParams* pp)
   p.tmem_cols = 512;
   long long T = (long long)p.tilesH * p.tilesW * D;
   if (T >= (1ll << 30)) return false;  // the kernel's plane-tile counters are 32-bit
-  int cps = sm_count() / N;
+  int cps = sm_count() / (N * (Cout / NT));  // one persistent CTA per SM over (sample, channel slice)
   if (cps < 1) cps = 1;
   if (const char* e = getenv("B200UNET_ZS_CTAS")) {  // tests: few CTAs per sample => long depth walks (ring wrap, mid-column segment cuts)
     const int v = atoi(e);
@@ -577,7 +589,7 @@ int conv_zs_launch(const void* x, const void* wf, ConvParams& p, cudaStream_t s)
   auto kern = p.KC == 64 ? conv3_zs_kernel<64> : (p.KC == 32 ? conv3_zs_kernel<32> : conv3_zs_kernel<16>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   B200_CHECK_ARG(e == cudaSuccess, "conv3_zs: cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e));
-  dim3 grid((unsigned)p.ctas_per_sample, (unsigned)p.N);
+  dim3 grid((unsigned)p.ctas_per_sample, (unsigned)p.N, (unsigned)(p.Cout / p.NT));
   kern<<<grid, ZS_THREADS, smem, s>>>(tmA, tmB, p);
   B200_CHECK_LAUNCH("conv3_zs");
   return 0;
