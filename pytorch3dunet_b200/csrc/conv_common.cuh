@@ -177,5 +177,7 @@ int conv_halo_launch(const void* x, const void* wf, ConvParams& p, cudaStream_t 
 void deconv_phase_table(signed char* k3, signed char* off, signed char* ntaps);
 bool conv_zs_plan(int N, int D, int H, int W, int Cin, int Cout, ConvParams* p);   // conv_zs_sm100.cu: depth taps stacked along N
 int conv_zs_launch(const void* x, const void* wf, ConvParams& p, cudaStream_t s);
+// upzs_sm100.cu: z-stacked phase conv of the virtual concat; returns -1 when the shape is not taken
+int conv3_upzs_run(const void* low, const void* wp, int n_w, int N, int d, int h, int w, int C1, int Cout, void* R, cudaStream_t s);
 
 }  // namespace b200

@@ -226,6 +226,116 @@ __global__ void __launch_bounds__(256, 2) stem_conv_fwd_kernel(const float* __re
   }
 }
 
+// register-tiled variant for C_in == 1, W % VW == 0: one thread = VW consecutive voxels of a line x all COUT channels.  The 3x3x(VW+2)
+// halo of x lives in registers (loaded once: 9*(VW+2) loads for VW voxels instead of 27 per voxel), every weight row read from shared
+// memory feeds VW*COUT FMAs: the loop is FMA-issue bound instead of load-latency bound (1 -> 16 @ 2x128^3: 0.38 -> ~0.1 ms).
+template <int COUT, int VW>
+__global__ void __launch_bounds__(256, 1) stem_conv_fwd_tiled_kernel(const float* __restrict__ x, const bf16* __restrict__ wf, int n_w,
+                                                                  const float* __restrict__ biascls, int n_b, int act, float slope, int D,
+                                                                  int H, int W, int P, bf16* __restrict__ y, int pmode,
+                                                                  float* __restrict__ partials) {
+  extern __shared__ float sm[];  // w[27][COUT] | bias[64][COUT] | red[8][COUT*2]
+  float* wsm = sm;
+  float* bsm = wsm + 27 * COUT;
+  float* red = bsm + 64 * COUT;
+  const int p = blockIdx.x, n = blockIdx.y;
+  const bf16* wn = wf + (size_t)(n_w > 1 ? n : 0) * 27 * COUT;
+  for (int i = threadIdx.x; i < 27 * COUT; i += 256) wsm[i] = from_act(wn[i]);  // [tap][co] (C_in == 1)
+  for (int i = threadIdx.x; i < 64 * COUT; i += 256) bsm[i] = n_b ? biascls[(size_t)(n_b > 1 ? n : 0) * 64 * COUT + i] : 0.f;
+  __syncthreads();
+  const long long vox = (long long)D * H * W;
+  const long long quads = vox / VW;
+  long long q0, q1;
+  ew_range(quads, p, P, q0, q1);
+  const float* xn = x + (size_t)n * vox;
+  const int WQ = W / VW;
+  float s[COUT], q[COUT];
+#pragma unroll
+  for (int i = 0; i < COUT; ++i) s[i] = q[i] = 0.f;
+  for (long long qi = q0 + threadIdx.x; qi < q1; qi += 256) {
+    const int xw0 = (int)(qi % WQ) * VW;
+    const long long r = qi / WQ;
+    const int xh = (int)(r % H), xd = (int)(r / H);
+    float xr[3][3][VW + 2];
+#pragma unroll
+    for (int td = 0; td < 3; ++td) {
+      const int zd = xd + td - 1;
+#pragma unroll
+      for (int th = 0; th < 3; ++th) {
+        const int zh = xh + th - 1;
+        const bool ok = zd >= 0 && zd < D && zh >= 0 && zh < H;
+        const float* xp = xn + ((size_t)(ok ? zd : 0) * H + (ok ? zh : 0)) * W + xw0;
+#pragma unroll
+        for (int j = 0; j < VW + 2; ++j) {
+          const int zw = xw0 + j - 1;
+          xr[td][th][j] = (ok && zw >= 0 && zw < W) ? __ldg(xp + j - 1) : 0.f;
+        }
+      }
+    }
+    float acc[VW][COUT];
+    const int cdh = (axis_cls(xd, D) << 4) | (axis_cls(xh, H) << 2);
+#pragma unroll
+    for (int v = 0; v < VW; ++v) {
+      const float* bp = bsm + (cdh | axis_cls(xw0 + v, W)) * COUT;
+#pragma unroll
+      for (int i = 0; i < COUT; ++i) acc[v][i] = bp[i];
+    }
+#pragma unroll
+    for (int td = 0; td < 3; ++td)
+#pragma unroll
+      for (int th = 0; th < 3; ++th)
+#pragma unroll
+        for (int tw = 0; tw < 3; ++tw) {
+          const float4* wp = reinterpret_cast<const float4*>(wsm + ((td * 3 + th) * 3 + tw) * COUT);
+#pragma unroll
+          for (int i4 = 0; i4 < COUT / 4; ++i4) {
+            const float4 w4 = wp[i4];
+#pragma unroll
+            for (int v = 0; v < VW; ++v) {
+              const float xv = xr[td][th][tw + v];
+              acc[v][4 * i4] = fmaf(xv, w4.x, acc[v][4 * i4]);
+              acc[v][4 * i4 + 1] = fmaf(xv, w4.y, acc[v][4 * i4 + 1]);
+              acc[v][4 * i4 + 2] = fmaf(xv, w4.z, acc[v][4 * i4 + 2]);
+              acc[v][4 * i4 + 3] = fmaf(xv, w4.w, acc[v][4 * i4 + 3]);
+            }
+          }
+        }
+    bf16x8* op = reinterpret_cast<bf16x8*>(y + ((size_t)n * vox + qi * VW) * COUT);
+#pragma unroll
+    for (int v = 0; v < VW; ++v) {
+#pragma unroll
+      for (int i = 0; i < COUT; ++i) {
+        acc[v][i] = bf16_round(act_fwd(acc[v][i], act, slope));
+        s[i] += acc[v][i];
+        q[i] += acc[v][i] * acc[v][i];
+      }
+#pragma unroll
+      for (int i = 0; i < COUT / 8; ++i) op[v * (COUT / 8) + i] = pack8(&acc[v][8 * i]);
+    }
+  }
+  if (pmode) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int i = 0; i < COUT; ++i) {
+      float a = s[i], b = q[i];
+      for (int o = 16; o; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+      }
+      if (lane == 0) {
+        red[(warp * COUT + i) * 2] = a;
+        red[(warp * COUT + i) * 2 + 1] = b;
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < COUT * 2; i += 256) {
+      float a = 0.f;
+      for (int wv = 0; wv < 8; ++wv) a += red[wv * COUT * 2 + i];
+      partials[((size_t)n * P + p) * COUT * 2 + i] = a;
+    }
+  }
+}
+
 // stem weight gradient: G[n][0][tap][ci][co] += sum_v dz[v,co] * x[v+tap-1,ci]   (fp32 x, C_in <= 4).
 // Shared-memory tiled: a block walks tiles of 2x8x32 voxels; per tile the fp32 x halo (4x10x34) and the dz tile (as fp32)
 // are staged in shared memory; a thread owns one (dd,dh) tap row x 8 output channels = 24 accumulators (3 dw taps) and
@@ -347,6 +457,19 @@ int b200_conv3_direct_fwd(const void* x, int x_is_f32, const void* wf, int n_w, 
   if (x_is_f32 && Cin <= 4 && (Cout == 8 || Cout == 16 || Cout == 32) && !residual && pmode != 2) {
     size_t sm2 = ((size_t)27 * Cin * Cout + 64 * Cout + 8 * Cout * 2) * sizeof(float);
     const float* xf = (const float*)x;
+    if (Cin == 1 && W % 4 == 0 && (Cout == 8 || Cout == 16)) {  // register-tiled: 4 voxels per thread
+      if (Cout == 8)
+        stem_conv_fwd_tiled_kernel<8, 4><<<grid, 256, sm2, ST(s)>>>(xf, (const bf16*)wf, n_w, biascls, n_b, act, slope, D, H, W, P, (bf16*)y, pmode, partials);
+      else
+        stem_conv_fwd_tiled_kernel<16, 4><<<grid, 256, sm2, ST(s)>>>(xf, (const bf16*)wf, n_w, biascls, n_b, act, slope, D, H, W, P, (bf16*)y, pmode, partials);
+      B200_CHECK_LAUNCH("stem_conv_fwd_tiled");
+      return 0;
+    }
+    if (Cin == 1 && W % 2 == 0 && Cout == 32) {
+      stem_conv_fwd_tiled_kernel<32, 2><<<grid, 256, sm2, ST(s)>>>(xf, (const bf16*)wf, n_w, biascls, n_b, act, slope, D, H, W, P, (bf16*)y, pmode, partials);
+      B200_CHECK_LAUNCH("stem_conv_fwd_tiled");
+      return 0;
+    }
     if (Cout == 8)
       stem_conv_fwd_kernel<8><<<grid, 256, sm2, ST(s)>>>(xf, (const bf16*)wf, n_w, biascls, n_b, act, slope, D, H, W, Cin, P, (bf16*)y, pmode, partials);
     else if (Cout == 16)

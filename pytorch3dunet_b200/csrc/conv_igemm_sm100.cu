@@ -450,6 +450,10 @@ int b200_conv3_up_supported(int N, int d, int h, int w, int C1, int Cout) {
 int b200_conv3_up_phase_fwd(const void* b, const void* wp, int n_w, int N, int d, int h, int w, int C1, int Cout, void* R, b200_stream_t s) {
   B200_CHECK_ARG(b200_conv3_up_supported(N, d, h, w, C1, Cout), "conv3_up_phase_fwd: unsupported N=%d %dx%dx%d C1=%d Cout=%d", N, d, h, w,
                  C1, Cout);
+  {  // large low-res planes, resident weights: the z-stacked kernel (upzs_sm100.cu, N = 4*C_out per instruction)
+    const int rc = conv3_upzs_run(b, wp, n_w, N, d, h, w, C1, Cout, R, (cudaStream_t)s);
+    if (rc >= 0) return rc;
+  }
   // one launch: every CTA owns a tile of 128 low-res voxels and all 8 phases (8 accumulators; the epilogue of phase k overlaps
   // the MMAs of phase k+1)
   PlainGeom g;

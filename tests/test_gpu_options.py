@@ -81,12 +81,14 @@ def test_flat_gradient_buffer_receives_the_engine_gradients():
         P.losses.bce_dice_loss(logits, t).backward()
     for (k, p1), (_, p2) in zip(m1.named_parameters(), m2.named_parameters()):
         assert p2.grad.data_ptr() == flat.grad_views[k].data_ptr(), k     # still the view of the flat buffer
-        assert torch.equal(p1.grad, p2.grad), k                              # and bit-identical to the autograd-accumulated path
+        # and equal to the autograd-accumulated path (not bit-for-bit: two small backward reductions -- the border-class sums and the
+        # fp32-input stem wgrad -- use floating-point atomics, so their summation order varies from run to run at the 1e-7 level)
+        assert torch.allclose(p1.grad, p2.grad, rtol=1e-4, atol=1e-7 * float(p1.grad.abs().max()) + 1e-12), k
     # a second step OVERWRITES (no accumulation): same values again
     before = flat.grad.clone()
     _, logits = m2(x, return_logits=True)
     P.losses.bce_dice_loss(logits, t).backward()
-    assert torch.equal(before, flat.grad)
+    assert torch.allclose(before, flat.grad, rtol=1e-4, atol=1e-7 * float(before.abs().max()))
 
 
 def test_fused_adam_matches_torch_adam():

@@ -26,7 +26,9 @@ def _ncdhw(t):
     return t.float().permute(0, 4, 1, 2, 3)
 
 
-SHAPES = [((4, 4, 4), 16, 32, 32), ((3, 5, 6), 16, 16, 16), ((8, 8, 8), 32, 64, 32), ((2, 2, 2), 64, 128, 64), ((16, 16, 16), 32, 64, 32)]
+SHAPES = [((4, 4, 4), 16, 32, 32), ((3, 5, 6), 16, 16, 16), ((8, 8, 8), 32, 64, 32), ((2, 2, 2), 64, 128, 64), ((16, 16, 16), 32, 64, 32),
+          # low-res planes large enough (h >= 18, w >= 10) for the z-stacked phase kernel (csrc/upzs_sm100.cu): N = 4*C_out per instruction
+          ((12, 20, 12), 32, 64, 32), ((5, 33, 17), 16, 32, 16), ((9, 18, 10), 16, 128, 64), ((1, 18, 10), 16, 16, 32)]
 
 
 @pytest.mark.parametrize("small,c0,c1,cout", SHAPES)
@@ -122,3 +124,42 @@ def test_virtual_concat_conv_matches_materialised(small, c0, c1, cout, mode):
     for k in pm:
         scale = float(pm[k].float().norm()) + 1e-6
         assert float((pv[k].float() - pm[k].float()).norm()) / scale < 2e-2, k
+
+
+@pytest.mark.parametrize("case", [((40, 20, 12), 32, 32, 1), ((40, 20, 12), 32, 32, 3), ((21, 36, 20), 64, 32, 2), ((30, 18, 10), 128, 64, 1)])
+def test_zstacked_phase_conv_matches_tap_loop_and_torch(case, monkeypatch):
+    """csrc/upzs_sm100.cu with few CTAs per sample (long depth walks: TMEM ring wrap, segment cuts inside a column, channel slices)
+    against the tap-loop phase kernel on the same operands and against conv3(nearest_up2x(.)) in fp32"""
+    U, E, L = _ctx()
+    (d, h, w), c1, cout, cps = case
+    N = 2
+    g = torch.Generator(device="cuda").manual_seed(9)
+    Wu = torch.randn((cout, c1, 3, 3, 3), device="cuda", generator=g) / (27 * c1) ** 0.5
+    b = _rand((N, d, h, w, c1), 6)
+    # phase weights straight from the definition (per axis: p=0: j=0 <- tap -1, j=1 <- taps 0,+1;  p=1: j=0 <- taps -1,0, j=1 <- tap +1)
+    sets = {(0, 0): [0], (0, 1): [1, 2], (1, 0): [0, 1], (1, 1): [2]}
+    wp = torch.zeros((1, 64, cout, c1), device="cuda")
+    for phase in range(8):
+        pp = ((phase >> 2) & 1, (phase >> 1) & 1, phase & 1)
+        for j in range(8):
+            jj = ((j >> 2) & 1, (j >> 1) & 1, j & 1)
+            acc = 0
+            for td in sets[(pp[0], jj[0])]:
+                for th in sets[(pp[1], jj[1])]:
+                    for tw in sets[(pp[2], jj[2])]:
+                        acc = acc + Wu[:, :, td, th, tw]
+            wp[0, phase * 8 + j] = acc
+    wp = wp.bfloat16()
+    monkeypatch.setenv("B200UNET_ZS_CTAS", str(cps))
+    R = torch.full((N, 2 * d, 2 * h, 2 * w, cout), float("nan"), dtype=torch.bfloat16, device="cuda")
+    L.call("b200_conv3_up_phase_fwd", U.p(b), U.p(wp), 1, N, d, h, w, c1, cout, U.p(R), U.stream())
+    monkeypatch.setenv("B200UNET_UPZS", "0")
+    R0 = torch.full_like(R, float("nan"))
+    L.call("b200_conv3_up_phase_fwd", U.p(b), U.p(wp), 1, N, d, h, w, c1, cout, U.p(R0), U.stream())
+    torch.cuda.synchronize()
+    # reference with the SAME bf16-rounded phase weights is what both kernels compute; against torch: the unrounded 27-tap weights
+    ref = F.conv3d(F.interpolate(_ncdhw(b), scale_factor=2, mode="nearest"), Wu, padding=1).permute(0, 2, 3, 4, 1)
+    print("upzs", case, "vs tap-loop", U.rel_l2(R, R0.float()), "vs torch", U.rel_l2(R, ref))
+    assert not torch.isnan(R.float()).any()
+    assert U.rel_l2(R, R0.float()) < 4e-3
+    assert U.rel_l2(R, ref) < 8e-3
