@@ -117,7 +117,7 @@ def test_virtual_concat_conv_matches_materialised(small, c0, c1, cout, mode):
     yv, sv, gev, glv, pv = run(True)
     ym, sm, gem, glm, pm = run(False)
     assert U.rel_l2(yv, ym) < 6e-3
-    assert U.rel_l2(sv, sm) < 2e-3
+    assert U.rel_l2(sv, sm) < 4e-3   # the statistics of two bf16 roundings of the same tensor (R is rounded once more on the virtual path)
     assert U.rel_l2(gev, gem) < 1e-2
     assert U.rel_l2(glv, glm) < 1e-2
     assert set(pv) == set(pm)
