@@ -373,14 +373,14 @@ def run_train(args, wl):
     achieved = tc_flops / (tc_ms / 1e3) / 1e12 if tc_ms > 0 else 0.0
     peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
     traffic, traffic_note = None, None
-    for fn in ("ncu_r02_full_summary.json", "ncu_r01_full_summary.json"):
-        try:  # dram bytes of one launch of the largest-share kernel, from the committed ncu --set full capture
-            prof = json.load(open(os.path.join(ROOT, "profiles", fn)))["wgrad_halo_kernel"]
-            traffic = (float(prof["dram__bytes_read.sum"]["value"]) + float(prof["dram__bytes_write.sum"]["value"])) * 1e6
-            traffic_note = f"dram read+write bytes of ONE wgrad_halo_kernel<32> launch (32->32 @ 2x128^3; algorithmic 537 MB: x + dz), profiles/{fn}"
-            break
-        except Exception:
-            pass
+    try:  # dram bytes of the longest launch of the largest-share kernel, from the committed ncu --set full capture of one cfg-2 step
+        prof = json.load(open(os.path.join(ROOT, "profiles", "ncu_r02_full_summary.json")))["conv3_zs_kernel"]
+        mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        traffic = sum(float(prof[k]["value"]) * mult.get(prof[k]["unit"], 1.0) for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+        traffic_note = ("dram read+write bytes of ONE conv3_zs_kernel launch (the longest of the step: a 32->32 layer @ 2x128^3, algorithmic "
+                        "537 MB = x + y), profiles/ncu_r02_full_summary.md")
+    except Exception:
+        pass
     roofline = {"bound": "tensor", "kernel": "tcgen05 conv kernels: conv3_halo_kernel / conv3_igemm_kernel (fprop+dgrad), wgrad_halo_kernel / conv3_wgrad_igemm_kernel",
                 "achieved": achieved, "peak": peak,
                 "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_note": traffic_note,
