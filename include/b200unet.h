@@ -106,6 +106,15 @@ int b200_conv3_wgrad(int impl, const void* x, int x_is_f32, const void* dz,
  * scratch: b200_border_tap_sums_workspace(...) floats */
 int b200_border_tap_sums_workspace(int N, int D, int H, int W, int C);
 int b200_border_tap_sums(const void* dz, int N, int D, int H, int W, int C, float* T, float* scratch, b200_stream_t s);
+/* same, with the per-channel totals of dz supplied as partial sums [N][Ptot][C][2] (column 0) by the kernel that produced dz */
+int b200_border_tap_sums_pre(const void* dz, int N, int D, int H, int W, int C, const float* tot_partials, int Ptot, float* T, float* scratch,
+                             b200_stream_t s);
+/* dgrad with the GroupNorm backward of the conv's input fused into the epilogue (replaces b200_conv3_fwd(dgrad) + b200_gn_bwd_apply on the
+ * layers the z-stacked kernel takes): out = (A*conv(dz, wd) + B*x + C) * act'(x) [+ gadd], coef [N][Cin][3]; partials [N][P][Cin][2] of out,
+ * P = b200_conv3_igemm_partials_count(N,D,H,W,Cout,Cin) */
+int b200_conv3_dgrad_gnbwd_supported(int N, int D, int H, int W, int Cout, int Cin);
+int b200_conv3_dgrad_gnbwd(const void* dz, const void* wd, int N, int D, int H, int W, int Cout, int Cin, const float* coef, const void* x,
+                           int x_act, float x_slope, const void* gadd, void* out, float* partials, b200_stream_t s);
 /* dW[co][ci][tap] = sum_n ( a[n][ci] * sum_split G + b[n][ci] * T[n][tap][co] ); ab == NULL -> a=1,b=0.
  * Gsum (optional) [N][27][Cin][Cout] receives sum_split G for b200_gn_bwd_sums_from_wgrad (then called with S = 1) */
 int b200_wgrad_finalize(const float* G, int N, int S, int Cin, int Cout, const float* ab, const float* T,

@@ -45,6 +45,11 @@ struct ConvParams {
   const float* biascls;
   const bf16* residual;
   const bf16* aux;
+  // GroupNorm-backward epilogue of a dgrad launch (z-stacked kernel): out = (A*acc + B*aux + C) * act'(aux) [+ residual], coef [N][Cout][3];
+  // aux = the conv input x (post-activation output of its producer), residual = an already accumulated gradient (dz form)
+  const float* gn_coef;
+  int aux_act;
+  float aux_slope;
   bf16* y;
   float* partials;
   // halo kernel only

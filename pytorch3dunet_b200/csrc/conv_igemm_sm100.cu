@@ -436,6 +436,34 @@ int b200_conv3_igemm_fwd(const void* x, const void* wf, int n_w, const float* bi
                                  (cudaStream_t)s);
 }
 
+// ---- dgrad with the GroupNorm backward of the conv's INPUT fused into the epilogue (z-stacked kernel only):
+//   out = (A * conv(dz, wd) + B * x + C) * act'(x) [+ gadd],  coef [N][Cin][3] = (A, B, C) from b200_gn_bwd_coeffs;
+//   partials [N][P][Cin][2] of out (P = b200_conv3_igemm_partials_count(N,D,H,W,Cout,Cin)): column 0 = per-channel totals, which
+//   b200_border_tap_sums_pre takes instead of re-reading the tensor.  Replaces b200_conv3_fwd(dgrad) + b200_gn_bwd_apply.
+int b200_conv3_dgrad_gnbwd_supported(int N, int D, int H, int W, int Cout, int Cin) {
+  ConvParams p;
+  return (b200_device_is_sm100() && conv_zs_plan(N, D, H, W, Cout, Cin, &p)) ? 1 : 0;
+}
+int b200_conv3_dgrad_gnbwd(const void* dz, const void* wd, int N, int D, int H, int W, int Cout, int Cin, const float* coef, const void* x,
+                           int x_act, float x_slope, const void* gadd, void* out, float* partials, b200_stream_t s) {
+  ConvParams p;
+  B200_CHECK_ARG(conv_zs_plan(N, D, H, W, Cout, Cin, &p), "conv3_dgrad_gnbwd: shape not taken by the z-stacked kernel N=%d %dx%dx%d %d->%d", N, D,
+                 H, W, Cout, Cin);
+  B200_CHECK_ARG(coef && x && out, "conv3_dgrad_gnbwd: coef, x and out are required");
+  p.n_w = 1;
+  p.n_b = 0;
+  p.act = B200_ACT_NONE;
+  p.pmode = partials ? 1 : 0;
+  p.gn_coef = coef;
+  p.aux = (const bf16*)x;
+  p.aux_act = x_act;
+  p.aux_slope = x_slope;
+  p.residual = (const bf16*)gadd;
+  p.y = (bf16*)out;
+  p.partials = partials;
+  return conv_zs_launch(dz, wd, p, (cudaStream_t)s);
+}
+
 // ---- conv3x3x3 over a nearest-2x-upsampled tensor WITHOUT materialising it (decoder concat path, buildingblocks.py:493 + :575).
 // Output parity phase p (per axis) of conv3(up(b)) is a 2x2x2 convolution of the low-res b with phase-specific summed weights:
 //   p = 0: low-res offsets {-1, 0} carry taps {-1}, {0,+1};   p = 1: offsets {0, +1} carry taps {-1,0}, {+1}

@@ -1255,6 +1255,12 @@ int b200_border_tap_sums_workspace(int N, int D, int H, int W, int C) {
   return (int)(f + 2 * ((size_t)N * 64 * C + (size_t)N * C * 2));
 }
 int b200_border_tap_sums(const void* dz, int N, int D, int H, int W, int C, float* T, float* scratch, b200_stream_t s) {
+  return b200_border_tap_sums_pre(dz, N, D, H, W, C, nullptr, 0, T, scratch, s);
+}
+// same, with the per-channel totals of dz given as partial sums [N][Ptot][C][2] (column 0) by the kernel that produced dz
+// (tot_partials == NULL: computed here by one streaming pass over dz)
+int b200_border_tap_sums_pre(const void* dz, int N, int D, int H, int W, int C, const float* tot_partials, int Ptot, float* T, float* scratch,
+                             b200_stream_t s) {
   B200_CHECK_ARG(C % 8 == 0 && C <= 2048, "border_tap_sums: C=%d must be a multiple of 8", C);
   const long long vox = (long long)D * H * W;
   int P = border_blocks(D, H);
@@ -1266,11 +1272,15 @@ int b200_border_tap_sums(const void* dz, int N, int D, int H, int W, int C, floa
   double* R = reinterpret_cast<double*>(scratch + f);
   double* tot = R + (size_t)N * 64 * C;
   {
-    dim3 grid(P2, N);
-    stats_ndhwc_bf16_kernel<<<grid, EW_THREADS, EW_THREADS * 16 * sizeof(float), ST(s)>>>((const bf16*)dz, C, vox, P2, totp);
-    B200_CHECK_LAUNCH("border_totals");
     dim3 g2(ceil_div(C * 2, 32), N), b2(32, 32);
-    partials_finalize_kernel<<<g2, b2, 0, ST(s)>>>(totp, P2, C, tot);
+    if (tot_partials) {
+      partials_finalize_kernel<<<g2, b2, 0, ST(s)>>>(tot_partials, Ptot, C, tot);
+    } else {
+      dim3 grid(P2, N);
+      stats_ndhwc_bf16_kernel<<<grid, EW_THREADS, EW_THREADS * 16 * sizeof(float), ST(s)>>>((const bf16*)dz, C, vox, P2, totp);
+      B200_CHECK_LAUNCH("border_totals");
+      partials_finalize_kernel<<<g2, b2, 0, ST(s)>>>(totp, P2, C, tot);
+    }
     B200_CHECK_LAUNCH("border_totals_reduce");
   }
   {

@@ -33,6 +33,7 @@ _ACT_OF = {"r": (ACT_RELU, 0.0), "l": (ACT_LEAKY, 0.01), "e": (ACT_ELU, 1.0)}
 DEBUG = None   # dict: when set, backward closures stash clones of their intermediates (tools/debug_block.py)
 TIMING = None
 VIRTUAL_CAT = os.environ.get("B200UNET_NO_VIRTUAL_CAT", "0") != "1"  # decoder concat without the concatenated tensor
+FUSED_GN_BWD = os.environ.get("B200UNET_FUSED_GN_BWD", "1") != "0"   # GroupNorm backward as the dgrad kernel's epilogue (z-stacked layers)
 DECONV_PHASES = os.environ.get("B200UNET_DECONV_PHASES", "1") != "0"  # transposed conv by output parity phases (exact 2x joins)
 EXPLICIT_GN = os.environ.get("B200UNET_EXPLICIT_GN", "1") != "0"      # deep levels: GroupNorm as its own pass instead of per-sample weights
 EXPLICIT_GN_VOX_PER_COUT = 40
@@ -53,7 +54,7 @@ def _p(t):
 class Act:
     """A bf16 NDHWC activation plus what the engine knows about it."""
 
-    __slots__ = ("t", "act", "slope", "partials", "P", "sums", "grad", "requires_grad")
+    __slots__ = ("t", "act", "slope", "partials", "P", "sums", "grad", "requires_grad", "grad_partials")
 
     def __init__(self, t, act=ACT_NONE, slope=0.0, partials=None, P=0, requires_grad=True):
         self.t = t
@@ -63,6 +64,7 @@ class Act:
         self.P = P
         self.sums = None        # double [N,C,2], finalised lazily
         self.grad = None        # bf16 NDHWC, gradient w.r.t. the producer's PRE-activation output ("dz form")
+        self.grad_partials = None  # (partials [N,P,C,2], P, grad tensor): per-channel totals of `grad` emitted by the kernel that wrote it
         self.requires_grad = requires_grad
 
     @property
@@ -78,7 +80,7 @@ class Act:
 class InputF32:
     """The network input kept in fp32 (reference: ToTensor -> float32, transforms.py:816-826), NDHWC view."""
 
-    __slots__ = ("t", "sums_src", "sums", "partials", "P", "requires_grad", "grad", "act", "slope")
+    __slots__ = ("t", "sums_src", "sums", "partials", "P", "requires_grad", "grad", "act", "slope", "grad_partials")
 
     def __init__(self, t_ndhwc, ncdhw_src):
         self.t = t_ndhwc
@@ -87,6 +89,7 @@ class InputF32:
         self.partials, self.P = None, 0
         self.requires_grad = False
         self.grad = None
+        self.grad_partials = None
         self.act, self.slope = ACT_NONE, 0.0
 
     @property
@@ -226,8 +229,38 @@ class Engine:
         if x.grad is None:
             x.grad = g
         else:
+            x.grad_partials = None  # accumulated in place below: the totals its producer emitted no longer describe it
             n, d, h, w, c = x.dims
             self.call("b200_act_bwd", _p(g), c, 0, _p(x.t), n, c, d * h * w, ACT_NONE, 0.0, _p(x.grad), _p(x.grad))
+
+    def border_tap_sums(self, out, dz, n, d, h, w, cout):
+        """T[n][tap][co] = sum of dz over the voxels whose tap is in bounds; the per-channel totals come from the kernel that produced dz
+        when it emitted them (fused dgrad + GroupNorm-backward epilogue), else from one more pass over dz"""
+        L = self.L
+        T = self.empty((n, 27, cout), torch.float32)
+        scratch = self.empty((L.query("b200_border_tap_sums_workspace", n, d, h, w, cout),), torch.float32)
+        gp = out.grad_partials
+        if gp is not None and gp[2] is dz:
+            self.call("b200_border_tap_sums_pre", _p(dz), n, d, h, w, cout, _p(gp[0]), gp[1], _p(T), _p(scratch), launches=4)
+        else:
+            self.call("b200_border_tap_sums", _p(dz), n, d, h, w, cout, _p(T), _p(scratch), launches=5)
+        return T
+
+    def dgrad_gn_bwd(self, dz, wd, coef, x, n, d, h, w, cout, cin, name):
+        """x.grad = (A * dgrad(dz) + B * x + C) * act'(x) [+ x.grad]: on the layers the z-stacked kernel takes, the GroupNorm backward is the
+        dgrad kernel's epilogue (no dxhat round trip through HBM) and the kernel emits the totals of what it wrote; returns False when
+        the shape is not taken (the caller runs dgrad + b200_gn_bwd_apply)."""
+        L = self.L
+        if not (FUSED_GN_BWD and self.impl != IMPL_DIRECT and L.query("b200_conv3_dgrad_gnbwd_supported", n, d, h, w, cout, cin)):
+            return False
+        P = L.query("b200_conv3_igemm_partials_count", n, d, h, w, cout, cin)
+        parts = self.empty((n, P, cin, 2), torch.float32)
+        dx = self.empty((n, d, h, w, cin), self.adt)
+        self.call("b200_conv3_dgrad_gnbwd", _p(dz), _p(wd), n, d, h, w, cout, cin, _p(coef), _p(x.t), x.act, float(x.slope), _p(x.grad), _p(dx),
+                  _p(parts), flops=2.0 * n * d * h * w * 27 * cin * cout, tag="dgrad_tc", layer=name)
+        x.grad = dx
+        x.grad_partials = (parts, P, dx)
+        return True
 
     # ---------------------------------------------------------------- input / output layout
     def input_f32(self, x_ncdhw):
@@ -324,11 +357,7 @@ class Engine:
                 if dz is None:
                     return
                 need_T = gn is not None or bias is not None
-                T = None
-                if need_T:
-                    T = self.empty((n, 27, cout), torch.float32)
-                    scratch = self.empty((L.query("b200_border_tap_sums_workspace", n, d, h, w, cout),), torch.float32)
-                    self.call("b200_border_tap_sums", _p(dz), n, d, h, w, cout, _p(T), _p(scratch), launches=5)
+                T = self.border_tap_sums(out, dz, n, d, h, w, cout) if need_T else None
                 wimpl = L.query("b200_conv3_wgrad_resolve_impl", self.impl, n, d, h, w, cin, cout, int(is_f32))
                 if wimpl < 0:
                     raise B200Error("tcgen05 wgrad requested but unsupported for this shape")
@@ -373,6 +402,9 @@ class Engine:
                         raise NotImplementedError("gradient w.r.t. the fp32 network input is not provided by the engine")
                     wd = self.empty((27, cin, cout), self.adt)
                     self.call("b200_prep_dgrad_weights", _p(W), cin, cout, _p(wd))
+                    if coef is not None and self.dgrad_gn_bwd(dz, wd, coef, x, n, d, h, w, cout, cin, name):
+                        out.grad = None
+                        return
                     dimpl = L.query("b200_conv3_resolve_impl", self.impl, n, d, h, w, cout, cin, 0)
                     if dimpl < 0:
                         raise B200Error("tcgen05 dgrad requested but unsupported for this shape")
@@ -581,11 +613,7 @@ class Engine:
                 dz = out.grad
                 if dz is None:
                     return
-                T = None
-                if gn is not None or bias is not None:
-                    T = self.empty((n, 27, cout), torch.float32)
-                    scratch = self.empty((L.query("b200_border_tap_sums_workspace", n, D, H, Wd, cout),), torch.float32)
-                    self.call("b200_border_tap_sums", _p(dz), n, D, H, Wd, cout, _p(T), _p(scratch), launches=5)
+                T = self.border_tap_sums(out, dz, n, D, H, Wd, cout) if (gn is not None or bias is not None) else None
                 S1 = L.query("b200_conv3_wgrad_splits", IMPL_TCGEN05, n, D, H, Wd, c0, cout, 0)
                 G_enc = self.empty((n, S1, 27, c0, cout), torch.float32)
                 self.call("b200_conv3_wgrad", IMPL_TCGEN05, _p(enc.t), 0, _p(dz), n, D, H, Wd, c0, cout, _p(G_enc),
@@ -618,7 +646,9 @@ class Engine:
                     wd_enc = self.empty((27, c0, cout), self.adt)
                     wd_up = self.empty((64, c1, cout), self.adt)
                     self.call("b200_upcat_prep_dgrad_weights", _p(W), c0, c1, cout, _p(wd_enc), _p(wd_up))
-                if enc.requires_grad:
+                if enc.requires_grad and coef is not None and self.dgrad_gn_bwd(dz, wd_enc, coef[:, :c0].contiguous(), enc, n, D, H, Wd, cout, c0, name):
+                    pass
+                elif enc.requires_grad:
                     dimpl = L.query("b200_conv3_resolve_impl", self.impl, n, D, H, Wd, cout, c0, 0)
                     if dimpl < 0:
                         raise B200Error("tcgen05 dgrad requested but unsupported for this shape")
