@@ -106,19 +106,10 @@ int b200_conv3_wgrad(int impl, const void* x, int x_is_f32, const void* dz,
  * scratch: b200_border_tap_sums_workspace(...) floats */
 int b200_border_tap_sums_workspace(int N, int D, int H, int W, int C);
 int b200_border_tap_sums(const void* dz, int N, int D, int H, int W, int C, float* T, float* scratch, b200_stream_t s);
-/* same, with the per-channel totals of dz supplied as partial sums [N][Ptot][C][2] (column 0) by the kernel that produced dz */
+/* same, with the per-channel totals of dz supplied as partial sums [N][Ptot][C][2] (column 0) by the kernel that produced dz
+ * (b200_gn_bwd_apply_stats) */
 int b200_border_tap_sums_pre(const void* dz, int N, int D, int H, int W, int C, const float* tot_partials, int Ptot, float* T, float* scratch,
                              b200_stream_t s);
-/* dgrad with the GroupNorm backward of the conv's input fused into the epilogue (replaces b200_conv3_fwd(dgrad) + b200_gn_bwd_apply on the
- * layers the z-stacked kernel takes): out = (A*conv(dz, wd) + B*x + C) * act'(x) [+ gadd], coef [N][Cin][3]; partials [N][P][Cin][2] of out,
- * P = b200_conv3_igemm_partials_count(N,D,H,W,Cout,Cin) */
-int b200_conv3_dgrad_gnbwd_supported(int N, int D, int H, int W, int Cout, int Cin);
-int b200_conv3_dgrad_gnbwd(const void* dz, const void* wd, int N, int D, int H, int W, int Cout, int Cin, const float* coef, const void* x,
-                           int x_act, float x_slope, const void* gadd, void* out, float* partials, b200_stream_t s);
-/* dW[co][ci][tap] = sum_n ( a[n][ci] * sum_split G + b[n][ci] * T[n][tap][co] ); ab == NULL -> a=1,b=0.
- * Gsum (optional) [N][27][Cin][Cout] receives sum_split G for b200_gn_bwd_sums_from_wgrad (then called with S = 1) */
-int b200_wgrad_finalize(const float* G, int N, int S, int Cin, int Cout, const float* ab, const float* T,
-                        float* dW, float* Gsum, b200_stream_t s);
 /* bias gradient for convs that have one: db[co] = sum_{n,tap=center...}: simply sum_n,v dz = T[n][13][co] summed */
 int b200_bias_grad_from_T(const float* T, int N, int C, float* db, b200_stream_t s);
 
@@ -136,6 +127,10 @@ int b200_gn_bwd_coeffs(const double* sums2, const float* gamma, const float* mea
  *  same shape in "dz form", may alias out) */
 int b200_gn_bwd_apply(const void* dxhat, const void* x, const float* coef, int N, int C, long long voxels,
                       int act, float slope, const void* gadd, void* out, b200_stream_t s);
+/* same, also emitting partials [N][P][C][2] = (sum out, sum out^2) per block (P = b200_stats_partials_count): the per-channel totals of the
+ * gradient it writes, which the NEXT layer's b200_border_tap_sums_pre takes instead of re-reading the tensor */
+int b200_gn_bwd_apply_stats(const void* dxhat, const void* x, const float* coef, int N, int C, long long voxels,
+                            int act, float slope, const void* gadd, void* out, float* partials, b200_stream_t s);
 /* out = g[..., g_co:g_co+C] * act'(y) [+ gadd] : plain masking / accumulation; g is read with channel stride g_cs */
 int b200_act_bwd(const void* g, int g_cs, int g_co, const void* y, int N, int C, long long voxels, int act, float slope,
                  const void* gadd, void* out, b200_stream_t s);
@@ -213,6 +208,9 @@ int b200_conv3_up_supported(int N, int d, int h, int w, int C1, int Cout);
 int b200_conv3_up_phase_fwd(const void* b, const void* wp, int n_w, int N, int d, int h, int w, int C1, int Cout, void* R, b200_stream_t s);
 int b200_upcat_prep_dgrad_weights(const float* W, int C0, int C1, int Cout, void* wd_enc, void* wd_up, b200_stream_t s);
 int b200_conv3_up_dgrad(const void* dz, const void* wd, int N, int d, int h, int w, int Cout, int C1, void* dxb, b200_stream_t s);
+/* z-stacked version of the same (large low-res planes): parts = scratch for 4 partial gradients [4][N][d][h][w][C1] (16-bit) */
+int b200_conv3_up_dgrad_zs_supported(int N, int d, int h, int w, int Cout, int C1);
+int b200_conv3_up_dgrad_zs(const void* dz, const void* wd, int N, int d, int h, int w, int Cout, int C1, void* parts, void* dxb, b200_stream_t s);
 int b200_conv3_up_wgrad_splits(int N, int d, int h, int w, int Cout, int C1);
 int b200_conv3_up_wgrad(const void* dz, const void* b, int N, int d, int h, int w, int Cout, int C1, float* Q, b200_stream_t s);
 int b200_upcat_assemble_wgrad(const float* G_enc, int S1, const float* Q, int S2, int N, int C0, int C1, int Cout, float* G,

@@ -45,11 +45,6 @@ struct ConvParams {
   const float* biascls;
   const bf16* residual;
   const bf16* aux;
-  // GroupNorm-backward epilogue of a dgrad launch (z-stacked kernel): out = (A*acc + B*aux + C) * act'(aux) [+ residual], coef [N][Cout][3];
-  // aux = the conv input x (post-activation output of its producer), residual = an already accumulated gradient (dz form)
-  const float* gn_coef;
-  int aux_act;
-  float aux_slope;
   bf16* y;
   float* partials;
   // halo kernel only
@@ -183,6 +178,9 @@ void deconv_phase_table(signed char* k3, signed char* off, signed char* ntaps);
 bool conv_zs_plan(int N, int D, int H, int W, int Cin, int Cout, ConvParams* p);   // conv_zs_sm100.cu: depth taps stacked along N
 int conv_zs_launch(const void* x, const void* wf, ConvParams& p, cudaStream_t s);
 // upzs_sm100.cu: z-stacked phase conv of the virtual concat; returns -1 when the shape is not taken
+// updzs_sm100.cu: its transpose (gradient w.r.t. the low-res tensor)
+bool conv3_updzs_supported(int N, int d, int h, int w, int Cout, int C1);
+int conv3_updzs_run(const void* dz, const void* wd, int N, int d, int h, int w, int Cout, int C1, void* parts, void* dxb, cudaStream_t s);
 int conv3_upzs_run(const void* low, const void* wp, int n_w, int N, int d, int h, int w, int C1, int Cout, void* R, cudaStream_t s);
 
 }  // namespace b200

@@ -283,6 +283,21 @@ int make_act_tmap_stride2(CUtensorMap* tm, const void* ptr, int N, int D, int H,
   return 0;
 }
 
+// one plane of an activation sampled with element stride 2 in h and w (depth stride 1): box of bh x bw SAMPLES (updzs_sm100.cu)
+int make_act_tmap_stride2_hw(CUtensorMap* tm, const void* ptr, int N, int D, int H, int W, int C, int kc, int bh, int bw) {
+  EncodeTiledFn enc = get_encode_tiled();
+  B200_CHECK_ARG(enc, "cuTensorMapEncodeTiled entry point not available");
+  B200_CHECK_ARG(2 * bh <= 256 && 2 * bw <= 256, "stride-2 box %dx%d too large", bh, bw);
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+  cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2, (cuuint64_t)D * H * W * C * 2};
+  cuuint32_t box[5] = {(cuuint32_t)kc, (cuuint32_t)(2 * bw), (cuuint32_t)(2 * bh), 1, 1};
+  cuuint32_t estr[5] = {1, 2, 2, 1, 1};
+  CUresult r = enc(tm, B200_TMAP_DTYPE, 5, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle_for_row_bytes(kc * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B200_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(stride-2 plane %dx%dx%dx%dx%d) failed: %d", N, D, H, W, C, (int)r);
+  return 0;
+}
+
 // plain (tap-loop) kernel launch over the tile domain (D,H,W) = the OUTPUT lattice the CTAs enumerate
 static int conv_igemm_plain_launch(const void* x, const void* wf, int n_w, const float* biascls, int n_b, const void* residual, int act,
                                    float slope, int N, int D, int H, int W, int Cin, int Cout, void* y, int pmode, const void* aux,
@@ -436,34 +451,6 @@ int b200_conv3_igemm_fwd(const void* x, const void* wf, int n_w, const float* bi
                                  (cudaStream_t)s);
 }
 
-// ---- dgrad with the GroupNorm backward of the conv's INPUT fused into the epilogue (z-stacked kernel only):
-//   out = (A * conv(dz, wd) + B * x + C) * act'(x) [+ gadd],  coef [N][Cin][3] = (A, B, C) from b200_gn_bwd_coeffs;
-//   partials [N][P][Cin][2] of out (P = b200_conv3_igemm_partials_count(N,D,H,W,Cout,Cin)): column 0 = per-channel totals, which
-//   b200_border_tap_sums_pre takes instead of re-reading the tensor.  Replaces b200_conv3_fwd(dgrad) + b200_gn_bwd_apply.
-int b200_conv3_dgrad_gnbwd_supported(int N, int D, int H, int W, int Cout, int Cin) {
-  ConvParams p;
-  return (b200_device_is_sm100() && conv_zs_plan(N, D, H, W, Cout, Cin, &p)) ? 1 : 0;
-}
-int b200_conv3_dgrad_gnbwd(const void* dz, const void* wd, int N, int D, int H, int W, int Cout, int Cin, const float* coef, const void* x,
-                           int x_act, float x_slope, const void* gadd, void* out, float* partials, b200_stream_t s) {
-  ConvParams p;
-  B200_CHECK_ARG(conv_zs_plan(N, D, H, W, Cout, Cin, &p), "conv3_dgrad_gnbwd: shape not taken by the z-stacked kernel N=%d %dx%dx%d %d->%d", N, D,
-                 H, W, Cout, Cin);
-  B200_CHECK_ARG(coef && x && out, "conv3_dgrad_gnbwd: coef, x and out are required");
-  p.n_w = 1;
-  p.n_b = 0;
-  p.act = B200_ACT_NONE;
-  p.pmode = partials ? 1 : 0;
-  p.gn_coef = coef;
-  p.aux = (const bf16*)x;
-  p.aux_act = x_act;
-  p.aux_slope = x_slope;
-  p.residual = (const bf16*)gadd;
-  p.y = (bf16*)out;
-  p.partials = partials;
-  return conv_zs_launch(dz, wd, p, (cudaStream_t)s);
-}
-
 // ---- conv3x3x3 over a nearest-2x-upsampled tensor WITHOUT materialising it (decoder concat path, buildingblocks.py:493 + :575).
 // Output parity phase p (per axis) of conv3(up(b)) is a 2x2x2 convolution of the low-res b with phase-specific summed weights:
 //   p = 0: low-res offsets {-1, 0} carry taps {-1}, {0,+1};   p = 1: offsets {0, +1} carry taps {-1,0}, {+1}
@@ -504,6 +491,15 @@ int b200_conv3_up_phase_fwd(const void* b, const void* wp, int n_w, int N, int d
 }
 // transpose of the above: d b[u] = sum over the 4x4x4 offsets e in {-1..2}^3 of Wd[e] dz[2u+e]  (stride-2 reads of dz through an
 // element-stride-2 tensor map).  wd: bf16 [64][C1][Cout].
+// z-stacked version (updzs_sm100.cu): needs a scratch of 4 partial gradients [4][N][d][h][w][C1] (16-bit)
+int b200_conv3_up_dgrad_zs_supported(int N, int d, int h, int w, int Cout, int C1) {
+  return (b200_device_is_sm100() && conv3_updzs_supported(N, d, h, w, Cout, C1)) ? 1 : 0;
+}
+int b200_conv3_up_dgrad_zs(const void* dz, const void* wd, int N, int d, int h, int w, int Cout, int C1, void* parts, void* dxb, b200_stream_t s) {
+  const int rc = conv3_updzs_run(dz, wd, N, d, h, w, Cout, C1, parts, dxb, (cudaStream_t)s);
+  B200_CHECK_ARG(rc >= 0, "conv3_up_dgrad_zs: shape not taken N=%d %dx%dx%d Cout=%d C1=%d", N, d, h, w, Cout, C1);
+  return rc;
+}
 int b200_conv3_up_dgrad(const void* dz, const void* wd, int N, int d, int h, int w, int Cout, int C1, void* dxb, b200_stream_t s) {
   B200_CHECK_ARG(b200_conv3_up_supported(N, d, h, w, C1, Cout), "conv3_up_dgrad: unsupported N=%d %dx%dx%d C1=%d Cout=%d", N, d, h, w, C1,
                  Cout);

@@ -87,11 +87,6 @@ conv3_zs_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
       const int cls = ((v & 4 ? 3 : 1) << 4) | ((v & 2 ? 3 : 1) << 2) | (v & 1 ? 3 : 1);
       bias_interior[i] = p.biascls[((size_t)(p.n_b > 1 ? n : 0) * 64 + cls) * p.Cout + n0 + c];
     }
-  if (p.gn_coef)  // (no bias table in this mode: the region holds the GroupNorm-backward coefficients [3][NT] of this sample)
-    for (int i = threadIdx.x; i < 3 * p.NT; i += ZS_THREADS) {
-      const int k = i / p.NT, c = i - k * p.NT;
-      bias_interior[i] = p.gn_coef[((size_t)n * p.Cout + n0 + c) * 3 + k];
-    }
   for (int i = threadIdx.x; i < 8 * p.NT * 2; i += ZS_THREADS) stat_acc[i] = 0.f;
   tc_fence_before();
   __syncthreads();
@@ -313,30 +308,7 @@ conv3_zs_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = i < cw ? __uint_as_float(raw[i]) : 0.f;
           const size_t goff = vox_off * p.Cout + n0 + c0;
-          if (valid && p.gn_coef) {
-            // GroupNorm backward fused into the dgrad epilogue: dx = (A*dxhat + B*x + C) * act'(x) [+ gadd]  (b200_gn_bwd_apply's contract,
-            // on the fp32 accumulator instead of a bf16 round trip through HBM)
-            const bf16x8* xp = reinterpret_cast<const bf16x8*>(p.aux + goff);
-            const float* cA = bias_interior + c0, *cB = cA + NT, *cC = cB + NT;
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              if (8 * i < cw) {
-                float f[8], ga[8];
-                unpack8(xp[i], f);
-                if (p.residual) unpack8(reinterpret_cast<const bf16x8*>(p.residual + goff)[i], ga);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  const int c = 8 * i + j;
-                  float g = (cA[c] * v[c] + cB[c] * f[j] + cC[c]) * act_grad_from_out(f[j], p.aux_act, p.aux_slope);
-                  if (p.residual) g += ga[j];
-                  v[c] = bf16_round(g);
-                }
-              }
-            bf16x8* op = reinterpret_cast<bf16x8*>(p.y + goff);
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              if (8 * i < cw) op[i] = pack8(&v[8 * i]);
-          } else if (valid) {
+          if (valid) {
             if (bias_row) {
               const float4* bp = reinterpret_cast<const float4*>(bias_row + c0);
 #pragma unroll

@@ -397,13 +397,17 @@ __global__ void gn_bwd_coeffs_kernel(const double* __restrict__ sums2, const flo
 }
 
 // out = (A*dxhat + B*x + Cc) * act'(x) [+ gadd]; grid (P, N).  gadd: gradient already in dz form (same shape), may alias out
+template <bool STATS>
 __global__ void gn_bwd_apply_kernel(const bf16* __restrict__ dxhat, const bf16* __restrict__ x, const float* __restrict__ coef,
-                                    int C, long long voxels, int P, int act, float slope, const bf16* gadd, bf16* out) {
+                                    int C, long long voxels, int P, int act, float slope, const bf16* gadd, bf16* out,
+                                    float* __restrict__ partials) {
+  extern __shared__ float red[];
   int p = blockIdx.x, n = blockIdx.y;
   EwMap m = ew_map(C);
   long long v0, v1;
   ew_range(voxels, p, P, v0, v1);
-  if (!m.active) return;
+  float s[8] = {0}, q[8] = {0};
+  if (m.active) {
   float A[8], B[8], Cc[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -424,10 +428,16 @@ __global__ void gn_bwd_apply_kernel(const bf16* __restrict__ dxhat, const bf16* 
     for (int i = 0; i < 8; ++i) {
       float g = (A[i] * d[i] + B[i] * f[i] + Cc[i]) * act_grad_from_out(f[i], act, slope);
       if (gadd) g += ga[i];
-      d[i] = g;
+      d[i] = STATS ? bf16_round(g) : g;
+      if (STATS) {
+        s[i] += d[i];
+        q[i] += d[i] * d[i];
+      }
     }
     op[v * m.CG + m.cg] = pack8(d);
   }
+  }
+  if (STATS) ew_write_partials(s, q, m, partials + ((size_t)n * P + p) * C * 2, red);
 }
 
 // out = g[..., g_co : g_co + C] * act'(y) [+ gadd]; g has channel stride g_cs; gadd (dz form, contiguous) may alias out
@@ -1171,9 +1181,19 @@ int b200_gn_bwd_apply(const void* dxhat, const void* x, const float* coef, int N
   B200_CHECK_ARG(C % 8 == 0 && C <= 2048, "gn_bwd_apply: C=%d must be a multiple of 8", C);
   int P = ew_blocks(voxels, C);
   dim3 grid(P, N);
-  gn_bwd_apply_kernel<<<grid, EW_THREADS, 0, ST(s)>>>((const bf16*)dxhat, (const bf16*)x, coef, C, voxels, P, act, slope,
-                                                      (const bf16*)gadd, (bf16*)out);
+  gn_bwd_apply_kernel<false><<<grid, EW_THREADS, 0, ST(s)>>>((const bf16*)dxhat, (const bf16*)x, coef, C, voxels, P, act, slope,
+                                                             (const bf16*)gadd, (bf16*)out, nullptr);
   B200_CHECK_LAUNCH("gn_bwd_apply");
+  return 0;
+}
+int b200_gn_bwd_apply_stats(const void* dxhat, const void* x, const float* coef, int N, int C, long long voxels, int act, float slope,
+                            const void* gadd, void* out, float* partials, b200_stream_t s) {
+  B200_CHECK_ARG(C % 8 == 0 && C <= 2048 && partials, "gn_bwd_apply_stats: C=%d must be a multiple of 8, partials required", C);
+  int P = ew_blocks(voxels, C);  // == b200_stats_partials_count
+  dim3 grid(P, N);
+  gn_bwd_apply_kernel<true><<<grid, EW_THREADS, EW_THREADS * 16 * sizeof(float), ST(s)>>>((const bf16*)dxhat, (const bf16*)x, coef, C, voxels, P,
+                                                                                        act, slope, (const bf16*)gadd, (bf16*)out, partials);
+  B200_CHECK_LAUNCH("gn_bwd_apply_stats");
   return 0;
 }
 

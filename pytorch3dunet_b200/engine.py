@@ -33,13 +33,13 @@ _ACT_OF = {"r": (ACT_RELU, 0.0), "l": (ACT_LEAKY, 0.01), "e": (ACT_ELU, 1.0)}
 DEBUG = None   # dict: when set, backward closures stash clones of their intermediates (tools/debug_block.py)
 TIMING = None
 VIRTUAL_CAT = os.environ.get("B200UNET_NO_VIRTUAL_CAT", "0") != "1"  # decoder concat without the concatenated tensor
-FUSED_GN_BWD = os.environ.get("B200UNET_FUSED_GN_BWD", "1") != "0"   # GroupNorm backward as the dgrad kernel's epilogue (z-stacked layers)
 DECONV_PHASES = os.environ.get("B200UNET_DECONV_PHASES", "1") != "0"  # transposed conv by output parity phases (exact 2x joins)
 EXPLICIT_GN = os.environ.get("B200UNET_EXPLICIT_GN", "1") != "0"      # deep levels: GroupNorm as its own pass instead of per-sample weights
 EXPLICIT_GN_VOX_PER_COUT = 40
 PMODE_PHASE_BIAS = 0x100  # B200_PMODE_PHASE_BIAS (include/b200unet.h)
 HOST_PROF = None  # dict name -> [calls, seconds] when host profiling is on
-TIMED = {"b200_conv3_fwd", "b200_conv3_wgrad", "b200_conv3_up_phase_fwd", "b200_conv3_up_dgrad", "b200_conv3_up_wgrad",
+TIMED = {"b200_conv3_fwd", "b200_conv3_wgrad", "b200_conv3_up_phase_fwd", "b200_conv3_up_dgrad", "b200_conv3_up_dgrad_zs", "b200_conv3_up_wgrad",
+
          "b200_pointwise_tc_fwd", "b200_pointwise_tc_wgrad", "b200_deconv_phase_fwd", "b200_deconv_phase_dgrad", "b200_deconv_phase_wgrad"}
 
 
@@ -235,7 +235,7 @@ class Engine:
 
     def border_tap_sums(self, out, dz, n, d, h, w, cout):
         """T[n][tap][co] = sum of dz over the voxels whose tap is in bounds; the per-channel totals come from the kernel that produced dz
-        when it emitted them (fused dgrad + GroupNorm-backward epilogue), else from one more pass over dz"""
+        when it emitted them (b200_gn_bwd_apply_stats), else from one more pass over dz"""
         L = self.L
         T = self.empty((n, 27, cout), torch.float32)
         scratch = self.empty((L.query("b200_border_tap_sums_workspace", n, d, h, w, cout),), torch.float32)
@@ -246,21 +246,14 @@ class Engine:
             self.call("b200_border_tap_sums", _p(dz), n, d, h, w, cout, _p(T), _p(scratch), launches=5)
         return T
 
-    def dgrad_gn_bwd(self, dz, wd, coef, x, n, d, h, w, cout, cin, name):
-        """x.grad = (A * dgrad(dz) + B * x + C) * act'(x) [+ x.grad]: on the layers the z-stacked kernel takes, the GroupNorm backward is the
-        dgrad kernel's epilogue (no dxhat round trip through HBM) and the kernel emits the totals of what it wrote; returns False when
-        the shape is not taken (the caller runs dgrad + b200_gn_bwd_apply)."""
-        L = self.L
-        if not (FUSED_GN_BWD and self.impl != IMPL_DIRECT and L.query("b200_conv3_dgrad_gnbwd_supported", n, d, h, w, cout, cin)):
-            return False
-        P = L.query("b200_conv3_igemm_partials_count", n, d, h, w, cout, cin)
-        parts = self.empty((n, P, cin, 2), torch.float32)
-        dx = self.empty((n, d, h, w, cin), self.adt)
-        self.call("b200_conv3_dgrad_gnbwd", _p(dz), _p(wd), n, d, h, w, cout, cin, _p(coef), _p(x.t), x.act, float(x.slope), _p(x.grad), _p(dx),
-                  _p(parts), flops=2.0 * n * d * h * w * 27 * cin * cout, tag="dgrad_tc", layer=name)
-        x.grad = dx
-        x.grad_partials = (parts, P, dx)
-        return True
+    def gn_bwd_apply(self, dxhat, x, coef, n, c, vox):
+        """x.grad = (A*dxhat + B*x + C) * act'(x) [+ x.grad], written over dxhat; the kernel also emits the per-channel totals of what it
+        writes, which spares the producer conv's border-tap-sum pass one read of the tensor"""
+        P = self.L.query("b200_stats_partials_count", n, c, vox)
+        parts = self.empty((n, P, c, 2), torch.float32)
+        self.call("b200_gn_bwd_apply_stats", _p(dxhat), _p(x.t), _p(coef), n, c, vox, x.act, float(x.slope), _p(x.grad), _p(dxhat), _p(parts))
+        x.grad = dxhat
+        x.grad_partials = (parts, P, dxhat)
 
     # ---------------------------------------------------------------- input / output layout
     def input_f32(self, x_ncdhw):
@@ -402,9 +395,6 @@ class Engine:
                         raise NotImplementedError("gradient w.r.t. the fp32 network input is not provided by the engine")
                     wd = self.empty((27, cin, cout), self.adt)
                     self.call("b200_prep_dgrad_weights", _p(W), cin, cout, _p(wd))
-                    if coef is not None and self.dgrad_gn_bwd(dz, wd, coef, x, n, d, h, w, cout, cin, name):
-                        out.grad = None
-                        return
                     dimpl = L.query("b200_conv3_resolve_impl", self.impl, n, d, h, w, cout, cin, 0)
                     if dimpl < 0:
                         raise B200Error("tcgen05 dgrad requested but unsupported for this shape")
@@ -413,11 +403,11 @@ class Engine:
                               n, d, h, w, cout, cin, _p(dxhat), 0, None, None, flops=2.0 * n * vox * 27 * cin * cout,
                               tag=("dgrad_tc" if dimpl == IMPL_TCGEN05 else "dgrad_direct"), layer=name)
                     if coef is not None:
-                        self.call("b200_gn_bwd_apply", _p(dxhat), _p(x.t), _p(coef), n, cin, vox, x.act, x.slope,
-                                  _p(x.grad), _p(dxhat))
-                    elif x.act != ACT_NONE or x.grad is not None:
-                        self.call("b200_act_bwd", _p(dxhat), cin, 0, _p(x.t), n, cin, vox, x.act, x.slope, _p(x.grad), _p(dxhat))
-                    x.grad = dxhat
+                        self.gn_bwd_apply(dxhat, x, coef, n, cin, vox)
+                    else:
+                        if x.act != ACT_NONE or x.grad is not None:
+                            self.call("b200_act_bwd", _p(dxhat), cin, 0, _p(x.t), n, cin, vox, x.act, x.slope, _p(x.grad), _p(dxhat))
+                        x.grad = dxhat
                     if DEBUG is not None:
                         DEBUG[name]["dx"] = dxhat.clone()
                 out.grad = None
@@ -539,6 +529,7 @@ class Engine:
                 g = x.grad if x.grad is not None else self.empty(x.t.shape, self.adt)
                 self.call(bwd, _p(out.grad), _p(x.t), n, d, h, w, c, x.act, x.slope, _p(x.grad), _p(g))
                 x.grad = g
+                x.grad_partials = None  # (possibly accumulated in place: totals emitted by an earlier writer no longer describe it)
                 out.grad = None
             self.tape.append(backward)
         return out
@@ -646,9 +637,7 @@ class Engine:
                     wd_enc = self.empty((27, c0, cout), self.adt)
                     wd_up = self.empty((64, c1, cout), self.adt)
                     self.call("b200_upcat_prep_dgrad_weights", _p(W), c0, c1, cout, _p(wd_enc), _p(wd_up))
-                if enc.requires_grad and coef is not None and self.dgrad_gn_bwd(dz, wd_enc, coef[:, :c0].contiguous(), enc, n, D, H, Wd, cout, c0, name):
-                    pass
-                elif enc.requires_grad:
+                if enc.requires_grad:
                     dimpl = L.query("b200_conv3_resolve_impl", self.impl, n, D, H, Wd, cout, c0, 0)
                     if dimpl < 0:
                         raise B200Error("tcgen05 dgrad requested but unsupported for this shape")
@@ -657,22 +646,28 @@ class Engine:
                               n, D, H, Wd, cout, c0, _p(ge), 0, None, None, flops=2.0 * n * vox * 27 * c0 * cout,
                               tag=("dgrad_tc" if dimpl == IMPL_TCGEN05 else "dgrad_direct"), layer=name)
                     if coef is not None:
-                        ce = coef[:, :c0].contiguous()
-                        self.call("b200_gn_bwd_apply", _p(ge), _p(enc.t), _p(ce), n, c0, vox, enc.act, enc.slope, _p(enc.grad), _p(ge))
-                    elif enc.act != ACT_NONE or enc.grad is not None:
-                        self.call("b200_act_bwd", _p(ge), c0, 0, _p(enc.t), n, c0, vox, enc.act, enc.slope, _p(enc.grad), _p(ge))
-                    enc.grad = ge
+                        self.gn_bwd_apply(ge, enc, coef[:, :c0].contiguous(), n, c0, vox)
+                    else:
+                        if enc.act != ACT_NONE or enc.grad is not None:
+                            self.call("b200_act_bwd", _p(ge), c0, 0, _p(enc.t), n, c0, vox, enc.act, enc.slope, _p(enc.grad), _p(ge))
+                        enc.grad = ge
                 if low.requires_grad:
                     gl = self.empty(low.t.shape, self.adt)
-                    self.call("b200_conv3_up_dgrad", _p(dz), _p(wd_up), n, d, h, w, cout, c1, _p(gl),
-                              flops=2.0 * n * lvox * 64 * c1 * cout, tag="dgrad_tc", layer=name)
+                    if self.impl != IMPL_DIRECT and L.query("b200_conv3_up_dgrad_zs_supported", n, d, h, w, cout, c1):
+                        parts = self.empty((4,) + tuple(low.t.shape), self.adt)   # one partial gradient per in-plane parity of dz
+                        self.call("b200_conv3_up_dgrad_zs", _p(dz), _p(wd_up), n, d, h, w, cout, c1, _p(parts), _p(gl), launches=2,
+                                  flops=2.0 * n * lvox * 64 * c1 * cout, tag="dgrad_tc", layer=name)
+                        del parts
+                    else:
+                        self.call("b200_conv3_up_dgrad", _p(dz), _p(wd_up), n, d, h, w, cout, c1, _p(gl),
+                                  flops=2.0 * n * lvox * 64 * c1 * cout, tag="dgrad_tc", layer=name)
                     if coef is not None:
                         # d b[u] = sum over its 8 copies of (A dxhat + B x + C) = A sum(dxhat) + 8B b + 8C
-                        cl = (coef[:, c0:] * self._k188).contiguous()
-                        self.call("b200_gn_bwd_apply", _p(gl), _p(low.t), _p(cl), n, c1, lvox, low.act, low.slope, _p(low.grad), _p(gl))
-                    elif low.act != ACT_NONE or low.grad is not None:
-                        self.call("b200_act_bwd", _p(gl), c1, 0, _p(low.t), n, c1, lvox, low.act, low.slope, _p(low.grad), _p(gl))
-                    low.grad = gl
+                        self.gn_bwd_apply(gl, low, (coef[:, c0:] * self._k188).contiguous(), n, c1, lvox)
+                    else:
+                        if low.act != ACT_NONE or low.grad is not None:
+                            self.call("b200_act_bwd", _p(gl), c1, 0, _p(low.t), n, c1, lvox, low.act, low.slope, _p(low.grad), _p(gl))
+                        low.grad = gl
                 out.grad = None
             self.tape.append(backward)
         return out

@@ -163,3 +163,23 @@ def test_zstacked_phase_conv_matches_tap_loop_and_torch(case, monkeypatch):
     assert not torch.isnan(R.float()).any()
     assert U.rel_l2(R, R0.float()) < 4e-3
     assert U.rel_l2(R, ref) < 8e-3
+    # the transpose (gradient w.r.t. the low-res tensor): z-stacked kernel vs the tap-loop one vs autograd
+    monkeypatch.delenv("B200UNET_UPZS")
+    dz = _rand((N, 2 * d, 2 * h, 2 * w, cout), 7)
+    Wfull = torch.cat([torch.zeros((cout, 16, 3, 3, 3), device="cuda"), Wu], 1)   # b200_upcat_prep_dgrad_weights wants (C_out, C0 + C1, 27)
+    wd_enc = torch.empty((27, 16, cout), dtype=torch.bfloat16, device="cuda")
+    wd_up = torch.empty((64, c1, cout), dtype=torch.bfloat16, device="cuda")
+    L.call("b200_upcat_prep_dgrad_weights", U.p(Wfull), 16, c1, cout, U.p(wd_enc), U.p(wd_up), U.stream())
+    assert L.query("b200_conv3_up_dgrad_zs_supported", N, d, h, w, cout, c1)
+    parts = torch.full((4, N, d, h, w, c1), float("nan"), dtype=torch.bfloat16, device="cuda")
+    g1 = torch.full((N, d, h, w, c1), float("nan"), dtype=torch.bfloat16, device="cuda")
+    L.call("b200_conv3_up_dgrad_zs", U.p(dz), U.p(wd_up), N, d, h, w, cout, c1, U.p(parts), U.p(g1), U.stream())
+    g0 = torch.full_like(g1, float("nan"))
+    L.call("b200_conv3_up_dgrad", U.p(dz), U.p(wd_up), N, d, h, w, cout, c1, U.p(g0), U.stream())
+    br = _ncdhw(b).requires_grad_(True)
+    F.conv3d(F.interpolate(br, scale_factor=2, mode="nearest"), Wu, padding=1).backward(_ncdhw(dz))
+    gref = br.grad.permute(0, 2, 3, 4, 1)
+    print("updzs", case, "vs tap-loop", U.rel_l2(g1, g0.float()), "vs torch", U.rel_l2(g1, gref))
+    assert not torch.isnan(g1.float()).any()
+    assert U.rel_l2(g1, g0.float()) < 6e-3      # four bf16 partials are rounded before their sum
+    assert U.rel_l2(g1, gref) < 1e-2
