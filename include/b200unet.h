@@ -110,6 +110,10 @@ int b200_border_tap_sums(const void* dz, int N, int D, int H, int W, int C, floa
  * (b200_gn_bwd_apply_stats) */
 int b200_border_tap_sums_pre(const void* dz, int N, int D, int H, int W, int C, const float* tot_partials, int Ptot, float* T, float* scratch,
                              b200_stream_t s);
+/* dW[co][ci][tap] = sum_n ( a[n][ci] * sum_split G + b[n][ci] * T[n][tap][co] ); ab == NULL -> a=1,b=0.
+ * Gsum (optional) [N][27][Cin][Cout] receives sum_split G for b200_gn_bwd_sums_from_wgrad (then called with S = 1) */
+int b200_wgrad_finalize(const float* G, int N, int S, int Cin, int Cout, const float* ab, const float* T,
+                        float* dW, float* Gsum, b200_stream_t s);
 /* bias gradient for convs that have one: db[co] = sum_{n,tap=center...}: simply sum_n,v dz = T[n][13][co] summed */
 int b200_bias_grad_from_T(const float* T, int N, int C, float* db, b200_stream_t s);
 

@@ -124,3 +124,19 @@ def test_planning_entry_points_over_the_model_shapes():
     assert L.query("b200_conv3_resolve_impl", E.IMPL_TCGEN05, 1, 8, 8, 8, 24, 8, 0) < 0
     assert L.query("b200_pointwise_tc_supported", 1, 512, 24, 8) == 0
     assert L.query("b200_conv3_up_supported", 1, 4, 4, 4, 24, 16) == 0
+
+
+def test_engine_only_calls_declared_entry_points():
+    """every `b200_*` name the Python host passes to the C-ABI is declared in include/b200unet.h (a prototype dropped from the header
+    would otherwise only surface on the GPU box)"""
+    import glob
+    import os
+    import re
+    from pytorch3dunet_b200 import _lib
+    protos = set(_lib.parse_header())
+    used = set()
+    root = os.path.dirname(os.path.abspath(_lib.__file__))
+    for f in glob.glob(os.path.join(root, "*.py")):
+        used |= set(re.findall(r'"(b200_\w+)"', open(f).read()))
+    missing = sorted(used - protos)
+    assert not missing, missing
