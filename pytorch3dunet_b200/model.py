@@ -81,8 +81,9 @@ class _EngineFn(torch.autograd.Function):
         ctx.param_meta = [(p.shape, p.dtype) for p in params]
         ctx.set_materialize_grads(False)
         ctx.device = x0.device
-        _STATS.launches_fwd = eng.launches
-        _STATS.tape_len = len(eng.tape)
+        h = _stats_holder()        # this (forward) thread's counters; backward runs on an autograd thread and writes into the same dict
+        h["fwd"], h["bwd"], h["tape"] = eng.launches, 0, len(eng.tape)
+        ctx.stats = h
         return tuple(outs)
 
     @staticmethod
@@ -96,7 +97,7 @@ class _EngineFn(torch.autograd.Function):
             ctx.seed(eng, grad_outs)
             eng.run_backward()
             in_grads = ctx.input_grads(eng)
-            _STATS.launches_bwd = eng.launches - l0
+            ctx.stats["bwd"] = eng.launches - l0
         pg = eng.param_grads
         grads = []
         for (shape, dtype), name in zip(ctx.param_meta, ctx.names):
@@ -109,14 +110,15 @@ class _EngineFn(torch.autograd.Function):
         return (None, None, None, None, None, None) + tuple(in_grads) + tuple(grads)
 
 
-class _Stats(threading.local):
-    """launch counters of the most recent call ON THIS HOST THREAD (nn.DataParallel runs replicas on Python threads)"""
-    launches_fwd = 0
-    launches_bwd = 0
-    tape_len = 0
+_STATS = threading.local()
 
 
-_STATS = _Stats()
+def _stats_holder():
+    """launch counters of the most recent call made FROM THIS HOST THREAD (nn.DataParallel runs replicas on Python threads)"""
+    h = getattr(_STATS, "h", None)
+    if h is None:
+        h = _STATS.h = {"fwd": 0, "bwd": 0, "tape": 0}
+    return h
 
 
 def _named_params(module):
@@ -166,12 +168,13 @@ def operand_options(module):
 
 def last_launch_counts():
     """(forward, backward) number of engine kernels launched by the most recent call (of this host thread)."""
-    return _STATS.launches_fwd, _STATS.launches_bwd
+    h = _stats_holder()
+    return h["fwd"], h["bwd"]
 
 
 def last_tape_length():
     """number of backward closures the most recent forward recorded (0 under torch.no_grad())"""
-    return _STATS.tape_len
+    return _stats_holder()["tape"]
 
 
 # ----------------------------------------------------------------------------------------------------
