@@ -186,6 +186,7 @@ int b200_conv3_direct_partials_count(int N, int D, int H, int W, int Cout);
 int b200_conv3_direct_fwd(const void* x, int x_is_f32, const void* wf, int n_w, const float* biascls, int n_b, const void* residual,
                           int act, float slope, int N, int D, int H, int W, int Cin, int Cout, void* y, int pmode, const void* aux,
                           float* partials, b200_stream_t s);
+int b200_conv3_direct_wgrad_splits(int N, int D, int H, int W, int Cin, int Cout, int x_is_f32);
 int b200_conv3_direct_wgrad(const void* x, int x_is_f32, const void* dz, int N, int D, int H, int W, int Cin, int Cout, float* G,
                             b200_stream_t s);
 int b200_conv3_wgrad_igemm_supported(int N, int D, int H, int W, int Cin, int Cout);

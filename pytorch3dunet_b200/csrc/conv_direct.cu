@@ -339,7 +339,8 @@ __global__ void __launch_bounds__(256, 1) stem_conv_fwd_tiled_kernel(const float
 // stem weight gradient: G[n][0][tap][ci][co] += sum_v dz[v,co] * x[v+tap-1,ci]   (fp32 x, C_in <= 4).
 // Shared-memory tiled: a block walks tiles of 2x8x32 voxels; per tile the fp32 x halo (4x10x34) and the dz tile (as fp32)
 // are staged in shared memory; a thread owns one (dd,dh) tap row x 8 output channels = 24 accumulators (3 dw taps) and
-// strides over the tile's voxels: 2 LDS.128 + 3 LDS per 24 FMA.  One block-level reduction + atomicAdd at the very end.
+// strides over the tile's voxels: 2 LDS.128 + 3 LDS per 24 FMA.  One block-level reduction at the very end into the block's own split slot
+// (no atomics: the weight gradient is bit-reproducible).
 constexpr int SW_TD = 2, SW_TH = 8, SW_TW = 32, SW_VOX = SW_TD * SW_TH * SW_TW;
 constexpr int SW_HD = SW_TD + 2, SW_HH = SW_TH + 2, SW_HW = SW_TW + 2, SW_HALO = SW_HD * SW_HH * SW_HW;
 template <int COUT>
@@ -430,7 +431,8 @@ __global__ void __launch_bounds__(256, 2) stem_wgrad_kernel(const float* __restr
       const int g = i / 24, a = (i % 24) / 8, j = i % 8;
       const int o8 = g % (COUT / 8), tr = g / (COUT / 8);
       const int tap = tr * 3 + a;
-      atomicAdd(&G[(((size_t)n * 27 + tap) * Cin + ci) * COUT + o8 * 8 + j], sum);
+      // one split slot per block (G [N][S = gridDim.x][27][Cin][COUT]): plain stores, summed in a fixed order by b200_wgrad_finalize
+      G[((((size_t)n * gridDim.x + blockIdx.x) * 27 + tap) * Cin + ci) * COUT + o8 * 8 + j] = sum;
     }
   }
 }
@@ -491,19 +493,31 @@ int b200_conv3_direct_fwd(const void* x, int x_is_f32, const void* wf, int n_w, 
   return 0;
 }
 
+static bool stem_wgrad_applies(int x_is_f32, int Cin, int Cout) { return x_is_f32 && Cin <= 4 && (Cout == 8 || Cout == 16 || Cout == 32); }
+static void stem_wgrad_grid(int N, int D, int H, int W, int* blocks, int* tpb_out) {
+  int ntiles = ceil_div(D, SW_TD) * ceil_div(H, SW_TH) * ceil_div(W, SW_TW);
+  const int sms4 = 4 * sm_count();
+  int tpb = ceil_div(ntiles, sms4 / (N > 0 ? N : 1) > 0 ? sms4 / N : 1);  // ~4 blocks per SM in total
+  if (tpb < 1) tpb = 1;
+  *blocks = ceil_div(ntiles, tpb);
+  *tpb_out = tpb;
+}
+// split slots of G the direct wgrad writes: one per block of the fp32-input stem kernel, else 1
+int b200_conv3_direct_wgrad_splits(int N, int D, int H, int W, int Cin, int Cout, int x_is_f32) {
+  if (!stem_wgrad_applies(x_is_f32, Cin, Cout)) return 1;
+  int blocks, tpb;
+  stem_wgrad_grid(N, D, H, W, &blocks, &tpb);
+  return blocks;
+}
+
 int b200_conv3_direct_wgrad(const void* x, int x_is_f32, const void* dz, int N, int D, int H, int W, int Cin, int Cout, float* G,
                             b200_stream_t s) {
-  size_t bytes = (size_t)N * 27 * Cin * Cout * sizeof(float);
-  cudaError_t e = cudaMemsetAsync(G, 0, bytes, ST(s));
-  B200_CHECK_ARG(e == cudaSuccess, "conv3_direct_wgrad: memset failed: %s", cudaGetErrorString(e));
   long long vox = (long long)D * H * W;
   int total = 27 * Cin * Cout;
-  if (x_is_f32 && Cin <= 4 && (Cout == 8 || Cout == 16 || Cout == 32)) {
-    int ntiles = ceil_div(D, SW_TD) * ceil_div(H, SW_TH) * ceil_div(W, SW_TW);
-    const int sms4 = 4 * sm_count();
-    int tpb = ceil_div(ntiles, sms4 / (N > 0 ? N : 1) > 0 ? sms4 / N : 1);  // ~4 blocks per SM in total
-    if (tpb < 1) tpb = 1;
-    dim3 g2(ceil_div(ntiles, tpb), N);
+  if (stem_wgrad_applies(x_is_f32, Cin, Cout)) {
+    int blocks, tpb;
+    stem_wgrad_grid(N, D, H, W, &blocks, &tpb);
+    dim3 g2(blocks, N);
     size_t red_floats = (size_t)(256 / (9 * (Cout / 8))) * 9 * (Cout / 8) * 24;
     size_t dz_floats = (size_t)SW_VOX * Cout;
     size_t sm2 = (SW_HALO + (dz_floats > red_floats ? dz_floats : red_floats)) * sizeof(float);
@@ -520,6 +534,9 @@ int b200_conv3_direct_wgrad(const void* x, int x_is_f32, const void* dz, int N, 
     B200_CHECK_LAUNCH("stem_wgrad");
     return 0;
   }
+  size_t bytes = (size_t)N * 27 * Cin * Cout * sizeof(float);
+  cudaError_t e = cudaMemsetAsync(G, 0, bytes, ST(s));
+  B200_CHECK_ARG(e == cudaSuccess, "conv3_direct_wgrad: memset failed: %s", cudaGetErrorString(e));
   dim3 grid(ceil_div(total, 256), N, ceil_div(vox, WG_CHUNK));  // outputs on x (no 65535 limit), voxel chunks on z
   B200_CHECK_ARG(grid.z <= 65535, "conv3_direct_wgrad: volume too large for the fallback kernel (%lld voxels)", vox);
   if (x_is_f32)

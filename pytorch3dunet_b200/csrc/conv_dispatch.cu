@@ -43,7 +43,7 @@ int b200_conv3_wgrad_resolve_impl(int impl, int N, int D, int H, int W, int Cin,
 int b200_conv3_wgrad_splits(int impl, int N, int D, int H, int W, int Cin, int Cout, int x_is_f32) {
   int r = b200_conv3_wgrad_resolve_impl(impl, N, D, H, W, Cin, Cout, x_is_f32);
   if (r == B200_IMPL_TCGEN05) return b200_conv3_wgrad_igemm_splits(N, D, H, W, Cin, Cout);
-  return 1;
+  return b200_conv3_direct_wgrad_splits(N, D, H, W, Cin, Cout, x_is_f32);
 }
 
 int b200_conv3_wgrad(int impl, const void* x, int x_is_f32, const void* dz, int N, int D, int H, int W, int Cin, int Cout, float* G,

@@ -357,7 +357,7 @@ class Engine:
                 S = L.query("b200_conv3_wgrad_splits", wimpl, n, d, h, w, cin, cout, int(is_f32))
                 G = self.empty((n, S, 27, cin, cout), torch.float32)
                 self.call("b200_conv3_wgrad", wimpl, _p(x.t), int(is_f32), _p(dz), n, d, h, w, cin, cout, _p(G),
-                          launches=1 if wimpl == IMPL_TCGEN05 else 2, flops=2.0 * n * vox * 27 * cin * cout,
+                          launches=1 if (wimpl == IMPL_TCGEN05 or S > 1) else 2, flops=2.0 * n * vox * 27 * cin * cout,
                           tag=("wgrad_tc" if wimpl == IMPL_TCGEN05 else "wgrad_direct"), layer=name)
                 dW = torch.empty_like(W) if grad_sink is not None else self.grad_like(name + "conv.weight", W)
                 Gsum = self.empty((n, 1, 27, cin, cout), torch.float32) if gn is not None else None
