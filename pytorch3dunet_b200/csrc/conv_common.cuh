@@ -183,4 +183,10 @@ bool conv3_updzs_supported(int N, int d, int h, int w, int Cout, int C1);
 int conv3_updzs_run(const void* dz, const void* wd, int N, int d, int h, int w, int Cout, int C1, void* parts, void* dxb, cudaStream_t s);
 int conv3_upzs_run(const void* low, const void* wp, int n_w, int N, int d, int h, int w, int C1, int Cout, void* R, cudaStream_t s);
 
+// stem_mma.cu: first conv of the network (C_in == 1, fp32 x) on warp-level MMA
+bool stem_mma_supported(int Cin, int Cout);
+int stem_mma_fwd(const float* x, const bf16* wf, int n_w, const float* biascls, int n_b, int act, float slope, int N, int D, int H, int W,
+                 int Cout, int P, bf16* y, int pmode, float* partials, cudaStream_t s);
+void stem_mma_wgrad_grid(int N, int D, int H, int W, int* blocks, int* tiles_per_block);
+int stem_mma_wgrad(const float* x, const bf16* dz, int N, int D, int H, int W, int Cout, float* G, cudaStream_t s);
 }  // namespace b200

@@ -2,8 +2,10 @@
 //   * the production path for the network stem (C_in < 16: 25 FLOP/B, HBM-bound, no tensor-core shape) and
 //   * the general on-GPU fallback / on-device checker for shapes the tcgen05 kernels do not take
 //     (odd channel counts, tiny spatial sizes).  Same operands and epilogue contract as the tcgen05 kernel.
+#include <cstdlib>
 #include "common.cuh"
 #include "ew.cuh"
+#include "conv_common.cuh"
 
 namespace b200 {
 
@@ -459,6 +461,8 @@ int b200_conv3_direct_fwd(const void* x, int x_is_f32, const void* wf, int n_w, 
   if (x_is_f32 && Cin <= 4 && (Cout == 8 || Cout == 16 || Cout == 32) && !residual && pmode != 2) {
     size_t sm2 = ((size_t)27 * Cin * Cout + 64 * Cout + 8 * Cout * 2) * sizeof(float);
     const float* xf = (const float*)x;
+    if (stem_mma_supported(Cin, Cout) && !getenv("B200UNET_STEM_FMA"))  // warp-level MMA, x split into hi + lo halves
+      return stem_mma_fwd(xf, (const bf16*)wf, n_w, biascls, n_b, act, slope, N, D, H, W, Cout, P, (bf16*)y, pmode, partials, ST(s));
     if (Cin == 1 && W % 4 == 0 && (Cout == 8 || Cout == 16)) {  // register-tiled: 4 voxels per thread
       if (Cout == 8)
         stem_conv_fwd_tiled_kernel<8, 4><<<grid, 256, sm2, ST(s)>>>(xf, (const bf16*)wf, n_w, biascls, n_b, act, slope, D, H, W, P, (bf16*)y, pmode, partials);
@@ -506,7 +510,10 @@ static void stem_wgrad_grid(int N, int D, int H, int W, int* blocks, int* tpb_ou
 int b200_conv3_direct_wgrad_splits(int N, int D, int H, int W, int Cin, int Cout, int x_is_f32) {
   if (!stem_wgrad_applies(x_is_f32, Cin, Cout)) return 1;
   int blocks, tpb;
-  stem_wgrad_grid(N, D, H, W, &blocks, &tpb);
+  if (stem_mma_supported(Cin, Cout) && !getenv("B200UNET_STEM_FMA"))
+    stem_mma_wgrad_grid(N, D, H, W, &blocks, &tpb);
+  else
+    stem_wgrad_grid(N, D, H, W, &blocks, &tpb);
   return blocks;
 }
 
@@ -514,6 +521,8 @@ int b200_conv3_direct_wgrad(const void* x, int x_is_f32, const void* dz, int N, 
                             b200_stream_t s) {
   long long vox = (long long)D * H * W;
   int total = 27 * Cin * Cout;
+  if (x_is_f32 && stem_mma_supported(Cin, Cout) && !getenv("B200UNET_STEM_FMA"))
+    return stem_mma_wgrad((const float*)x, (const bf16*)dz, N, D, H, W, Cout, G, ST(s));
   if (stem_wgrad_applies(x_is_f32, Cin, Cout)) {
     int blocks, tpb;
     stem_wgrad_grid(N, D, H, W, &blocks, &tpb);

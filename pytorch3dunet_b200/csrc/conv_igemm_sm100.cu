@@ -298,6 +298,21 @@ int make_act_tmap_stride2_hw(CUtensorMap* tm, const void* ptr, int N, int D, int
   return 0;
 }
 
+// one plane of an activation sampled with element stride 2 along w only: box of bh lines x bw SAMPLES (wgrad_up_sm100.cu)
+int make_act_tmap_stride2_w(CUtensorMap* tm, const void* ptr, int N, int D, int H, int W, int C, int kc, int bh, int bw) {
+  EncodeTiledFn enc = get_encode_tiled();
+  B200_CHECK_ARG(enc, "cuTensorMapEncodeTiled entry point not available");
+  B200_CHECK_ARG(bh <= 256 && 2 * bw <= 256, "stride-2 box %dx%d too large", bh, bw);
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+  cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2, (cuuint64_t)D * H * W * C * 2};
+  cuuint32_t box[5] = {(cuuint32_t)kc, (cuuint32_t)(2 * bw), (cuuint32_t)bh, 1, 1};
+  cuuint32_t estr[5] = {1, 2, 1, 1, 1};
+  CUresult r = enc(tm, B200_TMAP_DTYPE, 5, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle_for_row_bytes(kc * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B200_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(w-stride-2 plane %dx%dx%dx%dx%d) failed: %d", N, D, H, W, C, (int)r);
+  return 0;
+}
+
 // plain (tap-loop) kernel launch over the tile domain (D,H,W) = the OUTPUT lattice the CTAs enumerate
 static int conv_igemm_plain_launch(const void* x, const void* wf, int n_w, const float* biascls, int n_b, const void* residual, int act,
                                    float slope, int N, int D, int H, int W, int Cin, int Cout, void* y, int pmode, const void* aux,

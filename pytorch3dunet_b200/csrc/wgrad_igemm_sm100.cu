@@ -23,6 +23,8 @@ int make_act_tmap_stride2(CUtensorMap* tm, const void* ptr, int N, int D, int H,
 int choose_box(int D, int H, int W, int* bd, int* bh, int* bw);
 int wgrad_halo_splits(int N, int D, int H, int W, int Cin, int Cout);
 int wgrad_halo_run(const void* x, const void* dz, int N, int D, int H, int W, int Cin, int Cout, int co0, int CoutTotal, float* G, cudaStream_t s);
+int wgrad_up_splits(int N, int d, int h, int w, int Cout, int C1);
+int wgrad_up_run(const void* dz, const void* low, int N, int d, int h, int w, int Cout, int C1, float* Q, cudaStream_t s);
 
 constexpr int WG_THREADS = 192;
 constexpr int WG_MAX_A_STAGES = 8;
@@ -352,6 +354,7 @@ int b200_pointwise_tc_wgrad(const void* x, const void* dy, int N, long long vox,
 //   Q[n][split][e][co][c1] = sum_u dz[n, 2u+e, co] * b[n, u, c1],  e in {-1..2}^3
 // (dW[t] = sum over the parities r of Q[r - t], assembled by b200_upcat_assemble_wgrad).  The strided, shifted operand is dz.
 int b200_conv3_up_wgrad_splits(int N, int d, int h, int w, int Cout, int C1) {
+  if (const int S = wgrad_up_splits(N, d, h, w, Cout, C1)) return S;  // halo + stacked-offset kernel (wgrad_up_sm100.cu)
   if (!wgrad_supported(N, d, h, w, Cout, C1)) return 0;
   WgradParams p;
   wgrad_plan(N, d, h, w, Cout, cout_slice(C1), p, 64);
@@ -372,6 +375,7 @@ int b200_deconv_phase_wgrad(const void* gp, const void* x, int N, int d, int h, 
 int b200_conv3_up_wgrad(const void* dz, const void* b, int N, int d, int h, int w, int Cout, int C1, float* Q, b200_stream_t s) {
   B200_CHECK_ARG(b200_conv3_up_wgrad_splits(N, d, h, w, Cout, C1) > 0, "conv3_up_wgrad: unsupported N=%d %dx%dx%d Cout=%d C1=%d", N, d, h, w,
                  Cout, C1);
+  if (wgrad_up_splits(N, d, h, w, Cout, C1)) return wgrad_up_run(dz, b, N, d, h, w, Cout, C1, Q, (cudaStream_t)s);
   return wgrad_plain_launch(dz, b, N, d, h, w, Cout, C1, Q, 64, (cudaStream_t)s);
 }
 

@@ -36,6 +36,18 @@ VIRTUAL_CAT = os.environ.get("B200UNET_NO_VIRTUAL_CAT", "0") != "1"  # decoder c
 DECONV_PHASES = os.environ.get("B200UNET_DECONV_PHASES", "1") != "0"  # transposed conv by output parity phases (exact 2x joins)
 EXPLICIT_GN = os.environ.get("B200UNET_EXPLICIT_GN", "1") != "0"      # deep levels: GroupNorm as its own pass instead of per-sample weights
 EXPLICIT_GN_VOX_PER_COUT = 40
+# backward: the small reduction kernels that turn a weight gradient into dW / dgamma / dbeta / the GroupNorm-backward coefficients run
+# on a second stream, under the data-gradient convolution of the same layer (which does not depend on them)
+SIDE_STREAM = os.environ.get("B200UNET_SIDE_STREAM", "1") != "0"
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    st = _SIDE_STREAMS.get(key)
+    if st is None:
+        st = _SIDE_STREAMS[key] = torch.cuda.Stream(device=key)
+    return st
 PMODE_PHASE_BIAS = 0x100  # B200_PMODE_PHASE_BIAS (include/b200unet.h)
 HOST_PROF = None  # dict name -> [calls, seconds] when host profiling is on
 TIMED = {"b200_conv3_fwd", "b200_conv3_wgrad", "b200_conv3_up_phase_fwd", "b200_conv3_up_dgrad", "b200_conv3_up_dgrad_zs", "b200_conv3_up_wgrad",
@@ -175,6 +187,31 @@ class Engine:
         else:
             self.L.call(name, *args, self.stream)
         self.launches += launches
+
+    # ---- second stream for the weight-gradient tail (see SIDE_STREAM).  Every buffer the side kernels touch is allocated on the
+    # main stream BEFORE side_begin and outlives side_join, so the caching allocator never hands it out while the side stream uses it.
+    def side_begin(self):
+        if not SIDE_STREAM or DEBUG is not None or HOST_PROF is not None:
+            return False
+        main = torch.cuda.current_stream(self.device)
+        side = _side_stream(self.device)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        side.wait_event(ev)
+        self._main_handle, self.stream = self.stream, side.cuda_stream
+        return True
+
+    def side_end(self, on):
+        if not on:
+            return None
+        self.stream = self._main_handle
+        ev = torch.cuda.Event()
+        ev.record(_side_stream(self.device))
+        return ev
+
+    def side_join(self, ev):
+        if ev is not None:
+            torch.cuda.current_stream(self.device).wait_event(ev)
 
     def grad_like(self, name, like):
         """output buffer for the gradient of parameter `name`: its slot in the flat gradient buffer when there is one"""
@@ -361,25 +398,36 @@ class Engine:
                           tag=("wgrad_tc" if wimpl == IMPL_TCGEN05 else "wgrad_direct"), layer=name)
                 dW = torch.empty_like(W) if grad_sink is not None else self.grad_like(name + "conv.weight", W)
                 Gsum = self.empty((n, 1, 27, cin, cout), torch.float32) if gn is not None else None
-                self.call("b200_wgrad_finalize", _p(G), n, S, cin, cout, _p(ab), _p(T) if ab is not None else None, _p(dW), _p(Gsum))
-                if grad_sink is not None:
-                    grad_sink(dW)  # the weight is a derived tensor (e.g. the conv form of a ConvTranspose3d weight)
-                else:
-                    self._add_param_grad(name + "conv.weight", dW)
-                if bias is not None:
-                    db = torch.empty_like(bias)
-                    self.call("b200_bias_grad_from_T", _p(T), n, cout, _p(db))
-                    self._add_param_grad(name + "conv.bias", db)
+                db = torch.empty_like(bias) if bias is not None else None
                 coef = None
                 if gn is not None:
                     sums2 = self.empty((n, cin, 2), torch.float64)
-                    self.call("b200_gn_bwd_sums_from_wgrad", _p(Gsum), 1, _p(T), _p(W), n, cin, cout, _p(sums2))
                     coef = self.empty((n, cin, 3), torch.float32)
                     dgamma, dbeta = torch.empty_like(gamma), torch.empty_like(beta)
+                on_side = self.side_begin()
+                self.call("b200_wgrad_finalize", _p(G), n, S, cin, cout, _p(ab), _p(T) if ab is not None else None, _p(dW), _p(Gsum))
+                if bias is not None:
+                    self.call("b200_bias_grad_from_T", _p(T), n, cout, _p(db))
+                if gn is not None:
+                    self.call("b200_gn_bwd_sums_from_wgrad", _p(Gsum), 1, _p(T), _p(W), n, cin, cout, _p(sums2))
                     self.call("b200_gn_bwd_coeffs", _p(sums2), _p(gamma), _p(mean_rstd), groups, float(vox), n, cin,
                               _p(coef), _p(dgamma), _p(dbeta))
-                    self._add_param_grad(gn[3], dgamma)
-                    self._add_param_grad(gn[4], dbeta)
+                tail = self.side_end(on_side)
+
+                def publish():  # main stream, after the join: hand the finished parameter gradients over
+                    if grad_sink is not None:
+                        grad_sink(dW)  # the weight is a derived tensor (e.g. the conv form of a ConvTranspose3d weight)
+                    else:
+                        self._add_param_grad(name + "conv.weight", dW)
+                    if bias is not None:
+                        self._add_param_grad(name + "conv.bias", db)
+                    if gn is not None:
+                        self._add_param_grad(gn[3], dgamma)
+                        self._add_param_grad(gn[4], dbeta)
+                published = not x.requires_grad or DEBUG is not None
+                if published:
+                    self.side_join(tail)
+                    publish()
                 if DEBUG is not None:
                     DEBUG[name] = dict(dz=dz.clone(), T=None if T is None else T.clone(), G=G.clone(), dW=dW.clone(),
                                        ab=None if ab is None else ab.clone(), x=x.t.clone(), y=out.t.clone(),
@@ -402,6 +450,9 @@ class Engine:
                     self.call("b200_conv3_fwd", dimpl, _p(dz), 0, _p(wd), 1, None, 0, None, ACT_NONE, 0.0,
                               n, d, h, w, cout, cin, _p(dxhat), 0, None, None, flops=2.0 * n * vox * 27 * cin * cout,
                               tag=("dgrad_tc" if dimpl == IMPL_TCGEN05 else "dgrad_direct"), layer=name)
+                    if not published:
+                        self.side_join(tail)
+                        publish()
                     if coef is not None:
                         self.gn_bwd_apply(dxhat, x, coef, n, cin, vox)
                     else:
@@ -614,25 +665,33 @@ class Engine:
                 self.call("b200_conv3_up_wgrad", _p(dz), _p(low.t), n, d, h, w, cout, c1, _p(Q),
                           flops=2.0 * n * lvox * 64 * c1 * cout, tag="wgrad_tc", layer=name)
                 G = self.empty((n, 1, 27, C, cout), torch.float32)
-                self.call("b200_upcat_assemble_wgrad", _p(G_enc), S1, _p(Q), S2, n, c0, c1, cout, _p(G))
                 dW = self.grad_like(name + "conv.weight", W)
                 Gsum = self.empty((n, 1, 27, C, cout), torch.float32) if gn is not None else None
-                self.call("b200_wgrad_finalize", _p(G), n, 1, C, cout, _p(ab), _p(T) if ab is not None else None, _p(dW), _p(Gsum))
-                self._add_param_grad(name + "conv.weight", dW)
-                if bias is not None:
-                    db = torch.empty_like(bias)
-                    self.call("b200_bias_grad_from_T", _p(T), n, cout, _p(db))
-                    self._add_param_grad(name + "conv.bias", db)
+                db = torch.empty_like(bias) if bias is not None else None
                 coef = None
                 if gn is not None:
                     sums2 = self.empty((n, C, 2), torch.float64)
-                    self.call("b200_gn_bwd_sums_from_wgrad", _p(Gsum), 1, _p(T), _p(W), n, C, cout, _p(sums2))
                     coef = self.empty((n, C, 3), torch.float32)
                     dgamma, dbeta = torch.empty_like(gamma), torch.empty_like(beta)
+                on_side = self.side_begin()   # the reductions below run under the two data-gradient convolutions
+                self.call("b200_upcat_assemble_wgrad", _p(G_enc), S1, _p(Q), S2, n, c0, c1, cout, _p(G))
+                self.call("b200_wgrad_finalize", _p(G), n, 1, C, cout, _p(ab), _p(T) if ab is not None else None, _p(dW), _p(Gsum))
+                if bias is not None:
+                    self.call("b200_bias_grad_from_T", _p(T), n, cout, _p(db))
+                if gn is not None:
+                    self.call("b200_gn_bwd_sums_from_wgrad", _p(Gsum), 1, _p(T), _p(W), n, C, cout, _p(sums2))
                     self.call("b200_gn_bwd_coeffs", _p(sums2), _p(gamma), _p(mean_rstd), groups, float(vox), n, C,
                               _p(coef), _p(dgamma), _p(dbeta))
-                    self._add_param_grad(gn[3], dgamma)
-                    self._add_param_grad(gn[4], dbeta)
+                tail = self.side_end(on_side)
+                published = False
+
+                def publish():
+                    self._add_param_grad(name + "conv.weight", dW)
+                    if bias is not None:
+                        self._add_param_grad(name + "conv.bias", db)
+                    if gn is not None:
+                        self._add_param_grad(gn[3], dgamma)
+                        self._add_param_grad(gn[4], dbeta)
                 if enc.requires_grad or low.requires_grad:
                     wd_enc = self.empty((27, c0, cout), self.adt)
                     wd_up = self.empty((64, c1, cout), self.adt)
@@ -646,6 +705,10 @@ class Engine:
                               n, D, H, Wd, cout, c0, _p(ge), 0, None, None, flops=2.0 * n * vox * 27 * c0 * cout,
                               tag=("dgrad_tc" if dimpl == IMPL_TCGEN05 else "dgrad_direct"), layer=name)
                     if coef is not None:
+                        if not published:
+                            self.side_join(tail)
+                            publish()
+                            published = True
                         self.gn_bwd_apply(ge, enc, coef[:, :c0].contiguous(), n, c0, vox)
                     else:
                         if enc.act != ACT_NONE or enc.grad is not None:
@@ -662,12 +725,19 @@ class Engine:
                         self.call("b200_conv3_up_dgrad", _p(dz), _p(wd_up), n, d, h, w, cout, c1, _p(gl),
                                   flops=2.0 * n * lvox * 64 * c1 * cout, tag="dgrad_tc", layer=name)
                     if coef is not None:
+                        if not published:
+                            self.side_join(tail)
+                            publish()
+                            published = True
                         # d b[u] = sum over its 8 copies of (A dxhat + B x + C) = A sum(dxhat) + 8B b + 8C
                         self.gn_bwd_apply(gl, low, (coef[:, c0:] * self._k188).contiguous(), n, c1, lvox)
                     else:
                         if low.act != ACT_NONE or low.grad is not None:
                             self.call("b200_act_bwd", _p(gl), c1, 0, _p(low.t), n, c1, lvox, low.act, low.slope, _p(low.grad), _p(gl))
                         low.grad = gl
+                if not published:
+                    self.side_join(tail)
+                    publish()
                 out.grad = None
             self.tape.append(backward)
         return out

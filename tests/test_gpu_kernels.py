@@ -229,9 +229,11 @@ def test_probe_umma_row_shifted_swizzled_view(shift, group_rows):
     assert U.rel_l2(D, ref) < 1e-3
 
 
-@pytest.mark.parametrize("shape", [(2, 6, 9, 35, 1, 16), (1, 5, 8, 40, 2, 8), (1, 4, 17, 33, 1, 32), (1, 16, 16, 16, 3, 16)])
+@pytest.mark.parametrize("shape", [(2, 6, 9, 35, 1, 16), (1, 5, 8, 40, 2, 8), (1, 4, 17, 33, 1, 32), (1, 16, 16, 16, 3, 16),
+                                   (1, 3, 5, 70, 1, 8), (2, 7, 20, 64, 1, 16), (1, 2, 8, 8, 1, 32), (1, 1, 1, 1, 1, 16)])
 def test_stem_kernels_fp32_input(shape):
-    """network stem: fp32 NDHWC input with C_in <= 4 (dedicated CUDA-core kernels, HBM-bound)"""
+    """network stem: fp32 NDHWC input with C_in <= 4 (C_in == 1: warp-level MMA with x split into hi + lo halves, stem_mma.cu;
+    C_in 2..4: CUDA-core kernels); both HBM-bound"""
     from tests import gpu_util as U
     from pytorch3dunet_b200 import engine as E
     N, D, H, W, Cin, Cout = shape
@@ -248,3 +250,7 @@ def test_stem_kernels_fp32_input(shape):
     dz = torch.randn((N, D, H, W, Cout), device="cuda", generator=g).bfloat16()
     G = U.run_wgrad(E.IMPL_AUTO, x, dz)
     assert U.rel_l2(G, U.wgrad_contract_ref(x, dz)) < 1e-4
+    # no atomics anywhere on the stem path: bit-reproducible
+    y2, sums2 = U.run_conv3(E.IMPL_AUTO, x, wf, b, act=E.ACT_RELU, want_stats=True)
+    assert torch.equal(y, y2) and torch.equal(sums, sums2)
+    assert torch.equal(G, U.run_wgrad(E.IMPL_AUTO, x, dz))

@@ -28,7 +28,9 @@ def _ncdhw(t):
 
 SHAPES = [((4, 4, 4), 16, 32, 32), ((3, 5, 6), 16, 16, 16), ((8, 8, 8), 32, 64, 32), ((2, 2, 2), 64, 128, 64), ((16, 16, 16), 32, 64, 32),
           # low-res planes large enough (h >= 18, w >= 10) for the z-stacked phase kernel (csrc/upzs_sm100.cu): N = 4*C_out per instruction
-          ((12, 20, 12), 32, 64, 32), ((5, 33, 17), 16, 32, 16), ((9, 18, 10), 16, 128, 64), ((1, 18, 10), 16, 16, 32)]
+          ((12, 20, 12), 32, 64, 32), ((5, 33, 17), 16, 32, 16), ((9, 18, 10), 16, 128, 64), ((1, 18, 10), 16, 16, 32),
+          # c1 % 64 == 0, h >= 17, w >= 10, d >= 2: the stacked-offset weight-gradient kernel (csrc/wgrad_up_sm100.cu); C_out 16 / 128 slices
+          ((6, 34, 16), 32, 64, 16), ((4, 17, 10), 16, 64, 128), ((3, 40, 24), 32, 64, 32)]
 
 
 @pytest.mark.parametrize("small,c0,c1,cout", SHAPES)
@@ -74,6 +76,46 @@ def test_up_phase_fwd_dgrad_wgrad(small, c0, c1, cout):
     dWu = G[:, :, c0:].sum(0).permute(2, 1, 0).reshape(cout, c1, 3, 3, 3)  # [27][c1][co] -> [co][c1][27]
     assert U.rel_l2(dWu, Wu.grad) < 1e-3
     assert float(G[:, :, :c0].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("small,c1,cout", [((12, 20, 12), 64, 32), ((9, 18, 10), 128, 64), ((3, 40, 24), 64, 32), ((4, 17, 10), 64, 128)])
+@pytest.mark.parametrize("splits", [1, 3])
+def test_up_wgrad_stacked_matches_tap_loop(small, c1, cout, splits, monkeypatch):
+    """wgrad_up_kernel (offsets as views, M = 2 w-views x 64 channels, N = 4 h-offsets x C_out) against the tap-loop kernel and fp64"""
+    U, E, L = _ctx()
+    N = 2
+    d, h, w = small
+    b = _rand((N, d, h, w, c1), 21)
+    dz = _rand((N, 2 * d, 2 * h, 2 * w, cout), 22)
+
+    def run():
+        S = L.query("b200_conv3_up_wgrad_splits", N, d, h, w, cout, c1)
+        assert S > 0
+        Q = torch.full((N, S, 64, cout, c1), float("nan"), device="cuda")
+        L.call("b200_conv3_up_wgrad", U.p(dz), U.p(b), N, d, h, w, cout, c1, U.p(Q), U.stream())
+        torch.cuda.synchronize()
+        return Q.double().sum(1), S
+
+    monkeypatch.setenv("B200UNET_WGRAD_SPLITS", str(splits))
+    Q1, S1 = run()
+    assert S1 == splits
+    monkeypatch.delenv("B200UNET_WGRAD_SPLITS")
+    monkeypatch.setenv("B200UNET_UP_WGRAD_HS", "0")
+    Q0, _ = run()
+    # fp64 reference: Q[t] = sum_u dz[2u + t - 1] * b[u]
+    dzp = F.pad(dz.double().permute(0, 4, 1, 2, 3), (1, 2, 1, 2, 1, 2))  # index o + 1
+    bb = b.double()
+    ref = torch.zeros((N, 64, cout, c1), dtype=torch.float64, device="cuda")
+    for td in range(4):
+        for th in range(4):
+            for tw in range(4):
+                sub = dzp[:, :, td:td + 2 * d:2, th:th + 2 * h:2, tw:tw + 2 * w:2]  # dz[2u + t - 1]
+                ref[:, (td * 4 + th) * 4 + tw] = torch.einsum("ncdhw,ndhwk->nck", sub, bb)
+    print("up wgrad", small, c1, cout, splits, "vs fp64", U.rel_l2(Q1, ref), "tap loop vs fp64", U.rel_l2(Q0, ref))
+    assert U.rel_l2(Q1, ref) < 1e-4
+    assert U.rel_l2(Q1, Q0) < 1e-4
+    worst = max(U.rel_l2(Q1[:, t], ref[:, t]) for t in range(64))
+    assert worst < 1e-3, worst
 
 
 @pytest.mark.parametrize("small,c0,c1,cout", SHAPES)
