@@ -145,6 +145,11 @@ int b200_maxpool_partials_count(int N, int D, int H, int W, int C);
 /* dz_full = scatter(dpooled to first argmax of x_full) * act'(x_full) [+ gadd] */
 int b200_maxpool_bwd(const void* dpooled, const void* x_full, int N, int D, int H, int W, int C,
                      int act, float slope, const void* gadd, void* dz_full, b200_stream_t s);
+/* fused with a deferred GroupNorm backward of another consumer of x: dz = scatter(dpooled)*act'(x) + (A*dxhat + B*x + C)*act'(x); per-channel
+   totals of dz to partials [N][P][C][2], P = b200_maxpool_bwd_partials_count (engine.py maxpool backward) */
+int b200_maxpool_bwd_partials_count(int N, int D, int H, int W, int C);
+int b200_maxpool_bwd_gn(const void* dpooled, const void* x_full, int N, int D, int H, int W, int C, int act, float slope, const void* dxhat,
+                        const float* coef, void* dz_full, float* partials, b200_stream_t s);
 
 /* AvgPool3d(2) (Encoder pool_type='avg', buildingblocks.py:358-363 -> avg_pool3d), floor mode; P = b200_maxpool_partials_count */
 int b200_avgpool_fwd(const void* x, int N, int D, int H, int W, int C, void* y, float* partials, b200_stream_t s);

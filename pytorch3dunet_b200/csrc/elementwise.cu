@@ -509,8 +509,14 @@ __global__ void maxpool_fwd_kernel(const bf16* __restrict__ x, int D, int H, int
 }
 
 // iterates over 2x2x2 cells of the FULL-resolution grid (ceil), so ragged borders still get gadd*mask (or 0)
+// GN = true: `gadd` holds the RAW data gradient dxhat of another consumer of x (a GroupNorm -> conv whose backward was deferred) and the
+// term added is (A*dxhat + B*x + Cc) * act'(x) (gn_bwd_apply_kernel's formula); the per-channel totals of the 16-bit result go to
+// `partials` [N][P][C][2].  One pass over the tensor instead of two.
+template <bool GN>
 __global__ void maxpool_bwd_kernel(const bf16* __restrict__ dpooled, const bf16* __restrict__ xf, int D, int H, int W, int C, int P,
-                                   int act, float slope, const bf16* gadd, bf16* out) {
+                                   int act, float slope, const bf16* gadd, bf16* out, const float* __restrict__ coef,
+                                   float* __restrict__ partials) {
+  extern __shared__ float red[];
   const int p = blockIdx.x, n = blockIdx.y;
   const int oD = D / 2, oH = H / 2, oW = W / 2;
   const int cD = (D + 1) / 2, cH = (H + 1) / 2, cW = (W + 1) / 2;
@@ -518,7 +524,18 @@ __global__ void maxpool_bwd_kernel(const bf16* __restrict__ dpooled, const bf16*
   const LineMap lm = line_map(m, cW);
   int l0, l1;
   ew_range_i(cD * cH, p, P, l0, l1);
-  if (!lm.active) return;
+  if (!GN && !lm.active) return;
+  float A[8], B[8], Cc[8], ssum[8] = {0}, ssq[8] = {0};
+  if (GN && m.active) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float* cf = coef + ((size_t)n * C + m.cg * 8 + i) * 3;
+      A[i] = cf[0];
+      B[i] = cf[1];
+      Cc[i] = cf[2];
+    }
+  }
+  if (lm.active) {
   const size_t fvox = (size_t)D * H * W;
   const bf16x8* xp = reinterpret_cast<const bf16x8*>(xf + (size_t)n * fvox * C) + m.cg;
   const bf16x8* dp = reinterpret_cast<const bf16x8*>(dpooled + (size_t)n * oD * oH * oW * C) + m.cg;
@@ -568,14 +585,24 @@ __global__ void maxpool_bwd_kernel(const bf16* __restrict__ dpooled, const bf16*
         if (gp) unpack8(gp[iv], ga);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          float t = (pooled && arg[i] == k) ? g[i] * act_grad_from_out(f[i], act, slope) : 0.f;
-          if (gp) t += ga[i];
+          const float da = act_grad_from_out(f[i], act, slope);
+          float t = (pooled && arg[i] == k) ? g[i] * da : 0.f;
+          if (GN) {
+            t += (A[i] * ga[i] + B[i] * f[i] + Cc[i]) * da;
+            t = bf16_round(t);
+            ssum[i] += t;
+            ssq[i] += t * t;
+          } else if (gp) {
+            t += ga[i];
+          }
           o[i] = t;
         }
         op[iv] = pack8(o);
       }
     }
   }
+  }
+  if (GN) ew_write_partials(ssum, ssq, m, partials + ((size_t)n * P + p) * C * 2, red);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1229,9 +1256,24 @@ int b200_maxpool_bwd(const void* dpooled, const void* x_full, int N, int D, int 
   long long cells = (long long)((D + 1) / 2) * ((H + 1) / 2) * ((W + 1) / 2);
   int P = ew_blocks_dense(cells, C);
   dim3 grid(P, N);
-  maxpool_bwd_kernel<<<grid, EW_THREADS, 0, ST(s)>>>((const bf16*)dpooled, (const bf16*)x_full, D, H, W, C, P, act, slope,
-                                                     (const bf16*)gadd, (bf16*)dz_full);
+  maxpool_bwd_kernel<false><<<grid, EW_THREADS, 0, ST(s)>>>((const bf16*)dpooled, (const bf16*)x_full, D, H, W, C, P, act, slope,
+                                                            (const bf16*)gadd, (bf16*)dz_full, nullptr, nullptr);
   B200_CHECK_LAUNCH("maxpool_bwd");
+  return 0;
+}
+int b200_maxpool_bwd_partials_count(int N, int D, int H, int W, int C) {
+  (void)N;
+  return ew_blocks_dense((long long)((D + 1) / 2) * ((H + 1) / 2) * ((W + 1) / 2), C);
+}
+// dz_full = scatter(dpooled) * act'(x) + (A*dxhat + B*x + Cc) * act'(x)  (dz_full may alias dxhat); partials [N][P][C][2] of the result
+int b200_maxpool_bwd_gn(const void* dpooled, const void* x_full, int N, int D, int H, int W, int C, int act, float slope, const void* dxhat,
+                        const float* coef, void* dz_full, float* partials, b200_stream_t s) {
+  B200_CHECK_ARG(C % 8 == 0 && C <= 2048 && dxhat && coef && partials, "maxpool_bwd_gn: C=%d must be a multiple of 8; dxhat, coef, partials required", C);
+  int P = b200_maxpool_bwd_partials_count(N, D, H, W, C);
+  dim3 grid(P, N);
+  maxpool_bwd_kernel<true><<<grid, EW_THREADS, EW_THREADS * 16 * sizeof(float), ST(s)>>>(
+      (const bf16*)dpooled, (const bf16*)x_full, D, H, W, C, P, act, slope, (const bf16*)dxhat, (bf16*)dz_full, coef, partials);
+  B200_CHECK_LAUNCH("maxpool_bwd_gn");
   return 0;
 }
 

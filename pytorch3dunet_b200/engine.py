@@ -39,6 +39,8 @@ EXPLICIT_GN_VOX_PER_COUT = 40
 # backward: the small reduction kernels that turn a weight gradient into dW / dgamma / dbeta / the GroupNorm-backward coefficients run
 # on a second stream, under the data-gradient convolution of the same layer (which does not depend on them)
 SIDE_STREAM = os.environ.get("B200UNET_SIDE_STREAM", "1") != "0"
+# a skip connection's GroupNorm backward into an encoder output is applied INSIDE the max-pool backward of the same tensor (one pass)
+DEFER_GN_BWD = os.environ.get("B200UNET_DEFER_GN_BWD", "1") != "0"
 _SIDE_STREAMS = {}
 
 
@@ -66,9 +68,11 @@ def _p(t):
 class Act:
     """A bf16 NDHWC activation plus what the engine knows about it."""
 
-    __slots__ = ("t", "act", "slope", "partials", "P", "sums", "grad", "requires_grad", "grad_partials")
+    __slots__ = ("t", "act", "slope", "partials", "P", "sums", "_grad", "requires_grad", "grad_partials", "deferred", "pool_pending")
 
     def __init__(self, t, act=ACT_NONE, slope=0.0, partials=None, P=0, requires_grad=True):
+        self.deferred = None      # (dxhat, coef, engine): a GroupNorm backward into this tensor not yet applied (see Engine.defer_gn_bwd)
+        self.pool_pending = False  # a max-pool consumer whose backward has not run yet
         self.t = t
         self.act = act          # activation that produced this tensor (needed for the backward mask)
         self.slope = slope
@@ -78,6 +82,19 @@ class Act:
         self.grad = None        # bf16 NDHWC, gradient w.r.t. the producer's PRE-activation output ("dz form")
         self.grad_partials = None  # (partials [N,P,C,2], P, grad tensor): per-channel totals of `grad` emitted by the kernel that wrote it
         self.requires_grad = requires_grad
+
+    @property
+    def grad(self):
+        if self.deferred is not None:   # some other reader than the max-pool backward came first: apply the deferred term now
+            dxhat, coef, eng = self.deferred
+            self.deferred = None
+            n, d, h, w, c = self.dims
+            eng.gn_bwd_apply(dxhat, self, coef, n, c, d * h * w)
+        return self._grad
+
+    @grad.setter
+    def grad(self, v):
+        self._grad = v
 
     @property
     def dims(self):
@@ -574,8 +591,25 @@ class Engine:
         if DEBUG is not None and kind == "max":
             DEBUG.setdefault("pool", []).append(x.t)
         if self.record:
+            if kind == "max" and isinstance(x, Act):
+                x.pool_pending = True
+
             def backward():
+                if isinstance(x, Act):
+                    x.pool_pending = False
                 if out.grad is None or not x.requires_grad:
+                    return
+                if isinstance(x, Act) and x.deferred is not None and kind == "max":
+                    # the skip connection's GroupNorm backward and the pool scatter in ONE pass; the kernel also emits the channel totals
+                    dxhat, coef, _ = x.deferred
+                    x.deferred = None
+                    PP = self.L.query("b200_maxpool_bwd_partials_count", n, d, h, w, c)
+                    parts = self.empty((n, PP, c, 2), torch.float32)
+                    self.call("b200_maxpool_bwd_gn", _p(out.grad), _p(x.t), n, d, h, w, c, x.act, float(x.slope), _p(dxhat), _p(coef),
+                              _p(dxhat), _p(parts))
+                    x.grad = dxhat
+                    x.grad_partials = (parts, PP, dxhat)
+                    out.grad = None
                     return
                 g = x.grad if x.grad is not None else self.empty(x.t.shape, self.adt)
                 self.call(bwd, _p(out.grad), _p(x.t), n, d, h, w, c, x.act, x.slope, _p(x.grad), _p(g))
@@ -709,7 +743,10 @@ class Engine:
                             self.side_join(tail)
                             publish()
                             published = True
-                        self.gn_bwd_apply(ge, enc, coef[:, :c0].contiguous(), n, c0, vox)
+                        if DEFER_GN_BWD and DEBUG is None and enc.pool_pending and enc.deferred is None and enc._grad is None:
+                            enc.deferred = (ge, coef[:, :c0].contiguous(), self)   # applied by the max-pool backward of enc
+                        else:
+                            self.gn_bwd_apply(ge, enc, coef[:, :c0].contiguous(), n, c0, vox)
                     else:
                         if enc.act != ACT_NONE or enc.grad is not None:
                             self.call("b200_act_bwd", _p(ge), c0, 0, _p(enc.t), n, c0, vox, enc.act, enc.slope, _p(enc.grad), _p(ge))

@@ -169,6 +169,33 @@ def test_maxpool_fwd_bwd(dims):
     assert U.rel_l2(out, ref) < 5e-3
 
 
+@pytest.mark.parametrize("dims", [(8, 8, 8), (5, 9, 7), (16, 12, 20)])
+def test_maxpool_bwd_fused_with_deferred_groupnorm_backward(dims):
+    """b200_maxpool_bwd_gn == b200_gn_bwd_apply followed by b200_maxpool_bwd (+ the channel totals of the result), in place over dxhat"""
+    U, E, L = _ctx()
+    N, C = 2, 32
+    D, H, W = dims
+    x = F.relu(_rand((N, D, H, W, C), 21).float()).bfloat16()
+    dxhat = _rand((N, D, H, W, C), 22)
+    coef = (torch.randn((N, C, 3), device="cuda", generator=torch.Generator(device="cuda").manual_seed(23)) * 0.5).contiguous()
+    dp = _rand((N, D // 2, H // 2, W // 2, C), 24)
+    vox = D * H * W
+    tmp = torch.empty_like(x)
+    L.call("b200_gn_bwd_apply", U.p(dxhat), U.p(x), U.p(coef), N, C, vox, E.ACT_RELU, 0.0, None, U.p(tmp), U.stream())
+    ref = torch.empty_like(x)
+    L.call("b200_maxpool_bwd", U.p(dp), U.p(x), N, D, H, W, C, E.ACT_RELU, 0.0, U.p(tmp), U.p(ref), U.stream())
+    P = L.query("b200_maxpool_bwd_partials_count", N, D, H, W, C)
+    parts = torch.full((N, P, C, 2), float("nan"), device="cuda")
+    out = dxhat.clone()
+    L.call("b200_maxpool_bwd_gn", U.p(dp), U.p(x), N, D, H, W, C, E.ACT_RELU, 0.0, U.p(out), U.p(coef), U.p(out), U.p(parts), U.stream())
+    torch.cuda.synchronize()
+    # the two-pass route rounds the GroupNorm term to 16 bits before the scatter is added; the fused one rounds once
+    assert U.rel_l2(out, ref) < 4e-3
+    od = out.double()
+    assert U.rel_l2(parts.double().sum(1)[..., 0], od.sum((1, 2, 3))) < 1e-5
+    assert U.rel_l2(parts.double().sum(1)[..., 1], (od * od).sum((1, 2, 3))) < 1e-5
+
+
 @pytest.mark.parametrize("dims", [((8, 8, 8), (4, 4, 4)), ((5, 9, 7), (2, 4, 3)), ((3, 3, 3), (1, 1, 1))])
 def test_upcat_fwd_bwd(dims):
     U, E, L = _ctx()
