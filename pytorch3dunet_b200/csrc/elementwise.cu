@@ -6,6 +6,7 @@
 
 #include <string.h>
 
+#include <stdlib.h>
 #include "common.cuh"
 #include "ew.cuh"
 
@@ -419,22 +420,39 @@ __global__ void gn_bwd_apply_kernel(const bf16* __restrict__ dxhat, const bf16* 
   const bf16x8* dp = reinterpret_cast<const bf16x8*>(dxhat + (size_t)n * voxels * C);
   const bf16x8* xp = reinterpret_cast<const bf16x8*>(x + (size_t)n * voxels * C);
   bf16x8* op = reinterpret_cast<bf16x8*>(out + (size_t)n * voxels * C);
-  for (long long v = v0 + m.vl; v < v1; v += m.VL) {
-    float d[8], f[8], ga[8];
-    unpack8(dp[v * m.CG + m.cg], d);
-    unpack8(xp[v * m.CG + m.cg], f);
-    if (gadd) unpack8(*reinterpret_cast<const bf16x8*>(gadd + ((size_t)n * voxels + v) * C + m.cg * 8), ga);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float g = (A[i] * d[i] + B[i] * f[i] + Cc[i]) * act_grad_from_out(f[i], act, slope);
-      if (gadd) g += ga[i];
-      d[i] = STATS ? bf16_round(g) : g;
-      if (STATS) {
-        s[i] += d[i];
-        q[i] += d[i] * d[i];
-      }
+  const bf16x8* gq = gadd ? reinterpret_cast<const bf16x8*>(gadd + (size_t)n * voxels * C) : nullptr;
+  // two voxels per iteration: 4..6 independent 16-byte loads in flight per thread
+  for (long long v = v0 + m.vl; v < v1; v += 2 * m.VL) {
+    const long long vb = v + m.VL;
+    const bool two = vb < v1;
+    bf16x8 rd[2], rx[2], rg[2];
+    rd[0] = dp[v * m.CG + m.cg];
+    rx[0] = xp[v * m.CG + m.cg];
+    if (gq) rg[0] = gq[v * m.CG + m.cg];
+    if (two) {
+      rd[1] = dp[vb * m.CG + m.cg];
+      rx[1] = xp[vb * m.CG + m.cg];
+      if (gq) rg[1] = gq[vb * m.CG + m.cg];
     }
-    op[v * m.CG + m.cg] = pack8(d);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (u == 1 && !two) break;
+      float d[8], f[8], ga[8];
+      unpack8(rd[u], d);
+      unpack8(rx[u], f);
+      if (gq) unpack8(rg[u], ga);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float g = (A[i] * d[i] + B[i] * f[i] + Cc[i]) * act_grad_from_out(f[i], act, slope);
+        if (gq) g += ga[i];
+        d[i] = STATS ? bf16_round(g) : g;
+        if (STATS) {
+          s[i] += d[i];
+          q[i] += d[i] * d[i];
+        }
+      }
+      op[(u ? vb : v) * m.CG + m.cg] = pack8(d);
+    }
   }
   }
   if (STATS) ew_write_partials(s, q, m, partials + ((size_t)n * P + p) * C * 2, red);
@@ -601,6 +619,116 @@ __global__ void maxpool_bwd_kernel(const bf16* __restrict__ dpooled, const bf16*
       }
     }
   }
+  }
+  if (GN) ew_write_partials(ssum, ssq, m, partials + ((size_t)n * P + p) * C * 2, red);
+}
+
+// Lane-pair variant (C/8 a power of two <= 16): a thread owns the 2x2 (d,h) column of ONE fine w position of a cell, its neighbour
+// lane (xor C/8) the other w position; consecutive lanes read consecutive 16-byte chunks (fully coalesced, half the registers of
+// the one-thread-per-cell kernel above, twice the loads in flight) and the two halves of a cell settle the argmax with one shuffle
+// per channel: larger value wins, on a tie the smaller scan index k = (z, y, x) -- exactly max_pool3d_with_indices' first maximum.
+template <bool GN>
+__global__ void __launch_bounds__(EW_THREADS, 2) maxpool_bwd_pair_kernel(const bf16* __restrict__ dpooled, const bf16* __restrict__ xf, int D, int H, int W,
+                                                                      int C, int P, int act, float slope, const bf16* gadd, bf16* out,
+                                                                      const float* __restrict__ coef, float* __restrict__ partials) {
+  extern __shared__ float red[];
+  const int p = blockIdx.x, n = blockIdx.y;
+  const int oD = D / 2, oH = H / 2, oW = W / 2;
+  const int cD = (D + 1) / 2, cH = (H + 1) / 2, cW = (W + 1) / 2;
+  const int Wf = 2 * cW;  // fine w positions of a cell row (the last one may lie outside the tensor)
+  const EwMap m = ew_map(C);
+  const LineMap lm = line_map(m, Wf);
+  int l0, l1;
+  ew_range_i(cD * cH, p, P, l0, l1);
+  float A[8], B[8], Cc[8], ssum[8] = {0}, ssq[8] = {0};
+  if (GN) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float* cf = coef + ((size_t)n * C + (m.active ? m.cg : 0) * 8 + i) * 3;
+      A[i] = cf[0];
+      B[i] = cf[1];
+      Cc[i] = cf[2];
+    }
+  }
+  const size_t fvox = (size_t)D * H * W;
+  const bf16x8* xp = reinterpret_cast<const bf16x8*>(xf + (size_t)n * fvox * C) + m.cg;
+  const bf16x8* dp = reinterpret_cast<const bf16x8*>(dpooled + (size_t)n * oD * oH * oW * C) + m.cg;
+  const bf16x8* gp = gadd ? reinterpret_cast<const bf16x8*>(gadd + (size_t)n * fvox * C) + m.cg : nullptr;
+  bf16x8* op = reinterpret_cast<bf16x8*>(out + (size_t)n * fvox * C) + m.cg;
+  const bool lane_ok = m.active && lm.active;
+  // uniform trip counts: every lane of a warp reaches the shuffles
+  for (int lb = l0; lb < l1; lb += lm.LPB) {
+    const int l = lb + lm.ls;
+    const int ch = l % cH, cd = l / cH;
+    for (int fb = 0; fb < Wf; fb += lm.lpl) {
+      const int xx = fb + lm.lw, cw = xx >> 1;
+      const bool mine = lane_ok && l < l1 && xx < Wf;
+      const bool pooled = mine && cd < oD && ch < oH && cw < oW;
+      bf16x8 xr[4], gr[4];
+      bool inb[4];
+      const size_t iv0 = (((size_t)(2 * cd) * H + 2 * ch) * W + xx) * m.CG;  // voxel k: + (k>>1) planes + (k&1) lines
+      const size_t dplane = (size_t)H * W * m.CG, dline = (size_t)W * m.CG;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        inb[k] = mine && 2 * cd + (k >> 1) < D && 2 * ch + (k & 1) < H && xx < W;
+        const size_t iv = iv0 + (k >> 1) * dplane + (k & 1) * dline;
+        if (inb[k]) {
+          xr[k] = xp[iv];
+          if (gp) gr[k] = gp[iv];
+        }
+      }
+      float g[8] = {0};
+      if (pooled) unpack8(dp[(((size_t)cd * oH + ch) * oW + cw) * m.CG], g);
+      float mx[8];
+      int arg[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        mx[i] = -INFINITY;
+        arg[i] = 8;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (!inb[k]) continue;
+        float f[8];
+        unpack8(xr[k], f);
+        const int kk = (k << 1) | (xx & 1);  // scan index (z, y, x) of this voxel inside the cell
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (f[i] > mx[i]) {
+            mx[i] = f[i];
+            arg[i] = kk;
+          }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {  // the other w position of the cell
+        const float om = __shfl_xor_sync(0xffffffffu, mx[i], m.CG);
+        const int oa = __shfl_xor_sync(0xffffffffu, arg[i], m.CG);
+        if (om > mx[i] || (om == mx[i] && oa < arg[i])) arg[i] = oa;  // (value itself no longer needed)
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (!inb[k]) continue;
+        const int kk = (k << 1) | (xx & 1);
+        float ga[8], o[8], f[8];
+        unpack8(xr[k], f);
+        if (gp) unpack8(gr[k], ga);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float da = act_grad_from_out(f[i], act, slope);
+          float t = (pooled && arg[i] == kk) ? g[i] * da : 0.f;
+          if (GN) {
+            t += (A[i] * ga[i] + B[i] * f[i] + Cc[i]) * da;
+            t = bf16_round(t);
+            ssum[i] += t;
+            ssq[i] += t * t;
+          } else if (gp) {
+            t += ga[i];
+          }
+          o[i] = t;
+        }
+        op[iv0 + (k >> 1) * dplane + (k & 1) * dline] = pack8(o);
+      }
+    }
   }
   if (GN) ew_write_partials(ssum, ssq, m, partials + ((size_t)n * P + p) * C * 2, red);
 }
@@ -1250,20 +1378,33 @@ int b200_maxpool_fwd(const void* x, int N, int D, int H, int W, int C, void* y, 
   B200_CHECK_LAUNCH("maxpool_fwd");
   return 0;
 }
+// lane-pair kernel: the two w positions of a cell sit C/8 lanes apart in one warp
+static bool maxpool_pair_ok(int C) {
+  const int cg = C / 8;
+  const char* e = getenv("B200UNET_MAXPOOL_PAIR");
+  return (cg & (cg - 1)) == 0 && cg <= 16 && !(e && e[0] == '0');
+}
+static int maxpool_bwd_blocks(int D, int H, int W, int C) {
+  long long cells = (long long)((D + 1) / 2) * ((H + 1) / 2) * ((W + 1) / 2);
+  return maxpool_pair_ok(C) ? ew_blocks_dense(2 * cells, C) : ew_blocks_dense(cells, C);
+}
 int b200_maxpool_bwd(const void* dpooled, const void* x_full, int N, int D, int H, int W, int C, int act, float slope,
                      const void* gadd, void* dz_full, b200_stream_t s) {
   B200_CHECK_ARG(C % 8 == 0 && C <= 2048, "maxpool_bwd: C=%d must be a multiple of 8", C);
-  long long cells = (long long)((D + 1) / 2) * ((H + 1) / 2) * ((W + 1) / 2);
-  int P = ew_blocks_dense(cells, C);
+  int P = maxpool_bwd_blocks(D, H, W, C);
   dim3 grid(P, N);
-  maxpool_bwd_kernel<false><<<grid, EW_THREADS, 0, ST(s)>>>((const bf16*)dpooled, (const bf16*)x_full, D, H, W, C, P, act, slope,
-                                                            (const bf16*)gadd, (bf16*)dz_full, nullptr, nullptr);
+  if (maxpool_pair_ok(C))
+    maxpool_bwd_pair_kernel<false><<<grid, EW_THREADS, 0, ST(s)>>>((const bf16*)dpooled, (const bf16*)x_full, D, H, W, C, P, act, slope,
+                                                                   (const bf16*)gadd, (bf16*)dz_full, nullptr, nullptr);
+  else
+    maxpool_bwd_kernel<false><<<grid, EW_THREADS, 0, ST(s)>>>((const bf16*)dpooled, (const bf16*)x_full, D, H, W, C, P, act, slope,
+                                                              (const bf16*)gadd, (bf16*)dz_full, nullptr, nullptr);
   B200_CHECK_LAUNCH("maxpool_bwd");
   return 0;
 }
 int b200_maxpool_bwd_partials_count(int N, int D, int H, int W, int C) {
   (void)N;
-  return ew_blocks_dense((long long)((D + 1) / 2) * ((H + 1) / 2) * ((W + 1) / 2), C);
+  return maxpool_bwd_blocks(D, H, W, C);
 }
 // dz_full = scatter(dpooled) * act'(x) + (A*dxhat + B*x + Cc) * act'(x)  (dz_full may alias dxhat); partials [N][P][C][2] of the result
 int b200_maxpool_bwd_gn(const void* dpooled, const void* x_full, int N, int D, int H, int W, int C, int act, float slope, const void* dxhat,
@@ -1271,8 +1412,12 @@ int b200_maxpool_bwd_gn(const void* dpooled, const void* x_full, int N, int D, i
   B200_CHECK_ARG(C % 8 == 0 && C <= 2048 && dxhat && coef && partials, "maxpool_bwd_gn: C=%d must be a multiple of 8; dxhat, coef, partials required", C);
   int P = b200_maxpool_bwd_partials_count(N, D, H, W, C);
   dim3 grid(P, N);
-  maxpool_bwd_kernel<true><<<grid, EW_THREADS, EW_THREADS * 16 * sizeof(float), ST(s)>>>(
-      (const bf16*)dpooled, (const bf16*)x_full, D, H, W, C, P, act, slope, (const bf16*)dxhat, (bf16*)dz_full, coef, partials);
+  if (maxpool_pair_ok(C))
+    maxpool_bwd_pair_kernel<true><<<grid, EW_THREADS, EW_THREADS * 16 * sizeof(float), ST(s)>>>(
+        (const bf16*)dpooled, (const bf16*)x_full, D, H, W, C, P, act, slope, (const bf16*)dxhat, (bf16*)dz_full, coef, partials);
+  else
+    maxpool_bwd_kernel<true><<<grid, EW_THREADS, EW_THREADS * 16 * sizeof(float), ST(s)>>>(
+        (const bf16*)dpooled, (const bf16*)x_full, D, H, W, C, P, act, slope, (const bf16*)dxhat, (bf16*)dz_full, coef, partials);
   B200_CHECK_LAUNCH("maxpool_bwd_gn");
   return 0;
 }

@@ -180,11 +180,15 @@ class Engine:
         self.param_grads = {}
         self.launches = 0
         self.stream = torch.cuda.current_stream(device).cuda_stream
+        self._side_keep = None
         self._k188 = _const_188(device)
 
     # ---------------------------------------------------------------- helpers
     def empty(self, shape, dtype):
-        return torch.empty(shape, dtype=dtype, device=self.device)
+        t = torch.empty(shape, dtype=dtype, device=self.device)
+        if self._side_keep is not None:
+            self._side_keep.append(t)  # allocated while side-stream work is outstanding: must not be recycled before the join
+        return t
 
     def call(self, name, *args, launches=1, flops=0.0, tag=None, layer=""):
         if HOST_PROF is not None:  # tools/host_profile.py: host seconds spent inside each C-ABI entry point
@@ -205,8 +209,9 @@ class Engine:
             self.L.call(name, *args, self.stream)
         self.launches += launches
 
-    # ---- second stream for the weight-gradient tail (see SIDE_STREAM).  Every buffer the side kernels touch is allocated on the
-    # main stream BEFORE side_begin and outlives side_join, so the caching allocator never hands it out while the side stream uses it.
+    # ---- second stream for the weight-gradient tail (see SIDE_STREAM).  Every buffer the side kernels touch comes from the main
+    # stream's allocator and is kept alive until side_join (Engine.empty holds a reference while side work is outstanding), so the
+    # caching allocator never hands it out while the side stream uses it.
     def side_begin(self):
         if not SIDE_STREAM or DEBUG is not None or HOST_PROF is not None:
             return False
@@ -216,6 +221,8 @@ class Engine:
         ev.record(main)
         side.wait_event(ev)
         self._main_handle, self.stream = self.stream, side.cuda_stream
+        if self._side_keep is None:
+            self._side_keep = []
         return True
 
     def side_end(self, on):
@@ -229,6 +236,7 @@ class Engine:
     def side_join(self, ev):
         if ev is not None:
             torch.cuda.current_stream(self.device).wait_event(ev)
+        self._side_keep = None   # (frees are now ordered after the wait on the main stream)
 
     def grad_like(self, name, like):
         """output buffer for the gradient of parameter `name`: its slot in the flat gradient buffer when there is one"""
@@ -404,7 +412,11 @@ class Engine:
                 if dz is None:
                     return
                 need_T = gn is not None or bias is not None
-                T = self.border_tap_sums(out, dz, n, d, h, w, cout) if need_T else None
+                T = None
+                if need_T:   # only the reduction tail reads T: computed on the second stream, under the weight-gradient kernel
+                    on_side = self.side_begin()
+                    T = self.border_tap_sums(out, dz, n, d, h, w, cout)
+                    self.side_end(on_side)
                 wimpl = L.query("b200_conv3_wgrad_resolve_impl", self.impl, n, d, h, w, cin, cout, int(is_f32))
                 if wimpl < 0:
                     raise B200Error("tcgen05 wgrad requested but unsupported for this shape")
@@ -689,7 +701,11 @@ class Engine:
                 dz = out.grad
                 if dz is None:
                     return
-                T = self.border_tap_sums(out, dz, n, D, H, Wd, cout) if (gn is not None or bias is not None) else None
+                T = None
+                if gn is not None or bias is not None:
+                    on_side = self.side_begin()
+                    T = self.border_tap_sums(out, dz, n, D, H, Wd, cout)
+                    self.side_end(on_side)
                 S1 = L.query("b200_conv3_wgrad_splits", IMPL_TCGEN05, n, D, H, Wd, c0, cout, 0)
                 G_enc = self.empty((n, S1, 27, c0, cout), torch.float32)
                 self.call("b200_conv3_wgrad", IMPL_TCGEN05, _p(enc.t), 0, _p(dz), n, D, H, Wd, c0, cout, _p(G_enc),

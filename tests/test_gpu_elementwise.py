@@ -169,11 +169,12 @@ def test_maxpool_fwd_bwd(dims):
     assert U.rel_l2(out, ref) < 5e-3
 
 
+@pytest.mark.parametrize("C", [32, 48, 128])   # C/8 a power of two: lane-pair kernel; 48: one thread per cell
 @pytest.mark.parametrize("dims", [(8, 8, 8), (5, 9, 7), (16, 12, 20)])
-def test_maxpool_bwd_fused_with_deferred_groupnorm_backward(dims):
+def test_maxpool_bwd_fused_with_deferred_groupnorm_backward(dims, C, monkeypatch):
     """b200_maxpool_bwd_gn == b200_gn_bwd_apply followed by b200_maxpool_bwd (+ the channel totals of the result), in place over dxhat"""
     U, E, L = _ctx()
-    N, C = 2, 32
+    N = 2
     D, H, W = dims
     x = F.relu(_rand((N, D, H, W, C), 21).float()).bfloat16()
     dxhat = _rand((N, D, H, W, C), 22)
@@ -183,7 +184,12 @@ def test_maxpool_bwd_fused_with_deferred_groupnorm_backward(dims):
     tmp = torch.empty_like(x)
     L.call("b200_gn_bwd_apply", U.p(dxhat), U.p(x), U.p(coef), N, C, vox, E.ACT_RELU, 0.0, None, U.p(tmp), U.stream())
     ref = torch.empty_like(x)
+    monkeypatch.setenv("B200UNET_MAXPOOL_PAIR", "0")   # reference route: the one-thread-per-cell kernel
     L.call("b200_maxpool_bwd", U.p(dp), U.p(x), N, D, H, W, C, E.ACT_RELU, 0.0, U.p(tmp), U.p(ref), U.stream())
+    monkeypatch.delenv("B200UNET_MAXPOOL_PAIR")
+    ref_pair = torch.empty_like(x)
+    L.call("b200_maxpool_bwd", U.p(dp), U.p(x), N, D, H, W, C, E.ACT_RELU, 0.0, U.p(tmp), U.p(ref_pair), U.stream())
+    assert torch.equal(ref, ref_pair)   # same argmax (ties at the ReLU zeros included), same sums
     P = L.query("b200_maxpool_bwd_partials_count", N, D, H, W, C)
     parts = torch.full((N, P, C, 2), float("nan"), device="cuda")
     out = dxhat.clone()

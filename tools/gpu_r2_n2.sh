@@ -1,0 +1,9 @@
+#!/bin/bash
+# 2 GPUs: bucketed allreduce + second-stream backward together (cfg2, cfg3), and the 2-GPU DataParallel test
+mkdir -p gpurun_out
+for wl in cfg2 cfg3; do
+  ( timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus 2 --workload $wl --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-baseline ) > gpurun_out/n2_bench_${wl}.json 2> gpurun_out/n2_bench_${wl}.err
+done
+( timeout 300 python -m pytest tests/test_gpu_options.py -q -x -k "data_parallel or DataParallel or two_gpu" -p no:cacheprovider ) > gpurun_out/n2_dp.log 2>&1
+tail -3 gpurun_out/n2_dp.log
+for f in gpurun_out/n2_bench_*.json; do echo $f; grep '^{' $f | head -c 300; echo; tail -2 ${f%.json}.err; done
