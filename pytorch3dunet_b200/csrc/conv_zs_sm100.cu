@@ -31,8 +31,12 @@
 
 namespace b200 {
 
-template <int KC>
-__global__ void __launch_bounds__(ZS_THREADS, 1)
+// EW = epilogue warpgroups per lane.  One warpgroup (a single warp per SM sub-partition) drains a 128 x 32 plane block in ~3 300 cycles
+// (tcgen05.ld + ~250 dependent ALU instructions + stores, measured with the MMAs switched off: profiles/zs_debug_r02_v4_two_lanes.log),
+// more than the ~1 500 cycles its MMAs take: with EW = 2 the two warpgroups of a lane split every block's COLUMNS in 16-wide slabs
+// (warps w and w+4 may read the same TMEM lane quarter), which halves the per-thread work and the register footprint.
+template <int KC, int EW>
+__global__ void __launch_bounds__((8 * EW + 4) * 32, 1)
 conv3_zs_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, const ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full_[ZS_MAX_STAGES], a_empty_[ZS_MAX_STAGES];   // lane l owns entries [l*S, (l+1)*S)
@@ -43,8 +47,11 @@ conv3_zs_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
   uint8_t* smemB = smem;
   const int b_region = (p.b_total_bytes + 1023) & ~1023;
   uint8_t* smemA = smem + b_region;
-  float* stat_acc = reinterpret_cast<float*>(smemA + (size_t)p.a_stages * p.a_bytes);  // [8 epilogue warps][NT][2]
-  float* bias_interior = stat_acc + 8 * p.NT * 2;                                        // [8 parity variants][NT]
+  constexpr int NEW = 8 * EW;                      // epilogue warps
+  constexpr int THREADS = (NEW + 4) * 32;
+  constexpr int WARP_PRODUCER = NEW, WARP_MMA = NEW + 2;  // two producers, two issuers (lane = (warp - NEW) & 1)
+  float* stat_acc = reinterpret_cast<float*>(smemA + (size_t)p.a_stages * p.a_bytes);  // [NEW epilogue warps][NT][2]
+  float* bias_interior = stat_acc + NEW * p.NT * 2;                                      // [8 parity variants][NT]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = blockIdx.y, cta = blockIdx.x, cps = gridDim.x;
   const int n0 = blockIdx.z * p.NT;  // output-channel slice of this CTA (C_out > NT: the resident weights of NT channels fit, those of C_out do not)
@@ -54,7 +61,7 @@ conv3_zs_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
   const int S = p.a_stages / ZS_LANES;   // halo stages per lane
   const int D = p.D;
   // lane of this warp: epilogue warps 0..3 -> 0, 4..7 -> 1; producer / issuer warps alternate
-  const int lane_id = warp < 8 ? (warp >> 2) : (warp & 1);
+  const int lane_id = warp < NEW ? warp / (4 * EW) : ((warp - NEW) & 1);
   ZsWalk walk = zs_walk(p, cta * ZS_LANES + lane_id, cps * ZS_LANES);
   uint64_t* a_full = a_full_ + lane_id * S;
   uint64_t* a_empty = a_empty_ + lane_id * S;
@@ -72,29 +79,29 @@ conv3_zs_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
     mbar_init(&b_full, 1);
     for (int i = 0; i < ZS_LANES * R; ++i) {
       mbar_init(&tmem_full_[i], 1);
-      mbar_init(&tmem_empty_[i], 4);  // one arrival per epilogue warp of the lane's warpgroup
+      mbar_init(&tmem_empty_[i], 4 * (EW == 2 && p.NT >= 32 ? 2 : 1));  // one arrival per epilogue warp that drains a slab of the block
     }
     fence_mbar_init();
   }
-  if (warp == ZS_WARP_PRODUCER && lane == 0) {
+  if (warp == WARP_PRODUCER && lane == 0) {
     tma_prefetch_desc(&tmapA);
     tma_prefetch_desc(&tmapB);
   }
-  if (warp == ZS_WARP_MMA) tmem_alloc(&tmem_slot, (uint32_t)p.tmem_cols);
+  if (warp == WARP_MMA) tmem_alloc(&tmem_slot, (uint32_t)p.tmem_cols);
   if (p.n_b)
-    for (int i = threadIdx.x; i < 8 * p.NT; i += ZS_THREADS) {
+    for (int i = threadIdx.x; i < 8 * p.NT; i += THREADS) {
       const int v = i / p.NT, c = i - v * p.NT;
       const int cls = ((v & 4 ? 3 : 1) << 4) | ((v & 2 ? 3 : 1) << 2) | (v & 1 ? 3 : 1);
       bias_interior[i] = p.biascls[((size_t)(p.n_b > 1 ? n : 0) * 64 + cls) * p.Cout + n0 + c];
     }
-  for (int i = threadIdx.x; i < 8 * p.NT * 2; i += ZS_THREADS) stat_acc[i] = 0.f;
+  for (int i = threadIdx.x; i < NEW * p.NT * 2; i += THREADS) stat_acc[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot + (uint32_t)(lane_id * R * p.NT);   // this lane's half of the accumulator ring
   uint8_t* smemA_lane = smemA + (size_t)lane_id * S * p.a_bytes;
 
-  if (warp >= ZS_WARP_PRODUCER && warp < ZS_WARP_MMA) {
+  if (warp >= WARP_PRODUCER && warp < WARP_MMA) {
     // ================= TMA producer: resident weights once, then one halo tile per (input plane, channel chunk) =================
     if (lane == 0) {
       const int wsample = p.n_w > 1 ? n : 0;
@@ -133,7 +140,7 @@ conv3_zs_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
       (void)w_prod; (void)t_begin;
 #endif
     }
-  } else if (warp >= ZS_WARP_MMA) {
+  } else if (warp >= WARP_MMA) {
     // ================= MMA issuer of this lane (whole warp converged, one elected lane issues) =================
     const uint32_t lay = umma_layout_for_row_bytes(rb);
     const uint64_t hiA = umma_smem_desc(0, 16u, (uint32_t)(ZS_HW * rb), lay) & 0xFFFFFFFF00000000ull;
@@ -259,21 +266,24 @@ conv3_zs_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
     (void)w_afull; (void)w_tempty; (void)t_begin;
 #endif
   } else {
-    // ================= epilogue: warps 0..3 drain lane 0's planes, warps 4..7 lane 1's =================
-    const int qd = warp & 3;   // TMEM lane quarter
+    // ================= epilogue: the first 4*EW warps drain lane 0's planes, the next 4*EW lane 1's =================
+    constexpr int SW = EW == 2 ? 16 : 32;  // slab width: columns one warp handles at a time
+    const int wg = (warp >> 2) % EW;        // warpgroup of the lane: takes slabs wg, wg + EW, ...
+    const int qd = warp & 3;                // TMEM lane quarter
     const int row = qd * 32 + lane;
     const int bx = row % ZS_BW, by = row / ZS_BW;
     const int NT = p.NT;
-    const bool reg_stats = p.pmode != 0 && NT <= 32;
-    float rs[32], rq[32];
+    const bool drains = wg * SW < NT;       // (NT = 16 with EW = 2: the second warpgroup has no slab and never arrives)
+    const bool reg_stats = p.pmode != 0 && NT <= 32;   // then a warp meets exactly one slab per plane
+    float rs[SW], rq[SW];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) rs[i] = rq[i] = 0.f;
+    for (int i = 0; i < SW; ++i) rs[i] = rq[i] = 0.f;
     float* my_acc = stat_acc + (size_t)warp * NT * 2;
     ZsRing cur = {0, 0u};   // TMEM block of the plane being drained
     long long w_tfull = 0, t_ld = 0, t_begin = dbg_clock();
     const size_t HW = (size_t)p.H * p.W;
     ZsSeg sg;
-    while (walk.next(sg)) {
+    while (drains && walk.next(sg)) {
       const int th_i = sg.col / p.tilesW, tw_i = sg.col - th_i * p.tilesW;
       const int xh = th_i * ZS_BH + by, xw = tw_i * ZS_BW + bx;
       const bool valid = xh < p.H && xw < p.W;
@@ -294,25 +304,29 @@ conv3_zs_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
         __syncwarp();
         tc_fence_after();
         const uint32_t taddr = tmem_base + (uint32_t)(slot * NT) + ((uint32_t)(qd * 32) << 16);
-        for (int c0 = 0; c0 < NT; c0 += 32) {
-          const bool wide = c0 + 32 <= NT;  // else a 16-column tail
-          uint32_t raw[32];
+        for (int c0 = wg * SW; c0 < NT; c0 += EW * SW) {
+          const bool wide = SW == 32 && c0 + 32 <= NT;  // else 16 columns (a slab of the two-warpgroup split, or the tail of NT = 48)
+          uint32_t raw[SW];
           const long long cl0 = dbg_clock();
-          if (wide) tmem_ld_32x32b_x32(taddr + c0, raw);
-          else tmem_ld_32x32b_x16(taddr + c0, raw);
+          if constexpr (SW == 32) {
+            if (wide) tmem_ld_32x32b_x32(taddr + c0, raw);
+            else tmem_ld_32x32b_x16(taddr + c0, raw);
+          } else {
+            tmem_ld_32x32b_x16(taddr + c0, raw);
+          }
           tmem_ld_wait();
           t_ld += dbg_clock() - cl0;
           if (DBG_FLAG(p, 4)) continue;
           const int cw = wide ? 32 : 16;
-          float v[32];
+          float v[SW];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = i < cw ? __uint_as_float(raw[i]) : 0.f;
+          for (int i = 0; i < SW; ++i) v[i] = i < cw ? __uint_as_float(raw[i]) : 0.f;
           const size_t goff = vox_off * p.Cout + n0 + c0;
           if (valid) {
             if (bias_row) {
               const float4* bp = reinterpret_cast<const float4*>(bias_row + c0);
 #pragma unroll
-              for (int i = 0; i < 8; ++i)
+              for (int i = 0; i < SW / 4; ++i)
                 if (4 * i < cw) {
                   const float4 bb = bp[i];
                   v[4 * i] += bb.x; v[4 * i + 1] += bb.y; v[4 * i + 2] += bb.z; v[4 * i + 3] += bb.w;
@@ -321,7 +335,7 @@ conv3_zs_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
             if (p.residual) {
               const bf16x8* rp = reinterpret_cast<const bf16x8*>(p.residual + goff);
 #pragma unroll
-              for (int i = 0; i < 4; ++i)
+              for (int i = 0; i < SW / 8; ++i)
                 if (8 * i < cw) {
                   float f[8];
                   unpack8(rp[i], f);
@@ -331,41 +345,41 @@ conv3_zs_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
             }
             if (p.act == B200_ACT_RELU) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+              for (int i = 0; i < SW; ++i) v[i] = fmaxf(v[i], 0.f);
             } else if (p.act == B200_ACT_LEAKY) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * p.slope;
+              for (int i = 0; i < SW; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * p.slope;
             } else if (p.act == B200_ACT_ELU) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.f ? v[i] : expm1f(v[i]);
+              for (int i = 0; i < SW; ++i) v[i] = v[i] > 0.f ? v[i] : expm1f(v[i]);
             }
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = bf16_round(v[i]);
+            for (int i = 0; i < SW; ++i) v[i] = bf16_round(v[i]);
             bf16x8* op = reinterpret_cast<bf16x8*>(p.y + goff);
             if (!DBG_FLAG(p, 1)) {
 #pragma unroll
-              for (int i = 0; i < 4; ++i)
+              for (int i = 0; i < SW / 8; ++i)
                 if (8 * i < cw) op[i] = pack8(&v[8 * i]);
             }
           } else {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = 0.f;
+            for (int i = 0; i < SW; ++i) v[i] = 0.f;
           }
           if (p.pmode) {
-            if (reg_stats) {  // C_out <= 32: one slab; per-thread accumulators across all planes of the CTA
+            if (reg_stats) {  // C_out <= 32: one slab per warp; per-thread accumulators across all planes of the CTA
 #pragma unroll
-              for (int i = 0; i < 32; ++i) {
+              for (int i = 0; i < SW; ++i) {
                 rs[i] += v[i];
                 rq[i] += v[i] * v[i];
               }
             } else {          // wider: reduce over the warp's 32 rows now, accumulate per warp in shared memory
-              float w[32];
+              float w[SW];
 #pragma unroll
-              for (int i = 0; i < 32; ++i) w[i] = v[i] * v[i];
-              const float s = warp_reduce_scatter<32>(v, lane);
-              const float qq = warp_reduce_scatter<32>(w, lane);
+              for (int i = 0; i < SW; ++i) w[i] = v[i] * v[i];
+              const float sum = warp_reduce_scatter<SW>(v, lane);
+              const float qq = warp_reduce_scatter<SW>(w, lane);
               if (lane < cw) {
-                my_acc[(c0 + lane) * 2] += s;
+                my_acc[(c0 + lane) * 2] += sum;
                 my_acc[(c0 + lane) * 2 + 1] += qq;
               }
             }
@@ -387,27 +401,28 @@ conv3_zs_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
 #else
     (void)w_tfull; (void)t_ld; (void)t_begin;
 #endif
-    if (reg_stats) {
-      const float s = warp_reduce_scatter<32>(rs, lane);
-      const float qq = warp_reduce_scatter<32>(rq, lane);
-      if (lane < NT) {
-        my_acc[lane * 2] = s;
-        my_acc[lane * 2 + 1] = qq;
+    if (reg_stats && drains) {
+      const int c0 = wg * SW;  // the warp's only slab
+      const float sum = warp_reduce_scatter<SW>(rs, lane);
+      const float qq = warp_reduce_scatter<SW>(rq, lane);
+      if (lane < SW && c0 + lane < NT) {
+        my_acc[(c0 + lane) * 2] = sum;
+        my_acc[(c0 + lane) * 2 + 1] = qq;
       }
     }
     tc_fence_before();
   }
   __syncthreads();
-  if (p.pmode) {  // fixed-order sum over the 8 epilogue warps -> this CTA's partial row
+  if (p.pmode) {  // fixed-order sum over the epilogue warps -> this CTA's partial row
     float* out = p.partials + (((size_t)n * cps + cta) * p.Cout + n0) * 2;
-    for (int i = threadIdx.x; i < p.NT * 2; i += ZS_THREADS) {
+    for (int i = threadIdx.x; i < p.NT * 2; i += THREADS) {
       float acc = 0.f;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) acc += stat_acc[(size_t)w * p.NT * 2 + i];
+      for (int w = 0; w < NEW; ++w) acc += stat_acc[(size_t)w * p.NT * 2 + i];
       out[i] = acc;
     }
   }
-  if (warp == ZS_WARP_MMA) {
+  if (warp == WARP_MMA) {
     __syncwarp();
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
@@ -437,7 +452,7 @@ bool conv_zs_plan(int N, int D, int H, int W, int Cin, int Cout, ConvParams* pp)
   for (int nt : {Cout, 64, 48, 32}) {
     if (nt > Cout || Cout % nt != 0 || nt > 64 || (nt != Cout && (nt < 32 || 2 * nt < Cout))) continue;  // at most two slices
     const int bt = 27 * nt * Cin * 2;
-    const int scratch = (8 * nt * 2 + 8 * nt) * (int)sizeof(float);
+    const int scratch = (16 * nt * 2 + 8 * nt) * (int)sizeof(float);  // per-warp statistics rows (up to 16 epilogue warps) + interior bias variants
     int st = (budget - ((bt + 1023) & ~1023) - scratch - 1024) / a_bytes;
     if (st > ZS_MAX_STAGES) st = ZS_MAX_STAGES;
     st &= ~1;  // two lanes, half of the stages each
@@ -492,12 +507,15 @@ int conv_zs_launch(const void* x, const void* wf, ConvParams& p, cudaStream_t s)
   if (rc) return rc;
   rc = make_w_tmap(&tmB, wf, 27 * p.n_w, p.Cout, p.Cin, p.KC, p.NT, 1);
   if (rc) return rc;
-  size_t smem = (size_t)((p.b_total_bytes + 1023) & ~1023) + (size_t)p.a_stages * p.a_bytes + (size_t)(8 * p.NT * 2 + 8 * p.NT) * sizeof(float) + 1024;
-  auto kern = p.KC == 64 ? conv3_zs_kernel<64> : (p.KC == 32 ? conv3_zs_kernel<32> : conv3_zs_kernel<16>);
+  size_t smem = (size_t)((p.b_total_bytes + 1023) & ~1023) + (size_t)p.a_stages * p.a_bytes + (size_t)(16 * p.NT * 2 + 8 * p.NT) * sizeof(float) + 1024;
+  const char* e1 = getenv("B200UNET_ZS_EPI");  // "1": one epilogue warpgroup per lane (the round-2 first version)
+  const int ew = (e1 && e1[0] == '1') ? 1 : 2;
+  auto kern = ew == 2 ? (p.KC == 64 ? conv3_zs_kernel<64, 2> : (p.KC == 32 ? conv3_zs_kernel<32, 2> : conv3_zs_kernel<16, 2>))
+                      : (p.KC == 64 ? conv3_zs_kernel<64, 1> : (p.KC == 32 ? conv3_zs_kernel<32, 1> : conv3_zs_kernel<16, 1>));
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   B200_CHECK_ARG(e == cudaSuccess, "conv3_zs: cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e));
   dim3 grid((unsigned)p.ctas_per_sample, (unsigned)p.N, (unsigned)(p.Cout / p.NT));
-  kern<<<grid, ZS_THREADS, smem, s>>>(tmA, tmB, p);
+  kern<<<grid, (8 * ew + 4) * 32, smem, s>>>(tmA, tmB, p);
   B200_CHECK_LAUNCH("conv3_zs");
   return 0;
 }

@@ -198,7 +198,7 @@ constexpr int WS_XROWS = WH_HD * WS_XH * WS_XW;             // 480
 constexpr int WS_ZROWS = (WH_BH + 2) * WH_BW;               // dz box: 18 lines x 8 voxels = 144 rows
 
 template <int CA>
-__global__ void __launch_bounds__(WS_THREADS, 1)
+__global__ void __launch_bounds__(WS_THREADS, 3)
 wgrad_hs_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ CUtensorMap tmapZ, const WgradHaloParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[WH_MAX_A], a_empty[WH_MAX_A], b_full[WH_MAX_B], b_empty[WH_MAX_B], done_bar;
@@ -249,8 +249,8 @@ wgrad_hs_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constant
         mbar_arrive_expect_tx(&b_full[bs], (uint32_t)(WS_ZROWS * rbB));
         tma_load_5d(smemB + (size_t)bs * p.b_bytes, &tmapZ, &b_full[bs], p.co0, w0, h0 - 1, d0, n);
         mbar_wait(&a_empty[as], ((uint32_t)(it / p.a_stages) & 1u) ^ 1u);
-        mbar_arrive_expect_tx(&a_full[as], (uint32_t)(WS_XROWS * rbA));
-        tma_load_5d(smemA + (size_t)as * p.a_bytes, &tmapX, &a_full[as], slice * CA, w0 - 1, h0, d0 - 1, n);
+        mbar_arrive_expect_tx(&a_full[as], (uint32_t)(p.PG * WS_XH * WS_XW * rbA));
+        tma_load_5d(smemA + (size_t)as * p.a_bytes, &tmapX, &a_full[as], slice * CA, w0 - 1, h0, d0 - 1 + dd0, n);  // PG planes from dd0
       }
     }
   } else if (warp == 1) {
@@ -274,7 +274,7 @@ wgrad_hs_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constant
       const uint32_t accum = it != 0 ? 1u : 0u;
 #pragma unroll 1
       for (int g = 0; g < p.PG; ++g) {
-        const uint32_t a_g = a_lo + (uint32_t)((dd0 + g) * WS_XH) * A_LINE;
+        const uint32_t a_g = a_lo + (uint32_t)(g * WS_XH) * A_LINE;
         const uint32_t tacc = tmem_base + (uint32_t)(g * 3 * p.Cout);
 #pragma unroll
         for (int k = 0; k < 8; ++k)  // 128 voxels = 8 x K16 = lines (2k, 2k+1) of the tile; dz atoms start at halo lines 2k, 2k+1, 2k+2
@@ -345,11 +345,21 @@ bool wgrad_halo_plan(int N, int D, int H, int W, int Cin, int Cout, WgradHaloPar
     // h-stacked variant: N = 3 * C_out per instruction, one accumulator per depth tap
     p.hs = 1;
     p.PG = (9 * Cout <= 512) ? 3 : 1;
+    // C_out <= 32: ONE depth tap per CTA and THREE CTAs per SM (72 KB of shared memory and <= 128 TMEM columns each).  A single issuing
+    // warp needs ~80 cycles per instruction where the pipe wants one per 56 (N = 96); three co-resident CTAs give the SM three
+    // issuers, each on its own accumulator (deterministic), for the price of reading the dz tile three times from L2.
+    const char* pg1 = getenv("B200UNET_WGRAD_HS_PG1");
+    int per_sm = 1;
+    if (Cout <= 32 && !(pg1 && pg1[0] == '0')) {
+      p.PG = 1;
+      per_sm = 3;
+    }
     p.AWb = Cout;
-    p.a_bytes = (WS_XROWS * p.CA * 2 + 1023) & ~1023;
+    p.a_bytes = (p.PG * WS_XH * WS_XW * p.CA * 2 + 1023) & ~1023;
     p.b_bytes = (WS_ZROWS * Cout * 2 + 1023) & ~1023;
     p.b_stages = 3;
-    p.a_stages = (200 * 1024 - p.b_stages * p.b_bytes) / p.a_bytes;
+    const int budget = (per_sm == 3 ? 72 : 200) * 1024;
+    p.a_stages = (budget - p.b_stages * p.b_bytes) / p.a_bytes;
     if (p.a_stages > WH_MAX_A) p.a_stages = WH_MAX_A;
     if (p.a_stages < 2) return false;
     if (p.b_stages > p.a_stages) p.b_stages = p.a_stages;
@@ -357,7 +367,7 @@ bool wgrad_halo_plan(int N, int D, int H, int W, int Cin, int Cout, WgradHaloPar
     while (cols < p.PG * 3 * Cout) cols <<= 1;
     p.tmem_cols = cols;
     int ctas_per_split = N * p.nslices * (3 / p.PG);
-    int want = sm_count() / ctas_per_split;
+    int want = per_sm * sm_count() / ctas_per_split;
     if (const char* e = getenv("B200UNET_WGRAD_SPLITS")) {  // tests: few splits => many tiles accumulated per CTA
       const int v = atoi(e);
       if (v >= 1) want = v;
@@ -391,7 +401,7 @@ bool wgrad_halo_plan(int N, int D, int H, int W, int Cin, int Cout, WgradHaloPar
 int wgrad_halo_launch(const void* x, const void* dz, WgradHaloParams& p, cudaStream_t s) {
   CUtensorMap tmX, tmZ;
   if (p.hs) {
-    int rc = make_act_tmap(&tmX, x, p.N, p.D, p.H, p.W, p.Cin, p.CA, WH_HD, WS_XH, WS_XW);
+    int rc = make_act_tmap(&tmX, x, p.N, p.D, p.H, p.W, p.Cin, p.CA, p.PG, WS_XH, WS_XW);
     if (rc) return rc;
     rc = make_act_tmap(&tmZ, dz, p.N, p.D, p.H, p.W, p.CoutTotal, p.Cout, 1, WH_BH + 2, WH_BW);
     if (rc) return rc;
