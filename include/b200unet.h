@@ -69,6 +69,12 @@ int b200_partials_finalize(const float* partials, int N, int P, int C, double* s
 int b200_gn_fold(const double* sums, const float* gamma, const float* beta, int G, double count,
                  const float* W, const float* conv_bias, int N, int Cin, int Cout,
                  void* wf, float* biascls, float* mean_rstd, float* ab, b200_stream_t s);
+/* the same chain in two launches instead of four (engine.py conv3 / groupnorm_act): per-block partial sums -> fp64 sums + GroupNorm
+   coefficients; folded weights + border-class bias table */
+int b200_gn_stats_coeffs(const float* partials, int N, int P, int C, const float* gamma, const float* beta, int G, double count,
+                         double* sums, float* mean_rstd, float* ab, b200_stream_t s);
+int b200_fold_weights_bias(const float* W, const float* ab, const float* conv_bias, const double* sums, double count, int N, int Cin,
+                           int Cout, void* wf, float* biascls, b200_stream_t s);
 /* GroupNorm applied as a standalone op AFTER a conv (orders like 'cgr'): y = act(a*x+b), emits partials of y */
 int b200_gn_apply_act(const void* x, const float* ab, int N, int C, long long voxels, int act, float slope,
                       void* y, float* partials, b200_stream_t s);

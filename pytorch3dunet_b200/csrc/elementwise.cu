@@ -252,6 +252,62 @@ __global__ void gn_coeffs_kernel(const double* __restrict__ sums, const float* _
   }
 }
 
+// partials_finalize + gn_coeffs in one launch: grid N, block (32,32).  The column sums are formed exactly as partials_finalize_kernel
+// forms them (same order, fp64), so `sums` is bit-identical to the two-kernel route.
+__global__ void gn_stats_coeffs_kernel(const float* __restrict__ partials, int P, int C, const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, int G, double count, double* __restrict__ sums,
+                                       float* __restrict__ mean_rstd, float* __restrict__ ab) {
+  extern __shared__ double dsm[];      // [C*2] column sums, then [G*2] floats
+  __shared__ double red[32][33];
+  const int n = blockIdx.x;
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  for (int c0 = 0; c0 < C * 2; c0 += 32) {
+    const int col = c0 + threadIdx.x;
+    double acc = 0.0;
+    if (col < C * 2) {
+      const float* base = partials + (size_t)n * P * C * 2 + col;
+      for (int p = threadIdx.y; p < P; p += 32) acc += (double)base[(size_t)p * C * 2];
+    }
+    red[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && col < C * 2) {
+      double t = 0.0;
+      for (int i = 0; i < 32; ++i) t += red[i][threadIdx.x];
+      dsm[col] = t;
+      sums[(size_t)n * C * 2 + col] = t;
+    }
+    __syncthreads();
+  }
+  float* gsm = reinterpret_cast<float*>(dsm + (size_t)C * 2);
+  const int cpg = C / G;
+  for (int g = tid; g < G; g += 1024) {
+    double s = 0.0, q = 0.0;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+      s += dsm[c * 2];
+      q += dsm[c * 2 + 1];
+    }
+    const double m = count * cpg;
+    const double mean = s / m;
+    double var = q / m - mean * mean;  // biased variance, as native_group_norm
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + 1e-5));
+    gsm[g * 2] = (float)mean;
+    gsm[g * 2 + 1] = rstd;
+    if (mean_rstd) {
+      mean_rstd[((size_t)n * G + g) * 2] = (float)mean;
+      mean_rstd[((size_t)n * G + g) * 2 + 1] = rstd;
+    }
+  }
+  __syncthreads();
+  for (int c = tid; c < C; c += 1024) {
+    const int g = c / cpg;
+    const float a = gamma[c] * gsm[g * 2 + 1];
+    const float b = beta[c] - gsm[g * 2] * a;
+    ab[((size_t)n * C + c) * 2] = a;
+    ab[((size_t)n * C + c) * 2 + 1] = b;
+  }
+}
+
 // wf[n][tap][co][ci] = bf16(W[co][ci][tap] * a[n][ci]); one thread per output element
 __global__ void fold_weights_kernel(const float* __restrict__ W, const float* __restrict__ ab, int n_w, int Cin, int Cout,
                                     bf16* __restrict__ wf) {
@@ -303,6 +359,60 @@ __global__ void fold_bias_kernel(const float* __restrict__ W, const float* __res
             for (int tw = 0; tw < 3; ++tw)
               if (tap_valid(cw, tw)) acc += bt[(td * 3 + th) * 3 + tw];
     biascls[((size_t)n * 64 + cls) * Cout + co] = acc;
+  }
+}
+
+// fold_weights + fold_bias in one launch: blocks [0, nbw) fold the weights, block nbw + (n * Cout + co) builds bias row (n, co)
+__device__ __forceinline__ void fold_bias_block(const float* __restrict__ W, const float* __restrict__ ab, const float* __restrict__ conv_bias,
+                                                const double* __restrict__ sums, double count, int Cin, int Cout, float* __restrict__ biascls,
+                                                int co, int n, float* bt) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int tap = warp; tap < 27; tap += nwarps) {
+    float acc = 0.f;
+    if (ab)
+      for (int ci = lane; ci < Cin; ci += 32) {
+        float w = W[((size_t)co * Cin + ci) * 27 + tap];
+        float wa = w * ab[((size_t)n * Cin + ci) * 2];
+        float resid = wa - from_act(to_act(wa));
+        float mean = sums ? (float)(sums[((size_t)n * Cin + ci) * 2] / count) : 0.f;
+        acc += w * ab[((size_t)n * Cin + ci) * 2 + 1] + resid * mean;
+      }
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) bt[tap] = acc;
+  }
+  __syncthreads();
+  float cb = conv_bias ? conv_bias[co] : 0.f;
+  for (int cls = threadIdx.x; cls < 64; cls += blockDim.x) {
+    int cd = cls >> 4, ch = (cls >> 2) & 3, cw = cls & 3;
+    float acc = cb;
+    for (int td = 0; td < 3; ++td)
+      if (tap_valid(cd, td))
+        for (int th = 0; th < 3; ++th)
+          if (tap_valid(ch, th))
+            for (int tw = 0; tw < 3; ++tw)
+              if (tap_valid(cw, tw)) acc += bt[(td * 3 + th) * 3 + tw];
+    biascls[((size_t)n * 64 + cls) * Cout + co] = acc;
+  }
+}
+__global__ void fold_all_kernel(const float* __restrict__ W, const float* __restrict__ ab, const float* __restrict__ conv_bias,
+                                const double* __restrict__ sums, double count, int n_w, int Cin, int Cout, int nbw, bf16* __restrict__ wf,
+                                float* __restrict__ biascls) {
+  __shared__ float bt[27];
+  if ((int)blockIdx.x >= nbw) {
+    const int r = (int)blockIdx.x - nbw;
+    fold_bias_block(W, ab, conv_bias, sums, count, Cin, Cout, biascls, r % Cout, r / Cout, bt);
+    return;
+  }
+  const size_t total = (size_t)n_w * 27 * Cout * Cin;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)nbw * blockDim.x) {
+    int ci = (int)(i % Cin);
+    size_t r = i / Cin;
+    int co = (int)(r % Cout);
+    r /= Cout;
+    int tap = (int)(r % 27);
+    int n = (int)(r / 27);
+    float a = ab ? ab[((size_t)n * Cin + ci) * 2] : 1.f;
+    wf[i] = to_act(W[((size_t)co * Cin + ci) * 27 + tap] * a);
   }
 }
 
@@ -1297,6 +1407,29 @@ int b200_gn_fold(const double* sums, const float* gamma, const float* beta, int 
     fold_bias_kernel<<<grid, 256, 0, ST(s)>>>(W, abp, conv_bias, sums, count, Cin, Cout, biascls);
     B200_CHECK_LAUNCH("fold_bias");
   }
+  return 0;
+}
+
+// partials -> sums (fp64, as b200_partials_finalize) -> GroupNorm (mean, rstd) and the per-channel (a, b) in ONE launch
+int b200_gn_stats_coeffs(const float* partials, int N, int P, int C, const float* gamma, const float* beta, int G, double count,
+                         double* sums, float* mean_rstd, float* ab, b200_stream_t s) {
+  B200_CHECK_ARG(G > 0 && C % G == 0 && C <= 2048, "gn_stats_coeffs: C=%d G=%d unsupported", C, G);
+  dim3 block(32, 32);
+  size_t smem = (size_t)C * 2 * sizeof(double) + (size_t)G * 2 * sizeof(float);
+  gn_stats_coeffs_kernel<<<N, block, smem, ST(s)>>>(partials, P, C, gamma, beta, G, count, sums, mean_rstd, ab);
+  B200_CHECK_LAUNCH("gn_stats_coeffs");
+  return 0;
+}
+// folded weights wf[n_w][27][Cout][Cin] and border-class bias table [n_w][64][Cout] in ONE launch (ab == NULL: n_w = 1, plain cast)
+int b200_fold_weights_bias(const float* W, const float* ab, const float* conv_bias, const double* sums, double count, int N, int Cin,
+                           int Cout, void* wf, float* biascls, b200_stream_t s) {
+  const int n_w = ab ? N : 1;
+  size_t total = (size_t)n_w * 27 * Cout * Cin;
+  int nbw = (int)((total + 255) / 256);
+  if (nbw > 4096) nbw = 4096;
+  const int nbb = (biascls && (ab || conv_bias)) ? Cout * n_w : 0;
+  fold_all_kernel<<<nbw + nbb, 256, 0, ST(s)>>>(W, ab, conv_bias, sums, count, n_w, Cin, Cout, nbw, (bf16*)wf, biascls);
+  B200_CHECK_LAUNCH("fold_weights_bias");
   return 0;
 }
 

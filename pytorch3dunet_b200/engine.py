@@ -286,6 +286,22 @@ class Engine:
         x.partials = None
         return sums
 
+    def gn_coeffs_of(self, x, gamma, beta, groups, vox):
+        """(sums, mean_rstd, ab) of GroupNorm(x): straight from the producer's per-block partial sums in one launch when they are still
+        there, else sums_of + b200_gn_coeffs"""
+        n, c = x.dims[0], x.dims[4]
+        ab = self.empty((n, c, 2), torch.float32)
+        mean_rstd = self.empty((n, groups, 2), torch.float32)
+        if x.sums is None and x.partials is not None and not isinstance(x, InputF32):
+            sums = self.empty((n, c, 2), torch.float64)
+            self.call("b200_gn_stats_coeffs", _p(x.partials), n, x.P, c, _p(gamma), _p(beta), groups, float(vox), _p(sums), _p(mean_rstd),
+                      _p(ab))
+            x.sums, x.partials = sums, None
+        else:
+            sums = self.sums_of(x)
+            self.call("b200_gn_coeffs", _p(sums), _p(gamma), _p(beta), groups, float(vox), n, c, _p(mean_rstd), _p(ab))
+        return sums, mean_rstd, ab
+
     def accumulate_grad(self, x, g):
         """x.grad += g where g is already in x's dz form."""
         if x.grad is None:
@@ -378,21 +394,15 @@ class Engine:
         W = W.contiguous()
         ab = mean_rstd = None
         n_w = 1
+        sums = None
         if gn is not None:
             gamma, beta, groups = gn[0].contiguous(), gn[1].contiguous(), gn[2]
-            sums = self.sums_of(x)
+            sums, mean_rstd, ab = self.gn_coeffs_of(x, gamma, beta, groups, vox)
             n_w = n
-            ab = self.empty((n, cin, 2), torch.float32)
-            mean_rstd = self.empty((n, groups, 2), torch.float32)
         wf = self.empty((n_w, 27, cout, cin), self.adt)
         n_b = n_w if (gn is not None or bias is not None) else 0
         biascls = self.empty((n_b, 64, cout), torch.float32) if n_b else None
-        if gn is not None:
-            self.call("b200_gn_fold", _p(sums), _p(gamma), _p(beta), groups, float(vox), _p(W), _p(bias), n, cin, cout,
-                      _p(wf), _p(biascls), _p(mean_rstd), _p(ab), launches=3)
-        else:
-            self.call("b200_gn_fold", None, None, None, 1, float(vox), _p(W), _p(bias), n, cin, cout,
-                      _p(wf), _p(biascls), None, None, launches=2 if bias is not None else 1)
+        self.call("b200_fold_weights_bias", _p(W), _p(ab), _p(bias), _p(sums), float(vox), n, cin, cout, _p(wf), _p(biascls))
         y = self.empty((n, d, h, w, cout), self.adt)
         partials, P = None, 0
         if want_stats:
@@ -501,10 +511,7 @@ class Engine:
         n, d, h, w, c = z.dims
         vox = d * h * w
         gamma, beta = gamma.contiguous(), beta.contiguous()
-        sums = self.sums_of(z)
-        ab = self.empty((n, c, 2), torch.float32)
-        mean_rstd = self.empty((n, groups, 2), torch.float32)
-        self.call("b200_gn_coeffs", _p(sums), _p(gamma), _p(beta), groups, float(vox), n, c, _p(mean_rstd), _p(ab))
+        sums, mean_rstd, ab = self.gn_coeffs_of(z, gamma, beta, groups, vox)
         y = self.empty(z.t.shape, self.adt)
         partials, P = None, 0
         if want_stats:

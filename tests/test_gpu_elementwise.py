@@ -71,6 +71,42 @@ def test_gn_fold_matches_group_norm_then_conv():
     assert U.rel_l2(mr[..., 1], 1 / torch.sqrt(xg.var(-1, unbiased=False) + 1e-5)) < 1e-4
 
 
+@pytest.mark.parametrize("P,C,G", [(37, 32, 8), (1024, 64, 8), (5, 256, 8), (3, 16, 1)])
+def test_fused_stats_coeffs_and_fold_equal_the_four_kernel_chain(P, C, G):
+    """b200_gn_stats_coeffs == partials_finalize + gn_coeffs and b200_fold_weights_bias == gn_fold's two fold kernels, bit for bit"""
+    U, E, L = _ctx()
+    N, Cin, Cout, vox = 2, C, 32, 4096.0
+    g = torch.Generator(device="cuda").manual_seed(31)
+    partials = torch.rand((N, P, C, 2), device="cuda", generator=g) * 50 + 1.0
+    partials[..., 1] = partials[..., 0] ** 2 / 40 + partials[..., 1]   # sum of squares large enough for a positive variance
+    gamma = 1 + 0.2 * torch.randn(C, device="cuda", generator=g)
+    beta = 0.2 * torch.randn(C, device="cuda", generator=g)
+    Wt = torch.randn((Cout, Cin, 3, 3, 3), device="cuda", generator=g) * 0.05
+    cb = torch.randn(Cout, device="cuda", generator=g)
+    sums = torch.empty((N, C, 2), dtype=torch.float64, device="cuda")
+    L.call("b200_partials_finalize", U.p(partials), N, P, C, U.p(sums), U.stream())
+    wf = torch.empty((N, 27, Cout, Cin), dtype=torch.bfloat16, device="cuda")
+    bc = torch.empty((N, 64, Cout), device="cuda")
+    mr = torch.empty((N, G, 2), device="cuda")
+    ab = torch.empty((N, Cin, 2), device="cuda")
+    L.call("b200_gn_fold", U.p(sums), U.p(gamma), U.p(beta), G, vox, U.p(Wt), U.p(cb), N, Cin, Cout, U.p(wf), U.p(bc), U.p(mr), U.p(ab),
+           U.stream())
+    sums2, mr2, ab2 = torch.full_like(sums, float("nan")), torch.full_like(mr, float("nan")), torch.full_like(ab, float("nan"))
+    L.call("b200_gn_stats_coeffs", U.p(partials), N, P, C, U.p(gamma), U.p(beta), G, vox, U.p(sums2), U.p(mr2), U.p(ab2), U.stream())
+    assert torch.equal(sums, sums2) and torch.equal(mr, mr2) and torch.equal(ab, ab2)
+    wf2 = torch.zeros_like(wf)
+    bc2 = torch.full_like(bc, float("nan"))
+    L.call("b200_fold_weights_bias", U.p(Wt), U.p(ab2), U.p(cb), U.p(sums2), vox, N, Cin, Cout, U.p(wf2), U.p(bc2), U.stream())
+    assert torch.equal(wf, wf2) and torch.equal(bc, bc2)
+    # no GroupNorm: one weight copy, conv bias only
+    wf1 = torch.empty((1, 27, Cout, Cin), dtype=torch.bfloat16, device="cuda")
+    bc1 = torch.empty((1, 64, Cout), device="cuda")
+    L.call("b200_gn_fold", None, None, None, 1, vox, U.p(Wt), U.p(cb), N, Cin, Cout, U.p(wf1), U.p(bc1), None, None, U.stream())
+    wf3, bc3 = torch.zeros_like(wf1), torch.full_like(bc1, float("nan"))
+    L.call("b200_fold_weights_bias", U.p(Wt), None, U.p(cb), None, vox, N, Cin, Cout, U.p(wf3), U.p(bc3), U.stream())
+    assert torch.equal(wf1, wf3) and torch.equal(bc1, bc3)
+
+
 def test_border_tap_sums_and_gn_bwd_sums():
     U, E, L = _ctx()
     N, D, H, W, Cin, Cout = 2, 5, 6, 4, 16, 24
