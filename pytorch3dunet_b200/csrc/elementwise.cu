@@ -733,6 +733,60 @@ __global__ void maxpool_bwd_kernel(const bf16* __restrict__ dpooled, const bf16*
   if (GN) ew_write_partials(ssum, ssq, m, partials + ((size_t)n * P + p) * C * 2, red);
 }
 
+// Lane-pair forward (C/8 a power of two <= 16), the same mapping as maxpool_bwd_pair_kernel below: a thread reduces the 2x2 (d,h)
+// column of one fine w position (4 coalesced 16-byte loads), one shuffle per channel joins the two w positions, the even lane writes.
+__global__ void __launch_bounds__(EW_THREADS) maxpool_fwd_pair_kernel(const bf16* __restrict__ x, int D, int H, int W, int C, int P,
+                                                                      bf16* __restrict__ y, float* __restrict__ partials) {
+  extern __shared__ float red[];
+  const int p = blockIdx.x, n = blockIdx.y;
+  const int oD = D / 2, oH = H / 2, oW = W / 2;
+  const int Wf = 2 * oW;
+  const EwMap m = ew_map(C);
+  const LineMap lm = line_map(m, Wf);
+  int l0, l1;
+  ew_range_i(oD * oH, p, P, l0, l1);
+  float s[8] = {0}, q[8] = {0};
+  const bf16x8* xp = reinterpret_cast<const bf16x8*>(x + (size_t)n * D * H * W * C) + m.cg;
+  bf16x8* yp = reinterpret_cast<bf16x8*>(y + (size_t)n * oD * oH * oW * C) + m.cg;
+  const bool lane_ok = m.active && lm.active;
+  const size_t dplane = (size_t)H * W * m.CG, dline = (size_t)W * m.CG;
+  for (int lb = l0; lb < l1; lb += lm.LPB) {
+    const int l = lb + lm.ls;
+    const int oh = l % oH, od = l / oH;
+    for (int fb = 0; fb < Wf; fb += lm.lpl) {
+      const int xx = fb + lm.lw;
+      const bool mine = lane_ok && l < l1 && xx < Wf;
+      float mx[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) mx[i] = -INFINITY;
+      if (mine) {
+        const size_t iv0 = (((size_t)(2 * od) * H + 2 * oh) * W + xx) * m.CG;
+        bf16x8 xr[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) xr[k] = xp[iv0 + (k >> 1) * dplane + (k & 1) * dline];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float f[8];
+          unpack8(xr[k], f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) mx[i] = fmaxf(mx[i], f[i]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) mx[i] = fmaxf(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], m.CG));
+      if (mine && !(xx & 1)) {
+        yp[(((size_t)od * oH + oh) * oW + (xx >> 1)) * m.CG] = pack8(mx);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          s[i] += mx[i];
+          q[i] += mx[i] * mx[i];
+        }
+      }
+    }
+  }
+  if (partials) ew_write_partials(s, q, m, partials + ((size_t)n * P + p) * C * 2, red);
+}
+
 // Lane-pair variant (C/8 a power of two <= 16): a thread owns the 2x2 (d,h) column of ONE fine w position of a cell, its neighbour
 // lane (xor C/8) the other w position; consecutive lanes read consecutive 16-byte chunks (fully coalesced, half the registers of
 // the one-thread-per-cell kernel above, twice the loads in flight) and the two halves of a cell settle the argmax with one shuffle
@@ -1188,6 +1242,71 @@ __global__ void final_conv_fwd_kernel(const bf16* __restrict__ x, long long voxe
     }
 }
 
+// Same result with C/8 lanes per voxel (C/8 a power of two <= 32): every lane reads one 16-byte chunk (coalesced), the partial dot
+// products are joined by shuffles in a fixed order, the first lane of the voxel applies the final activation and writes.
+__global__ void __launch_bounds__(EW_THREADS) final_conv_fwd_cg_kernel(const bf16* __restrict__ x, long long voxels, int C,
+                                                                       const float* __restrict__ Wt, const float* __restrict__ bias, int Cout,
+                                                                       int final_act, float* __restrict__ logits, float* __restrict__ probs) {
+  extern __shared__ float wsm[];  // [Cout][C] + [Cout]
+  const int n = blockIdx.y;
+  for (int i = threadIdx.x; i < Cout * C; i += blockDim.x) wsm[i] = Wt[i];
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) wsm[Cout * C + i] = bias ? bias[i] : 0.f;
+  __syncthreads();
+  const int CG = C >> 3, cg = threadIdx.x % CG, vl = threadIdx.x / CG, VL = EW_THREADS / CG;
+  const bf16x8* xp = reinterpret_cast<const bf16x8*>(x + (size_t)n * voxels * C);
+  // 4 voxels per thread per block: blockIdx.x covers 4*VL voxels
+  const long long vbase = (long long)blockIdx.x * 4 * VL;
+  bf16x8 xr[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const long long v = vbase + u * VL + vl;
+    if (v < voxels) xr[u] = xp[v * CG + cg];
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const long long v = vbase + u * VL + vl;  // (the same for all CG lanes of a voxel: the shuffles below stay converged per voxel group)
+    float f[8];
+    if (v < voxels) unpack8(xr[u], f);
+    else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = 0.f;
+    }
+    float acc[FC_MAXO];
+#pragma unroll
+    for (int o = 0; o < FC_MAXO; ++o) {
+      acc[o] = 0.f;
+      if (o < Cout) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[o] += f[i] * wsm[o * C + cg * 8 + i];
+        for (int sft = 1; sft < CG; sft <<= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], sft);
+        acc[o] += wsm[Cout * C + o];
+      }
+    }
+    if (cg != 0 || v >= voxels) continue;
+    float mx = -INFINITY, den = 0.f;
+    if (final_act == B200_FINAL_SOFTMAX) {
+#pragma unroll
+      for (int o = 0; o < FC_MAXO; ++o)
+        if (o < Cout) mx = fmaxf(mx, acc[o]);
+#pragma unroll
+      for (int o = 0; o < FC_MAXO; ++o)
+        if (o < Cout) den += expf(acc[o] - mx);
+    }
+#pragma unroll
+    for (int o = 0; o < FC_MAXO; ++o)
+      if (o < Cout) {
+        const size_t idx = ((size_t)n * Cout + o) * voxels + v;
+        logits[idx] = acc[o];
+        if (probs) {
+          float pr = acc[o];
+          if (final_act == B200_FINAL_SIGMOID) pr = 1.f / (1.f + expf(-acc[o]));
+          else if (final_act == B200_FINAL_SOFTMAX) pr = expf(acc[o] - mx) / den;
+          probs[idx] = pr;
+        }
+      }
+  }
+}
+
 // dz = (sum_o dl[o] W[o][c]) * act'(x); partial sums of dW[o][c] and db[o]; grid (P, N)
 // partials row layout: [Cout*C] dW then [Cout] db
 __global__ void final_conv_bwd_kernel(const float* __restrict__ dl, const bf16* __restrict__ x, long long voxels, int C,
@@ -1210,32 +1329,49 @@ __global__ void final_conv_bwd_kernel(const float* __restrict__ dl, const bf16* 
     float s[8] = {0}, q[8] = {0};  // dW[o0][8ch], dW[o0+1][8ch]
     float db0 = 0.f, db1 = 0.f;
     if (m.active) {
-      for (long long v = v0 + m.vl; v < v1; v += m.VL) {
-        float f[8];
-        unpack8(xp[v * m.CG + m.cg], f);
-        float d0 = dl[((size_t)n * Cout + o0) * voxels + v];
-        float d1 = (o0 + 1 < Cout) ? dl[((size_t)n * Cout + o0 + 1) * voxels + v] : 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          s[i] += d0 * f[i];
-          q[i] += d1 * f[i];
+      // two voxels per iteration (independent loads in flight); accumulation order per thread unchanged (v, then v + VL)
+      for (long long va = v0 + m.vl; va < v1; va += 2 * m.VL) {
+        const long long vb = va + m.VL;
+        const bool two = vb < v1;
+        bf16x8 xr[2];
+        float d0r[2], d1r[2];
+        xr[0] = xp[va * m.CG + m.cg];
+        d0r[0] = dl[((size_t)n * Cout + o0) * voxels + va];
+        d1r[0] = (o0 + 1 < Cout) ? dl[((size_t)n * Cout + o0 + 1) * voxels + va] : 0.f;
+        if (two) {
+          xr[1] = xp[vb * m.CG + m.cg];
+          d0r[1] = dl[((size_t)n * Cout + o0) * voxels + vb];
+          d1r[1] = (o0 + 1 < Cout) ? dl[((size_t)n * Cout + o0 + 1) * voxels + vb] : 0.f;
         }
-        if (m.cg == 0) {
-          db0 += d0;
-          db1 += d1;
-        }
-        if (o0 == 0) {
-          float g[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) g[i] = 0.f;
-          for (int o = 0; o < Cout; ++o) {
-            float d = dl[((size_t)n * Cout + o) * voxels + v];
+        for (int u = 0; u < 2; ++u) {
+          if (u == 1 && !two) break;
+          const long long v = u ? vb : va;
+          float f[8];
+          unpack8(xr[u], f);
+          const float d0 = d0r[u], d1 = d1r[u];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) g[i] += d * wsm[o * C + m.cg * 8 + i];
+          for (int i = 0; i < 8; ++i) {
+            s[i] += d0 * f[i];
+            q[i] += d1 * f[i];
           }
+          if (m.cg == 0) {
+            db0 += d0;
+            db1 += d1;
+          }
+          if (o0 == 0) {
+            float g[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) g[i] *= act_grad_from_out(f[i], act, slope);
-          zp[v * m.CG + m.cg] = pack8(g);
+            for (int i = 0; i < 8; ++i) g[i] = 0.f;
+            for (int o = 0; o < Cout; ++o) {
+              float d = o == 0 ? d0 : (o == 1 ? d1 : dl[((size_t)n * Cout + o) * voxels + v]);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) g[i] += d * wsm[o * C + m.cg * 8 + i];
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) g[i] *= act_grad_from_out(f[i], act, slope);
+            zp[v * m.CG + m.cg] = pack8(g);
+          }
         }
       }
     }
@@ -1497,6 +1633,7 @@ int b200_act_bwd(const void* g, int g_cs, int g_co, const void* y, int N, int C,
   return 0;
 }
 
+static bool maxpool_pair_ok(int C);  // lane-pair kernels: the two w positions of a cell sit C/8 lanes apart in one warp
 int b200_maxpool_partials_count(int N, int D, int H, int W, int C) {
   (void)N;
   return ew_blocks((long long)(D / 2) * (H / 2) * (W / 2), C);
@@ -1506,8 +1643,11 @@ int b200_maxpool_fwd(const void* x, int N, int D, int H, int W, int C, void* y, 
   B200_CHECK_ARG(D >= 2 && H >= 2 && W >= 2, "maxpool_fwd: spatial size (%d,%d,%d) too small for MaxPool3d(2)", D, H, W);
   int P = b200_maxpool_partials_count(N, D, H, W, C);
   dim3 grid(P, N);
-  maxpool_fwd_kernel<<<grid, EW_THREADS, EW_THREADS * 16 * sizeof(float), ST(s)>>>((const bf16*)x, D, H, W, C, P, (bf16*)y,
-                                                                                 partials);
+  if (maxpool_pair_ok(C))
+    maxpool_fwd_pair_kernel<<<grid, EW_THREADS, EW_THREADS * 16 * sizeof(float), ST(s)>>>((const bf16*)x, D, H, W, C, P, (bf16*)y, partials);
+  else
+    maxpool_fwd_kernel<<<grid, EW_THREADS, EW_THREADS * 16 * sizeof(float), ST(s)>>>((const bf16*)x, D, H, W, C, P, (bf16*)y,
+                                                                                   partials);
   B200_CHECK_LAUNCH("maxpool_fwd");
   return 0;
 }
@@ -1656,8 +1796,16 @@ int b200_final_conv_fwd(const void* x, int N, long long voxels, int C, const flo
                         int final_act, float* logits, float* probs, b200_stream_t s) {
   B200_CHECK_ARG(C % 8 == 0, "final_conv_fwd: C=%d must be a multiple of 8", C);
   B200_CHECK_ARG(Cout >= 1 && Cout <= FC_MAXO, "final_conv_fwd: out_channels=%d unsupported (max %d)", Cout, FC_MAXO);
-  dim3 grid(ceil_div(voxels, 128), N);
   size_t smem = ((size_t)Cout * C + Cout) * sizeof(float);
+  const int cgn = C / 8;
+  if ((cgn & (cgn - 1)) == 0 && cgn <= 32 && !getenv("B200UNET_FINAL_CONV_PLAIN")) {
+    const int VL = EW_THREADS / cgn;
+    dim3 grid2(ceil_div(voxels, 4ll * VL), N);
+    final_conv_fwd_cg_kernel<<<grid2, EW_THREADS, smem, ST(s)>>>((const bf16*)x, voxels, C, W, bias, Cout, final_act, logits, probs);
+    B200_CHECK_LAUNCH("final_conv_fwd_cg");
+    return 0;
+  }
+  dim3 grid(ceil_div(voxels, 128), N);
   final_conv_fwd_kernel<<<grid, 128, smem, ST(s)>>>((const bf16*)x, voxels, C, W, bias, Cout, final_act, logits, probs);
   B200_CHECK_LAUNCH("final_conv_fwd");
   return 0;

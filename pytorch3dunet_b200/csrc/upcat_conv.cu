@@ -247,7 +247,7 @@ int b200_gn_fold_upcat(const double* sums, const float* gamma, const float* beta
   }
   if (biascls && (abp || conv_bias)) {
     dim3 grid(Cout, n_w);
-    upcat_fold_bias_kernel<<<grid, 256, 0, ST(s)>>>(W, abp, conv_bias, abp ? sums : nullptr, count, C0, C1, Cout, biascls);
+    upcat_fold_bias_kernel<<<grid, 1024, 0, ST(s)>>>(W, abp, conv_bias, abp ? sums : nullptr, count, C0, C1, Cout, biascls);
     B200_CHECK_LAUNCH("upcat_fold_bias");
   }
   return 0;
