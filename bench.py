@@ -381,7 +381,7 @@ def run_train(args, wl):
                         "537 MB = x + y), profiles/ncu_r02_full_summary.md")
     except Exception:
         pass
-    roofline = {"bound": "tensor", "kernel": "tcgen05 conv kernels: conv3_halo_kernel / conv3_igemm_kernel (fprop+dgrad), wgrad_halo_kernel / conv3_wgrad_igemm_kernel",
+    roofline = {"bound": "tensor", "kernel": "tcgen05 conv kernels: conv3_zs_kernel / conv3_upzs_kernel / conv3_updzs_kernel / conv3_igemm_kernel (fprop+dgrad), wgrad_hs_kernel / wgrad_up_kernel / wgrad_halo_kernel / conv3_wgrad_igemm_kernel",
                 "achieved": achieved, "peak": peak,
                 "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_note": traffic_note,
                 "peak_source": pk_src + " sustained bf16",
