@@ -342,6 +342,14 @@ static int conv_igemm_plain_launch(const void* x, const void* wf, int n_w, const
   p.n_b = biascls ? n_b : 0;
   p.NT = pick_nt(Cout);
   while (g.nacc * p.NT > 512 && p.NT % 32 == 0) p.NT /= 2;  // all accumulators of a CTA live in its 512 TMEM columns
+  {
+    // small volumes (16^3 and below: 64 tiles for 148 SMs): split the output channels over more CTAs while that at least doubles the
+    // number of busy SMs; N = 128 -> 64 costs 48 instead of 32 cycles per 64 columns, twice the SMs more than pays for it
+    static const bool split = [] { const char* e = getenv("B200UNET_IGEMM_NSPLIT"); return !(e && e[0] == '0'); }();
+    const long long tiles = (long long)N * p.tilesD * p.tilesH * p.tilesW;
+    const int sms = sm_count();
+    while (split && tiles * (Cout / p.NT) * 2 <= sms && p.NT >= 128 && p.NT % 32 == 0) p.NT /= 2;
+  }
   B200_CHECK_ARG(g.nacc * p.NT <= 512 && Cout % p.NT == 0, "conv3_igemm: %d accumulators of %d columns do not fit TMEM", g.nacc, p.NT);
   p.KC = (Cin % 64 == 0) ? 64 : (Cin % 32 == 0 ? 32 : 16);
   p.kchunks = Cin / p.KC;

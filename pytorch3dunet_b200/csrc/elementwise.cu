@@ -1242,71 +1242,6 @@ __global__ void final_conv_fwd_kernel(const bf16* __restrict__ x, long long voxe
     }
 }
 
-// Same result with C/8 lanes per voxel (C/8 a power of two <= 32): every lane reads one 16-byte chunk (coalesced), the partial dot
-// products are joined by shuffles in a fixed order, the first lane of the voxel applies the final activation and writes.
-__global__ void __launch_bounds__(EW_THREADS) final_conv_fwd_cg_kernel(const bf16* __restrict__ x, long long voxels, int C,
-                                                                       const float* __restrict__ Wt, const float* __restrict__ bias, int Cout,
-                                                                       int final_act, float* __restrict__ logits, float* __restrict__ probs) {
-  extern __shared__ float wsm[];  // [Cout][C] + [Cout]
-  const int n = blockIdx.y;
-  for (int i = threadIdx.x; i < Cout * C; i += blockDim.x) wsm[i] = Wt[i];
-  for (int i = threadIdx.x; i < Cout; i += blockDim.x) wsm[Cout * C + i] = bias ? bias[i] : 0.f;
-  __syncthreads();
-  const int CG = C >> 3, cg = threadIdx.x % CG, vl = threadIdx.x / CG, VL = EW_THREADS / CG;
-  const bf16x8* xp = reinterpret_cast<const bf16x8*>(x + (size_t)n * voxels * C);
-  // 4 voxels per thread per block: blockIdx.x covers 4*VL voxels
-  const long long vbase = (long long)blockIdx.x * 4 * VL;
-  bf16x8 xr[4];
-#pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const long long v = vbase + u * VL + vl;
-    if (v < voxels) xr[u] = xp[v * CG + cg];
-  }
-#pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const long long v = vbase + u * VL + vl;  // (the same for all CG lanes of a voxel: the shuffles below stay converged per voxel group)
-    float f[8];
-    if (v < voxels) unpack8(xr[u], f);
-    else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) f[i] = 0.f;
-    }
-    float acc[FC_MAXO];
-#pragma unroll
-    for (int o = 0; o < FC_MAXO; ++o) {
-      acc[o] = 0.f;
-      if (o < Cout) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[o] += f[i] * wsm[o * C + cg * 8 + i];
-        for (int sft = 1; sft < CG; sft <<= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], sft);
-        acc[o] += wsm[Cout * C + o];
-      }
-    }
-    if (cg != 0 || v >= voxels) continue;
-    float mx = -INFINITY, den = 0.f;
-    if (final_act == B200_FINAL_SOFTMAX) {
-#pragma unroll
-      for (int o = 0; o < FC_MAXO; ++o)
-        if (o < Cout) mx = fmaxf(mx, acc[o]);
-#pragma unroll
-      for (int o = 0; o < FC_MAXO; ++o)
-        if (o < Cout) den += expf(acc[o] - mx);
-    }
-#pragma unroll
-    for (int o = 0; o < FC_MAXO; ++o)
-      if (o < Cout) {
-        const size_t idx = ((size_t)n * Cout + o) * voxels + v;
-        logits[idx] = acc[o];
-        if (probs) {
-          float pr = acc[o];
-          if (final_act == B200_FINAL_SIGMOID) pr = 1.f / (1.f + expf(-acc[o]));
-          else if (final_act == B200_FINAL_SOFTMAX) pr = expf(acc[o] - mx) / den;
-          probs[idx] = pr;
-        }
-      }
-  }
-}
-
 // dz = (sum_o dl[o] W[o][c]) * act'(x); partial sums of dW[o][c] and db[o]; grid (P, N)
 // partials row layout: [Cout*C] dW then [Cout] db
 __global__ void final_conv_bwd_kernel(const float* __restrict__ dl, const bf16* __restrict__ x, long long voxels, int C,
@@ -1797,14 +1732,6 @@ int b200_final_conv_fwd(const void* x, int N, long long voxels, int C, const flo
   B200_CHECK_ARG(C % 8 == 0, "final_conv_fwd: C=%d must be a multiple of 8", C);
   B200_CHECK_ARG(Cout >= 1 && Cout <= FC_MAXO, "final_conv_fwd: out_channels=%d unsupported (max %d)", Cout, FC_MAXO);
   size_t smem = ((size_t)Cout * C + Cout) * sizeof(float);
-  const int cgn = C / 8;
-  if ((cgn & (cgn - 1)) == 0 && cgn <= 32 && !getenv("B200UNET_FINAL_CONV_PLAIN")) {
-    const int VL = EW_THREADS / cgn;
-    dim3 grid2(ceil_div(voxels, 4ll * VL), N);
-    final_conv_fwd_cg_kernel<<<grid2, EW_THREADS, smem, ST(s)>>>((const bf16*)x, voxels, C, W, bias, Cout, final_act, logits, probs);
-    B200_CHECK_LAUNCH("final_conv_fwd_cg");
-    return 0;
-  }
   dim3 grid(ceil_div(voxels, 128), N);
   final_conv_fwd_kernel<<<grid, 128, smem, ST(s)>>>((const bf16*)x, voxels, C, W, bias, Cout, final_act, logits, probs);
   B200_CHECK_LAUNCH("final_conv_fwd");
