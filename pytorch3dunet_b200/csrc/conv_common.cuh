@@ -14,7 +14,7 @@ namespace b200 {
 #endif
 
 constexpr int CONV_THREADS = 192;
-constexpr int CONV_MAX_STAGES = 8;
+constexpr int CONV_MAX_STAGES = 12;
 constexpr int HALO_MAX_STAGES = 6;
 
 struct ConvParams {

@@ -361,6 +361,11 @@ static int conv_igemm_plain_launch(const void* x, const void* wf, int n_w, const
   // ring to ~96 KB (two CTAs per SM); 72 / 48 KB measured no different (env B200UNET_IGEMM_SMEM_KB overrides, for experiments)
   static const int smem_kb = [] { const char* e = getenv("B200UNET_IGEMM_SMEM_KB"); return e ? atoi(e) : 96; }();
   int stages = (smem_kb * 1024) / stage_bytes;
+  {
+    // fewer CTAs than SMs: nothing to co-reside with, the K loop is a chain of TMA round trips -> spend the whole SM on pipeline depth
+    const long long ctas = (long long)N * p.tilesD * p.tilesH * p.tilesW * (Cout / p.NT);
+    if (ctas <= sm_count() && !getenv("B200UNET_IGEMM_SMEM_KB")) stages = (196 * 1024) / stage_bytes;
+  }
   if (stages > numK) stages = numK;  // short K loops: keep the CTA small so several fit on an SM
   if (stages < 3 && numK >= 3) stages = 3;
   if (stages < 1) stages = 1;
