@@ -144,6 +144,10 @@ int b200_gn_bwd_apply_stats(const void* dxhat, const void* x, const float* coef,
 /* out = g[..., g_co:g_co+C] * act'(y) [+ gadd] : plain masking / accumulation; g is read with channel stride g_cs */
 int b200_act_bwd(const void* g, int g_cs, int g_co, const void* y, int N, int C, long long voxels, int act, float slope,
                  const void* gadd, void* out, b200_stream_t s);
+/* the same, also emitting the per-channel totals of the result (partials [N][b200_stats_partials_count][C][2]) for the producer conv's
+   border-tap sums */
+int b200_act_bwd_stats(const void* g, int g_cs, int g_co, const void* y, int N, int C, long long voxels, int act, float slope,
+                       const void* gadd, void* out, float* partials, b200_stream_t s);
 
 /* ---- MaxPool3d(2) (buildingblocks.py:356 -> max_pool3d_with_indices), floor mode ---------------- */
 int b200_maxpool_fwd(const void* x, int N, int D, int H, int W, int C, void* y, float* partials, b200_stream_t s);

@@ -569,28 +569,39 @@ __global__ void gn_bwd_apply_kernel(const bf16* __restrict__ dxhat, const bf16* 
 }
 
 // out = g[..., g_co : g_co + C] * act'(y) [+ gadd]; g has channel stride g_cs; gadd (dz form, contiguous) may alias out
+// STATS: also the per-channel (sum, sum of squares) of the 16-bit result -> partials [N][P][C][2] (as gn_bwd_apply_kernel<true>)
+template <bool STATS>
 __global__ void act_bwd_kernel(const bf16* g, int g_cs, int g_co, const bf16* __restrict__ y, int C, long long voxels, int P, int act,
-                               float slope, const bf16* gadd, bf16* out) {
+                               float slope, const bf16* gadd, bf16* out, float* __restrict__ partials) {
+  extern __shared__ float red[];
   int p = blockIdx.x, n = blockIdx.y;
   EwMap m = ew_map(C);
   long long v0, v1;
   ew_range(voxels, p, P, v0, v1);
-  if (!m.active) return;
-  const bf16x8* yp = reinterpret_cast<const bf16x8*>(y + (size_t)n * voxels * C);
-  bf16x8* op = reinterpret_cast<bf16x8*>(out + (size_t)n * voxels * C);
-  for (long long v = v0 + m.vl; v < v1; v += m.VL) {
-    float d[8], f[8], ga[8];
-    unpack8(*reinterpret_cast<const bf16x8*>(g + ((size_t)n * voxels + v) * g_cs + g_co + m.cg * 8), d);
-    unpack8(yp[v * m.CG + m.cg], f);
-    if (gadd) unpack8(*reinterpret_cast<const bf16x8*>(gadd + ((size_t)n * voxels + v) * C + m.cg * 8), ga);
+  if (!STATS && !m.active) return;
+  float s[8] = {0}, q[8] = {0};
+  if (m.active) {
+    const bf16x8* yp = reinterpret_cast<const bf16x8*>(y + (size_t)n * voxels * C);
+    bf16x8* op = reinterpret_cast<bf16x8*>(out + (size_t)n * voxels * C);
+    for (long long v = v0 + m.vl; v < v1; v += m.VL) {
+      float d[8], f[8], ga[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(g + ((size_t)n * voxels + v) * g_cs + g_co + m.cg * 8), d);
+      unpack8(yp[v * m.CG + m.cg], f);
+      if (gadd) unpack8(*reinterpret_cast<const bf16x8*>(gadd + ((size_t)n * voxels + v) * C + m.cg * 8), ga);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float t = d[i] * act_grad_from_out(f[i], act, slope);
-      if (gadd) t += ga[i];
-      d[i] = t;
+      for (int i = 0; i < 8; ++i) {
+        float t = d[i] * act_grad_from_out(f[i], act, slope);
+        if (gadd) t += ga[i];
+        d[i] = STATS ? bf16_round(t) : t;
+        if (STATS) {
+          s[i] += d[i];
+          q[i] += d[i] * d[i];
+        }
+      }
+      op[v * m.CG + m.cg] = pack8(d);
     }
-    op[v * m.CG + m.cg] = pack8(d);
   }
+  if (STATS) ew_write_partials(s, q, m, partials + ((size_t)n * P + p) * C * 2, red);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1562,9 +1573,21 @@ int b200_act_bwd(const void* g, int g_cs, int g_co, const void* y, int N, int C,
   B200_CHECK_ARG(g && g_cs % 8 == 0 && g_co % 8 == 0 && g_co + C <= g_cs, "act_bwd: bad gradient slice (cs=%d co=%d C=%d)", g_cs, g_co, C);
   int P = ew_blocks(voxels, C);
   dim3 grid(P, N);
-  act_bwd_kernel<<<grid, EW_THREADS, 0, ST(s)>>>((const bf16*)g, g_cs, g_co, (const bf16*)y, C, voxels, P, act, slope,
-                                                 (const bf16*)gadd, (bf16*)out);
+  act_bwd_kernel<false><<<grid, EW_THREADS, 0, ST(s)>>>((const bf16*)g, g_cs, g_co, (const bf16*)y, C, voxels, P, act, slope,
+                                                        (const bf16*)gadd, (bf16*)out, nullptr);
   B200_CHECK_LAUNCH("act_bwd");
+  return 0;
+}
+// the same + per-channel totals of the result: partials [N][b200_stats_partials_count][C][2]
+int b200_act_bwd_stats(const void* g, int g_cs, int g_co, const void* y, int N, int C, long long voxels, int act, float slope,
+                       const void* gadd, void* out, float* partials, b200_stream_t s) {
+  B200_CHECK_ARG(C % 8 == 0 && C <= 2048 && partials, "act_bwd_stats: C=%d must be a multiple of 8, partials required", C);
+  B200_CHECK_ARG(g && g_cs % 8 == 0 && g_co % 8 == 0 && g_co + C <= g_cs, "act_bwd_stats: bad gradient slice (cs=%d co=%d C=%d)", g_cs, g_co, C);
+  int P = ew_blocks(voxels, C);
+  dim3 grid(P, N);
+  act_bwd_kernel<true><<<grid, EW_THREADS, EW_THREADS * 16 * sizeof(float), ST(s)>>>((const bf16*)g, g_cs, g_co, (const bf16*)y, C, voxels, P,
+                                                                                    act, slope, (const bf16*)gadd, (bf16*)out, partials);
+  B200_CHECK_LAUNCH("act_bwd_stats");
   return 0;
 }
 

@@ -307,9 +307,21 @@ class Engine:
         if x.grad is None:
             x.grad = g
         else:
-            x.grad_partials = None  # accumulated in place below: the totals its producer emitted no longer describe it
-            n, d, h, w, c = x.dims
-            self.call("b200_act_bwd", _p(g), c, 0, _p(x.t), n, c, d * h * w, ACT_NONE, 0.0, _p(x.grad), _p(x.grad))
+            # accumulated in place; the totals an earlier writer emitted no longer describe it, the kernel emits the new ones
+            self.act_bwd_into(x, g, x.dims[4], 0, x.grad, ACT_NONE, 0.0)
+
+    def act_bwd_into(self, target, g, g_cs, g_co, out, act=None, slope=None):
+        """target.grad = g[..., g_co:g_co+C] * act'(target) [+ target.grad], written to `out` (may be g or target.grad itself); the kernel
+        also emits the per-channel totals of the result, which spares the producer conv's border-tap sums one read of the tensor"""
+        n, d, h, w, c = target.dims
+        vox = d * h * w
+        act = target.act if act is None else act
+        slope = target.slope if slope is None else slope
+        P = self.L.query("b200_stats_partials_count", n, c, vox)
+        parts = self.empty((n, P, c, 2), torch.float32)
+        self.call("b200_act_bwd_stats", _p(g), g_cs, g_co, _p(target.t), n, c, vox, act, float(slope), _p(target.grad), _p(out), _p(parts))
+        target.grad = out
+        target.grad_partials = (parts, P, out)
 
     def border_tap_sums(self, out, dz, n, d, h, w, cout):
         """T[n][tap][co] = sum of dz over the voxels whose tap is in bounds; the per-channel totals come from the kernel that produced dz
@@ -473,10 +485,7 @@ class Engine:
                                        sums2=None if gn is None else sums2.clone(), coef=None if coef is None else coef.clone(),
                                        mean_rstd=None if mean_rstd is None else mean_rstd.clone())
                 if residual is not None and residual.requires_grad:
-                    g = self.empty(residual.t.shape, self.adt)
-                    self.call("b200_act_bwd", _p(dz), cout, 0, _p(residual.t), n, cout, vox, residual.act, residual.slope,
-                              _p(residual.grad), _p(g))
-                    residual.grad = g
+                    self.act_bwd_into(residual, dz, cout, 0, self.empty(residual.t.shape, self.adt))
                 if x.requires_grad:
                     if is_f32:
                         raise NotImplementedError("gradient w.r.t. the fp32 network input is not provided by the engine")
@@ -496,8 +505,9 @@ class Engine:
                         self.gn_bwd_apply(dxhat, x, coef, n, cin, vox)
                     else:
                         if x.act != ACT_NONE or x.grad is not None:
-                            self.call("b200_act_bwd", _p(dxhat), cin, 0, _p(x.t), n, cin, vox, x.act, x.slope, _p(x.grad), _p(dxhat))
-                        x.grad = dxhat
+                            self.act_bwd_into(x, dxhat, cin, 0, dxhat)
+                        else:
+                            x.grad = dxhat
                     if DEBUG is not None:
                         DEBUG[name]["dx"] = dxhat.clone()
                 out.grad = None
@@ -541,14 +551,9 @@ class Engine:
                 self._add_param_grad(gname, dgamma)
                 self._add_param_grad(bname, dbeta)
                 if residual is not None and residual.requires_grad:
-                    gr = self.empty(residual.t.shape, self.adt)
-                    self.call("b200_act_bwd", _p(du), c, 0, _p(residual.t), n, c, vox, residual.act, residual.slope,
-                              _p(residual.grad), _p(gr))
-                    residual.grad = gr
+                    self.act_bwd_into(residual, du, c, 0, self.empty(residual.t.shape, self.adt))
                 if z.requires_grad:
-                    g = self.empty(z.t.shape, self.adt)
-                    self.call("b200_gn_bwd_apply", _p(du), _p(z.t), _p(coef), n, c, vox, z.act, z.slope, _p(z.grad), _p(g))
-                    z.grad = g
+                    self.gn_bwd_apply(du, z, coef, n, c, vox)   # in place over du (not read again), channel totals emitted
                 out.grad = None
             self.tape.append(backward)
         return out
@@ -772,8 +777,9 @@ class Engine:
                             self.gn_bwd_apply(ge, enc, coef[:, :c0].contiguous(), n, c0, vox)
                     else:
                         if enc.act != ACT_NONE or enc.grad is not None:
-                            self.call("b200_act_bwd", _p(ge), c0, 0, _p(enc.t), n, c0, vox, enc.act, enc.slope, _p(enc.grad), _p(ge))
-                        enc.grad = ge
+                            self.act_bwd_into(enc, ge, c0, 0, ge)
+                        else:
+                            enc.grad = ge
                 if low.requires_grad:
                     gl = self.empty(low.t.shape, self.adt)
                     if self.impl != IMPL_DIRECT and L.query("b200_conv3_up_dgrad_zs_supported", n, d, h, w, cout, c1):
@@ -793,8 +799,9 @@ class Engine:
                         self.gn_bwd_apply(gl, low, (coef[:, c0:] * self._k188).contiguous(), n, c1, lvox)
                     else:
                         if low.act != ACT_NONE or low.grad is not None:
-                            self.call("b200_act_bwd", _p(gl), c1, 0, _p(low.t), n, c1, lvox, low.act, low.slope, _p(low.grad), _p(gl))
-                        low.grad = gl
+                            self.act_bwd_into(low, gl, c1, 0, gl)
+                        else:
+                            low.grad = gl
                 if not published:
                     self.side_join(tail)
                     publish()
@@ -822,11 +829,8 @@ class Engine:
                     self.call(bwd, _p(dcat), c0, c1, _p(x.t), n, D, H, W, d, h, w, x.act, x.slope, _p(g))
                     self.accumulate_grad(x, g)
                 if enc.requires_grad:
-                    ge = self.empty(enc.t.shape, self.adt)
-                    # ge = dcat[..., :c0] * act'(enc) + enc.grad (enc.grad, if any, is already in dz form)
-                    self.call("b200_act_bwd", _p(dcat), c0 + c1, 0, _p(enc.t), n, c0, D * H * W, enc.act, enc.slope,
-                              _p(enc.grad), _p(ge))
-                    enc.grad = ge
+                    # enc.grad = dcat[..., :c0] * act'(enc) + enc.grad (enc.grad, if any, is already in dz form)
+                    self.act_bwd_into(enc, dcat, c0 + c1, 0, self.empty(enc.t.shape, self.adt))
                 out.grad = None
             self.tape.append(backward)
         return out
@@ -892,8 +896,9 @@ class Engine:
                     else:
                         self.call("b200_pointwise_fwd", _p(dy), 0, _p(W2), 1, None, n, vox, cout, cin, _p(g), None)
                     if x.act != ACT_NONE or x.grad is not None:
-                        self.call("b200_act_bwd", _p(g), cin, 0, _p(x.t), n, cin, vox, x.act, x.slope, _p(x.grad), _p(g))
-                    x.grad = g
+                        self.act_bwd_into(x, g, cin, 0, g)
+                    else:
+                        x.grad = g
                 out.grad = None
             self.tape.append(backward)
         return out
@@ -956,9 +961,7 @@ class Engine:
                 self.call("b200_deconv_gather", _p(g), n, d, h, w, D, H, W_, cout, _p(dT))
                 self.accumulate_grad(T, dT)
                 if enc.requires_grad:
-                    ge = self.empty(enc.t.shape, self.adt)
-                    self.call("b200_act_bwd", _p(g), cout, 0, _p(enc.t), n, cout, D * H * W_, enc.act, enc.slope, _p(enc.grad), _p(ge))
-                    enc.grad = ge
+                    self.act_bwd_into(enc, g, cout, 0, self.empty(enc.t.shape, self.adt))
                 out.grad = None
             self.tape.append(backward)
         return out
@@ -1001,12 +1004,11 @@ class Engine:
                     self.call("b200_deconv_phase_dgrad", _p(gp), _p(wd), n, d, h, w, cout, cin, _p(gx),
                               flops=2.0 * n * d * h * w * 27 * cin * cout, tag="dgrad_tc", layer=wname)
                     if x.act != ACT_NONE or x.grad is not None:
-                        self.call("b200_act_bwd", _p(gx), cin, 0, _p(x.t), n, cin, d * h * w, x.act, x.slope, _p(x.grad), _p(gx))
-                    x.grad = gx
+                        self.act_bwd_into(x, gx, cin, 0, gx)
+                    else:
+                        x.grad = gx
                 if enc.requires_grad:
-                    ge = self.empty(enc.t.shape, self.adt)
-                    self.call("b200_act_bwd", _p(g), cout, 0, _p(enc.t), n, cout, D * H * W_, enc.act, enc.slope, _p(enc.grad), _p(ge))
-                    enc.grad = ge
+                    self.act_bwd_into(enc, g, cout, 0, self.empty(enc.t.shape, self.adt))
                 out.grad = None
             self.tape.append(backward)
         return out

@@ -205,6 +205,26 @@ def test_maxpool_fwd_bwd(dims):
     assert U.rel_l2(out, ref) < 5e-3
 
 
+def test_act_bwd_stats_variant_matches_plain_and_emits_totals():
+    U, E, L = _ctx()
+    N, D, H, W, C, CS = 2, 5, 6, 7, 24, 40
+    g = _rand((N, D, H, W, CS), 41)
+    y = F.elu(_rand((N, D, H, W, C), 42).float()).bfloat16()
+    gadd = _rand((N, D, H, W, C), 43)
+    vox = D * H * W
+    ref = torch.empty_like(y)
+    L.call("b200_act_bwd", U.p(g), CS, 8, U.p(y), N, C, vox, E.ACT_ELU, 0.0, U.p(gadd), U.p(ref), U.stream())
+    P = L.query("b200_stats_partials_count", N, C, vox)
+    parts = torch.full((N, P, C, 2), float("nan"), device="cuda")
+    out = gadd.clone()   # in place over the accumulated gradient, as Engine.accumulate_grad uses it
+    L.call("b200_act_bwd_stats", U.p(g), CS, 8, U.p(y), N, C, vox, E.ACT_ELU, 0.0, U.p(out), U.p(out), U.p(parts), U.stream())
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)
+    od = out.double()
+    assert U.rel_l2(parts.double().sum(1)[..., 0], od.sum((1, 2, 3))) < 1e-5
+    assert U.rel_l2(parts.double().sum(1)[..., 1], (od * od).sum((1, 2, 3))) < 1e-5
+
+
 @pytest.mark.parametrize("C", [32, 48, 128])   # C/8 a power of two: lane-pair kernel; 48: one thread per cell
 @pytest.mark.parametrize("dims", [(8, 8, 8), (5, 9, 7), (16, 12, 20)])
 def test_maxpool_bwd_fused_with_deferred_groupnorm_backward(dims, C, monkeypatch):
