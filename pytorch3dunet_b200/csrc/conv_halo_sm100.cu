@@ -66,7 +66,7 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
   uint8_t* smemA = smem + b_region;
   float* scratch_base = reinterpret_cast<float*>(smemA + (size_t)p.a_stages * p.a_bytes);  // [2 groups][2 alternating][4 warps][NT][2]
   float* bias_interior = scratch_base + 4 * 4 * p.NT * 2;                                    // [8 parity variants][NT]
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // provably warp-uniform
   const int n = blockIdx.y, cta = blockIdx.x, cps = gridDim.x;
   const int tiles = p.tilesD * p.tilesH * p.tilesW;
   const int nchunksA = p.Cin / KC;

@@ -25,7 +25,7 @@ conv3_igemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_const
   __shared__ uint32_t tmem_slot;
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // provably warp-uniform
   const int stage_bytes = p.a_bytes + p.b_bytes;
 
   // tile coordinates

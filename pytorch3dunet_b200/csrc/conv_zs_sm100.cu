@@ -52,7 +52,7 @@ conv3_zs_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
   constexpr int WARP_PRODUCER = NEW, WARP_MMA = NEW + 2;  // two producers, two issuers (lane = (warp - NEW) & 1)
   float* stat_acc = reinterpret_cast<float*>(smemA + (size_t)p.a_stages * p.a_bytes);  // [NEW epilogue warps][NT][2]
   float* bias_interior = stat_acc + NEW * p.NT * 2;                                      // [8 parity variants][NT]
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // provably warp-uniform: the role branches and descriptor math below stay on the uniform datapath
   const int n = blockIdx.y, cta = blockIdx.x, cps = gridDim.x;
   const int n0 = blockIdx.z * p.NT;  // output-channel slice of this CTA (C_out > NT: the resident weights of NT channels fit, those of C_out do not)
   const int nchunks = p.Cin / KC;

@@ -74,7 +74,7 @@ conv3_upzs_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
   uint8_t* smemB = smem;
   const int b_region = (p.b_total_bytes + 1023) & ~1023;
   uint8_t* smemA = smem + b_region;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // provably warp-uniform
   const int n = blockIdx.y, cta = blockIdx.x, cps = gridDim.x;
   const int nslices = p.Cout / p.NT;
   const int ipz = blockIdx.z / nslices;             // in-plane phase (ph, pw)

@@ -51,7 +51,7 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_consta
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smemA = smem;
   uint8_t* smemB = smem + (size_t)p.a_stages * p.a_bytes;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // provably warp-uniform
   constexpr int rbA = CA * 2;
 
   const int split = blockIdx.x % p.S, n = blockIdx.x / p.S;
@@ -206,7 +206,7 @@ wgrad_hs_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constant
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smemA = smem;
   uint8_t* smemB = smem + (size_t)p.a_stages * p.a_bytes;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // provably warp-uniform
   constexpr int rbA = CA * 2;
   const int rbB = p.Cout * 2;
 

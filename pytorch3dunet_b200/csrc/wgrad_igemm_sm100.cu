@@ -59,7 +59,7 @@ conv3_wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smemB = smem;                                           // WG_B_STAGES * b_stage_bytes
   uint8_t* smemA = smem + (size_t)WG_B_STAGES * p.b_stage_bytes;   // a_stages * WG_A_STAGE_BYTES
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // provably warp-uniform
 
   const int split = blockIdx.x % p.S;
   const int n = blockIdx.x / p.S;

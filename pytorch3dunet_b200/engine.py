@@ -225,6 +225,14 @@ class Engine:
             self._side_keep = []
         return True
 
+    def side_mark(self, on):
+        """event at the current point of an open side section (None when the section is not open)"""
+        if not on:
+            return None
+        ev = torch.cuda.Event()
+        ev.record(_side_stream(self.device))
+        return ev
+
     def side_end(self, on):
         if not on:
             return None
@@ -232,6 +240,11 @@ class Engine:
         ev = torch.cuda.Event()
         ev.record(_side_stream(self.device))
         return ev
+
+    def side_join_event(self, ev):
+        """main stream waits for a point of the side stream (side work stays outstanding: buffers are kept)"""
+        if ev is not None:
+            torch.cuda.current_stream(self.device).wait_event(ev)
 
     def side_join(self, ev):
         if ev is not None:
@@ -434,10 +447,18 @@ class Engine:
                 if dz is None:
                     return
                 need_T = gn is not None or bias is not None
-                T = None
-                if need_T:   # only the reduction tail reads T: computed on the second stream, under the weight-gradient kernel
+                T = wd = wd_ready = None
+                want_dx = x.requires_grad and not is_f32
+                if need_T or want_dx:
+                    # second stream, under the weight-gradient kernel: the tap-flipped 16-bit weights of the data-gradient conv (needs
+                    # only W) and the border tap sums T (only the reduction tail reads them)
                     on_side = self.side_begin()
-                    T = self.border_tap_sums(out, dz, n, d, h, w, cout)
+                    if want_dx:
+                        wd = self.empty((27, cin, cout), self.adt)
+                        self.call("b200_prep_dgrad_weights", _p(W), cin, cout, _p(wd))
+                        wd_ready = self.side_mark(on_side)
+                    if need_T:
+                        T = self.border_tap_sums(out, dz, n, d, h, w, cout)
                     self.side_end(on_side)
                 wimpl = L.query("b200_conv3_wgrad_resolve_impl", self.impl, n, d, h, w, cin, cout, int(is_f32))
                 if wimpl < 0:
@@ -489,8 +510,7 @@ class Engine:
                 if x.requires_grad:
                     if is_f32:
                         raise NotImplementedError("gradient w.r.t. the fp32 network input is not provided by the engine")
-                    wd = self.empty((27, cin, cout), self.adt)
-                    self.call("b200_prep_dgrad_weights", _p(W), cin, cout, _p(wd))
+                    self.side_join_event(wd_ready)
                     dimpl = L.query("b200_conv3_resolve_impl", self.impl, n, d, h, w, cout, cin, 0)
                     if dimpl < 0:
                         raise B200Error("tcgen05 dgrad requested but unsupported for this shape")
@@ -713,10 +733,17 @@ class Engine:
                 dz = out.grad
                 if dz is None:
                     return
-                T = None
-                if gn is not None or bias is not None:
-                    on_side = self.side_begin()
-                    T = self.border_tap_sums(out, dz, n, D, H, Wd, cout)
+                T = wd_enc = wd_up = wd_ready = None
+                want_dx = enc.requires_grad or low.requires_grad
+                if gn is not None or bias is not None or want_dx:
+                    on_side = self.side_begin()   # under the two weight-gradient kernels
+                    if want_dx:
+                        wd_enc = self.empty((27, c0, cout), self.adt)
+                        wd_up = self.empty((64, c1, cout), self.adt)
+                        self.call("b200_upcat_prep_dgrad_weights", _p(W), c0, c1, cout, _p(wd_enc), _p(wd_up))
+                        wd_ready = self.side_mark(on_side)
+                    if gn is not None or bias is not None:
+                        T = self.border_tap_sums(out, dz, n, D, H, Wd, cout)
                     self.side_end(on_side)
                 S1 = L.query("b200_conv3_wgrad_splits", IMPL_TCGEN05, n, D, H, Wd, c0, cout, 0)
                 G_enc = self.empty((n, S1, 27, c0, cout), torch.float32)
@@ -754,10 +781,7 @@ class Engine:
                     if gn is not None:
                         self._add_param_grad(gn[3], dgamma)
                         self._add_param_grad(gn[4], dbeta)
-                if enc.requires_grad or low.requires_grad:
-                    wd_enc = self.empty((27, c0, cout), self.adt)
-                    wd_up = self.empty((64, c1, cout), self.adt)
-                    self.call("b200_upcat_prep_dgrad_weights", _p(W), c0, c1, cout, _p(wd_enc), _p(wd_up))
+                self.side_join_event(wd_ready)
                 if enc.requires_grad:
                     dimpl = L.query("b200_conv3_resolve_impl", self.impl, n, D, H, Wd, cout, c0, 0)
                     if dimpl < 0:
