@@ -374,11 +374,12 @@ def run_train(args, wl):
     peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
     traffic, traffic_note = None, None
     try:  # dram bytes of the longest launch of the largest-share kernel, from the committed ncu --set full capture of one cfg-2 step
-        prof = json.load(open(os.path.join(ROOT, "profiles", "ncu_r02_full_summary.json")))["conv3_zs_kernel"]
+        prof = json.load(open(os.path.join(ROOT, "profiles", "ncu_r02_full_summary.json")))["conv3_zs_kernel<32, 2>"]
         mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         traffic = sum(float(prof[k]["value"]) * mult.get(prof[k]["unit"], 1.0) for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
-        traffic_note = ("dram read+write bytes of ONE conv3_zs_kernel launch (the longest of the step: a 32->32 layer @ 2x128^3, algorithmic "
-                        "537 MB = x + y), profiles/ncu_r02_full_summary.md")
+        traffic_note = ("dram read+write bytes of ONE conv3_zs_kernel<32,2> launch, the longest of the step: decoders.2.SingleConv1's encoder "
+                        "half, 32->32 @ 2x128^3 with the phase-conv result as residual input (algorithmic 805 MB = x + R + y; the plain "
+                        "32->32 launches move 701 MB against 537 MB = x + y), profiles/ncu_r02_full_summary.md")
     except Exception:
         pass
     roofline = {"bound": "tensor", "kernel": "tcgen05 conv kernels: conv3_zs_kernel / conv3_upzs_kernel / conv3_updzs_kernel / conv3_igemm_kernel (fprop+dgrad), wgrad_hs_kernel / wgrad_up_kernel / wgrad_halo_kernel / conv3_wgrad_igemm_kernel",

@@ -41,7 +41,7 @@ for r in data:
     by.setdefault(name, []).append(r)
 out_json = {}
 md = ["# ncu --set full captures, round 02: every launch of the tensor-core kernel families in ONE cfg-2 training step\n",
-      "Command: `tools/gpu_ncu_full_r02.sh` (`ncu --set full --clock-control none --import-source on -k regex:<families> -c 80 python tools/one_step.py cfg2 1`).",
+      "Command: `tools/gpu_ncu_full_r02.sh` (`ncu --set full --clock-control none --import-source on -k regex:<families> -c 34 python tools/one_step.py cfg2 1`).",
       "UNet3D f_maps=32 depth=4, batch 2x1x128^3, forward + BCEDice + backward.  Times under ncu are cold-cache and serialised (replayed",
       "passes): read tensor-pipe %, DRAM bytes and L2->SM bytes, not absolute durations (those are in `profiles/bench_r02_*.json`).\n",
       "## all captured launches\n",
@@ -55,7 +55,7 @@ for name, rs in by.items():
 md.append("\n## the longest launch of every kernel (full metric set used by the roofline)\n")
 for name, rs in by.items():
     r = max(rs, key=to_us)
-    key = name.replace("b200::", "").split("<")[0]
+    key = name.replace("b200::", "")   # full name with template arguments: conv3_zs_kernel<32, 2> != conv3_zs_kernel<64, 2>
     out_json.setdefault(key, {})
     md += [f"### {name}\n", "| metric | value | unit |", "|---|---:|---|"]
     for w in WANT:
