@@ -252,37 +252,38 @@ __global__ void gn_coeffs_kernel(const double* __restrict__ sums, const float* _
   }
 }
 
-// partials_finalize + gn_coeffs in one launch: grid N, block (32,32).  The column sums are formed exactly as partials_finalize_kernel
-// forms them (same order, fp64), so `sums` is bit-identical to the two-kernel route.
+// partials_finalize + gn_coeffs in one launch: grid (N, G) -- one block per (sample, GroupNorm group) -- block (32,32).  The column sums
+// are formed exactly as partials_finalize_kernel forms them (same order, fp64), so `sums` is bit-identical to the two-kernel route.
 __global__ void gn_stats_coeffs_kernel(const float* __restrict__ partials, int P, int C, const float* __restrict__ gamma,
                                        const float* __restrict__ beta, int G, double count, double* __restrict__ sums,
                                        float* __restrict__ mean_rstd, float* __restrict__ ab) {
-  extern __shared__ double dsm[];      // [C*2] column sums, then [G*2] floats
+  extern __shared__ double dsm[];      // [cpg*2] column sums of this group
   __shared__ double red[32][33];
-  const int n = blockIdx.x;
+  __shared__ float gst[2];
+  const int n = blockIdx.x, g = blockIdx.y;
   const int tid = threadIdx.y * 32 + threadIdx.x;
-  for (int c0 = 0; c0 < C * 2; c0 += 32) {
-    const int col = c0 + threadIdx.x;
+  const int cpg = C / G;
+  const int col0 = g * cpg * 2, ncol = cpg * 2;
+  for (int c0 = 0; c0 < ncol; c0 += 32) {
+    const int lc = c0 + threadIdx.x;
     double acc = 0.0;
-    if (col < C * 2) {
-      const float* base = partials + (size_t)n * P * C * 2 + col;
+    if (lc < ncol) {
+      const float* base = partials + (size_t)n * P * C * 2 + col0 + lc;
       for (int p = threadIdx.y; p < P; p += 32) acc += (double)base[(size_t)p * C * 2];
     }
     red[threadIdx.y][threadIdx.x] = acc;
     __syncthreads();
-    if (threadIdx.y == 0 && col < C * 2) {
+    if (threadIdx.y == 0 && lc < ncol) {
       double t = 0.0;
       for (int i = 0; i < 32; ++i) t += red[i][threadIdx.x];
-      dsm[col] = t;
-      sums[(size_t)n * C * 2 + col] = t;
+      dsm[lc] = t;
+      sums[(size_t)n * C * 2 + col0 + lc] = t;
     }
     __syncthreads();
   }
-  float* gsm = reinterpret_cast<float*>(dsm + (size_t)C * 2);
-  const int cpg = C / G;
-  for (int g = tid; g < G; g += 1024) {
+  if (tid == 0) {
     double s = 0.0, q = 0.0;
-    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+    for (int c = 0; c < cpg; ++c) {
       s += dsm[c * 2];
       q += dsm[c * 2 + 1];
     }
@@ -291,18 +292,18 @@ __global__ void gn_stats_coeffs_kernel(const float* __restrict__ partials, int P
     double var = q / m - mean * mean;  // biased variance, as native_group_norm
     if (var < 0.0) var = 0.0;
     const float rstd = (float)(1.0 / sqrt(var + 1e-5));
-    gsm[g * 2] = (float)mean;
-    gsm[g * 2 + 1] = rstd;
+    gst[0] = (float)mean;
+    gst[1] = rstd;
     if (mean_rstd) {
       mean_rstd[((size_t)n * G + g) * 2] = (float)mean;
       mean_rstd[((size_t)n * G + g) * 2 + 1] = rstd;
     }
   }
   __syncthreads();
-  for (int c = tid; c < C; c += 1024) {
-    const int g = c / cpg;
-    const float a = gamma[c] * gsm[g * 2 + 1];
-    const float b = beta[c] - gsm[g * 2] * a;
+  for (int lc = tid; lc < cpg; lc += 1024) {
+    const int c = g * cpg + lc;
+    const float a = gamma[c] * gst[1];
+    const float b = beta[c] - gst[0] * a;
     ab[((size_t)n * C + c) * 2] = a;
     ab[((size_t)n * C + c) * 2 + 1] = b;
   }
@@ -1496,9 +1497,9 @@ int b200_gn_fold(const double* sums, const float* gamma, const float* beta, int 
 int b200_gn_stats_coeffs(const float* partials, int N, int P, int C, const float* gamma, const float* beta, int G, double count,
                          double* sums, float* mean_rstd, float* ab, b200_stream_t s) {
   B200_CHECK_ARG(G > 0 && C % G == 0 && C <= 2048, "gn_stats_coeffs: C=%d G=%d unsupported", C, G);
-  dim3 block(32, 32);
-  size_t smem = (size_t)C * 2 * sizeof(double) + (size_t)G * 2 * sizeof(float);
-  gn_stats_coeffs_kernel<<<N, block, smem, ST(s)>>>(partials, P, C, gamma, beta, G, count, sums, mean_rstd, ab);
+  dim3 grid(N, G), block(32, 32);
+  size_t smem = (size_t)(C / G) * 2 * sizeof(double);
+  gn_stats_coeffs_kernel<<<grid, block, smem, ST(s)>>>(partials, P, C, gamma, beta, G, count, sums, mean_rstd, ab);
   B200_CHECK_LAUNCH("gn_stats_coeffs");
   return 0;
 }
