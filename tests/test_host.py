@@ -140,3 +140,39 @@ def test_engine_only_calls_declared_entry_points():
         used |= set(re.findall(r'"(b200_\w+)"', open(f).read()))
     missing = sorted(used - protos - {"b200_stream_t"})
     assert not missing, missing
+
+
+def test_deferred_groupnorm_backward_is_applied_by_any_reader_of_grad():
+    """engine.Act: a skip connection's GroupNorm backward left pending for the max-pool backward (Act.deferred) must not get lost when
+    something else reads `.grad` first -- the read applies it (host logic, stub engine)."""
+    import torch
+    from pytorch3dunet_b200 import engine as E
+
+    class StubEngine:
+        def __init__(self):
+            self.calls = []
+
+        def gn_bwd_apply(self, dxhat, x, coef, n, c, vox):
+            self.calls.append((n, c, vox, x._grad))
+            x.grad = dxhat + 1   # stands for the kernel's result
+
+    a = E.Act(torch.zeros(2, 3, 4, 5, 8))
+    assert a.grad is None and a.deferred is None and not a.pool_pending
+    eng = StubEngine()
+    dxhat = torch.full((2, 3, 4, 5, 8), 2.0)
+    a.deferred = (dxhat, torch.zeros(2, 8, 3), eng)
+    g = a.grad                                   # first reader: applies the pending term exactly once
+    assert torch.equal(g, dxhat + 1) and a.deferred is None
+    assert eng.calls == [(2, 8, 60, None)]
+    assert a.grad is g and len(eng.calls) == 1   # later reads do not re-apply
+    a.grad = None
+    assert a.grad is None
+
+
+def test_partials_count_of_new_entry_points_without_gpu():
+    """query-style entry points added in round 2 answer on the host (no device work)"""
+    from pytorch3dunet_b200._lib import lib
+    L = lib()
+    assert L.query("b200_maxpool_bwd_partials_count", 2, 16, 16, 16, 32) >= 1
+    assert L.query("b200_conv3_direct_wgrad_splits", 2, 16, 16, 16, 1, 16, 1) >= 1      # first conv: one split slot per block
+    assert L.query("b200_conv3_direct_wgrad_splits", 2, 16, 16, 16, 24, 16, 0) == 1     # generic CUDA-core fallback
